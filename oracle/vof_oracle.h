@@ -1,0 +1,108 @@
+/* TEST INFRASTRUCTURE — not part of the product.
+ *
+ * CPU restatement (serial, FP64, OpenFOAM face-loop order) of the OpenFOAM-13
+ * `incompressibleVoF` PIMPLE time step that elvis-aguero/openfoam-TPP runs through
+ * `foamRun` (circularSloshingTank/Makefile:71-99, system/controlDict:17).  Only tests/,
+ * __graft_entry__.smoke() and bench.py's cpu_baseline / --impl reference legs may load it.
+ *
+ * PARITY UNPINNED at the bit level: the arithmetic lives in OpenFOAM Foundation 13
+ * (build 13-cde978a97c93, circularSloshingTank/result.txt:8), which is neither vendored in
+ * the reference nor installed here, and the reference holds no test for this path.  The
+ * restatement follows the reference's dictionaries (which algorithm) and OpenFOAM's
+ * published algorithm as recalled ([OF13-MEM] in SURVEY.md §2.4); it is pinned only through
+ * the committed run artefacts G1-G5 - see tests/test_golden.py.
+ */
+#ifndef VOF_ORACLE_H
+#define VOF_ORACLE_H
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+/* boundary-condition codes (0/U, 0/alpha.water, 0/p_rgh of the case template) */
+enum { ORC_U_MOVING_WALL = 0, ORC_U_PRESSURE_INLET_OUTLET = 1 };
+enum { ORC_A_ZERO_GRADIENT = 0, ORC_A_INLET_OUTLET = 1 };
+enum { ORC_P_FIXED_FLUX = 0, ORC_P_TOTAL_PRESSURE = 1 };
+
+typedef struct {
+    int n_points, n_faces, n_internal, n_cells, n_patches;
+    const double* points;    /* n_points x 3, undisplaced (constant/polyMesh/points) */
+    const int* face_offsets; /* n_faces + 1 */
+    const int* face_labels;
+    const int* owner;        /* n_faces */
+    const int* neighbour;    /* n_internal */
+    const int* patch_start;  /* n_patches */
+    const int* patch_size;
+    const int* patch_bc_u;   /* ORC_U_* */
+    const int* patch_bc_alpha;
+    const int* patch_bc_p;
+    const double* patch_inlet_alpha; /* inletOutlet inletValue */
+    const double* patch_p0;          /* totalPressure p0 */
+} orc_mesh_t;
+
+typedef struct {
+    int type;      /* 0 = PCG, 1 = GAMG */
+    int precond;   /* PCG: 0 = DIC, 1 = GAMG */
+    int smoother;  /* GAMG: 0 = DIC, 1 = DICGaussSeidel, 2 = GaussSeidel */
+    double tolerance, rel_tol;
+    int max_iter;
+    int n_vcycles, n_pre_sweeps, n_post_sweeps, n_finest_sweeps;
+    int n_cells_coarsest, merge_levels;
+} orc_solver_t;
+
+typedef struct {
+    /* system/controlDict */
+    double start_time, end_time, delta_t, write_interval;
+    double max_co, max_alpha_co, max_delta_t;
+    int adjust_time_step;
+    /* constant/ */
+    double g[3];
+    double rho1, rho2, nu1, nu2, sigma;
+    /* system/fvSolution: alpha.water */
+    int n_alpha_subcycles, n_alpha_corr, n_limiter_iter;
+    double c_alpha;
+    /* PIMPLE */
+    int n_correctors, n_non_orth;
+    double p_ref_point[3], p_ref_value;
+    orc_solver_t p_rgh, p_rgh_final;
+    /* constant/dynamicMeshDict + 6DoF.dat */
+    double cofg[3];
+    int n_motion;          /* 0: static mesh */
+    const double* motion;  /* n_motion x 7: t, tx ty tz, rx ry rz (deg) */
+} orc_config_t;
+
+typedef struct orc_state orc_state;
+
+orc_state* orc_create(const orc_mesh_t* mesh, const orc_config_t* cfg);
+void orc_destroy(orc_state*);
+const char* orc_last_error(void);
+
+/* named arrays: returns element count (doubles) or -1; copies in/out */
+long orc_size(orc_state*, const char* name);
+long orc_get(orc_state*, const char* name, double* out, long cap);
+long orc_set(orc_state*, const char* name, const double* in, long n);
+long orc_get_int(orc_state*, const char* name, int* out, long cap);
+
+/* run one named stage on the current state; 0 on success */
+int orc_stage(orc_state*, const char* name);
+/* n full time steps (Courant -> deltaT -> move -> alpha -> momentum -> pressure) */
+int orc_step(orc_state*, int n);
+/* run until the next write time or end_time; returns 1 if a write time was hit, 0 at end */
+int orc_run_to_write(orc_state*, long max_steps);
+
+/* t, deltaT, step index, Co, alphaCo, last solver iterations (2 correctors) + residuals */
+void orc_info(orc_state*, double* out16);
+
+/* linear-solver entry used by tests: solve A x = b on the mesh's LDU addressing */
+int orc_solve(orc_state*, const orc_solver_t* ctl, const double* diag, const double* upper,
+              const double* b, double* x, double* init_res, double* final_res);
+
+/* probes: cell labels (or -1) sampled every step into an internal log */
+void orc_set_probes(orc_state*, int n, const int* cells);
+long orc_probe_log(orc_state*, double* out, long cap_rows); /* rows of (t, v0..vn-1); drains */
+int orc_find_cell(orc_state*, const double* xyz);
+
+#ifdef __cplusplus
+}
+#endif
+#endif
