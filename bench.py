@@ -1,0 +1,301 @@
+#!/usr/bin/env python
+"""bench.py — whole-step throughput of the incompressibleVoF PIMPLE time step.
+
+Workload (BASELINE.json configs[3], the configuration the metric is quoted on): the
+D = 0.2 m, H = 0.208 m flat-bottom tank, orbital shaking R = 4 mm at 1.88 Hz
+(case_H0.208_D0.2_flat_R0.004_f1.88_d20.0_m0.009), tet mesh synthetically refined to
+--cells per GPU (default ~2.1 M; the 8-GPU run of the ~50 M-cell case is 6.2 M per GPU).
+A "step" is one full time step: Courant -> deltaT -> mesh motion -> 3 MULES sub-cycles ->
+momentum assembly -> 2 pressure correctors (GAMG-PCG solves).
+
+  python bench.py [--gpus N] [--steps K] [--warmup W] [--impl reference]
+
+Prints ONE JSON line (see the task contract): value = cell-steps/s with the state resident
+in HBM; e2e = the same metric through the C-ABI with pinned host buffers copied in and out
+every step; roofline = the dominant kernel's algorithmic bytes / CUDA-event time against the
+measured HBM peak; cpu_baseline = the CPU oracle (a restatement, not OpenFOAM) on a bounded
+sample of the same workload.
+"""
+import argparse
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+import numpy as np  # noqa: E402
+
+METRIC = "cell_steps_per_s"
+UNIT = "Mcell-steps/s"
+CASE = dict(H=0.208, D=0.2, R=0.004, freq=1.88, duration=20.0, dt=0.001, ramp=2.0)
+
+
+def mesh_for(cells_target):
+    """n_rings / n_layers giving ~cells_target tets with near-isotropic cells."""
+    from openfoam_tpp_b200 import meshgen
+
+    # cells = 18 nr^2 nl ; isotropy: (D/2)/nr ~ H/nl  ->  nl = nr * H/(D/2)
+    ratio = CASE["H"] / (CASE["D"] / 2)
+    nr = max(4, int(round((cells_target / (18.0 * ratio)) ** (1.0 / 3.0))))
+    nl = max(4, int(round(nr * ratio)))
+    return meshgen.cylinder_mesh(CASE["H"], CASE["D"], nr, nl, "flat", "tet"), nr, nl
+
+
+def make_config(mesh):
+    """The reference's numerics (case template) on the synthetic mesh, without touching disk."""
+    import tempfile
+
+    from openfoam_tpp_b200 import case as cs
+    from openfoam_tpp_b200 import foamfile as ff
+    from openfoam_tpp_b200 import motion
+
+    with tempfile.TemporaryDirectory() as tmp:
+        cs.write_template(tmp, end_time=CASE["duration"], fill_z=CASE["H"] / 2)
+        rows = motion.orbital_table(CASE["R"], CASE["freq"], 3.0, CASE["dt"], CASE["ramp"])
+        motion.write_table(os.path.join(tmp, "constant", "6DoF.dat"), rows)
+        cfg = cs.read_config(tmp, None)
+        fields = {n: ff.read_field(os.path.join(tmp, "0", n)) for n in ("U", "alpha.water", "p_rgh")}
+        cs._bc_tables(cfg, mesh, fields, "0")
+    cfg.start_time = 0.0
+    return cfg
+
+
+def initial_alpha(mesh):
+    from openfoam_tpp_b200 import meshgen
+
+    C, _ = meshgen.cell_geometry(mesh)
+    return (C[:, 2] <= CASE["H"] / 2).astype(np.float64)
+
+
+ALG_BYTES = {
+    # algorithmic bytes per launch (SURVEY.md §8d convention: each distinct array once; FP64 8 B,
+    # label 4 B; C cells, F internal faces)
+    "jacobi": lambda C, F: 32 * C + 16 * F,            # x, b, diag in; x out; upper + addressing
+    "spmv_dot": lambda C, F: 24 * C + 16 * F,
+    "restrict_residual": lambda C, F: 24 * C + 16 * F + 8 * C / 4,
+    "grad_scalar": lambda C, F: 32 * C + 40 * F,
+    "alpha_flux": lambda C, F: 56 * C + 56 * F,
+    "mules_setup": lambda C, F: 40 * C + 32 * F,
+    "mules_cell": lambda C, F: 16 * C + 32 * F,
+    "mules_face": lambda C, F: 16 * C + 24 * F,
+    "mules_update": lambda C, F: 24 * C + 16 * F,
+    "grad_U": lambda C, F: 96 * C + 40 * F,
+    "mom_face": lambda C, F: 120 * C + 100 * F,
+    "phiHbyA": lambda C, F: 100 * C + 120 * F,
+    "p_cell": lambda C, F: 16 * C + 32 * F,
+    "U_recon": lambda C, F: 56 * C + 48 * F,
+}
+
+
+class ClockSampler(threading.Thread):
+    def __init__(self, index=0):
+        super().__init__(daemon=True)
+        self.index, self.samples, self.stop_flag = index, [], False
+
+    def run(self):
+        q = "clocks.sm,clocks.max.sm,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap"
+        while not self.stop_flag:
+            try:
+                out = subprocess.run(["nvidia-smi", f"--query-gpu={q}", "--format=csv,noheader,nounits", "-i", str(self.index)], capture_output=True, text=True, timeout=5).stdout
+                self.samples.append([x.strip() for x in out.strip().split(",")])
+            except Exception:
+                pass
+            time.sleep(0.2)
+
+    def summary(self):
+        sm = [float(s[0]) for s in self.samples if len(s) >= 6 and s[0].replace(".", "").isdigit()]
+        mx = [float(s[1]) for s in self.samples if len(s) >= 6 and s[1].replace(".", "").isdigit()]
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        reasons = sorted({names[i] for s in self.samples if len(s) >= 6 for i in range(4) if s[2 + i].lower().startswith("active")})
+        return {"sm_mhz": float(np.median(sm)) if sm else None, "sm_max_mhz": max(mx) if mx else None, "reasons": reasons, "samples": len(sm)}
+
+
+def cpu_sample(cells_target, steps):
+    """The CPU oracle (serial FP64 restatement of the OpenFOAM algorithm; NOT OpenFOAM) on a
+    reduced-resolution mesh of the same case: `steps` steps after 3 warm-up steps."""
+    sys.path.insert(0, os.path.join(ROOT, "oracle"))
+    import oracle
+
+    mesh, nr, nl = mesh_for(cells_target)
+    cfg = make_config(mesh)
+    o = oracle.Oracle(mesh, cfg)
+    o.set("alpha", initial_alpha(mesh))
+    o.stage("alphaBCs")
+    o.stage("mixture")
+    o.step(3)
+    t0 = time.perf_counter()
+    o.step(steps)
+    dt = time.perf_counter() - t0
+    return mesh.n_cells * steps / dt / 1e6, mesh.n_cells, dt / steps
+
+
+def run_reference(args):
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return
+    t0 = time.perf_counter()
+    val, ncell, sps = cpu_sample(args.cpu_cells, max(1, args.steps))
+    line = {
+        "impl": "reference", "metric": METRIC, "value": val, "unit": UNIT, "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup,
+        "ms_per_step": sps * 1e3, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
+        "config": {"workload": f"cfg4 D=0.2 H=0.208 flat tank, orbital 4 mm @ 1.88 Hz, tets; CPU sample mesh {ncell} cells"},
+        "cpu_baseline": {"value": val, "unit": UNIT, "cores": 1, "kind": "port",
+                         "sample": f"oracle (CPU restatement, not OpenFOAM: OpenFOAM 13 is not installed) on a {ncell}-cell mesh of the same case, {args.steps} steps after 3 warm-up"},
+        "e2e": {"value": val, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+        "wall_s": time.perf_counter() - t0,
+    }
+    print(json.dumps(line))
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=10)
+    ap.add_argument("--warmup", type=int, default=5)
+    ap.add_argument("--impl", default="ours")
+    ap.add_argument("--cells", type=float, default=2.1e6, help="target cells per GPU")
+    ap.add_argument("--cpu-cells", type=float, default=1.2e5, help="cells of the CPU-baseline sample mesh")
+    ap.add_argument("--cpu-steps", type=int, default=4)
+    ap.add_argument("--no-cpu", action="store_true")
+    args = ap.parse_args()
+    if args.impl == "reference":
+        return run_reference(args)
+    if args.warmup < 3:
+        args.warmup = 3
+
+    import torch
+
+    from openfoam_tpp_b200 import solver as sv
+
+    rank = int(os.environ.get("RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    if not torch.cuda.is_available():
+        raise SystemExit("bench.py needs a CUDA device: the solver has no CPU path")
+    torch.cuda.set_device(local)
+    if world > 1:
+        import torch.distributed as dist
+
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local))
+
+    mesh, nr, nl = mesh_for(args.cells)
+    cfg = make_config(mesh)
+    nC, nI, nF = mesh.n_cells, mesh.n_internal, mesh.n_faces
+    g = sv.Solver(mesh, cfg, device=local)
+    stream = torch.cuda.current_stream()
+    g.use_stream(stream.cuda_stream)
+    a0 = initial_alpha(mesh)
+    g.set("alpha", a0)
+    g.init_fields()
+
+    def barrier():
+        torch.cuda.synchronize()
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    # ---- resident-state throughput ---------------------------------------------------------
+    g.step(args.warmup)
+    l0 = g.info()["launches"]
+    sampler = ClockSampler(local)
+    sampler.start()
+    barrier()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record(stream)
+    g.step(args.steps)
+    e1.record(stream)
+    barrier()
+    sec = e0.elapsed_time(e1) / 1e3
+    sampler.stop_flag = True
+    launches = int(g.info()["launches"] - l0)
+    info = g.info()
+
+    # ---- per-kernel CUDA-event timing (separate pass, same state) ---------------------------
+    g.profile(True)
+    g.step(2)
+    prof = g.profile_report()
+    g.profile(False)
+    tot_ms = sum(v[1] for v in prof.values())
+    top = sorted(prof.items(), key=lambda kv: -kv[1][1])
+    dom, (dom_n, dom_ms) = top[0]
+    peaks = {}
+    pk = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.exists(pk):
+        peaks = json.load(open(pk))
+    peak = float(peaks.get("hbm_gbs", 6650.0))
+    alg = ALG_BYTES.get(dom)
+    achieved = alg(nC, nI) / (dom_ms / dom_n * 1e-3) / 1e9 if alg else None
+    roofline = {"bound": "hbm", "kernel": f"k_{dom}", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak if achieved else None,
+                "traffic": None, "peak_source": "measured (MEASURED_PEAKS.json)" if peaks else "fallback",
+                "share_of_step": dom_ms / tot_ms, "top": [[k, v[0], round(v[1], 3)] for k, v in top[:8]]}
+
+    # ---- end to end: pinned host state in, one step, host state out, every step ---------------
+    names_in = ["alpha", "U", "p_rgh", "phi", "Uf"]
+    names_out = ["alpha", "U", "p_rgh", "p"]
+    host_in = {n: torch.from_numpy(g.get(n)).pin_memory() for n in names_in}
+    host_out = {n: torch.empty(g.size(n), dtype=torch.float64).pin_memory() for n in names_out}
+    import ctypes as C
+
+    from openfoam_tpp_b200 import abi
+
+    def dp(tn):
+        return C.cast(tn.data_ptr(), abi.c_double_p)
+
+    h2d_b = sum(t.numel() * 8 for t in host_in.values())
+    d2h_b = sum(t.numel() * 8 for t in host_out.values())
+    e2e_steps = max(2, args.steps // 2)
+    barrier()
+    t0 = time.perf_counter()
+    e0.record(stream)
+    for _ in range(e2e_steps):
+        for n, tn in host_in.items():
+            g.L.tpp_set(g.h, n.encode(), dp(tn), tn.numel())
+        g.step(1)
+        for n, tn in host_out.items():
+            g.L.tpp_get(g.h, n.encode(), dp(tn), tn.numel())
+        # the next step's input is this step's output state
+        for n in ("alpha", "U", "p_rgh"):
+            host_in[n].copy_(host_out[n])
+        g.L.tpp_get(g.h, b"phi", dp(host_in["phi"]), host_in["phi"].numel())
+        g.L.tpp_get(g.h, b"Uf", dp(host_in["Uf"]), host_in["Uf"].numel())
+    e1.record(stream)
+    barrier()
+    sec_e2e = time.perf_counter() - t0
+
+    times = torch.tensor([sec, sec_e2e], dtype=torch.float64, device="cuda")
+    if world > 1:
+        dist.all_reduce(times, op=dist.ReduceOp.MAX)
+    sec, sec_e2e = times.tolist()
+    total_cells = nC * world
+    value = total_cells * args.steps / sec / 1e6
+    e2e = total_cells * e2e_steps / sec_e2e / 1e6
+
+    cpu = None
+    if rank == 0 and world == 1 and not args.no_cpu:
+        v, ncell, sps = cpu_sample(args.cpu_cells, args.cpu_steps)
+        cpu = {"value": v, "unit": UNIT, "cores": 1, "kind": "port",
+               "sample": f"CPU oracle (restatement, not OpenFOAM) on a {ncell}-cell mesh of the same case, {args.cpu_steps} steps after 3 warm-up, {sps * 1e3:.0f} ms/step"}
+
+    if rank == 0:
+        line = {
+            "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
+            "ms_per_step": sec / args.steps * 1e3, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
+            "config": {"workload": f"cfg4 case_H0.208_D0.2_flat_R0.004_f1.88 tet mesh refined to {nC} cells per GPU (n_rings {nr}, n_layers {nl})",
+                       "cells_per_gpu": nC, "internal_faces_per_gpu": nI, "parallelism": "single GPU" if world == 1 else f"{world} independent replicas (halo exchange not built yet)",
+                       "l2": "working set (>1 kB/cell) far exceeds the 126 MB L2; no flush needed",
+                       "vof_steps_per_s": args.steps / sec, "solver_iters_last_step": [int(info["it0"]), int(info["it1"])], "amg_levels": int(info["levels"])},
+            "clocks": sampler.summary(), "gpu_launches": launches,
+            "e2e": {"value": e2e, "unit": UNIT, "h2d_bytes_per_step": h2d_b, "d2h_bytes_per_step": d2h_b + (host_in["phi"].numel() + host_in["Uf"].numel()) * 8, "steps": e2e_steps},
+            "roofline": roofline, "cpu_baseline": cpu,
+        }
+        print(json.dumps(line))
+    if world > 1:
+        dist.destroy_process_group()
+
+
+if __name__ == "__main__":
+    main()

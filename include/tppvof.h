@@ -1,0 +1,151 @@
+/* tppvof.h — C-ABI of libtppvof.so, the B200-native drop-in for the OpenFOAM-13
+ * `incompressibleVoF` PIMPLE time step of elvis-aguero/openfoam-TPP.
+ *
+ * Boundary being replaced.  The reference has no in-process FFI for this path: its Python
+ * orchestrator shells out to OpenFOAM,
+ *     run_case_local -> subprocess.run(["make","-C",case,"run"|"resume",...], check=True)
+ *                                              (/root/reference/main.py:333-348)
+ *     make run/resume -> [mpirun -np N] foamRun [-parallel]
+ *                                              (circularSloshingTank/Makefile:71-99)
+ * so the entry points below are what a ctypes binding of that call needs (INTEGRATION.md
+ * shows the stub): open a solver on a mesh + dictionaries (tpp_create), advance it the way
+ * `foamRun` does (tpp_run_to_write / tpp_step), read fields back for the time-directory
+ * writer (tpp_get), and the per-step probes log of system/functions:17-33.
+ *
+ * Conventions: plain C, caller owns every buffer it passes, the handle owns all device and
+ * host memory it allocates.  Every function returns 0 (or a count) on success and a
+ * negative code on failure; tpp_last_error() gives the message.  No exceptions cross the
+ * ABI.  There is no CPU path: tpp_create fails when no CUDA device is usable.
+ * Handles are independent (one CUDA stream each) and may be driven from different host
+ * threads; one handle is not re-entrant.
+ */
+#ifndef TPPVOF_H
+#define TPPVOF_H
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+/* boundary conditions of 0/U, 0/alpha.water, 0/p_rgh (circularSloshingTank/0/*:22-31) */
+enum { TPP_U_MOVING_WALL = 0, TPP_U_PRESSURE_INLET_OUTLET = 1 };
+enum { TPP_A_ZERO_GRADIENT = 0, TPP_A_INLET_OUTLET = 1 };
+enum { TPP_P_FIXED_FLUX = 0, TPP_P_TOTAL_PRESSURE = 1 };
+/* a patch whose three codes are -1 is a processor patch (multi-GPU halo) */
+
+/* constant/polyMesh as gmshToFoam leaves it (Makefile:73): OpenFOAM face/cell order */
+typedef struct {
+    int n_points, n_faces, n_internal, n_cells, n_patches;
+    const double* points;    /* n_points x 3, undisplaced */
+    const int* face_offsets; /* n_faces + 1 */
+    const int* face_labels;
+    const int* owner;        /* n_faces */
+    const int* neighbour;    /* n_internal */
+    const int* patch_start;  /* n_patches */
+    const int* patch_size;
+    const int* patch_bc_u;
+    const int* patch_bc_alpha;
+    const int* patch_bc_p;
+    const double* patch_inlet_alpha; /* inletOutlet inletValue (0/alpha.water:27) */
+    const double* patch_p0;          /* totalPressure p0 (0/p_rgh:30) */
+} tpp_mesh_t;
+
+/* one entry of system/fvSolution:solvers (p_rgh:42-48, p_rghFinal:50-66) */
+typedef struct {
+    int type;      /* 0 = PCG, 1 = GAMG */
+    int precond;   /* PCG: 0 = DIC (run as Jacobi-PCG on the GPU), 1 = GAMG */
+    int smoother;  /* requested OpenFOAM smoother (0 DIC, 1 DICGaussSeidel, 2 GaussSeidel);
+                      sequential sweeps have no parallel form: see DESIGN.md */
+    double tolerance, rel_tol;
+    int max_iter;
+    int n_vcycles, n_pre_sweeps, n_post_sweeps, n_finest_sweeps;
+    int n_cells_coarsest, merge_levels;
+} tpp_solver_t;
+
+typedef struct {
+    /* system/controlDict:19-51 */
+    double start_time, end_time, delta_t, write_interval;
+    double max_co, max_alpha_co, max_delta_t;
+    int adjust_time_step;
+    /* constant/g:18, physicalProperties.{water,air}:17-21, phaseProperties:19 */
+    double g[3];
+    double rho1, rho2, nu1, nu2, sigma;
+    /* system/fvSolution:19-23 (+ MULES nLimiterIter), system/fvSchemes:30 (cAlpha) */
+    int n_alpha_subcycles, n_alpha_corr, n_limiter_iter;
+    double c_alpha;
+    /* system/fvSolution:78-87 */
+    int n_correctors, n_non_orth;
+    double p_ref_point[3], p_ref_value;
+    tpp_solver_t p_rgh, p_rgh_final;
+    /* constant/dynamicMeshDict:17-44 + constant/6DoF.dat (generate_motion.py:13-42) */
+    double cofg[3];
+    int n_motion;         /* 0: static mesh */
+    const double* motion; /* n_motion x 7: t, tx ty tz, rx ry rz (degrees) */
+} tpp_config_t;
+
+typedef struct tpp_solver* tpp_handle;
+
+/* Build a solver on CUDA device `device` (>= 0).  Fields start at zero / rho2; set the
+ * start fields with tpp_set, then call tpp_init_fields once. */
+int tpp_create(const tpp_mesh_t* mesh, const tpp_config_t* cfg, int device, tpp_handle* out);
+int tpp_destroy(tpp_handle);
+const char* tpp_last_error(void);
+const char* tpp_version(void);
+
+/* Named arrays (host buffers, FP64).  Names: alpha U p_rgh p rho phi Uf (restart state),
+ * alpha_b U_b p_rgh_b rho_b (boundary values), points (moved mesh points), V C Sf ...
+ * tpp_size returns the element count, tpp_get/tpp_set copy device<->host. */
+long tpp_size(tpp_handle, const char* name);
+long tpp_get(tpp_handle, const char* name, double* out, long cap);
+long tpp_set(tpp_handle, const char* name, const double* in, long n);
+/* device pointer of a named array for zero-copy glue (torch.from_blob / DLPack);
+ * borrowed, valid until the next tpp_step / tpp_run_to_write / tpp_destroy */
+int tpp_device_ptr(tpp_handle, const char* name, void** ptr, long* n);
+
+/* boundary values and mixture density from the fields just set (start / restart) */
+int tpp_init_fields(tpp_handle);
+/* restart: deltaT of the run being resumed (<time>/uniform/time) */
+int tpp_set_delta_t(tpp_handle, double delta_t);
+/* place the solver at time t with step deltaT (restart / tests): re-evaluates the motion */
+int tpp_set_time(tpp_handle, double t, double delta_t);
+
+/* n full time steps: Courant -> deltaT -> mesh motion -> alphaPredictor -> momentum
+ * assembly -> pressure correctors  (what one `foamRun` iteration does) */
+int tpp_step(tpp_handle, int n);
+/* step until a write time or end_time: 1 = write time reached, 0 = end of run,
+ * 2 = max_steps exhausted */
+int tpp_run_to_write(tpp_handle, long max_steps);
+/* one named stage on the current state (parity tests): courant adjustDeltaT advanceTime
+ * moveMesh alphaBCs UBCs mixture alphaSubCycle alphaPredictor momentum HbyA pcPrepare
+ * pcAssemble pcFinish pcEnd pressureCorrector:0 pressureCorrector:1 */
+int tpp_stage(tpp_handle, const char* name);
+
+/* out[16]: t, deltaT, step, Co, alphaCo, iters/initial/final residual of the last p_rgh and
+ * p_rghFinal solves, reference cell, deltaN, write index, AMG levels, kernel launches */
+int tpp_info(tpp_handle, double* out16);
+
+/* solve A x = b on the mesh's LDU addressing with the positive Laplacian coefficients
+ * `upper` (off-diagonals are -upper); returns iterations */
+int tpp_solve(tpp_handle, const tpp_solver_t* ctl, const double* diag, const double* upper,
+              const double* b, double* x, double* init_res, double* final_res);
+
+/* `probes` function object: cell labels (or -1 = not found) sampled on p every step */
+int tpp_set_probes(tpp_handle, int n, const int* cells);
+long tpp_probe_log(tpp_handle, double* out, long cap_rows); /* rows (t, v0..); drains */
+int tpp_find_cell(tpp_handle, const double* xyz);
+
+/* run on the caller's CUDA stream (e.g. torch.cuda.current_stream().cuda_stream) instead
+ * of the handle's own, so the caller's CUDA events bracket the solver's kernels */
+int tpp_use_stream(tpp_handle, void* cuda_stream);
+/* per-kernel CUDA-event timing: tpp_profile(h,1) ... steps ... tpp_profile_report -> text
+ * lines "kernel launches total_ms"; returns the length, or -(needed) if cap is too small */
+int tpp_profile(tpp_handle, int on);
+long tpp_profile_report(tpp_handle, char* buf, long cap);
+
+/* multi-GPU: NCCL communicator over the ranks that own the processor patches */
+int tpp_nccl_unique_id(char* out128);
+int tpp_comm_init(tpp_handle, int rank, int n_ranks, const char* id128);
+
+#ifdef __cplusplus
+}
+#endif
+#endif

@@ -1,0 +1,329 @@
+// p_rgh linear solver on the GPU (SURVEY.md §8a rows a11/a12;
+// ref: circularSloshingTank/system/fvSolution:42-66).
+//
+// OpenFOAM's GAMG smoothers (DIC, DICGaussSeidel) are sequential face/cell sweeps with no
+// parallel form.  The GPU path keeps OpenFOAM's *convergence contract* — the same L1
+// residual normalised by lduMatrix::normFactor, the same tolerance / relTol / maxIter tests
+// — and reaches it with a conjugate-gradient iteration preconditioned by an aggregation
+// multigrid built on the device:
+//   * agglomeration: pairwise handshake matching on the faceAreaPair weights (the weights
+//     OpenFOAM's faceAreaPair agglomerator uses), two matching passes merged per level
+//     (the equivalent of mergeLevels 2), built once and cached (the mesh moves rigidly);
+//   * Galerkin coarse operators re-summed every solve by segment gathers (no atomics);
+//   * damped-Jacobi pre/post smoothing (symmetric V-cycle), single-CTA CG on the coarsest
+//     level;
+//   * SpMV is cell-gathered over the ELL table (fine level) / CSR rows (coarse levels);
+//     dot products are two-stage with a fixed grid, so every sum has a fixed order.
+#pragma once
+#include "tpp_common.h"
+
+#include <algorithm>
+#include <numeric>
+
+namespace tpp {
+
+// One multigrid level (also used for the finest level, aliasing the solver's arrays).
+struct LV {
+    int n, nf, nCp, W, ell;       // rows, faces, ELL stride/width, ell=1: ELL, 0: CSR
+    const int *cf, *cn, *rs;      // adjacency: (face<<1|side), other row; CSR row starts
+    const int *own, *nei;         // [nf]
+    double *diag, *upper, *rsum;  // matrix: diag, positive off-diagonal magnitude, row sums
+    // transfer from the next finer level
+    const int *agg;               // [n_fine] fine row -> this level's row
+    const int *aggStart, *aggRows;   // CSR: members of each row of this level
+    const int *segStart, *segFaces;  // CSR: fine faces summed into each face of this level
+    // work vectors
+    double *x, *b, *t0, *t1;
+    // kernel arguments
+    const double *in, *in2;
+    double* out;
+    const LV* unused;
+    double omega;
+    // fine-level view used by transfer kernels running on the coarse grid
+    int fn, fnCp, fW, fell;
+    const int *fcf, *fcn, *frs;
+    const double *fdiag, *fupper, *frsum, *fx, *fb;
+    double* fxw;
+    // matching work
+    int *match, *prop, *root;
+    const double* fw;  // face weights
+};
+
+#define FOR_ROW(L, c)                                                     \
+    {                                                                     \
+        const int cnt_ = (L).ell ? (L).W : (L).rs[(c) + 1] - (L).rs[(c)]; \
+        const size_t base_ = (L).ell ? (size_t)(c) : (size_t)(L).rs[(c)]; \
+        const size_t str_ = (L).ell ? (size_t)(L).nCp : 1;                \
+        for (int s_ = 0; s_ < cnt_; s_++) {                               \
+            const int e_ = (L).cf[base_ + s_ * str_];                     \
+            if (e_ < 0) break;                                            \
+            const int f = e_ >> 1;                                        \
+            const int o = (L).cn[base_ + s_ * str_];                      \
+            if (o < 0) continue;
+#define END_ROW }}
+
+// y = A x on a level: out = diag*in - sum upper[f]*in[o]
+HD double row_Ax(const LV& L, int c, const double* x) {
+    double s = L.diag[c] * x[c];
+    FOR_ROW(L, c) s -= L.upper[f] * x[o]; END_ROW
+    return s;
+}
+HD void b_spmv(const LV& L, int c) { L.out[c] = row_Ax(L, c, L.in); }
+// out = in + omega*(b - A in)/diag   (damped Jacobi, in != out)
+HD void b_jacobi(const LV& L, int c) { L.out[c] = L.in[c] + L.omega * (L.b[c] - row_Ax(L, c, L.in)) / L.diag[c]; }
+// first sweep from a zero guess: out = omega*b/diag
+HD void b_jacobi0(const LV& L, int c) { L.out[c] = L.omega * L.b[c] / L.diag[c]; }
+// rsum = diag - sum upper  (what is left of the row after the Laplacian part: boundary terms)
+HD void b_rowsum(const LV& L, int c) {
+    double s = 0;
+    FOR_ROW(L, c) s += L.upper[f]; END_ROW
+    L.rsum[c] = L.diag[c] - s;
+}
+// Galerkin: coarse face coefficient = sum of the fine faces in its segment (fixed order)
+HD void b_coarse_upper(const LV& L, int F) {
+    double s = 0;
+    for (int k = L.segStart[F]; k < L.segStart[F + 1]; k++) s += L.fupper[L.segFaces[k]];
+    L.upper[F] = s;
+}
+// coarse row sum = sum of member row sums ; coarse diag = row sum + sum of coarse off-diagonals
+HD void b_coarse_diag(const LV& L, int I) {
+    double r = 0;
+    for (int k = L.aggStart[I]; k < L.aggStart[I + 1]; k++) r += L.frsum[L.aggRows[k]];
+    L.rsum[I] = r;
+    double s = 0;
+    FOR_ROW(L, I) s += L.upper[f]; END_ROW
+    L.diag[I] = r + s;
+}
+// restriction of the fine residual, computed on the fly: b_c[I] = sum_{i in I} (fb - A fx)_i
+HD void b_restrict_residual(const LV& L, int I) {
+    double r = 0;
+    for (int k = L.aggStart[I]; k < L.aggStart[I + 1]; k++) {
+        int i = L.aggRows[k];
+        double s = L.fdiag[i] * L.fx[i];
+        const int cnt = L.fell ? L.fW : L.frs[i + 1] - L.frs[i];
+        const size_t base = L.fell ? (size_t)i : (size_t)L.frs[i];
+        const size_t str = L.fell ? (size_t)L.fnCp : 1;
+        for (int s_ = 0; s_ < cnt; s_++) {
+            int e = L.fcf[base + s_ * str];
+            if (e < 0) break;
+            int o = L.fcn[base + s_ * str];
+            if (o < 0) continue;
+            s -= L.fupper[e >> 1] * L.fx[o];
+        }
+        r += L.fb[i] - s;
+    }
+    L.b[I] = r;
+}
+// prolongation: fine x += coarse x[agg]   (runs over fine rows; L = coarse level)
+HD void b_prolong_add(const LV& L, int i) { L.fxw[i] += L.x[L.agg[i]]; }
+
+// ---- pairwise matching (handshake) on face weights --------------------------------------------
+HD void b_match_propose(const LV& L, int c) {
+    if (L.match[c] >= 0) { L.prop[c] = -1; return; }
+    int best = -1;
+    double bw = -1.0;
+    FOR_ROW(L, c)
+        if (L.match[o] < 0) {
+            double w = L.fw[f];
+            if (w > bw || (w == bw && o < best)) { bw = w; best = o; }
+        }
+    END_ROW
+    L.prop[c] = best;
+}
+HD void b_match_accept(const LV& L, int c) {
+    int p = L.prop[c];
+    if (p >= 0 && L.prop[p] == c) L.match[c] = p;
+}
+// roots: pair -> min(c, partner); unmatched -> joins the aggregate of its heaviest matched
+// neighbour, or stays single
+HD void b_match_root(const LV& L, int c) {
+    int m = L.match[c];
+    if (m >= 0) { L.root[c] = c < m ? c : m; return; }
+    int best = -1;
+    double bw = -1.0;
+    FOR_ROW(L, c)
+        if (L.match[o] >= 0) {
+            double w = L.fw[f];
+            if (w > bw || (w == bw && o < best)) { bw = w; best = o; }
+        }
+    END_ROW
+    if (best < 0) L.root[c] = c;
+    else { int bm = L.match[best]; L.root[c] = best < bm ? best : bm; }
+}
+
+DEF_KERNEL(spmv, LV)
+DEF_KERNEL(jacobi, LV)
+DEF_KERNEL(jacobi0, LV)
+DEF_KERNEL(rowsum, LV)
+DEF_KERNEL(coarse_upper, LV)
+DEF_KERNEL(coarse_diag, LV)
+DEF_KERNEL(restrict_residual, LV)
+DEF_KERNEL(prolong_add, LV)
+DEF_KERNEL(match_propose, LV)
+DEF_KERNEL(match_accept, LV)
+DEF_KERNEL(match_root, LV)
+
+// ---------------------------------------------------------------------------------------
+// reductions and fused Krylov kernels (fixed grid -> fixed summation order)
+// ---------------------------------------------------------------------------------------
+// scal[] layout on the device
+enum { S_WARA = 0, S_WARA_OLD, S_WAPA, S_RES, S_NORM, S_XSUM, S_TMP0, S_TMP1, S_MAX0, S_MAX1, S_COUNT = 16 };
+
+#ifndef TPP_EMU
+DEV double block_sum(double v) {
+    __shared__ double sh[BLOCK / 32];
+    for (int o = 16; o > 0; o >>= 1) v += __shfl_down_sync(0xffffffffu, v, o);
+    int lane = threadIdx.x & 31, wp = threadIdx.x >> 5;
+    __syncthreads();
+    if (lane == 0) sh[wp] = v;
+    __syncthreads();
+    if (wp == 0) {
+        v = lane < BLOCK / 32 ? sh[lane] : 0.0;
+        for (int o = 4; o > 0; o >>= 1) v += __shfl_down_sync(0xffffffffu, v, o);
+    }
+    return v;  // valid in thread 0
+}
+DEV double block_max(double v) {
+    __shared__ double shm[BLOCK / 32];
+    for (int o = 16; o > 0; o >>= 1) v = fmax(v, __shfl_down_sync(0xffffffffu, v, o));
+    int lane = threadIdx.x & 31, wp = threadIdx.x >> 5;
+    __syncthreads();
+    if (lane == 0) shm[wp] = v;
+    __syncthreads();
+    if (wp == 0) {
+        v = lane < BLOCK / 32 ? shm[lane] : 0.0;
+        for (int o = 4; o > 0; o >>= 1) v = fmax(v, __shfl_down_sync(0xffffffffu, v, o));
+    }
+    return v;
+}
+// mode 0: sum a*b ; 1: sum |a| ; 2: sum a ; 3: max a (a >= 0)
+__global__ void __launch_bounds__(256) k_reduce(const double* a, const double* b, int n, int mode, double* partial) {
+    double v = 0;
+    for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x) {
+        if (mode == 0) v += a[i] * b[i];
+        else if (mode == 1) v += fabs(a[i]);
+        else if (mode == 2) v += a[i];
+        else v = fmax(v, a[i]);
+    }
+    v = mode == 3 ? block_max(v) : block_sum(v);
+    if (threadIdx.x == 0) partial[blockIdx.x] = v;
+}
+__global__ void __launch_bounds__(256) k_reduce_final(const double* partial, int np, int mode, double* out) {
+    double v = 0;
+    for (int i = threadIdx.x; i < np; i += blockDim.x) v = mode == 3 ? fmax(v, partial[i]) : v + partial[i];
+    v = mode == 3 ? block_max(v) : block_sum(v);
+    if (threadIdx.x == 0) *out = v;
+}
+// wA = A pA fused with partial sums of wA.pA
+__global__ void __launch_bounds__(256) k_spmv_dot(LV L, double* partial) {
+    double v = 0;
+    for (int c = blockIdx.x * blockDim.x + threadIdx.x; c < L.n; c += gridDim.x * blockDim.x) {
+        double y = row_Ax(L, c, L.in);
+        L.out[c] = y;
+        v += y * L.in[c];
+    }
+    v = block_sum(v);
+    if (threadIdx.x == 0) partial[blockIdx.x] = v;
+}
+// x += alpha pA ; r -= alpha wA ; partial sums of |r|   (alpha = scal[WARA]/scal[WAPA])
+__global__ void __launch_bounds__(256) k_update_xr(int n, double* x, double* r, const double* pA, const double* wA, const double* scal, double* partial) {
+    double alpha = scal[S_WARA] / scal[S_WAPA];
+    double v = 0;
+    for (int c = blockIdx.x * blockDim.x + threadIdx.x; c < n; c += gridDim.x * blockDim.x) {
+        x[c] += alpha * pA[c];
+        double rr = r[c] - alpha * wA[c];
+        r[c] = rr;
+        v += fabs(rr);
+    }
+    v = block_sum(v);
+    if (threadIdx.x == 0) partial[blockIdx.x] = v;
+}
+// pA = z + beta pA  (beta = WARA/WARA_OLD; first iteration: pA = z)
+__global__ void __launch_bounds__(256) k_update_p(int n, double* pA, const double* z, const double* scal, int first) {
+    double beta = first ? 0.0 : scal[S_WARA] / scal[S_WARA_OLD];
+    for (int c = blockIdx.x * blockDim.x + threadIdx.x; c < n; c += gridDim.x * blockDim.x) pA[c] = first ? z[c] : z[c] + beta * pA[c];
+}
+// r = b - Ax ; normFactor pieces: |Ax - xbar*sumA| + |b - xbar*sumA| ; sumA = rsum
+__global__ void __launch_bounds__(256) k_init_residual(LV L, const double* x, const double* b, double* r, const double* scal, double* partialRes, double* partialNorm) {
+    double xbar = scal[S_XSUM] / (double)L.n;
+    double v = 0, w = 0;
+    for (int c = blockIdx.x * blockDim.x + threadIdx.x; c < L.n; c += gridDim.x * blockDim.x) {
+        double ax = row_Ax(L, c, x);
+        double rr = b[c] - ax;
+        r[c] = rr;
+        v += fabs(rr);
+        double p = L.rsum[c] * xbar;
+        w += fabs(ax - p) + fabs(b[c] - p);
+    }
+    v = block_sum(v);
+    __syncthreads();
+    w = block_sum(w);
+    if (threadIdx.x == 0) { partialRes[blockIdx.x] = v; partialNorm[blockIdx.x] = w; }
+}
+__global__ void k_scal_copy(double* scal, int dst, int src) { scal[dst] = scal[src]; }
+
+// Jacobi-preconditioned CG on the coarsest level, one CTA (n is a few thousand at most).
+__global__ void __launch_bounds__(1024) k_coarse_cg(LV L, int maxIter, double relTol) {
+    __shared__ double red[1024];
+    __shared__ double s_rz, s_pAp, s_rz0;
+    const int n = L.n, t = threadIdx.x, T = blockDim.x;
+    double* x = L.x; const double* b = L.b; double *r = L.t0, *p = L.t1, *Ap = L.out;
+    auto bsum = [&](double v) {
+        red[t] = v;
+        __syncthreads();
+        for (int s = T / 2; s > 0; s >>= 1) { if (t < s) red[t] += red[t + s]; __syncthreads(); }
+        double o = red[0];
+        __syncthreads();
+        return o;
+    };
+    double loc = 0;
+    for (int i = t; i < n; i += T) { x[i] = 0; r[i] = b[i]; double z = b[i] / L.diag[i]; p[i] = z; loc += b[i] * z; }
+    double rz = bsum(loc);
+    if (t == 0) { s_rz = rz; s_rz0 = rz; }
+    __syncthreads();
+    if (rz <= 0) return;
+    for (int it = 0; it < maxIter; it++) {
+        loc = 0;
+        for (int i = t; i < n; i += T) { double y = row_Ax(L, i, p); Ap[i] = y; loc += y * p[i]; }
+        double pAp = bsum(loc);
+        double alpha = s_rz / pAp;
+        loc = 0;
+        for (int i = t; i < n; i += T) { x[i] += alpha * p[i]; double rr = r[i] - alpha * Ap[i]; r[i] = rr; loc += rr * rr / L.diag[i]; }
+        double rzn = bsum(loc);
+        if (rzn <= relTol * relTol * s_rz0) break;
+        double beta = rzn / s_rz;
+        __syncthreads();
+        if (t == 0) s_rz = rzn;
+        for (int i = t; i < n; i += T) p[i] = r[i] / L.diag[i] + beta * p[i];
+        __syncthreads();
+    }
+}
+#endif
+
+struct Reducer {
+    double *partial = nullptr, *partial2 = nullptr;
+    void init() { partial = dalloc<double>(RED_BLOCKS); partial2 = dalloc<double>(RED_BLOCKS); }
+    void free() { dev_free(partial); dev_free(partial2); }
+    // mode as k_reduce
+    void reduce(Ctx& ctx, const double* a, const double* b, int n, int mode, double* out) {
+#ifdef TPP_EMU
+        double v = 0;
+        for (int i = 0; i < n; i++) {
+            if (mode == 0) v += a[i] * b[i];
+            else if (mode == 1) v += std::fabs(a[i]);
+            else if (mode == 2) v += a[i];
+            else v = std::max(v, a[i]);
+        }
+        *out = v;
+        ctx.launches += 2;
+#else
+        prof_begin(ctx, "reduce");
+        k_reduce<<<RED_BLOCKS, BLOCK, 0, ctx.stream>>>(a, b, n, mode, partial);
+        k_reduce_final<<<1, BLOCK, 0, ctx.stream>>>(partial, RED_BLOCKS, mode, out);
+        prof_end(ctx);
+        ctx.launches += 2;
+#endif
+    }
+};
+
+}  // namespace tpp

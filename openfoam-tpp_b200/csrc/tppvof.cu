@@ -1,0 +1,1087 @@
+// libtppvof.so — host driver + C-ABI (include/tppvof.h) of the sm_100a incompressibleVoF step.
+//
+// Replaces, for one case, what `foamRun` does between reading the case and writing time
+// directories (/root/reference/circularSloshingTank/Makefile:85,98; main.py:333-348).
+// Layout in HBM: SoA arrays in OpenFOAM cell/face order (internal faces first, then the
+// patches), vectors interleaved xyz; the cell->face ELL table drives every cell-gathered sum.
+#include "../../include/tppvof.h"
+#include "tpp_kernels.h"
+#include "tpp_linsolve.h"
+
+#include <map>
+
+using namespace tpp;
+
+namespace {
+
+std::string g_err;
+
+struct Level {
+    int n = 0, nf = 0;
+    // device
+    int *cf = nullptr, *cn = nullptr, *rs = nullptr, *own = nullptr, *nei = nullptr;
+    int *agg = nullptr, *aggStart = nullptr, *aggRows = nullptr, *segStart = nullptr, *segFaces = nullptr;
+    double *diag = nullptr, *upper = nullptr, *rsum = nullptr, *x = nullptr, *b = nullptr, *t0 = nullptr, *t1 = nullptr, *t2 = nullptr;
+    void free() {
+        for (void* p : {(void*)cf, (void*)cn, (void*)rs, (void*)own, (void*)nei, (void*)agg, (void*)aggStart, (void*)aggRows, (void*)segStart, (void*)segFaces,
+                        (void*)diag, (void*)upper, (void*)rsum, (void*)x, (void*)b, (void*)t0, (void*)t1, (void*)t2})
+            dev_free(p);
+    }
+};
+
+struct SolveStats { int iters = 0; double r0 = 0, r = 0; };
+
+}  // namespace
+
+struct tpp_solver {
+    Ctx ctx;
+    int device = 0;
+    // host mesh
+    int nP = 0, nF = 0, nI = 0, nC = 0, nB = 0, nPatch = 0, W = 0, nCp = 0;
+    std::vector<double> points0;
+    std::vector<int> fOff, fLab, own, nei;
+    std::vector<int> pStart, pSize, bcU, bcA, bcP;
+    std::vector<double> C0, Cf0, V, Sf0, magSf;
+    tpp_config_t cfg;
+    std::vector<double> motion;
+    bool hasRotation = false;
+    // device
+    DV d;
+    std::vector<void*> allocs;
+    std::map<std::string, std::pair<double*, long>> reg;
+    double* scal = nullptr;       // device scalars
+    double* hscal = nullptr;      // pinned host mirror
+    Reducer red;
+    // multigrid
+    std::vector<Level> levels;  // coarse levels (level 0 = first coarse)
+    double *kr = nullptr, *kz = nullptr, *kp = nullptr, *kw = nullptr, *kt = nullptr, *kt2 = nullptr, *kt3 = nullptr, *fineRsum = nullptr, *fw0 = nullptr;
+    int *match = nullptr, *prop = nullptr, *root = nullptr;
+    bool amgBuilt = false;
+    // time
+    double t = 0, dt = 0, dt0 = 0, startTime = 0, Co = 0, alphaCo = 0;
+    long step = 0;
+    int writeTimeIndex = 0;
+    double Rn[9], Ro[9], Tn[3], To[3];
+    SolveStats lastSolve[2];
+    // probes
+    std::vector<int> probeCells;
+    std::vector<double> probeLog;
+    double* probeDev = nullptr;
+    int* probeIdx = nullptr;
+
+    template <class T> T* A(size_t n) { T* p = dalloc<T>(n); allocs.push_back(p); return p; }
+    double* AD(const char* name, size_t n) { double* p = A<double>(n); reg[name] = {p, (long)n}; return p; }
+
+    // ---- rigid motion (Function1s::Table linear + clamp; sixDoFMotion XYZ quaternion) --------
+    void motionAt(double time, double R[9], double T[3]) const {
+        double v[6] = {0, 0, 0, 0, 0, 0};
+        int n = cfg.n_motion;
+        if (n > 0) {
+            const double* m = motion.data();
+            if (time <= m[0]) for (int k = 0; k < 6; k++) v[k] = m[1 + k];
+            else if (time >= m[7 * (n - 1)]) for (int k = 0; k < 6; k++) v[k] = m[7 * (n - 1) + 1 + k];
+            else {
+                int lo = 0, hi = n - 1;
+                while (hi - lo > 1) { int mid = (lo + hi) / 2; if (m[7 * mid] <= time) lo = mid; else hi = mid; }
+                double s = (time - m[7 * lo]) / (m[7 * hi] - m[7 * lo]);
+                for (int k = 0; k < 6; k++) v[k] = m[7 * lo + 1 + k] + s * (m[7 * hi + 1 + k] - m[7 * lo + 1 + k]);
+            }
+        }
+        const double d2r = M_PI / 180.0;
+        double ax = v[3] * d2r, ay = v[4] * d2r, az = v[5] * d2r;
+        double cx = cos(ax), sx = sin(ax), cy = cos(ay), sy = sin(ay), cz = cos(az), sz = sin(az);
+        R[0] = cy * cz;                 R[1] = -cy * sz;                R[2] = sy;
+        R[3] = sx * sy * cz + cx * sz;  R[4] = -sx * sy * sz + cx * cz; R[5] = -sx * cy;
+        R[6] = -cx * sy * cz + sx * sz; R[7] = cx * sy * sz + sx * cz;  R[8] = cx * cy;
+        T[0] = v[0]; T[1] = v[1]; T[2] = v[2];
+    }
+
+    // ---- host geometry at the undisplaced points (primitiveMesh conventions) -------------------
+    void hostGeometry(std::vector<double>& w, std::vector<double>& dc, std::vector<double>& corr, std::vector<double>& dPN) {
+        const double* P = points0.data();
+        Cf0.assign(3 * nF, 0); Sf0.assign(3 * nF, 0); magSf.assign(nF, 0);
+        for (int f = 0; f < nF; f++) {
+            int s = fOff[f], n = fOff[f + 1] - s;
+            const int* l = &fLab[s];
+            double* cfp = &Cf0[3 * f]; double* sfp = &Sf0[3 * f];
+            if (n == 3) {
+                const double *a = P + 3 * l[0], *b = P + 3 * l[1], *c = P + 3 * l[2];
+                double e1[3], e2[3];
+                for (int k = 0; k < 3; k++) { cfp[k] = (1.0 / 3.0) * (a[k] + b[k] + c[k]); e1[k] = b[k] - a[k]; e2[k] = c[k] - a[k]; }
+                sfp[0] = 0.5 * (e1[1] * e2[2] - e1[2] * e2[1]);
+                sfp[1] = 0.5 * (e1[2] * e2[0] - e1[0] * e2[2]);
+                sfp[2] = 0.5 * (e1[0] * e2[1] - e1[1] * e2[0]);
+            } else {
+                double fc[3] = {0, 0, 0}, sumN[3] = {0, 0, 0}, sumA = 0, sumAc[3] = {0, 0, 0};
+                for (int i = 0; i < n; i++) for (int k = 0; k < 3; k++) fc[k] += P[3 * l[i] + k];
+                for (int k = 0; k < 3; k++) fc[k] /= n;
+                for (int i = 0; i < n; i++) {
+                    const double *a = P + 3 * l[i], *b = P + 3 * l[(i + 1) % n];
+                    double c[3], e1[3], e2[3], nn[3];
+                    for (int k = 0; k < 3; k++) { c[k] = a[k] + b[k] + fc[k]; e1[k] = b[k] - a[k]; e2[k] = fc[k] - a[k]; }
+                    nn[0] = e1[1] * e2[2] - e1[2] * e2[1]; nn[1] = e1[2] * e2[0] - e1[0] * e2[2]; nn[2] = e1[0] * e2[1] - e1[1] * e2[0];
+                    double an = sqrt(nn[0] * nn[0] + nn[1] * nn[1] + nn[2] * nn[2]);
+                    sumA += an;
+                    for (int k = 0; k < 3; k++) { sumN[k] += nn[k]; sumAc[k] += an * c[k]; }
+                }
+                for (int k = 0; k < 3; k++) { cfp[k] = sumA < ROOTVSMALL ? fc[k] : (1.0 / 3.0) * sumAc[k] / sumA; sfp[k] = 0.5 * sumN[k]; }
+            }
+            magSf[f] = sqrt(sfp[0] * sfp[0] + sfp[1] * sfp[1] + sfp[2] * sfp[2]);
+        }
+        std::vector<double> cEst(3 * nC, 0.0);
+        std::vector<int> nCF(nC, 0);
+        for (int f = 0; f < nF; f++) { for (int k = 0; k < 3; k++) cEst[3 * own[f] + k] += Cf0[3 * f + k]; nCF[own[f]]++; }
+        for (int f = 0; f < nI; f++) { for (int k = 0; k < 3; k++) cEst[3 * nei[f] + k] += Cf0[3 * f + k]; nCF[nei[f]]++; }
+        for (int c = 0; c < nC; c++) for (int k = 0; k < 3; k++) cEst[3 * c + k] /= nCF[c];
+        C0.assign(3 * nC, 0.0); V.assign(nC, 0.0);
+        for (int f = 0; f < nF; f++) {
+            int o = own[f];
+            double dd[3];
+            for (int k = 0; k < 3; k++) dd[k] = Cf0[3 * f + k] - cEst[3 * o + k];
+            double pyr = Sf0[3 * f] * dd[0] + Sf0[3 * f + 1] * dd[1] + Sf0[3 * f + 2] * dd[2];
+            for (int k = 0; k < 3; k++) C0[3 * o + k] += pyr * (0.75 * Cf0[3 * f + k] + 0.25 * cEst[3 * o + k]);
+            V[o] += pyr;
+        }
+        for (int f = 0; f < nI; f++) {
+            int n = nei[f];
+            double dd[3];
+            for (int k = 0; k < 3; k++) dd[k] = cEst[3 * n + k] - Cf0[3 * f + k];
+            double pyr = Sf0[3 * f] * dd[0] + Sf0[3 * f + 1] * dd[1] + Sf0[3 * f + 2] * dd[2];
+            for (int k = 0; k < 3; k++) C0[3 * n + k] += pyr * (0.75 * Cf0[3 * f + k] + 0.25 * cEst[3 * n + k]);
+            V[n] += pyr;
+        }
+        for (int c = 0; c < nC; c++) {
+            for (int k = 0; k < 3; k++) C0[3 * c + k] = fabs(V[c]) > VSMALL ? C0[3 * c + k] / V[c] : cEst[3 * c + k];
+            V[c] *= (1.0 / 3.0);
+        }
+        w.assign(nF, 1.0); dc.assign(nF, 0.0); corr.assign(3 * (size_t)nI, 0.0); dPN.assign(3 * (size_t)nI, 0.0);
+        for (int f = 0; f < nF; f++) {
+            const double* S = &Sf0[3 * f];
+            double nf[3] = {S[0] / magSf[f], S[1] / magSf[f], S[2] / magSf[f]};
+            if (f < nI) {
+                double dO[3], dN[3], dd[3];
+                for (int k = 0; k < 3; k++) {
+                    dO[k] = Cf0[3 * f + k] - C0[3 * own[f] + k];
+                    dN[k] = C0[3 * nei[f] + k] - Cf0[3 * f + k];
+                    dd[k] = C0[3 * nei[f] + k] - C0[3 * own[f] + k];
+                    dPN[3 * f + k] = dd[k];
+                }
+                double so = fabs(dot3(S, dO)), sn = fabs(dot3(S, dN));
+                w[f] = sn / (so + sn);
+                dc[f] = 1.0 / dmax(dot3(nf, dd), 0.05 * mag3(dd));
+                for (int k = 0; k < 3; k++) corr[3 * f + k] = nf[k] - dd[k] * dc[f];
+            } else {
+                double dd[3];
+                for (int k = 0; k < 3; k++) dd[k] = Cf0[3 * f + k] - C0[3 * own[f] + k];
+                double nd = dot3(nf, dd);
+                double dl[3] = {nf[0] * nd, nf[1] * nd, nf[2] * nd};
+                dc[f] = 1.0 / dmax(dot3(nf, dl), 0.05 * mag3(dl));
+            }
+        }
+    }
+
+    template <class T> T* upload(const std::vector<T>& v) {
+        T* p = A<T>(v.size());
+        if (!v.empty()) h2d(ctx, p, v.data(), v.size() * sizeof(T));
+        return p;
+    }
+    double* uploadD(const char* name, const std::vector<double>& v) {
+        double* p = upload(v);
+        reg[name] = {p, (long)v.size()};
+        return p;
+    }
+
+    bool build(const tpp_mesh_t* m, const tpp_config_t* c) {
+        nP = m->n_points; nF = m->n_faces; nI = m->n_internal; nC = m->n_cells; nB = nF - nI; nPatch = m->n_patches;
+        points0.assign(m->points, m->points + 3 * (size_t)nP);
+        fOff.assign(m->face_offsets, m->face_offsets + nF + 1);
+        fLab.assign(m->face_labels, m->face_labels + fOff[nF]);
+        own.assign(m->owner, m->owner + nF);
+        nei.assign(m->neighbour, m->neighbour + nI);
+        pStart.assign(m->patch_start, m->patch_start + nPatch);
+        pSize.assign(m->patch_size, m->patch_size + nPatch);
+        bcU.assign(m->patch_bc_u, m->patch_bc_u + nPatch);
+        bcA.assign(m->patch_bc_alpha, m->patch_bc_alpha + nPatch);
+        bcP.assign(m->patch_bc_p, m->patch_bc_p + nPatch);
+        cfg = *c;
+        if (c->n_motion > 0) motion.assign(c->motion, c->motion + 7 * (size_t)c->n_motion);
+        cfg.motion = nullptr;
+        for (int i = 0; i < cfg.n_motion; i++)
+            for (int k = 4; k < 7; k++) if (motion[7 * i + k] != 0.0) hasRotation = true;
+        // per boundary face BC tables
+        std::vector<signed char> fU(nB, -1), fA(nB, -1), fP(nB, -1);
+        std::vector<double> fInlet(nB, 0.0), fP0(nB, 0.0);
+        for (int p = 0; p < nPatch; p++) {
+            if (bcU[p] < 0 || bcA[p] < 0 || bcP[p] < 0) {
+                if (pSize[p] > 0) { g_err = "processor patches need tpp_comm_init (multi-GPU path) - not available in this build"; return false; }
+                continue;
+            }
+            for (int i = 0; i < pSize[p]; i++) {
+                int b = pStart[p] - nI + i;
+                if (b < 0 || b >= nB) { g_err = "patch range outside the boundary faces"; return false; }
+                fU[b] = (signed char)bcU[p]; fA[b] = (signed char)bcA[p]; fP[b] = (signed char)bcP[p];
+                fInlet[b] = m->patch_inlet_alpha[p]; fP0[b] = m->patch_p0[p];
+            }
+        }
+        for (int b = 0; b < nB; b++) if (fU[b] < 0) { g_err = "boundary face without a patch"; return false; }
+        // ELL cell->face table, slots ascending in face index
+        std::vector<int> cnt(nC, 0);
+        for (int f = 0; f < nF; f++) cnt[own[f]]++;
+        for (int f = 0; f < nI; f++) cnt[nei[f]]++;
+        W = 0;
+        for (int c = 0; c < nC; c++) W = std::max(W, cnt[c]);
+        nCp = (nC + 31) / 32 * 32;
+        std::vector<int> cf((size_t)W * nCp, -1), cn((size_t)W * nCp, -1), fill(nC, 0);
+        // a cell's neighbour-side faces and owner-side faces interleave in face order: visit faces ascending
+        for (int f = 0; f < nF; f++) {
+            int o = own[f];
+            cf[(size_t)fill[o] * nCp + o] = f << 1;
+            cn[(size_t)fill[o] * nCp + o] = f < nI ? nei[f] : -1;
+            fill[o]++;
+            if (f < nI) {
+                int n = nei[f];
+                cf[(size_t)fill[n] * nCp + n] = (f << 1) | 1;
+                cn[(size_t)fill[n] * nCp + n] = o;
+                fill[n]++;
+            }
+        }
+        std::vector<double> w, dc, corr, dPN;
+        hostGeometry(w, dc, corr, dPN);
+        memset(&d, 0, sizeof(d));
+        d.nC = nC; d.nF = nF; d.nI = nI; d.nB = nB; d.nCp = nCp; d.W = W;
+        d.own = upload(own); d.nei = upload(nei); d.cf = upload(cf); d.cn = upload(cn);
+        d.bcU = upload(fU); d.bcA = upload(fA); d.bcP = upload(fP);
+        d.bInletAlpha = upload(fInlet); d.bP0 = upload(fP0);
+        d.Sf = uploadD("Sf", Sf0); d.magSf = uploadD("magSf", magSf); d.w = uploadD("w", w); d.dc = uploadD("dc", dc);
+        d.corrVec = uploadD("corrVec", corr); d.dPN = uploadD("dPN", dPN); d.V = uploadD("V", V);
+        d.C0 = uploadD("C0", C0); d.Cf0 = uploadD("Cf0", Cf0);
+        if (hasRotation) { d.Sf0 = upload(Sf0); d.dPN0 = upload(dPN); d.corrVec0 = upload(corr); }
+        d.gh = AD("gh", nC); d.ghf = AD("ghf", nF); d.meshPhi = AD("meshPhi", nF);
+        d.alpha = AD("alpha", nC); d.alpha0 = AD("alpha0", nC); d.alpha_b = AD("alpha_b", nB);
+        d.U = AD("U", 3 * (size_t)nC); d.U_b = AD("U_b", 3 * (size_t)nB); d.U0 = AD("U0", 3 * (size_t)nC); d.U0_b = AD("U0_b", 3 * (size_t)nB);
+        d.p_rgh = AD("p_rgh", nC); d.p_rgh_b = AD("p_rgh_b", nB); d.pGrad_b = AD("pGrad_b", nB); d.p = AD("p", nC);
+        d.rho = AD("rho", nC); d.rho_b = AD("rho_b", nB); d.rho0 = AD("rho0", nC);
+        d.phi = AD("phi", nF); d.Uf = AD("Uf", 3 * (size_t)nF); d.Uf0 = AD("Uf0", 3 * (size_t)nF);
+        d.alphaPhi = AD("alphaPhi", nF); d.rhoPhi = AD("rhoPhi", nF);
+        d.grad = AD("grad", 3 * (size_t)nC); d.phiBD = AD("phiBD", nF); d.phiCorr = AD("phiCorr", nI); d.lambda = AD("lambda", nI);
+        d.alphaPhiUn = AD("alphaPhiUn", nF); d.sumPhip = AD("sumPhip", nC); d.mSumPhim = AD("mSumPhim", nC);
+        d.psiMaxn = AD("psiMaxn", nC); d.psiMinn = AD("psiMinn", nC); d.lambdap = AD("lambdap", nC); d.lambdam = AD("lambdam", nC);
+        d.gradU = AD("gradU", 9 * (size_t)nC); d.mLower = AD("mLower", nI); d.mUpper = AD("mUpper", nI); d.mExpl = AD("mExpl", 3 * (size_t)nF);
+        d.mDiag = AD("mDiag", nC); d.mSource = AD("mSource", 3 * (size_t)nC); d.mBIC = AD("mBIC", 3 * (size_t)nB); d.mBBC = AD("mBBC", 3 * (size_t)nB);
+        d.rAU = AD("rAU", nC); d.HbyA = AD("HbyA", 3 * (size_t)nC); d.HbyA_b = AD("HbyA_b", 3 * (size_t)nB); d.rAUf = AD("rAUf", nF);
+        d.phiHbyA = AD("phiHbyA", nF); d.phig = AD("phig", nF); d.pUpper = AD("pUpper", nI); d.pCorrFlux = AD("pCorrFlux", nI);
+        d.pDiag = AD("pDiag", nC); d.pSource = AD("pSource", nC); d.rec = AD("rec", nF);
+        d.cellTmp = A<double>(2 * (size_t)nC);
+        kr = A<double>(nC); kz = A<double>(nC); kp = A<double>(nC); kw = A<double>(nC); kt = A<double>(nC); kt2 = A<double>(nC); kt3 = A<double>(nC); fineRsum = A<double>(nC);
+        scal = A<double>(S_COUNT);
+#ifdef TPP_EMU
+        hscal = (double*)calloc(S_COUNT, sizeof(double));
+#else
+        CUDA_CHECK(cudaMallocHost(&hscal, S_COUNT * sizeof(double)));
+#endif
+        red.init();
+        d.cAlpha = cfg.c_alpha; d.rho1 = cfg.rho1; d.rho2 = cfg.rho2; d.nu1 = cfg.nu1; d.nu2 = cfg.nu2;
+        for (int k = 0; k < 3; k++) { d.g[k] = cfg.g[k]; d.cofg[k] = cfg.cofg[k]; }
+        d.moving = cfg.n_motion > 0; d.rotating = hasRotation;
+        double vs = 0;
+        for (double v : V) vs += v;
+        d.deltaN = 1e-8 / cbrt(vs / nC);
+        t = startTime = cfg.start_time; dt = dt0 = cfg.delta_t;
+        motionAt(t, Rn, Tn);
+        memcpy(Ro, Rn, sizeof(Rn)); memcpy(To, Tn, sizeof(Tn));
+        setTransform();
+        orientGeometry();
+        // rho = rho2, alpha = 0 ...
+        std::vector<double> r2(nC, cfg.rho2), r2b(nB, cfg.rho2);
+        h2d(ctx, d.rho, r2.data(), nC * sizeof(double)); h2d(ctx, d.rho0, r2.data(), nC * sizeof(double));
+        if (nB) h2d(ctx, d.rho_b, r2b.data(), nB * sizeof(double));
+        // pressure reference
+        d.needRef = 1;
+        for (int p = 0; p < nPatch; p++) if (bcP[p] == TPP_P_TOTAL_PRESSURE && pSize[p] > 0) d.needRef = 0;
+        d.refCell = -1;
+        if (d.needRef) {
+            d.refCell = findCell(cfg.p_ref_point);
+            if (d.refCell < 0) { g_err = "pRefPoint is outside the mesh and p_rgh needs a reference"; return false; }
+        }
+        return true;
+    }
+
+    void setTransform() {
+        memcpy(d.R, Rn, sizeof(Rn)); memcpy(d.Rold, Ro, sizeof(Ro));
+        for (int k = 0; k < 3; k++) { d.Tn[k] = Tn[k]; d.To[k] = To[k]; d.dT[k] = Tn[k] - To[k]; d.wallU[k] = (Tn[k] - To[k]) / dt; }
+    }
+    void orientGeometry() {
+        if (hasRotation) LAUNCH(ctx, rotate_face, d, nF);
+        LAUNCH(ctx, gh_face, d, nF);
+        LAUNCH(ctx, gh_cell, d, nC);
+    }
+
+    int findCell(const double* x) const {
+        // on the mesh at its current rigid position: map the point back to the body frame
+        double q[3] = {x[0] - cfg.cofg[0] - Tn[0], x[1] - cfg.cofg[1] - Tn[1], x[2] - cfg.cofg[2] - Tn[2]}, y[3];
+        for (int k = 0; k < 3; k++) y[k] = Rn[k] * q[0] + Rn[3 + k] * q[1] + Rn[6 + k] * q[2] + cfg.cofg[k];  // R^T q
+        std::vector<int> nbad(nC, 0);
+        for (int f = 0; f < nF; f++) {
+            double dd[3] = {y[0] - Cf0[3 * f], y[1] - Cf0[3 * f + 1], y[2] - Cf0[3 * f + 2]};
+            double s = dot3(dd, &Sf0[3 * f]);
+            double tol = 1e-12 * magSf[f] * sqrt(magSf[f]);
+            if (s > tol) nbad[own[f]]++;
+            if (f < nI && s < -tol) nbad[nei[f]]++;
+        }
+        int best = -1;
+        double bd = 1e300;
+        for (int c = 0; c < nC; c++)
+            if (nbad[c] == 0) {
+                double dd[3] = {y[0] - C0[3 * c], y[1] - C0[3 * c + 1], y[2] - C0[3 * c + 2]};
+                double q2 = dot3(dd, dd);
+                if (q2 < bd) { bd = q2; best = c; }
+            }
+        return best;
+    }
+
+    // ---- stages -------------------------------------------------------------------------------
+    void readScal() { d2h(ctx, hscal, scal, S_COUNT * sizeof(double)); }
+
+    void courant() {
+        LAUNCH(ctx, courant, d, nC);
+        red.reduce(ctx, d.cellTmp, nullptr, nC, 3, scal + S_MAX0);
+        red.reduce(ctx, d.cellTmp + nC, nullptr, nC, 3, scal + S_MAX1);
+        readScal();
+        Co = 0.5 * hscal[S_MAX0] * dt;
+        alphaCo = 0.5 * hscal[S_MAX1] * dt;
+    }
+    void adjustDeltaT() {
+        if (!cfg.adjust_time_step) return;
+        double dd = cfg.max_delta_t;
+        if (Co > SMALL) dd = std::min(dd, cfg.max_co / Co * dt);
+        if (alphaCo > SMALL) dd = std::min(dd, cfg.max_alpha_co / alphaCo * dt);
+        dt = std::min(1.2 * dt, dd);
+        double timeToNextWrite = std::max(0.0, (writeTimeIndex + 1) * cfg.write_interval - (t - startTime));
+        double nSteps = timeToNextWrite / dt - SMALL;
+        if (nSteps < 2147483647.0) {
+            int n = (int)nSteps + 1;
+            double nd = timeToNextWrite / n;
+            if (nd >= dt) dt = std::min(nd, 2.0 * dt); else dt = std::max(nd, 0.2 * dt);
+        }
+    }
+    bool advanceTime() {
+        dt0 = dt;
+        t += dt;
+        step++;
+        d2d(ctx, d.U0, d.U, 3 * (size_t)nC * sizeof(double));
+        d2d(ctx, d.U0_b, d.U_b, 3 * (size_t)nB * sizeof(double));
+        d2d(ctx, d.rho0, d.rho, nC * sizeof(double));
+        d2d(ctx, d.Uf0, d.Uf, 3 * (size_t)nF * sizeof(double));
+        int wi = (int)(((t - startTime) + 0.5 * dt) / cfg.write_interval);
+        if (wi > writeTimeIndex) { writeTimeIndex = wi; return true; }
+        return false;
+    }
+    void moveMesh() {
+        d.dt = dt;
+        if (cfg.n_motion <= 0) return;
+        memcpy(Ro, Rn, sizeof(Rn)); memcpy(To, Tn, sizeof(Tn));
+        motionAt(t, Rn, Tn);
+        setTransform();
+        bool rotStep = false;
+        for (int k = 0; k < 9; k++) if (Rn[k] != Ro[k]) rotStep = true;
+        if (rotStep) {
+            g_err = "rotating solid-body motion: swept-volume kernel not implemented yet";
+        }
+        orientGeometry();
+        LAUNCH(ctx, meshphi_trans, d, nF);
+    }
+    void alphaBCs() { LAUNCH(ctx, alpha_bc, d, nB); }
+    void UBCs() { d.dt = dt; LAUNCH(ctx, U_bc, d, nB); }
+    void mixture() { LAUNCH(ctx, mixture_cell, d, nC); LAUNCH(ctx, mixture_bnd, d, nB); }
+    void gradScalar(const double* s, const double* sb, double* out) {
+        d.gs = s; d.gsb = sb; d.gout = out;
+        LAUNCH(ctx, grad_scalar, d, nC);
+    }
+    void alphaSubCycle(double dts) {
+        d.rDeltaT = 1.0 / dts;
+        d2d(ctx, d.alpha0, d.alpha, nC * sizeof(double));
+        alphaBCs();
+        gradScalar(d.alpha, d.alpha_b, d.grad);
+        LAUNCH(ctx, alpha_flux, d, nF);
+        LAUNCH(ctx, mules_setup, d, nC);
+        for (int j = 0; j < cfg.n_limiter_iter; j++) {
+            LAUNCH(ctx, mules_cell, d, nC);
+            LAUNCH(ctx, mules_face, d, nI);
+        }
+        LAUNCH(ctx, mules_phipsi, d, nF);
+        LAUNCH(ctx, mules_update, d, nC);
+        alphaBCs();
+    }
+    void alphaPredictor() {
+        int n = cfg.n_alpha_subcycles;
+        if (n > 1) {
+            double total = dt, dts = dt / n;
+            dev_zero(ctx, d.alphaPhi, nF * sizeof(double));
+            d.subW = dts / total;
+            for (int s = 0; s < n; s++) {
+                for (int a = 0; a < cfg.n_alpha_corr; a++) alphaSubCycle(dts);
+                LAUNCH(ctx, alphaphi_acc, d, nF);
+            }
+        } else {
+            for (int a = 0; a < cfg.n_alpha_corr; a++) alphaSubCycle(dt);
+            d2d(ctx, d.alphaPhi, d.alphaPhiUn, nF * sizeof(double));
+        }
+        mixture();
+        LAUNCH(ctx, rhophi, d, nF);
+    }
+    void momentum() {
+        UBCs();
+        d.rDeltaT = 1.0 / dt;
+        LAUNCH(ctx, grad_U, d, nC);
+        LAUNCH(ctx, mom_face, d, nI);
+        LAUNCH(ctx, mom_bnd, d, nB);
+        LAUNCH(ctx, mom_cell, d, nC);
+    }
+    void computeHbyA() {
+        LAUNCH(ctx, HbyA, d, nC);
+        LAUNCH(ctx, HbyA_bnd, d, nB);
+    }
+    void pcPrepare() {
+        d.dt = dt; d.rDeltaT = 1.0 / dt;
+        computeHbyA();
+        gradScalar(d.rho, d.rho_b, d.grad);
+        LAUNCH(ctx, phiHbyA, d, nF);
+    }
+    void pcAssemble() {
+        LAUNCH(ctx, p_total, d, nB);
+        gradScalar(d.p_rgh, d.p_rgh_b, d.grad);
+        LAUNCH(ctx, p_face, d, nI);
+        LAUNCH(ctx, p_cell, d, nC);
+    }
+    void pcFinish() {
+        LAUNCH(ctx, flux, d, nF);
+        LAUNCH(ctx, U_recon, d, nC);
+        UBCs();
+    }
+    void pcEnd() {
+        if (cfg.n_motion > 0) LAUNCH(ctx, Uf, d, nF);
+        LAUNCH(ctx, p, d, nC);
+        if (d.needRef) {
+            double pc;
+            d2h(ctx, &pc, d.p + d.refCell, sizeof(double));
+            d.pRefShift = cfg.p_ref_value - pc;
+            LAUNCH(ctx, p_shift, d, nC);
+            LAUNCH(ctx, p_evaluate, d, nB);
+        }
+    }
+    void pressureCorrector(bool finalIter) {
+        pcPrepare();
+        for (int nonOrth = 0; nonOrth <= cfg.n_non_orth; nonOrth++) {
+            bool finalNonOrth = nonOrth == cfg.n_non_orth;
+            pcAssemble();
+            int which = (finalIter && finalNonOrth) ? 1 : 0;
+            const tpp_solver_t& ctl = which ? cfg.p_rgh_final : cfg.p_rgh;
+            lastSolve[which] = solve(ctl, d.pDiag, d.pUpper, d.pSource, d.p_rgh);
+            LAUNCH(ctx, p_evaluate, d, nB);
+            if (finalNonOrth) pcFinish();
+        }
+        pcEnd();
+    }
+    bool oneStep() {
+        courant();
+        adjustDeltaT();
+        bool wr = advanceTime();
+        moveMesh();
+        alphaPredictor();
+        momentum();
+        for (int corr = 0; corr < cfg.n_correctors; corr++) pressureCorrector(corr == cfg.n_correctors - 1);
+        if (!probeCells.empty()) sampleProbes();
+        return wr;
+    }
+    void sampleProbes() {
+        probeLog.push_back(t);
+        for (int c : probeCells) {
+            double v = -1.79769e+307;
+            if (c >= 0) d2h(ctx, &v, d.p + c, sizeof(double));
+            probeLog.push_back(v);
+        }
+    }
+
+    // ---- multigrid hierarchy (cached: the mesh only moves rigidly) ------------------------------
+    LV fineView(double* diag, double* upper) {
+        LV L;
+        memset(&L, 0, sizeof(L));
+        L.n = nC; L.nf = nI; L.nCp = nCp; L.W = W; L.ell = 1;
+        L.cf = d.cf; L.cn = d.cn; L.own = d.own; L.nei = d.nei;
+        L.diag = diag; L.upper = upper; L.rsum = fineRsum;
+        return L;
+    }
+    LV levelView(int l) {
+        Level& v = levels[l];
+        LV L;
+        memset(&L, 0, sizeof(L));
+        L.n = v.n; L.nf = v.nf; L.ell = 0; L.cf = v.cf; L.cn = v.cn; L.rs = v.rs; L.own = v.own; L.nei = v.nei;
+        L.diag = v.diag; L.upper = v.upper; L.rsum = v.rsum;
+        L.agg = v.agg; L.aggStart = v.aggStart; L.aggRows = v.aggRows; L.segStart = v.segStart; L.segFaces = v.segFaces;
+        L.x = v.x; L.b = v.b; L.t0 = v.t0; L.t1 = v.t1; L.out = v.t2;
+        return L;
+    }
+    static void setFine(LV& L, const LV& F) {
+        L.fn = F.n; L.fnCp = F.nCp; L.fW = F.W; L.fell = F.ell; L.fcf = F.cf; L.fcn = F.cn; L.frs = F.rs;
+        L.fdiag = F.diag; L.fupper = F.upper; L.frsum = F.rsum;
+    }
+
+    // one pairwise matching pass on the device; returns host `root`
+    void matchPass(LV G, int n, const double* fwDev, std::vector<int>& rootH) {
+        std::vector<int> m1(n, -1);
+        h2d(ctx, match, m1.data(), n * sizeof(int));
+        G.match = match; G.prop = prop; G.root = root; G.fw = fwDev;
+        for (int r = 0; r < 6; r++) {
+            LAUNCH(ctx, match_propose, G, n);
+            LAUNCH(ctx, match_accept, G, n);
+        }
+        LAUNCH(ctx, match_root, G, n);
+        rootH.resize(n);
+        d2h(ctx, rootH.data(), root, n * sizeof(int));
+    }
+
+    struct HostGraph {
+        int n = 0, nf = 0;
+        std::vector<int> own, nei;
+        std::vector<double> fw;
+    };
+    // CSR rows (neighbour-side faces then owner-side faces: ascending face index)
+    static void csrOf(const HostGraph& g, std::vector<int>& rs, std::vector<int>& cf, std::vector<int>& cn) {
+        rs.assign(g.n + 1, 0);
+        for (int f = 0; f < g.nf; f++) { rs[g.own[f] + 1]++; rs[g.nei[f] + 1]++; }
+        for (int c = 0; c < g.n; c++) rs[c + 1] += rs[c];
+        cf.assign(2 * (size_t)g.nf, -1); cn.assign(2 * (size_t)g.nf, -1);
+        std::vector<int> cur(rs.begin(), rs.end() - 1);
+        for (int f = 0; f < g.nf; f++) {
+            int o = g.own[f], n = g.nei[f];
+            cf[cur[o]] = f << 1; cn[cur[o]] = n; cur[o]++;
+            cf[cur[n]] = (f << 1) | 1; cn[cur[n]] = o; cur[n]++;
+        }
+    }
+    // aggregate `g` by `root`; returns the coarse graph, the map and, per coarse face, its fine faces
+    static void coarsen(const HostGraph& g, const std::vector<int>& root, HostGraph& c, std::vector<int>& agg, std::vector<int>& segStart, std::vector<int>& segFaces) {
+        std::vector<int> rank(g.n, -1);
+        int nc = 0;
+        for (int i = 0; i < g.n; i++) if (root[i] == i) rank[i] = nc++;
+        agg.resize(g.n);
+        for (int i = 0; i < g.n; i++) agg[i] = rank[root[i]];
+        std::vector<std::pair<unsigned long long, int>> keys;
+        keys.reserve(g.nf);
+        for (int f = 0; f < g.nf; f++) {
+            int a = agg[g.own[f]], b = agg[g.nei[f]];
+            if (a != b) keys.push_back({((unsigned long long)std::min(a, b) << 32) | (unsigned)std::max(a, b), f});
+        }
+        std::sort(keys.begin(), keys.end());
+        c.n = nc; c.own.clear(); c.nei.clear(); c.fw.clear();
+        segStart.clear(); segFaces.resize(keys.size());
+        unsigned long long last = ~0ull;
+        for (size_t k = 0; k < keys.size(); k++) {
+            if (keys[k].first != last) {
+                c.own.push_back((int)(keys[k].first >> 32));
+                c.nei.push_back((int)(keys[k].first & 0xffffffffu));
+                c.fw.push_back(0.0);
+                segStart.push_back((int)k);
+                last = keys[k].first;
+            }
+            segFaces[k] = keys[k].second;
+            c.fw.back() += g.fw[keys[k].second];
+        }
+        segStart.push_back((int)keys.size());
+        c.nf = (int)c.own.size();
+    }
+
+    void buildAMG() {
+        amgBuilt = true;
+        const int coarsestTarget = 1500, maxLevels = 24;
+        if (nC <= coarsestTarget) return;
+        match = A<int>(nC); prop = A<int>(nC); root = A<int>(nC);
+        // faceAreaPair weights |Sf/sqrt(|Sf|) * (1, 1.01, 1.02)|
+        HostGraph g;
+        g.n = nC; g.nf = nI; g.own.assign(own.begin(), own.begin() + nI); g.nei = nei; g.fw.resize(nI);
+        for (int f = 0; f < nI; f++) {
+            double s = sqrt(magSf[f]);
+            double v[3] = {Sf0[3 * f] / s * 1.0, Sf0[3 * f + 1] / s * 1.01, Sf0[3 * f + 2] / s * 1.02};
+            g.fw[f] = mag3(v);
+        }
+        double* fwDev = A<double>(nI);
+        LV G = fineView(nullptr, nullptr);
+        while ((int)levels.size() < maxLevels && g.n > coarsestTarget) {
+            // two matching passes merged into one level
+            std::vector<int> aggTot, segS, segF;
+            HostGraph cur = g, nxt;
+            bool first = true;
+            int passes = 0;
+            for (int pass = 0; pass < 2; pass++) {
+                h2d(ctx, fwDev, cur.fw.data(), cur.nf * sizeof(double));
+                LV M;
+                std::vector<int> rs, cf, cn;
+                int *drs = nullptr, *dcf = nullptr, *dcn = nullptr;
+                if (first && levels.empty()) M = G;
+                else {
+                    csrOf(cur, rs, cf, cn);
+                    drs = dalloc<int>(rs.size()); dcf = dalloc<int>(cf.size()); dcn = dalloc<int>(cn.size());
+                    h2d(ctx, drs, rs.data(), rs.size() * sizeof(int));
+                    if (!cf.empty()) { h2d(ctx, dcf, cf.data(), cf.size() * sizeof(int)); h2d(ctx, dcn, cn.data(), cn.size() * sizeof(int)); }
+                    memset(&M, 0, sizeof(M));
+                    M.n = cur.n; M.nf = cur.nf; M.ell = 0; M.rs = drs; M.cf = dcf; M.cn = dcn;
+                }
+                std::vector<int> rootH, agg, sS, sF;
+                matchPass(M, cur.n, fwDev, rootH);
+                dev_sync(ctx);
+                dev_free(drs); dev_free(dcf); dev_free(dcn);
+                coarsen(cur, rootH, nxt, agg, sS, sF);
+                passes++;
+                if (first) { aggTot = agg; segS = sS; segF = sF; first = false; }
+                else {
+                    for (auto& a : aggTot) a = agg[a];
+                    // flatten: coarse face -> intermediate faces -> fine faces
+                    std::vector<int> nS(1, 0), nF2;
+                    for (int F = 0; F < nxt.nf; F++) {
+                        for (int k = sS[F]; k < sS[F + 1]; k++) {
+                            int mid = sF[k];
+                            for (int q = segS[mid]; q < segS[mid + 1]; q++) nF2.push_back(segF[q]);
+                        }
+                        nS.push_back((int)nF2.size());
+                    }
+                    segS.swap(nS); segF.swap(nF2);
+                }
+                cur = nxt;
+                if (cur.n <= coarsestTarget) break;
+            }
+            if (cur.n >= 0.9 * g.n) break;  // stalled
+            Level v;
+            v.n = cur.n; v.nf = cur.nf;
+            std::vector<int> rs, cf, cn;
+            csrOf(cur, rs, cf, cn);
+            auto up = [&](const std::vector<int>& h) { int* p = dalloc<int>(h.size()); if (!h.empty()) h2d(ctx, p, h.data(), h.size() * sizeof(int)); return p; };
+            v.rs = up(rs); v.cf = up(cf); v.cn = up(cn); v.own = up(cur.own); v.nei = up(cur.nei);
+            v.agg = up(aggTot); v.segStart = up(segS); v.segFaces = up(segF);
+            // members of each aggregate, ascending fine index
+            std::vector<int> aS(cur.n + 1, 0), aR(g.n);
+            for (int i = 0; i < g.n; i++) aS[aggTot[i] + 1]++;
+            for (int c = 0; c < cur.n; c++) aS[c + 1] += aS[c];
+            std::vector<int> pos(aS.begin(), aS.end() - 1);
+            for (int i = 0; i < g.n; i++) aR[pos[aggTot[i]]++] = i;
+            v.aggStart = up(aS); v.aggRows = up(aR);
+            v.diag = dalloc<double>(v.n); v.upper = dalloc<double>(std::max(v.nf, 1)); v.rsum = dalloc<double>(v.n);
+            v.x = dalloc<double>(v.n); v.b = dalloc<double>(v.n); v.t0 = dalloc<double>(v.n); v.t1 = dalloc<double>(v.n); v.t2 = dalloc<double>(v.n);
+            levels.push_back(v);
+            g = cur;
+        }
+    }
+
+    // Galerkin coefficients of every level from the fine matrix
+    void galerkin(LV& F0) {
+        LAUNCH(ctx, rowsum, F0, F0.n);
+        LV F = F0;
+        for (size_t l = 0; l < levels.size(); l++) {
+            LV L = levelView((int)l);
+            setFine(L, F);
+            LAUNCH(ctx, coarse_upper, L, L.nf);
+            LAUNCH(ctx, coarse_diag, L, L.n);
+            F = L;
+        }
+    }
+
+    void coarseSolve(LV L) {
+#ifdef TPP_EMU
+        int n = L.n;
+        std::vector<double> r(n), p(n), Ap(n);
+        double rz = 0;
+        for (int i = 0; i < n; i++) { L.x[i] = 0; r[i] = L.b[i]; p[i] = L.b[i] / L.diag[i]; rz += L.b[i] * p[i]; }
+        double rz0 = rz;
+        if (rz > 0)
+            for (int it = 0; it < 200; it++) {
+                double pAp = 0;
+                for (int i = 0; i < n; i++) { Ap[i] = row_Ax(L, i, p.data()); pAp += Ap[i] * p[i]; }
+                double alpha = rz / pAp, rzn = 0;
+                for (int i = 0; i < n; i++) { L.x[i] += alpha * p[i]; r[i] -= alpha * Ap[i]; rzn += r[i] * r[i] / L.diag[i]; }
+                if (rzn <= 1e-6 * rz0) break;
+                double beta = rzn / rz;
+                rz = rzn;
+                for (int i = 0; i < n; i++) p[i] = r[i] / L.diag[i] + beta * p[i];
+            }
+        ctx.launches++;
+#else
+        prof_begin(ctx, "coarse_cg");
+        k_coarse_cg<<<1, 1024, 0, ctx.stream>>>(L, 200, 1e-3);
+        prof_end(ctx);
+        ctx.launches++;
+#endif
+    }
+
+    // x (output) ~= A^-1 b on level l (l = -1: fine).  zeroGuess: x is overwritten.
+    void vcycle(int l, LV& F0, const double* b, double* x, double* tmp, bool zeroGuess, int nPre, int nPost) {
+        LV L = l < 0 ? F0 : levelView(l);
+        const double omega = 0.8;
+        if (l == (int)levels.size() - 1 && l >= 0) {
+            L.b = const_cast<double*>(b); L.x = x;
+            coarseSolve(L);
+            return;
+        }
+        L.omega = omega; L.b = const_cast<double*>(b);
+        double *cur = x, *oth = tmp;
+        int sweeps = std::max(nPre, 1);
+        for (int s = 0; s < sweeps; s++) {
+            if (s == 0 && zeroGuess) { L.out = cur; LAUNCH(ctx, jacobi0, L, L.n); }
+            else { L.in = cur; L.out = oth; LAUNCH(ctx, jacobi, L, L.n); std::swap(cur, oth); }
+        }
+        // restrict residual, recurse, prolong
+        LV Cn = levelView(l + 1);
+        setFine(Cn, L);
+        Cn.fx = cur; Cn.fb = b;
+        LAUNCH(ctx, restrict_residual, Cn, Cn.n);
+        Level& cv = levels[l + 1];
+        vcycle(l + 1, F0, cv.b, cv.x, cv.t0, true, nPre, nPost);
+        Cn.fxw = cur;
+        LAUNCH(ctx, prolong_add, Cn, L.n);
+        for (int s = 0; s < std::max(nPost, 1); s++) {
+            L.in = cur; L.out = oth;
+            LAUNCH(ctx, jacobi, L, L.n);
+            std::swap(cur, oth);
+        }
+        if (cur != x) d2d(ctx, x, cur, L.n * sizeof(double));
+    }
+
+    void precondition(LV& F0, const tpp_solver_t& ctl, const double* r, double* z) {
+        if (ctl.type == 0 && ctl.precond == 0) {  // PCG + DIC requested: diagonal preconditioning
+            LV L = F0;
+            L.omega = 1.0; L.b = const_cast<double*>(r); L.out = z;
+            LAUNCH(ctx, jacobi0, L, L.n);
+            return;
+        }
+        if (levels.empty()) {  // mesh no larger than a coarsest level: one-CTA CG is the "multigrid"
+            LV L = F0;
+            L.b = const_cast<double*>(r); L.x = z; L.t0 = kt; L.t1 = kt2; L.out = kt3;
+            coarseSolve(L);
+            return;
+        }
+        int nv = ctl.type == 1 ? 1 : std::max(ctl.n_vcycles, 1);
+        int nPre = 2, nPost = 2;
+        for (int cyc = 0; cyc < nv; cyc++) vcycle(-1, F0, r, z, kt, cyc == 0, nPre, nPost);
+    }
+
+    SolveStats solve(const tpp_solver_t& ctl, double* diag, double* upper, const double* b, double* x) {
+        SolveStats st;
+        if (!amgBuilt) buildAMG();
+        LV F0 = fineView(diag, upper);
+        bool useAMG = !levels.empty() && !(ctl.type == 0 && ctl.precond == 0);
+        if (useAMG) galerkin(F0); else LAUNCH(ctx, rowsum, F0, F0.n);
+        red.reduce(ctx, x, nullptr, nC, 2, scal + S_XSUM);
+        initResidual(F0, x, b);
+        readScal();
+        double nf = hscal[S_NORM] + 1e-20;
+        st.r0 = st.r = hscal[S_RES] / nf;
+        auto conv = [&](double r) { return r < ctl.tolerance || (ctl.rel_tol > 0 && r < ctl.rel_tol * st.r0); };
+        if (conv(st.r)) return st;
+        do {
+            precondition(F0, ctl, kr, kz);
+            scalCopy(S_WARA_OLD, S_WARA);
+            red.reduce(ctx, kz, kr, nC, 0, scal + S_WARA);
+            updateP(st.iters == 0);
+            spmvDot(F0);
+            updateXR(x);
+            readScal();
+            st.r = hscal[S_RES] / nf;
+            if (!(fabs(hscal[S_WAPA]) / nf >= VSMALL)) break;
+        } while (++st.iters < ctl.max_iter && !conv(st.r));
+        return st;
+    }
+
+    void scalCopy(int dst, int src) {
+#ifdef TPP_EMU
+        scal[dst] = scal[src];
+#else
+        k_scal_copy<<<1, 1, 0, ctx.stream>>>(scal, dst, src);
+#endif
+        ctx.launches++;
+    }
+    void initResidual(LV& F0, const double* x, const double* b) {
+#ifdef TPP_EMU
+        double xbar = scal[S_XSUM] / nC, v = 0, w = 0;
+        for (int c = 0; c < nC; c++) {
+            double ax = row_Ax(F0, c, x), rr = b[c] - ax;
+            kr[c] = rr; v += fabs(rr);
+            double p = F0.rsum[c] * xbar;
+            w += fabs(ax - p) + fabs(b[c] - p);
+        }
+        scal[S_RES] = v; scal[S_NORM] = w;
+        ctx.launches += 3;
+#else
+        prof_begin(ctx, "init_residual");
+        k_init_residual<<<RED_BLOCKS, BLOCK, 0, ctx.stream>>>(F0, x, b, kr, scal, red.partial, red.partial2);
+        k_reduce_final<<<1, BLOCK, 0, ctx.stream>>>(red.partial, RED_BLOCKS, 2, scal + S_RES);
+        k_reduce_final<<<1, BLOCK, 0, ctx.stream>>>(red.partial2, RED_BLOCKS, 2, scal + S_NORM);
+        prof_end(ctx);
+        ctx.launches += 3;
+#endif
+    }
+    void updateP(bool first) {
+#ifdef TPP_EMU
+        double beta = first ? 0.0 : scal[S_WARA] / scal[S_WARA_OLD];
+        for (int c = 0; c < nC; c++) kp[c] = first ? kz[c] : kz[c] + beta * kp[c];
+#else
+        prof_begin(ctx, "update_p");
+        k_update_p<<<RED_BLOCKS, BLOCK, 0, ctx.stream>>>(nC, kp, kz, scal, first ? 1 : 0);
+        prof_end(ctx);
+#endif
+        ctx.launches++;
+    }
+    void spmvDot(LV& F0) {
+#ifdef TPP_EMU
+        double v = 0;
+        for (int c = 0; c < nC; c++) { kw[c] = row_Ax(F0, c, kp); v += kw[c] * kp[c]; }
+        scal[S_WAPA] = v;
+#else
+        LV L = F0;
+        L.in = kp; L.out = kw;
+        prof_begin(ctx, "spmv_dot");
+        k_spmv_dot<<<RED_BLOCKS, BLOCK, 0, ctx.stream>>>(L, red.partial);
+        k_reduce_final<<<1, BLOCK, 0, ctx.stream>>>(red.partial, RED_BLOCKS, 2, scal + S_WAPA);
+        prof_end(ctx);
+#endif
+        ctx.launches += 2;
+    }
+    void updateXR(double* x) {
+#ifdef TPP_EMU
+        double alpha = scal[S_WARA] / scal[S_WAPA], v = 0;
+        for (int c = 0; c < nC; c++) { x[c] += alpha * kp[c]; kr[c] -= alpha * kw[c]; v += fabs(kr[c]); }
+        scal[S_RES] = v;
+#else
+        prof_begin(ctx, "update_xr");
+        k_update_xr<<<RED_BLOCKS, BLOCK, 0, ctx.stream>>>(nC, x, kr, kp, kw, scal, red.partial);
+        k_reduce_final<<<1, BLOCK, 0, ctx.stream>>>(red.partial, RED_BLOCKS, 2, scal + S_RES);
+        prof_end(ctx);
+#endif
+        ctx.launches += 2;
+    }
+
+    void destroy() {
+        for (void* p : allocs) dev_free(p);
+        for (auto& l : levels) l.free();
+        red.free();
+#ifdef TPP_EMU
+        free(hscal);
+#else
+        if (hscal) cudaFreeHost(hscal);
+        if (ctx.stream && ctx.ownStream) cudaStreamDestroy(ctx.stream);
+#endif
+    }
+};
+
+// ------------------------------------------------------------------------------------
+// C-ABI
+// ------------------------------------------------------------------------------------
+extern "C" {
+
+const char* tpp_last_error(void) { return g_err.c_str(); }
+const char* tpp_version(void) {
+#ifdef TPP_EMU
+    return "tppvof 0.1 (HOST EMULATION - tests only)";
+#else
+    return "tppvof 0.1 (sm_100a)";
+#endif
+}
+
+int tpp_create(const tpp_mesh_t* mesh, const tpp_config_t* cfg, int device, tpp_handle* out) {
+    *out = nullptr;
+#ifndef TPP_EMU
+    int ndev = 0;
+    cudaError_t e = cudaGetDeviceCount(&ndev);
+    if (e != cudaSuccess || ndev == 0) {
+        g_err = std::string("no usable CUDA device (") + cudaGetErrorString(e) + "): libtppvof has no CPU path";
+        return -2;
+    }
+    if (device < 0 || device >= ndev) { g_err = "device index out of range"; return -3; }
+    CUDA_CHECK(cudaSetDevice(device));
+#endif
+    tpp_solver* s = new tpp_solver();
+    s->device = device;
+#ifndef TPP_EMU
+    CUDA_CHECK(cudaStreamCreate(&s->ctx.stream));
+    s->ctx.ownStream = true;
+#endif
+    if (!s->build(mesh, cfg)) { s->destroy(); delete s; return -1; }
+    dev_sync(s->ctx);
+    *out = s;
+    return 0;
+}
+
+int tpp_destroy(tpp_handle s) {
+    if (!s) return 0;
+#ifndef TPP_EMU
+    cudaSetDevice(s->device);
+    cudaStreamSynchronize(s->ctx.stream);
+#endif
+    s->destroy();
+    delete s;
+    return 0;
+}
+
+static void pointsNow(tpp_solver* s, std::vector<double>& out) {
+    out.resize(3 * (size_t)s->nP);
+    for (int i = 0; i < s->nP; i++) {
+        double q[3] = {s->points0[3 * i] - s->cfg.cofg[0], s->points0[3 * i + 1] - s->cfg.cofg[1], s->points0[3 * i + 2] - s->cfg.cofg[2]};
+        for (int k = 0; k < 3; k++) out[3 * i + k] = (s->Rn[3 * k] * q[0] + s->Rn[3 * k + 1] * q[1] + s->Rn[3 * k + 2] * q[2]) + s->cfg.cofg[k] + s->Tn[k];
+    }
+}
+
+long tpp_size(tpp_handle s, const char* name) {
+    if (!strcmp(name, "points")) return 3L * s->nP;
+    auto it = s->reg.find(name);
+    return it == s->reg.end() ? -1 : it->second.second;
+}
+long tpp_get(tpp_handle s, const char* name, double* out, long cap) {
+    if (!strcmp(name, "points")) {
+        std::vector<double> p;
+        pointsNow(s, p);
+        memcpy(out, p.data(), std::min<long>(cap, (long)p.size()) * sizeof(double));
+        return (long)p.size();
+    }
+    auto it = s->reg.find(name);
+    if (it == s->reg.end()) { g_err = std::string("unknown array ") + name; return -1; }
+    long n = std::min<long>(cap, it->second.second);
+    d2h(s->ctx, out, it->second.first, n * sizeof(double));
+    return it->second.second;
+}
+long tpp_set(tpp_handle s, const char* name, const double* in, long n) {
+    auto it = s->reg.find(name);
+    if (it == s->reg.end()) { g_err = std::string("unknown array ") + name; return -1; }
+    if (n != it->second.second) { g_err = std::string("size mismatch for ") + name; return -2; }
+    h2d(s->ctx, it->second.first, in, n * sizeof(double));
+    return n;
+}
+int tpp_device_ptr(tpp_handle s, const char* name, void** ptr, long* n) {
+    auto it = s->reg.find(name);
+    if (it == s->reg.end()) { g_err = std::string("unknown array ") + name; return -1; }
+    *ptr = it->second.first;
+    *n = it->second.second;
+    return 0;
+}
+int tpp_init_fields(tpp_handle s) {
+    s->alphaBCs();
+    s->mixture();
+    d2d(s->ctx, s->d.rho0, s->d.rho, s->nC * sizeof(double));
+    dev_sync(s->ctx);
+    return 0;
+}
+int tpp_set_delta_t(tpp_handle s, double dt) { s->dt = s->dt0 = dt; return 0; }
+int tpp_set_time(tpp_handle s, double t, double dt) {
+    s->t = t; s->dt = s->dt0 = dt;
+    s->motionAt(t, s->Rn, s->Tn);
+    memcpy(s->Ro, s->Rn, sizeof(s->Rn)); memcpy(s->To, s->Tn, sizeof(s->Tn));
+    s->setTransform();
+    s->orientGeometry();
+    dev_sync(s->ctx);
+    return 0;
+}
+
+int tpp_step(tpp_handle s, int n) {
+    for (int i = 0; i < n; i++) s->oneStep();
+    dev_sync(s->ctx);
+    return 0;
+}
+int tpp_run_to_write(tpp_handle s, long max_steps) {
+    for (long i = 0; i < max_steps; i++) {
+        if (!(s->t < s->cfg.end_time - 0.5 * s->dt)) { dev_sync(s->ctx); return 0; }
+        if (s->oneStep()) { dev_sync(s->ctx); return 1; }
+    }
+    dev_sync(s->ctx);
+    return 2;
+}
+int tpp_stage(tpp_handle s, const char* name) {
+    std::string n(name);
+    s->d.dt = s->dt;
+    if (n == "courant") s->courant();
+    else if (n == "adjustDeltaT") s->adjustDeltaT();
+    else if (n == "advanceTime") s->advanceTime();
+    else if (n == "moveMesh") s->moveMesh();
+    else if (n == "alphaBCs") s->alphaBCs();
+    else if (n == "UBCs") s->UBCs();
+    else if (n == "mixture") s->mixture();
+    else if (n == "alphaSubCycle") s->alphaSubCycle(s->dt / s->cfg.n_alpha_subcycles);
+    else if (n == "alphaPredictor") s->alphaPredictor();
+    else if (n == "momentum") s->momentum();
+    else if (n == "HbyA") s->computeHbyA();
+    else if (n == "pcPrepare") s->pcPrepare();
+    else if (n == "pcAssemble") s->pcAssemble();
+    else if (n == "pcFinish") { LAUNCH(s->ctx, p_evaluate, s->d, s->nB); s->pcFinish(); }
+    else if (n == "pcEnd") s->pcEnd();
+    else if (n == "pressureCorrector:0") s->pressureCorrector(false);
+    else if (n == "pressureCorrector:1") s->pressureCorrector(true);
+    else { g_err = "unknown stage " + n; return -1; }
+    dev_sync(s->ctx);
+    return 0;
+}
+int tpp_info(tpp_handle s, double* o) {
+    o[0] = s->t; o[1] = s->dt; o[2] = (double)s->step; o[3] = s->Co; o[4] = s->alphaCo;
+    o[5] = s->lastSolve[0].iters; o[6] = s->lastSolve[0].r0; o[7] = s->lastSolve[0].r;
+    o[8] = s->lastSolve[1].iters; o[9] = s->lastSolve[1].r0; o[10] = s->lastSolve[1].r;
+    o[11] = s->d.needRef ? s->d.refCell : -1; o[12] = s->d.deltaN; o[13] = s->writeTimeIndex;
+    o[14] = (double)s->levels.size(); o[15] = (double)s->ctx.launches;
+    return 0;
+}
+int tpp_solve(tpp_handle s, const tpp_solver_t* ctl, const double* diag, const double* upper, const double* b, double* x, double* r0, double* r) {
+    h2d(s->ctx, s->d.pDiag, diag, s->nC * sizeof(double));
+    h2d(s->ctx, s->d.pUpper, upper, s->nI * sizeof(double));
+    h2d(s->ctx, s->d.pSource, b, s->nC * sizeof(double));
+    double* xd = s->d.cellTmp;
+    h2d(s->ctx, xd, x, s->nC * sizeof(double));
+    SolveStats st = s->solve(*ctl, s->d.pDiag, s->d.pUpper, s->d.pSource, xd);
+    d2h(s->ctx, x, xd, s->nC * sizeof(double));
+    *r0 = st.r0; *r = st.r;
+    return st.iters;
+}
+int tpp_set_probes(tpp_handle s, int n, const int* cells) { s->probeCells.assign(cells, cells + n); return 0; }
+long tpp_probe_log(tpp_handle s, double* out, long cap_rows) {
+    long w = 1 + (long)s->probeCells.size();
+    long rows = (long)s->probeLog.size() / w;
+    long n = std::min(rows, cap_rows);
+    memcpy(out, s->probeLog.data(), n * w * sizeof(double));
+    s->probeLog.erase(s->probeLog.begin(), s->probeLog.begin() + n * w);
+    return n;
+}
+int tpp_find_cell(tpp_handle s, const double* xyz) { return s->findCell(xyz); }
+int tpp_use_stream(tpp_handle s, void* stream) {
+#ifndef TPP_EMU
+    cudaStreamSynchronize(s->ctx.stream);
+    if (s->ctx.ownStream) cudaStreamDestroy(s->ctx.stream);
+    s->ctx.stream = (cudaStream_t)stream;
+    s->ctx.ownStream = false;
+#else
+    (void)s; (void)stream;
+#endif
+    return 0;
+}
+int tpp_profile(tpp_handle s, int on) {
+    s->ctx.prof = on != 0;
+    return 0;
+}
+long tpp_profile_report(tpp_handle s, char* buf, long cap) {
+    dev_sync(s->ctx);
+    std::map<std::string, std::pair<long, double>> agg;
+    for (auto& r : s->ctx.recs) {
+        float ms = 0;
+#ifndef TPP_EMU
+        cudaEventElapsedTime(&ms, r.e0, r.e1);
+        cudaEventDestroy(r.e0);
+        cudaEventDestroy(r.e1);
+#endif
+        auto& a = agg[r.name];
+        a.first++;
+        a.second += ms;
+    }
+    s->ctx.recs.clear();
+    std::string out;
+    char line[160];
+    for (auto& kv : agg) {
+        snprintf(line, sizeof(line), "%s %ld %.6f\n", kv.first.c_str(), kv.second.first, kv.second.second);
+        out += line;
+    }
+    if ((long)out.size() + 1 > cap) return -(long)out.size() - 1;
+    memcpy(buf, out.c_str(), out.size() + 1);
+    return (long)out.size();
+}
+int tpp_nccl_unique_id(char*) { g_err = "multi-GPU halo path is not built yet"; return -1; }
+int tpp_comm_init(tpp_handle, int, int, const char*) { g_err = "multi-GPU halo path is not built yet"; return -1; }
+}

@@ -1,0 +1,189 @@
+"""ctypes binding of libtppvof.so (include/tppvof.h) — the thin host layer over the CUDA solver.
+
+There is no CPU path: `Solver` raises when the CUDA library is missing or no GPU is usable.
+(`lib_path` exists so the unit tests can point the same binding at tests/_emu's host
+emulation of the kernel bodies; the package itself never does.)
+"""
+from __future__ import annotations
+
+import ctypes as C
+import os
+
+import numpy as np
+
+from . import abi
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+LIB_PATH = os.path.join(_HERE, "libtppvof.so")
+_LIBS = {}
+
+INFO_KEYS = ["t", "dt", "step", "Co", "alphaCo", "it0", "r00", "r0", "it1", "r01", "r1", "refCell", "deltaN", "writeIndex", "levels", "launches"]
+
+
+class SolverError(RuntimeError):
+    pass
+
+
+def load(lib_path=None):
+    path = lib_path or LIB_PATH
+    if path in _LIBS:
+        return _LIBS[path]
+    if not os.path.exists(path):
+        raise SolverError(f"{path} is missing: build it with `python -c 'import __graft_entry__ as g; g.build()'` (nvcc, sm_100a). There is no CPU fallback.")
+    L = C.CDLL(path)
+    H = C.c_void_p
+    L.tpp_create.argtypes = [C.POINTER(abi.MeshStruct), C.POINTER(abi.ConfigStruct), C.c_int, C.POINTER(H)]
+    L.tpp_destroy.argtypes = [H]
+    L.tpp_last_error.restype = C.c_char_p
+    L.tpp_version.restype = C.c_char_p
+    L.tpp_size.restype = C.c_long
+    L.tpp_size.argtypes = [H, C.c_char_p]
+    for f in (L.tpp_get, L.tpp_set):
+        f.restype = C.c_long
+        f.argtypes = [H, C.c_char_p, abi.c_double_p, C.c_long]
+    L.tpp_device_ptr.argtypes = [H, C.c_char_p, C.POINTER(C.c_void_p), C.POINTER(C.c_long)]
+    L.tpp_init_fields.argtypes = [H]
+    L.tpp_set_delta_t.argtypes = [H, C.c_double]
+    L.tpp_set_time.argtypes = [H, C.c_double, C.c_double]
+    L.tpp_step.argtypes = [H, C.c_int]
+    L.tpp_run_to_write.argtypes = [H, C.c_long]
+    L.tpp_stage.argtypes = [H, C.c_char_p]
+    L.tpp_info.argtypes = [H, abi.c_double_p]
+    L.tpp_solve.argtypes = [H, C.POINTER(abi.SolverStruct)] + [abi.c_double_p] * 6
+    L.tpp_set_probes.argtypes = [H, C.c_int, abi.c_int_p]
+    L.tpp_probe_log.restype = C.c_long
+    L.tpp_probe_log.argtypes = [H, abi.c_double_p, C.c_long]
+    L.tpp_find_cell.argtypes = [H, abi.c_double_p]
+    L.tpp_use_stream.argtypes = [H, C.c_void_p]
+    L.tpp_profile.argtypes = [H, C.c_int]
+    L.tpp_profile_report.restype = C.c_long
+    L.tpp_profile_report.argtypes = [H, C.c_char_p, C.c_long]
+    _LIBS[path] = L
+    return L
+
+
+class Solver:
+    """One case on one GPU."""
+
+    def __init__(self, mesh, cfg, device=0, lib_path=None):
+        self.L = load(lib_path)
+        m, c, self._keep = abi.build_structs(mesh, cfg)
+        h = C.c_void_p()
+        rc = self.L.tpp_create(C.byref(m), C.byref(c), device, C.byref(h))
+        if rc != 0:
+            raise SolverError(f"tpp_create failed ({rc}): {self.L.tpp_last_error().decode()}")
+        self.h = h
+        self.mesh, self.cfg = mesh, cfg
+        self._nprobe = 0
+
+    def close(self):
+        if getattr(self, "h", None):
+            self.L.tpp_destroy(self.h)
+            self.h = None
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    def _err(self, what):
+        raise SolverError(f"{what}: {self.L.tpp_last_error().decode()}")
+
+    def size(self, name):
+        return self.L.tpp_size(self.h, name.encode())
+
+    def get(self, name):
+        n = self.size(name)
+        if n < 0:
+            raise KeyError(name)
+        a = np.empty(n, dtype=np.float64)
+        if self.L.tpp_get(self.h, name.encode(), a.ctypes.data_as(abi.c_double_p), n) < 0:
+            self._err("tpp_get")
+        return a
+
+    def set(self, name, a):
+        a = np.ascontiguousarray(a, dtype=np.float64).reshape(-1)
+        if self.L.tpp_set(self.h, name.encode(), a.ctypes.data_as(abi.c_double_p), a.size) < 0:
+            self._err("tpp_set")
+
+    def device_ptr(self, name):
+        p, n = C.c_void_p(), C.c_long()
+        if self.L.tpp_device_ptr(self.h, name.encode(), C.byref(p), C.byref(n)) != 0:
+            self._err("tpp_device_ptr")
+        return p.value, n.value
+
+    def init_fields(self):
+        self.L.tpp_init_fields(self.h)
+
+    def set_delta_t(self, dt):
+        self.L.tpp_set_delta_t(self.h, dt)
+
+    def set_time(self, t, dt):
+        self.L.tpp_set_time(self.h, t, dt)
+
+    def stage(self, name):
+        if self.L.tpp_stage(self.h, name.encode()) != 0:
+            self._err("tpp_stage")
+
+    def step(self, n=1):
+        if self.L.tpp_step(self.h, n) != 0:
+            self._err("tpp_step")
+
+    def run_to_write(self, max_steps=10**9):
+        return self.L.tpp_run_to_write(self.h, max_steps)
+
+    def info(self):
+        o = np.zeros(16)
+        self.L.tpp_info(self.h, o.ctypes.data_as(abi.c_double_p))
+        return dict(zip(INFO_KEYS, o))
+
+    def solve(self, ctl, diag, upper, b, x0=None):
+        x = np.zeros(self.mesh.n_cells) if x0 is None else np.array(x0, dtype=np.float64)
+        r0, r = C.c_double(), C.c_double()
+        s = abi.solver_struct(ctl)
+        d_, u_, b_ = (np.ascontiguousarray(v, dtype=np.float64) for v in (diag, upper, b))
+        it = self.L.tpp_solve(self.h, C.byref(s), d_.ctypes.data_as(abi.c_double_p), u_.ctypes.data_as(abi.c_double_p), b_.ctypes.data_as(abi.c_double_p),
+                              x.ctypes.data_as(abi.c_double_p), C.cast(C.byref(r0), abi.c_double_p), C.cast(C.byref(r), abi.c_double_p))
+        return x, it, r0.value, r.value
+
+    def set_probes(self, cells):
+        a = np.ascontiguousarray(cells, dtype=np.int32)
+        self._nprobe = a.size
+        self.L.tpp_set_probes(self.h, a.size, a.ctypes.data_as(abi.c_int_p))
+
+    def probe_log(self, cap=1 << 16):
+        w = 1 + self._nprobe
+        a = np.empty((cap, w))
+        n = self.L.tpp_probe_log(self.h, a.ctypes.data_as(abi.c_double_p), cap)
+        return a[:n].copy()
+
+    def find_cell(self, xyz):
+        a = np.ascontiguousarray(xyz, dtype=np.float64)
+        return self.L.tpp_find_cell(self.h, a.ctypes.data_as(abi.c_double_p))
+
+    def use_stream(self, cuda_stream):
+        self.L.tpp_use_stream(self.h, C.c_void_p(cuda_stream))
+
+    def profile(self, on=True):
+        self.L.tpp_profile(self.h, int(on))
+
+    def profile_report(self):
+        """{kernel: (launches, total_ms)} since profiling was switched on / last report."""
+        buf = C.create_string_buffer(1 << 16)
+        n = self.L.tpp_profile_report(self.h, buf, len(buf))
+        out = {}
+        for line in buf.value.decode().splitlines():
+            k, c, ms = line.split()
+            out[k] = (int(c), float(ms))
+        return out
+
+    def load_case_fields(self, case):
+        """Start fields from a Case (0/ or the latest time directory: restart)."""
+        nC, nF = self.mesh.n_cells, self.mesh.n_faces
+        self.set("alpha", case.fields["alpha.water"].internal_array(nC))
+        self.set("U", case.fields["U"].internal_array(nC))
+        self.set("p_rgh", case.fields["p_rgh"].internal_array(nC))
+        self.init_fields()
+        if case.restart_delta_t is not None:
+            self.set_delta_t(case.restart_delta_t)

@@ -1121,8 +1121,10 @@ struct orc_state {
             }
         }
         for (int c = 0; c < 3 * nC; c++) H[c] += lduH[c] + mSource[c];
+        dvec bbc(3 * nC, 0.0);
         for (int b = 0; b < nB; b++)
-            for (int k = 0; k < 3; k++) H[3 * own[nI + b] + k] += mBBC[3 * b + k];
+            for (int k = 0; k < 3; k++) bbc[3 * own[nI + b] + k] += mBBC[3 * b + k];
+        for (int c = 0; c < 3 * nC; c++) H[c] += bbc[c];
         rAU.resize(nC); HbyA.resize(3 * nC); HbyA_b.resize(3 * nB);
         for (int c = 0; c < nC; c++) {
             double A = D[c] / V[c];
@@ -1136,7 +1138,7 @@ struct orc_state {
         }
     }
 
-    void pressureCorrector(bool finalIter) {
+    void pcPrepare() {
         computeHbyA();
         const double rDeltaT = 1.0 / dt;
         rAUf.resize(nF); phiHbyA.resize(nF); phig.resize(nF);
@@ -1183,8 +1185,8 @@ struct orc_state {
             if (bcP[facePatch[b]] == ORC_P_FIXED_FLUX)
                 pGrad_b[b] = (phiHbyA[f] - dot3(&Sf[3 * f], &U_b[3 * b])) / (magSf[f] * rAUf[f]);
         }
-        for (int nonOrth = 0; nonOrth <= cfg.n_non_orth; nonOrth++) {
-            bool finalNonOrth = nonOrth == cfg.n_non_orth;
+    }
+    void pcAssemble() {
             pTotalPressure();
             gradScalar(p_rgh, p_rgh_b, gradP);
             pUpper.assign(nI, 0.0); pDiag.assign(nC, 0.0); pSource.assign(nC, 0.0); pCorrFlux.assign(nI, 0.0);
@@ -1222,11 +1224,8 @@ struct orc_state {
                 pSource[refCell] += pDiag[refCell] * p_rgh[refCell];
                 pDiag[refCell] += pDiag[refCell];
             }
-            const orc_solver_t& ctl = (finalIter && finalNonOrth) ? cfg.p_rgh_final : cfg.p_rgh;
-            int which = (finalIter && finalNonOrth) ? 1 : 0;
-            lastSolve[which] = solveP(ctl, which, pDiag, pUpper, pSource, p_rgh);
-            pEvaluate();
-            if (finalNonOrth) {
+    }
+    void pcFinish() {
                 // phi = phiHbyA - flux(p) ; U = HbyA + rAU*reconstruct((phig - flux)/rAUf)
                 dvec T(9 * nC, 0.0), rv(3 * nC, 0.0);
                 for (int f = 0; f < nF; f++) {
@@ -1264,8 +1263,8 @@ struct orc_state {
                     }
                 }
                 UBCs();
-            }
-        }
+    }
+    void pcEnd() {
         // fvc::correctUf ; fvc::makeRelative ; p = p_rgh + rho*gh
         if (cfg.n_motion > 0) {
             for (int f = 0; f < nF; f++) {
@@ -1289,6 +1288,19 @@ struct orc_state {
             }
             pEvaluateAfterShift(shift);
         }
+    }
+    void pressureCorrector(bool finalIter) {
+        pcPrepare();
+        for (int nonOrth = 0; nonOrth <= cfg.n_non_orth; nonOrth++) {
+            bool finalNonOrth = nonOrth == cfg.n_non_orth;
+            pcAssemble();
+            const orc_solver_t& ctl = (finalIter && finalNonOrth) ? cfg.p_rgh_final : cfg.p_rgh;
+            int which = (finalIter && finalNonOrth) ? 1 : 0;
+            lastSolve[which] = solveP(ctl, which, pDiag, pUpper, pSource, p_rgh);
+            pEvaluate();
+            if (finalNonOrth) pcFinish();
+        }
+        pcEnd();
     }
     void pEvaluateAfterShift(double shift) {
         for (int b = 0; b < nB; b++)
@@ -1475,6 +1487,10 @@ int orc_stage(orc_state* s, const char* name) {
     else if (n == "alphaPredictor") s->alphaPredictor();
     else if (n == "momentum") s->momentum();
     else if (n == "HbyA") s->computeHbyA();
+    else if (n == "pcPrepare") s->pcPrepare();
+    else if (n == "pcAssemble") s->pcAssemble();
+    else if (n == "pcFinish") { s->pEvaluate(); s->pcFinish(); }
+    else if (n == "pcEnd") s->pcEnd();
     else if (n == "pressureCorrector:0") s->pressureCorrector(false);
     else if (n == "pressureCorrector:1") s->pressureCorrector(true);
     else {

@@ -1,0 +1,120 @@
+"""Parity of every per-step kernel with the CPU oracle, stage by stage, on identical inputs.
+
+* static mesh: every explicit kernel output must be BIT-EXACT (integer/index work, and the
+  FP64 sums, which are cell-gathered in the oracle's face-loop order with FMA contraction
+  off on both sides);
+* moving mesh: the oracle recomputes geometry from the moved points each step as OpenFOAM
+  does, the GPU applies the rigid transform, so the two differ by geometric round-off:
+  tolerance 1e-9 relative to the field's scale;
+* the p_rgh solve uses a different (parallel) preconditioner: both sides must meet the
+  OpenFOAM convergence contract, and the solutions agree to the solver tolerance.
+
+The `emu` variant runs the same kernel bodies as host loops (CPU CI of the launch logic); the
+`gpu` variant runs the real sm_100a library through the C-ABI.
+"""
+import numpy as np
+import pytest
+
+import parity as P
+from openfoam_tpp_b200 import case as cs
+from openfoam_tpp_b200 import solver as sv
+
+ALPHA = ["alpha", "alpha_b", "phiBD", "phiCorr", "lambda", "alphaPhiUn", "alphaPhi", "rho", "rho_b", "rhoPhi", "grad:gradAlpha"]
+MOM = ["U_b", "gradU", "mLower", "mUpper", "mDiag", "mSource", "mBIC", "mBBC"]
+PREP = ["rAU", "HbyA", "HbyA_b", "rAUf", "phiHbyA", "phig", "pGrad_b", "grad:gradRho"]
+ASM = ["p_rgh_b", "pUpper", "pCorrFlux", "pDiag", "pSource", "grad:gradP"]
+FIN = ["p_rgh_b", "phi", "U", "U_b", "Uf", "p", "p_rgh"]
+
+
+def _check(g, o, names, exact, what, rtol=1e-9):
+    for nm in names:
+        gn, on = nm.split(":") if ":" in nm else (nm, nm)
+        a, b = g.get(gn), o.get(on)
+        n = min(a.size, b.size)
+        a, b = a[:n], b[:n]
+        if exact:
+            assert np.array_equal(a, b), f"{what}: {gn} not bit-exact (max abs diff {np.abs(a - b).max():.3e}, scale {np.abs(b).max():.3e})"
+        else:
+            scale = max(np.abs(b).max(), 1e-300) if n else 1.0
+            err = np.abs(a - b).max() / scale if n else 0.0
+            assert err <= rtol, f"{what}: {gn} differs by {err:.3e} of its scale (> {rtol})"
+
+
+def _run(case_dir, lib, moving, n_steps, geo="flat", cell="tet"):
+    import oracle
+
+    cs.setup_case(case_dir, H=0.004, D=0.0221, geo=geo, R=0.005, freq=2.0, duration=1.0, n_rings=6, n_layers=4, cell=cell)
+    c = cs.Case(case_dir)
+    if not moving:
+        c.cfg.motion = None
+    o = oracle.Oracle(c.mesh, c.cfg)
+    o.load_case_fields(c)
+    g = sv.Solver(c.mesh, c.cfg, lib_path=lib)
+    g.load_case_fields(c)
+    exact = not moving
+    for step in range(n_steps):
+        for st in ("courant", "adjustDeltaT", "advanceTime", "moveMesh"):
+            o.stage(st)
+            g.stage(st)
+        io, ig = o.info(), g.info()
+        assert io["t"] == ig["t"] and io["dt"] == ig["dt"], "time-step control diverged"
+        assert io["Co"] == ig["Co"] and io["alphaCo"] == ig["alphaCo"], "Courant numbers are not bit-exact"
+        if moving:
+            _check(g, o, ["meshPhi", "Sf"], False, f"step {step} moveMesh", 1e-9)
+            o.set("V0", o.get("V"))  # rigid body: the GPU uses V for both
+        P.sync_geometry(g, o, c.mesh, c.cfg)
+        P.sync_state(g, o)
+        o.stage("alphaPredictor")
+        g.stage("alphaPredictor")
+        _check(g, o, ALPHA, exact, f"step {step} alphaPredictor")
+        P.sync_state(g, o)
+        o.stage("momentum")
+        g.stage("momentum")
+        _check(g, o, MOM, exact, f"step {step} momentum")
+        for corr in (0, 1):
+            P.sync_state(g, o)
+            o.stage("pcPrepare")
+            g.stage("pcPrepare")
+            _check(g, o, PREP, exact, f"step {step} corr {corr} pcPrepare")
+            o.stage("pcAssemble")
+            g.stage("pcAssemble")
+            _check(g, o, ASM, exact, f"step {step} corr {corr} pcAssemble")
+            ctl = c.cfg.p_rgh_final if corr else c.cfg.p_rgh
+            args = (o.get("pDiag"), o.get("pUpper"), o.get("pSource"), o.get("p_rgh"))
+            xo, ito, r0o, ro = o.solve(ctl, *args)
+            xg, itg, r0g, rg = g.solve(ctl, *args)
+            assert abs(r0o - r0g) <= 1e-10 * r0o, "initial residual (normFactor) differs"
+            for r, r0 in ((ro, r0o), (rg, r0g)):
+                assert r < ctl.tolerance or r < ctl.rel_tol * r0, "solver stopped unconverged"
+            if corr:  # tight tolerance: solutions agree (up to the constant-free part)
+                assert np.abs(xo - xg).max() <= 1e-4 * max(np.abs(xo).max(), 1e-30)
+            o.set("p_rgh", xo)
+            g.set("p_rgh", xo)
+            for st in ("pcFinish", "pcEnd"):
+                o.stage(st)
+                g.stage(st)
+            _check(g, o, FIN, exact, f"step {step} corr {corr} pcFinish/pcEnd")
+        P.sync_state(g, o)
+    assert g.info()["launches"] > 0
+    g.close()
+    o.close()
+
+
+@pytest.mark.parametrize("cell,geo", [("tet", "flat"), ("prism", "cap")])
+def test_static_bit_exact_emu(tmp_path, emu_lib, cell, geo):
+    _run(str(tmp_path / "c"), emu_lib, moving=False, n_steps=3, geo=geo, cell=cell)
+
+
+def test_moving_tolerance_emu(tmp_path, emu_lib):
+    _run(str(tmp_path / "c"), emu_lib, moving=True, n_steps=3)
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("cell,geo", [("tet", "flat"), ("prism", "cap")])
+def test_static_bit_exact_gpu(tmp_path, gpu_lib, cell, geo):
+    _run(str(tmp_path / "c"), gpu_lib, moving=False, n_steps=3, geo=geo, cell=cell)
+
+
+@pytest.mark.gpu
+def test_moving_tolerance_gpu(tmp_path, gpu_lib):
+    _run(str(tmp_path / "c"), gpu_lib, moving=True, n_steps=3)
