@@ -94,38 +94,60 @@ HD void b_coarse_diag(const LV& L, int I) {
     FOR_ROW(L, I) s += L.upper[f]; END_ROW
     L.diag[I] = r + s;
 }
-// restriction of the fine residual, computed on the fly: b_c[I] = sum_{i in I} (fb - A fx)_i
-HD void b_restrict_residual(const LV& L, int I) {
+// fine residual out = b - A in  (runs over the rows of L)
+HD void b_residual(const LV& L, int c) { L.out[c] = L.b[c] - row_Ax(L, c, L.in); }
+// restriction: b_c[I] = sum of the fine residual over the members of I (fixed order)
+HD void b_restrict_sum(const LV& L, int I) {
     double r = 0;
-    for (int k = L.aggStart[I]; k < L.aggStart[I + 1]; k++) {
-        int i = L.aggRows[k];
-        double s = L.fdiag[i] * L.fx[i];
-        const int cnt = L.fell ? L.fW : L.frs[i + 1] - L.frs[i];
-        const size_t base = L.fell ? (size_t)i : (size_t)L.frs[i];
-        const size_t str = L.fell ? (size_t)L.fnCp : 1;
-        for (int s_ = 0; s_ < cnt; s_++) {
-            int e = L.fcf[base + s_ * str];
-            if (e < 0) break;
-            int o = L.fcn[base + s_ * str];
-            if (o < 0) continue;
-            s -= L.fupper[e >> 1] * L.fx[o];
-        }
-        r += L.fb[i] - s;
-    }
+    for (int k = L.aggStart[I]; k < L.aggStart[I + 1]; k++) r += L.in[L.aggRows[k]];
     L.b[I] = r;
+}
+// row i of A applied to the prolonged coarse correction c = x_c[agg]  (L = coarse level with
+// its fine view): returns (A c)_i
+HD double fine_row_Ac(const LV& L, int i) {
+    double s = L.fdiag[i] * L.x[L.agg[i]];
+    const int cnt = L.fell ? L.fW : L.frs[i + 1] - L.frs[i];
+    const size_t base = L.fell ? (size_t)i : (size_t)L.frs[i];
+    const size_t str = L.fell ? (size_t)L.fnCp : 1;
+    for (int s_ = 0; s_ < cnt; s_++) {
+        int e = L.fcf[base + s_ * str];
+        if (e < 0) break;
+        int o = L.fcn[base + s_ * str];
+        if (o < 0) continue;
+        s -= L.fupper[e >> 1] * L.x[L.agg[o]];
+    }
+    return s;
+}
+// GAMGSolver::scale: x += sf*c + (r - sf*A c)/diag with sf = (r.c)/(c.Ac) read from the device
+// scalars in2[0], in2[1]; in = r, out = A c (runs over fine rows; L = coarse level)
+HD void b_scale_apply(const LV& L, int i) {
+    double den = L.in2[1];
+    double sf = L.in2[0] / (fabs(den) < VSMALL ? (den >= 0 ? VSMALL : -VSMALL) : den);
+    double c = L.x[L.agg[i]];
+    L.fxw[i] += sf * c + (L.in[i] - sf * L.out[i]) / L.fdiag[i];
 }
 // prolongation: fine x += coarse x[agg]   (runs over fine rows; L = coarse level)
 HD void b_prolong_add(const LV& L, int i) { L.fxw[i] += L.x[L.agg[i]]; }
 
 // ---- pairwise matching (handshake) on face weights --------------------------------------------
+// Exact weight ties are the rule on extruded meshes; breaking them by cell index makes the
+// handshake degenerate into chains (one pair per round).  A symmetric hash of the edge gives
+// both ends the same pseudo-random order, so every locally dominant edge matches each round.
+HD unsigned long long edge_hash(int a, int b) {
+    unsigned long long x = ((unsigned long long)(unsigned)(a < b ? a : b) << 32) | (unsigned)(a < b ? b : a);
+    x ^= x >> 33; x *= 0xff51afd7ed558ccdULL; x ^= x >> 33; x *= 0xc4ceb9fe1a85ec53ULL; x ^= x >> 33;
+    return x;
+}
 HD void b_match_propose(const LV& L, int c) {
     if (L.match[c] >= 0) { L.prop[c] = -1; return; }
     int best = -1;
     double bw = -1.0;
+    unsigned long long bh = 0;
     FOR_ROW(L, c)
         if (L.match[o] < 0) {
             double w = L.fw[f];
-            if (w > bw || (w == bw && o < best)) { bw = w; best = o; }
+            unsigned long long h = edge_hash(c, o);
+            if (w > bw || (w == bw && h > bh)) { bw = w; best = o; bh = h; }
         }
     END_ROW
     L.prop[c] = best;
@@ -141,10 +163,12 @@ HD void b_match_root(const LV& L, int c) {
     if (m >= 0) { L.root[c] = c < m ? c : m; return; }
     int best = -1;
     double bw = -1.0;
+    unsigned long long bh = 0;
     FOR_ROW(L, c)
         if (L.match[o] >= 0) {
             double w = L.fw[f];
-            if (w > bw || (w == bw && o < best)) { bw = w; best = o; }
+            unsigned long long h = edge_hash(c, o);
+            if (w > bw || (w == bw && h > bh)) { bw = w; best = o; bh = h; }
         }
     END_ROW
     if (best < 0) L.root[c] = c;
@@ -157,7 +181,9 @@ DEF_KERNEL(jacobi0, LV)
 DEF_KERNEL(rowsum, LV)
 DEF_KERNEL(coarse_upper, LV)
 DEF_KERNEL(coarse_diag, LV)
-DEF_KERNEL(restrict_residual, LV)
+DEF_KERNEL(residual, LV)
+DEF_KERNEL(restrict_sum, LV)
+DEF_KERNEL(scale_apply, LV)
 DEF_KERNEL(prolong_add, LV)
 DEF_KERNEL(match_propose, LV)
 DEF_KERNEL(match_accept, LV)
@@ -259,6 +285,21 @@ __global__ void __launch_bounds__(256) k_init_residual(LV L, const double* x, co
     __syncthreads();
     w = block_sum(w);
     if (threadIdx.x == 0) { partialRes[blockIdx.x] = v; partialNorm[blockIdx.x] = w; }
+}
+// A c for the prolonged coarse correction fused with the partial sums of r.c and c.Ac
+__global__ void __launch_bounds__(256) k_corr_dots(LV L, int nFine, const double* r, double* Ac, double* partialNum, double* partialDen) {
+    double v = 0, w = 0;
+    for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < nFine; i += gridDim.x * blockDim.x) {
+        double c = L.x[L.agg[i]];
+        double a = fine_row_Ac(L, i);
+        Ac[i] = a;
+        v += r[i] * c;
+        w += a * c;
+    }
+    v = block_sum(v);
+    __syncthreads();
+    w = block_sum(w);
+    if (threadIdx.x == 0) { partialNum[blockIdx.x] = v; partialDen[blockIdx.x] = w; }
 }
 __global__ void k_scal_copy(double* scal, int dst, int src) { scal[dst] = scal[src]; }
 

@@ -31,6 +31,10 @@ struct Level {
 
 struct SolveStats { int iters = 0; double r0 = 0, r = 0; };
 
+// tuning knobs (environment overrides of the multigrid defaults; used by the tuning scripts)
+inline int knob(const char* name, int dflt) { const char* v = getenv(name); return v ? atoi(v) : dflt; }
+inline double knobd(const char* name, double dflt) { const char* v = getenv(name); return v ? atof(v) : dflt; }
+
 }  // namespace
 
 struct tpp_solver {
@@ -531,7 +535,7 @@ struct tpp_solver {
         std::vector<int> m1(n, -1);
         h2d(ctx, match, m1.data(), n * sizeof(int));
         G.match = match; G.prop = prop; G.root = root; G.fw = fwDev;
-        for (int r = 0; r < 6; r++) {
+        for (int r = 0; r < knob("TPP_ROUNDS", 8); r++) {
             LAUNCH(ctx, match_propose, G, n);
             LAUNCH(ctx, match_accept, G, n);
         }
@@ -592,7 +596,7 @@ struct tpp_solver {
 
     void buildAMG() {
         amgBuilt = true;
-        const int coarsestTarget = 1500, maxLevels = 24;
+        const int coarsestTarget = knob("TPP_COARSEST", 1500), maxLevels = 24;
         if (nC <= coarsestTarget) return;
         match = A<int>(nC); prop = A<int>(nC); root = A<int>(nC);
         // faceAreaPair weights |Sf/sqrt(|Sf|) * (1, 1.01, 1.02)|
@@ -611,7 +615,7 @@ struct tpp_solver {
             HostGraph cur = g, nxt;
             bool first = true;
             int passes = 0;
-            for (int pass = 0; pass < 2; pass++) {
+            for (int pass = 0; pass < knob("TPP_PASSES", 2); pass++) {
                 h2d(ctx, fwDev, cur.fw.data(), cur.nf * sizeof(double));
                 LV M;
                 std::vector<int> rs, cf, cn;
@@ -630,6 +634,7 @@ struct tpp_solver {
                 dev_sync(ctx);
                 dev_free(drs); dev_free(dcf); dev_free(dcn);
                 coarsen(cur, rootH, nxt, agg, sS, sF);
+                if (knob("TPP_VERBOSE", 0)) { int nm = 0, ns = 0; for (int i = 0; i < cur.n; i++) { if (rootH[i] == i) ns++; } fprintf(stderr, "amg pass: n %d nf %d -> n %d nf %d (avg degree %.1f)\n", cur.n, cur.nf, nxt.n, nxt.nf, 2.0 * nxt.nf / std::max(nxt.n, 1)); (void)nm; }
                 passes++;
                 if (first) { aggTot = agg; segS = sS; segF = sF; first = false; }
                 else {
@@ -691,12 +696,12 @@ struct tpp_solver {
         for (int i = 0; i < n; i++) { L.x[i] = 0; r[i] = L.b[i]; p[i] = L.b[i] / L.diag[i]; rz += L.b[i] * p[i]; }
         double rz0 = rz;
         if (rz > 0)
-            for (int it = 0; it < 200; it++) {
+            for (int it = 0; it < knob("TPP_CITER", 200); it++) {
                 double pAp = 0;
                 for (int i = 0; i < n; i++) { Ap[i] = row_Ax(L, i, p.data()); pAp += Ap[i] * p[i]; }
                 double alpha = rz / pAp, rzn = 0;
                 for (int i = 0; i < n; i++) { L.x[i] += alpha * p[i]; r[i] -= alpha * Ap[i]; rzn += r[i] * r[i] / L.diag[i]; }
-                if (rzn <= 1e-6 * rz0) break;
+                { double ct = knobd("TPP_CTOL", 1e-3); if (rzn <= ct * ct * rz0) break; }
                 double beta = rzn / rz;
                 rz = rzn;
                 for (int i = 0; i < n; i++) p[i] = r[i] / L.diag[i] + beta * p[i];
@@ -704,7 +709,7 @@ struct tpp_solver {
         ctx.launches++;
 #else
         prof_begin(ctx, "coarse_cg");
-        k_coarse_cg<<<1, 1024, 0, ctx.stream>>>(L, 200, 1e-3);
+        k_coarse_cg<<<1, 1024, 0, ctx.stream>>>(L, knob("TPP_CITER", 200), knobd("TPP_CTOL", 1e-3));
         prof_end(ctx);
         ctx.launches++;
 #endif
@@ -713,7 +718,8 @@ struct tpp_solver {
     // x (output) ~= A^-1 b on level l (l = -1: fine).  zeroGuess: x is overwritten.
     void vcycle(int l, LV& F0, const double* b, double* x, double* tmp, bool zeroGuess, int nPre, int nPost) {
         LV L = l < 0 ? F0 : levelView(l);
-        const double omega = 0.8;
+        const double omega = knobd("TPP_OMEGA", 0.8);
+        const bool scaleCorr = knob("TPP_SCALE", 1) != 0;
         if (l == (int)levels.size() - 1 && l >= 0) {
             L.b = const_cast<double*>(b); L.x = x;
             coarseSolve(L);
@@ -726,15 +732,24 @@ struct tpp_solver {
             if (s == 0 && zeroGuess) { L.out = cur; LAUNCH(ctx, jacobi0, L, L.n); }
             else { L.in = cur; L.out = oth; LAUNCH(ctx, jacobi, L, L.n); std::swap(cur, oth); }
         }
-        // restrict residual, recurse, prolong
+        // residual, restriction, coarse solve, scaled correction (GAMGSolver::scale)
+        Level* cvp = &levels[l + 1];
+        double* rbuf = l < 0 ? kt2 : levels[l].t1;
+        double* acbuf = l < 0 ? kt3 : levels[l].t2;
+        L.in = cur; L.out = rbuf;
+        LAUNCH(ctx, residual, L, L.n);
         LV Cn = levelView(l + 1);
         setFine(Cn, L);
-        Cn.fx = cur; Cn.fb = b;
-        LAUNCH(ctx, restrict_residual, Cn, Cn.n);
-        Level& cv = levels[l + 1];
-        vcycle(l + 1, F0, cv.b, cv.x, cv.t0, true, nPre, nPost);
+        Cn.in = rbuf;
+        LAUNCH(ctx, restrict_sum, Cn, Cn.n);
+        vcycle(l + 1, F0, cvp->b, cvp->x, cvp->t0, true, nPre, nPost);
         Cn.fxw = cur;
-        LAUNCH(ctx, prolong_add, Cn, L.n);
+        if (scaleCorr) {
+            corrDots(Cn, L.n, rbuf, acbuf);
+            Cn.in = rbuf; Cn.out = acbuf; Cn.in2 = scal + S_TMP0;
+            LAUNCH(ctx, scale_apply, Cn, L.n);
+        } else
+            LAUNCH(ctx, prolong_add, Cn, L.n);
         for (int s = 0; s < std::max(nPost, 1); s++) {
             L.in = cur; L.out = oth;
             LAUNCH(ctx, jacobi, L, L.n);
@@ -757,7 +772,7 @@ struct tpp_solver {
             return;
         }
         int nv = ctl.type == 1 ? 1 : std::max(ctl.n_vcycles, 1);
-        int nPre = 2, nPost = 2;
+        int nPre = knob("TPP_NPRE", 2), nPost = knob("TPP_NPOST", 2);
         for (int cyc = 0; cyc < nv; cyc++) vcycle(-1, F0, r, z, kt, cyc == 0, nPre, nPost);
     }
 
@@ -788,6 +803,23 @@ struct tpp_solver {
         return st;
     }
 
+    void corrDots(LV& Cn, int nFine, const double* r, double* Ac) {
+#ifdef TPP_EMU
+        double v = 0, w = 0;
+        for (int i = 0; i < nFine; i++) {
+            double c = Cn.x[Cn.agg[i]], a = fine_row_Ac(Cn, i);
+            Ac[i] = a; v += r[i] * c; w += a * c;
+        }
+        scal[S_TMP0] = v; scal[S_TMP1] = w;
+#else
+        prof_begin(ctx, "corr_dots");
+        k_corr_dots<<<RED_BLOCKS, BLOCK, 0, ctx.stream>>>(Cn, nFine, r, Ac, red.partial, red.partial2);
+        k_reduce_final<<<1, BLOCK, 0, ctx.stream>>>(red.partial, RED_BLOCKS, 2, scal + S_TMP0);
+        k_reduce_final<<<1, BLOCK, 0, ctx.stream>>>(red.partial2, RED_BLOCKS, 2, scal + S_TMP1);
+        prof_end(ctx);
+#endif
+        ctx.launches += 3;
+    }
     void scalCopy(int dst, int src) {
 #ifdef TPP_EMU
         scal[dst] = scal[src];

@@ -817,8 +817,8 @@ def write_field(path, fld: Field, binary=True, precision=6, location=None):
     with open(path, "wb") as f:
         f.write(_hdr(fld.cls, fld.name, location, "binary" if binary else "ascii").encode())
         dims = fld.dimensions
-        if isinstance(dims, list):
-            dims = "[" + " ".join(str(x) for x in dims) + "]"
+        if isinstance(dims, list):  # tokens of `[0 1 -2 0 0 0 0]` as the parser split them
+            dims = " ".join(str(x) for x in dims)
         f.write(f"dimensions      {dims};\n\n".encode())
         f.write(b"internalField   ")
         _write_value(f, fld.internal, typ, binary, precision)

@@ -1,0 +1,98 @@
+"""Whole time steps through the C-ABI against the oracle, plus the size-independent
+properties the domain offers (boundedness, volume conservation up to boundary fluxes).
+
+Tolerances (FP64):
+  * both sides solve p_rgh to 1e-13 (normalised L1 residual): the reference's own loose
+    first-corrector tolerance (fvSolution:46 relTol 0.01) makes two valid solvers differ by
+    ~1e-2 in U, so algorithmic parity is shown with tight solves: time-step sequence equal to
+    1e-12 relative, alpha to 1e-9, U and p_rgh to 1e-8 / 1e-7 of their scale;
+  * with the reference's tolerances the comparison is on integrated quantities:
+    total water volume (exactly conserved up to the boundary flux) and bounded alpha.
+"""
+import numpy as np
+import pytest
+
+from openfoam_tpp_b200 import case as cs
+from openfoam_tpp_b200 import solver as sv
+
+
+def _tight(cfg):
+    for s in (cfg.p_rgh, cfg.p_rgh_final):
+        s.tolerance, s.rel_tol, s.max_iter = 1e-13, 0.0, 500
+
+
+def _full_steps(case_dir, lib, n_steps, geo="flat", cell="tet", n_rings=8):
+    import oracle
+
+    cs.setup_case(case_dir, H=0.004, D=0.0221, geo=geo, R=0.005, freq=2.0, duration=1.0, n_rings=n_rings, n_layers=4, cell=cell)
+    c = cs.Case(case_dir)
+    _tight(c.cfg)
+    g = sv.Solver(c.mesh, c.cfg, lib_path=lib)
+    g.load_case_fields(c)
+    o = oracle.Oracle(c.mesh, c.cfg)
+    o.load_case_fields(c)
+    for i in range(n_steps):
+        g.step(1)
+        o.step(1)
+        gi, oi = g.info(), o.info()
+        assert abs(gi["t"] - oi["t"]) <= 1e-12 * oi["t"], f"step {i}: time diverged"
+        assert abs(gi["dt"] - oi["dt"]) <= 1e-9 * oi["dt"]
+        for nm, tol in (("alpha", 1e-9), ("U", 1e-8), ("p_rgh", 1e-7), ("phi", 1e-8), ("p", 1e-7)):
+            a, b = g.get(nm), o.get(nm)
+            err = np.abs(a - b).max() / max(np.abs(b).max(), 1e-300)
+            assert err <= tol, f"step {i}: {nm} differs by {err:.2e} of its scale (> {tol})"
+    g.close()
+    o.close()
+
+
+def test_full_steps_emu(tmp_path, emu_lib):
+    _full_steps(str(tmp_path / "c"), emu_lib, 6)
+
+
+def test_full_steps_cap_prism_emu(tmp_path, emu_lib):
+    _full_steps(str(tmp_path / "c"), emu_lib, 4, geo="cap", cell="prism")
+
+
+@pytest.mark.gpu
+def test_full_steps_gpu(tmp_path, gpu_lib):
+    _full_steps(str(tmp_path / "c"), gpu_lib, 6)
+
+
+@pytest.mark.gpu
+def test_full_steps_cap_prism_gpu(tmp_path, gpu_lib):
+    _full_steps(str(tmp_path / "c"), gpu_lib, 4, geo="cap", cell="prism", n_rings=10)
+
+
+def _conservation(case_dir, lib, n_steps, n_rings, n_layers):
+    """Reference tolerances.  Sum(alpha V) may change only through the boundary flux
+    alphaPhi_b: |d(sum alpha V) + dt*sum_b alphaPhi_b| <= 1e-10 * sum(alpha V) per step
+    (BASELINE.json: total alpha volume conserved to 1e-10 relative); 0 <= alpha <= 1."""
+    cs.setup_case(case_dir, H=0.004, D=0.0221, R=0.005, freq=2.0, duration=1.0, n_rings=n_rings, n_layers=n_layers)
+    c = cs.Case(case_dir)
+    g = sv.Solver(c.mesh, c.cfg, lib_path=lib)
+    g.load_case_fields(c)
+    V = g.get("V")
+    nI = c.mesh.n_internal
+    vol0 = float((g.get("alpha") * V).sum())
+    vol = vol0
+    for i in range(n_steps):
+        g.step(1)
+        a = g.get("alpha")
+        dt = g.info()["dt"]
+        out = float(g.get("alphaPhi")[nI:].sum()) * dt
+        new = float((a * V).sum())
+        assert abs(new - vol + out) <= 1e-10 * vol0, f"step {i}: water volume not conserved ({new - vol + out:.3e})"
+        assert a.min() >= -1e-9 and a.max() <= 1 + 1e-6, f"step {i}: alpha out of bounds [{a.min()}, {a.max()}]"
+        vol = new
+        gi = g.info()
+        assert gi["r1"] < c.cfg.p_rgh_final.tolerance or gi["it1"] >= c.cfg.p_rgh_final.max_iter
+    g.close()
+
+
+def test_conservation_emu(tmp_path, emu_lib):
+    _conservation(str(tmp_path / "c"), emu_lib, 12, 8, 4)
+
+
+@pytest.mark.gpu
+def test_conservation_gpu(tmp_path, gpu_lib):
+    _conservation(str(tmp_path / "c"), gpu_lib, 25, 24, 12)
