@@ -301,6 +301,67 @@ __global__ void __launch_bounds__(256) k_corr_dots(LV L, int nFine, const double
     w = block_sum(w);
     if (threadIdx.x == 0) { partialNum[blockIdx.x] = v; partialDen[blockIdx.x] = w; }
 }
+// ---- coarse (CSR) levels: COOP lanes per row, fixed-order shuffle reduction ---------------------
+// A thread per row is latency-bound on the coarse levels (rows of 10-30 entries, few rows);
+// eight lanes per row walk the row together.
+constexpr int COOP = 8;
+DEV double coop_offdiag(const LV& L, int c, const double* x, int lane) {
+    double s = 0;
+    const int b = L.rs[c], e = L.rs[c + 1];
+    for (int k = b + lane; k < e; k += COOP) {
+        int o = L.cn[k];
+        if (o >= 0) s += L.upper[L.cf[k] >> 1] * x[o];
+    }
+    for (int off = COOP / 2; off > 0; off >>= 1) s += __shfl_xor_sync(0xffffffffu, s, off);
+    return s;
+}
+// mode 0: out = in + omega (b - A in)/diag ; 1: out = b - A in ; 2: out = A in
+__global__ void __launch_bounds__(256) k_csr_row_op(const LV L, int mode) {
+    int gid = blockIdx.x * blockDim.x + threadIdx.x;
+    int c = gid / COOP, lane = gid % COOP;
+    bool live = c < L.n;
+    int cc = live ? c : L.n - 1;
+    double off = coop_offdiag(L, cc, L.in, lane);
+    if (live && lane == 0) {
+        double ax = L.diag[c] * L.in[c] - off;
+        if (mode == 0) L.out[c] = L.in[c] + L.omega * (L.b[c] - ax) / L.diag[c];
+        else if (mode == 1) L.out[c] = L.b[c] - ax;
+        else L.out[c] = ax;
+    }
+}
+// A c for the prolonged correction on a CSR fine level (L = coarse level with fine view), COOP lanes
+__global__ void __launch_bounds__(256) k_corr_dots_csr(LV L, int nFine, const double* r, double* Ac, double* partialNum, double* partialDen) {
+    double v = 0, w = 0;
+    const int lane = threadIdx.x % COOP;
+    const int sub = (threadIdx.x % 32) / COOP;  // row within the warp
+    const int rowsPerWarp = 32 / COOP;
+    const int warpId = (blockIdx.x * blockDim.x + threadIdx.x) / 32;
+    const int nWarps = gridDim.x * blockDim.x / 32;
+    // warp-uniform loop: every lane of a warp runs the same number of trips (shuffles inside)
+    for (int base = warpId * rowsPerWarp; base < nFine; base += nWarps * rowsPerWarp) {
+        int i0 = base + sub;
+        bool live = i0 < nFine;
+        int i = live ? i0 : nFine - 1;
+        double s = 0;
+        const int b = L.frs[i], e = L.frs[i + 1];
+        for (int k = b + lane; k < e; k += COOP) {
+            int o = L.fcn[k];
+            if (o >= 0) s += L.fupper[L.fcf[k] >> 1] * L.x[L.agg[o]];
+        }
+        for (int off = COOP / 2; off > 0; off >>= 1) s += __shfl_xor_sync(0xffffffffu, s, off);
+        if (live && lane == 0) {
+            double c = L.x[L.agg[i]];
+            double a = L.fdiag[i] * c - s;
+            Ac[i] = a;
+            v += r[i] * c;
+            w += a * c;
+        }
+    }
+    v = block_sum(v);
+    __syncthreads();
+    w = block_sum(w);
+    if (threadIdx.x == 0) { partialNum[blockIdx.x] = v; partialDen[blockIdx.x] = w; }
+}
 __global__ void k_scal_copy(double* scal, int dst, int src) { scal[dst] = scal[src]; }
 
 // Jacobi-preconditioned CG on the coarsest level, one CTA (n is a few thousand at most).

@@ -688,6 +688,21 @@ struct tpp_solver {
         }
     }
 
+    // out = op(in) on level L: ELL fine level -> one thread per row; CSR levels -> COOP lanes per row
+    void rowOp(LV& L, int mode) {
+#ifndef TPP_EMU
+        if (!L.ell) {
+            prof_begin(ctx, mode == 0 ? "jacobi_csr" : (mode == 1 ? "residual_csr" : "spmv_csr"));
+            k_csr_row_op<<<(L.n * COOP + 255) / 256, 256, 0, ctx.stream>>>(L, mode);
+            prof_end(ctx);
+            ctx.launches++;
+            return;
+        }
+#endif
+        if (mode == 0) LAUNCH(ctx, jacobi, L, L.n);
+        else if (mode == 1) LAUNCH(ctx, residual, L, L.n);
+        else LAUNCH(ctx, spmv, L, L.n);
+    }
     void coarseSolve(LV L) {
 #ifdef TPP_EMU
         int n = L.n;
@@ -696,12 +711,12 @@ struct tpp_solver {
         for (int i = 0; i < n; i++) { L.x[i] = 0; r[i] = L.b[i]; p[i] = L.b[i] / L.diag[i]; rz += L.b[i] * p[i]; }
         double rz0 = rz;
         if (rz > 0)
-            for (int it = 0; it < knob("TPP_CITER", 200); it++) {
+            for (int it = 0; it < knob("TPP_CITER", 16); it++) {
                 double pAp = 0;
                 for (int i = 0; i < n; i++) { Ap[i] = row_Ax(L, i, p.data()); pAp += Ap[i] * p[i]; }
                 double alpha = rz / pAp, rzn = 0;
                 for (int i = 0; i < n; i++) { L.x[i] += alpha * p[i]; r[i] -= alpha * Ap[i]; rzn += r[i] * r[i] / L.diag[i]; }
-                { double ct = knobd("TPP_CTOL", 1e-3); if (rzn <= ct * ct * rz0) break; }
+                { double ct = knobd("TPP_CTOL", 0.05); if (rzn <= ct * ct * rz0) break; }
                 double beta = rzn / rz;
                 rz = rzn;
                 for (int i = 0; i < n; i++) p[i] = r[i] / L.diag[i] + beta * p[i];
@@ -709,7 +724,7 @@ struct tpp_solver {
         ctx.launches++;
 #else
         prof_begin(ctx, "coarse_cg");
-        k_coarse_cg<<<1, 1024, 0, ctx.stream>>>(L, knob("TPP_CITER", 200), knobd("TPP_CTOL", 1e-3));
+        k_coarse_cg<<<1, 1024, 0, ctx.stream>>>(L, knob("TPP_CITER", 16), knobd("TPP_CTOL", 0.05));
         prof_end(ctx);
         ctx.launches++;
 #endif
@@ -730,14 +745,14 @@ struct tpp_solver {
         int sweeps = std::max(nPre, 1);
         for (int s = 0; s < sweeps; s++) {
             if (s == 0 && zeroGuess) { L.out = cur; LAUNCH(ctx, jacobi0, L, L.n); }
-            else { L.in = cur; L.out = oth; LAUNCH(ctx, jacobi, L, L.n); std::swap(cur, oth); }
+            else { L.in = cur; L.out = oth; rowOp(L, 0); std::swap(cur, oth); }
         }
         // residual, restriction, coarse solve, scaled correction (GAMGSolver::scale)
         Level* cvp = &levels[l + 1];
         double* rbuf = l < 0 ? kt2 : levels[l].t1;
         double* acbuf = l < 0 ? kt3 : levels[l].t2;
         L.in = cur; L.out = rbuf;
-        LAUNCH(ctx, residual, L, L.n);
+        rowOp(L, 1);
         LV Cn = levelView(l + 1);
         setFine(Cn, L);
         Cn.in = rbuf;
@@ -752,7 +767,7 @@ struct tpp_solver {
             LAUNCH(ctx, prolong_add, Cn, L.n);
         for (int s = 0; s < std::max(nPost, 1); s++) {
             L.in = cur; L.out = oth;
-            LAUNCH(ctx, jacobi, L, L.n);
+            rowOp(L, 0);
             std::swap(cur, oth);
         }
         if (cur != x) d2d(ctx, x, cur, L.n * sizeof(double));
@@ -812,10 +827,14 @@ struct tpp_solver {
         }
         scal[S_TMP0] = v; scal[S_TMP1] = w;
 #else
-        prof_begin(ctx, "corr_dots");
-        k_corr_dots<<<RED_BLOCKS, BLOCK, 0, ctx.stream>>>(Cn, nFine, r, Ac, red.partial, red.partial2);
-        k_reduce_final<<<1, BLOCK, 0, ctx.stream>>>(red.partial, RED_BLOCKS, 2, scal + S_TMP0);
-        k_reduce_final<<<1, BLOCK, 0, ctx.stream>>>(red.partial2, RED_BLOCKS, 2, scal + S_TMP1);
+        prof_begin(ctx, Cn.fell ? "corr_dots" : "corr_dots_csr");
+        if (Cn.fell) k_corr_dots<<<RED_BLOCKS, BLOCK, 0, ctx.stream>>>(Cn, nFine, r, Ac, red.partial, red.partial2);
+        else k_corr_dots_csr<<<std::min(RED_BLOCKS, (nFine * COOP + 255) / 256), BLOCK, 0, ctx.stream>>>(Cn, nFine, r, Ac, red.partial, red.partial2);
+        {
+            int nb = Cn.fell ? RED_BLOCKS : std::min(RED_BLOCKS, (nFine * COOP + 255) / 256);
+            k_reduce_final<<<1, BLOCK, 0, ctx.stream>>>(red.partial, nb, 2, scal + S_TMP0);
+            k_reduce_final<<<1, BLOCK, 0, ctx.stream>>>(red.partial2, nb, 2, scal + S_TMP1);
+        }
         prof_end(ctx);
 #endif
         ctx.launches += 3;
