@@ -186,7 +186,10 @@ def main():
     cfg = make_config(mesh)
     nC, nI, nF = mesh.n_cells, mesh.n_internal, mesh.n_faces
     g = sv.Solver(mesh, cfg, device=local)
-    stream = torch.cuda.current_stream()
+    # a side stream shared with the solver: CUDA events recorded here bracket its kernels, and
+    # (unlike the legacy default stream) it can be graph-captured
+    stream = torch.cuda.Stream()
+    torch.cuda.set_stream(stream)
     g.use_stream(stream.cuda_stream)
     a0 = initial_alpha(mesh)
     g.set("alpha", a0)

@@ -28,6 +28,8 @@ struct LV {
     const int *cf, *cn, *rs;      // adjacency: (face<<1|side), other row; CSR row starts
     const int *own, *nei;         // [nf]
     double *diag, *upper, *rsum;  // matrix: diag, positive off-diagonal magnitude, row sums
+    double *ev;                   // off-diagonal magnitudes per adjacency entry (ELL / CSR order)
+    const double* fev;            // ... of the fine-level view
     // transfer from the next finer level
     const int *agg;               // [n_fine] fine row -> this level's row
     const int *aggStart, *aggRows;   // CSR: members of each row of this level
@@ -63,10 +65,48 @@ struct LV {
 #define END_ROW }}
 
 // y = A x on a level: out = diag*in - sum upper[f]*in[o]
-HD double row_Ax(const LV& L, int c, const double* x) {
-    double s = L.diag[c] * x[c];
-    FOR_ROW(L, c) s -= L.upper[f] * x[o]; END_ROW
+// ELL row with a compile-time width: all index/coefficient loads are issued before the gathers
+// (no early exit), which is what a latency-bound gather kernel needs; padded / boundary slots
+// carry o < 0.  The sum runs in slot order, so it equals the generic loop bit for bit.
+template <int W>
+HD double ell_offdiag(const int* cn, const double* ev, size_t nCp, int c, const double* x) {
+    int o[W];
+    double v[W], xv[W];
+#pragma unroll
+    for (int k = 0; k < W; k++) { o[k] = cn[(size_t)k * nCp + c]; v[k] = ev[(size_t)k * nCp + c]; }
+#pragma unroll
+    for (int k = 0; k < W; k++) xv[k] = o[k] >= 0 ? x[o[k]] : 0.0;
+    double s = 0;
+#pragma unroll
+    for (int k = 0; k < W; k++) if (o[k] >= 0) s += v[k] * xv[k];
     return s;
+}
+// sum of offdiag magnitude * x[other] over the row (per-entry coefficients ev)
+HD double row_offdiag(const int* cn, const double* ev, const int* rs, int ell, int W, size_t nCp, int c, const double* x) {
+    if (ell) {
+        if (W == 4) return ell_offdiag<4>(cn, ev, nCp, c, x);
+        if (W == 5) return ell_offdiag<5>(cn, ev, nCp, c, x);
+        if (W == 6) return ell_offdiag<6>(cn, ev, nCp, c, x);
+        double s = 0;
+        for (int k = 0; k < W; k++) { int o = cn[(size_t)k * nCp + c]; if (o >= 0) s += ev[(size_t)k * nCp + c] * x[o]; }
+        return s;
+    }
+    double s = 0;
+    for (int k = rs[c]; k < rs[c + 1]; k++) { int o = cn[k]; if (o >= 0) s += ev[k] * x[o]; }
+    return s;
+}
+HD double row_Ax(const LV& L, int c, const double* x) {
+    return L.diag[c] * x[c] - row_offdiag(L.cn, L.ev, L.rs, L.ell, L.W, (size_t)L.nCp, c, x);
+}
+// per-entry coefficients from the per-face ones (once per solve and level)
+HD void b_fill_ev(const LV& L, int c) {
+    const int cnt = L.ell ? L.W : L.rs[c + 1] - L.rs[c];
+    const size_t base = L.ell ? (size_t)c : (size_t)L.rs[c];
+    const size_t str = L.ell ? (size_t)L.nCp : 1;
+    for (int k = 0; k < cnt; k++) {
+        int e = L.cf[base + k * str], o = L.cn[base + k * str];
+        L.ev[base + k * str] = (e >= 0 && o >= 0) ? L.upper[e >> 1] : 0.0;
+    }
 }
 HD void b_spmv(const LV& L, int c) { L.out[c] = row_Ax(L, c, L.in); }
 // out = in + omega*(b - A in)/diag   (damped Jacobi, in != out)
@@ -106,16 +146,16 @@ HD void b_restrict_sum(const LV& L, int I) {
 // its fine view): returns (A c)_i
 HD double fine_row_Ac(const LV& L, int i) {
     double s = L.fdiag[i] * L.x[L.agg[i]];
-    const int cnt = L.fell ? L.fW : L.frs[i + 1] - L.frs[i];
-    const size_t base = L.fell ? (size_t)i : (size_t)L.frs[i];
-    const size_t str = L.fell ? (size_t)L.fnCp : 1;
-    for (int s_ = 0; s_ < cnt; s_++) {
-        int e = L.fcf[base + s_ * str];
-        if (e < 0) break;
-        int o = L.fcn[base + s_ * str];
-        if (o < 0) continue;
-        s -= L.fupper[e >> 1] * L.x[L.agg[o]];
-    }
+    if (L.fell) {
+        for (int k = 0; k < L.fW; k++) {
+            int o = L.fcn[(size_t)k * L.fnCp + i];
+            if (o >= 0) s -= L.fev[(size_t)k * L.fnCp + i] * L.x[L.agg[o]];
+        }
+    } else
+        for (int k = L.frs[i]; k < L.frs[i + 1]; k++) {
+            int o = L.fcn[k];
+            if (o >= 0) s -= L.fev[k] * L.x[L.agg[o]];
+        }
     return s;
 }
 // GAMGSolver::scale: x += sf*c + (r - sf*A c)/diag with sf = (r.c)/(c.Ac) read from the device
@@ -124,7 +164,7 @@ HD void b_scale_apply(const LV& L, int i) {
     double den = L.in2[1];
     double sf = L.in2[0] / (fabs(den) < VSMALL ? (den >= 0 ? VSMALL : -VSMALL) : den);
     double c = L.x[L.agg[i]];
-    L.fxw[i] += sf * c + (L.in[i] - sf * L.out[i]) / L.fdiag[i];
+    L.fxw[i] += sf * c + L.omega * (L.in[i] - sf * L.out[i]) / L.fdiag[i];
 }
 // prolongation: fine x += coarse x[agg]   (runs over fine rows; L = coarse level)
 HD void b_prolong_add(const LV& L, int i) { L.fxw[i] += L.x[L.agg[i]]; }
@@ -176,6 +216,7 @@ HD void b_match_root(const LV& L, int c) {
 }
 
 DEF_KERNEL(spmv, LV)
+DEF_KERNEL(fill_ev, LV)
 DEF_KERNEL(jacobi, LV)
 DEF_KERNEL(jacobi0, LV)
 DEF_KERNEL(rowsum, LV)
@@ -265,10 +306,12 @@ __global__ void __launch_bounds__(256) k_update_xr(int n, double* x, double* r, 
     if (threadIdx.x == 0) partial[blockIdx.x] = v;
 }
 // pA = z + beta pA  (beta = WARA/WARA_OLD; first iteration: pA = z)
-__global__ void __launch_bounds__(256) k_update_p(int n, double* pA, const double* z, const double* scal, int first) {
+__global__ void __launch_bounds__(256) k_update_p(int n, double* pA, const double* z, const double* scal) {
+    const bool first = scal[S_WARA_OLD] == 0.0;
     double beta = first ? 0.0 : scal[S_WARA] / scal[S_WARA_OLD];
     for (int c = blockIdx.x * blockDim.x + threadIdx.x; c < n; c += gridDim.x * blockDim.x) pA[c] = first ? z[c] : z[c] + beta * pA[c];
 }
+__global__ void k_scal_set(double* scal, int dst, double v) { scal[dst] = v; }
 // r = b - Ax ; normFactor pieces: |Ax - xbar*sumA| + |b - xbar*sumA| ; sumA = rsum
 __global__ void __launch_bounds__(256) k_init_residual(LV L, const double* x, const double* b, double* r, const double* scal, double* partialRes, double* partialNorm) {
     double xbar = scal[S_XSUM] / (double)L.n;
@@ -310,7 +353,7 @@ DEV double coop_offdiag(const LV& L, int c, const double* x, int lane) {
     const int b = L.rs[c], e = L.rs[c + 1];
     for (int k = b + lane; k < e; k += COOP) {
         int o = L.cn[k];
-        if (o >= 0) s += L.upper[L.cf[k] >> 1] * x[o];
+        if (o >= 0) s += L.ev[k] * x[o];
     }
     for (int off = COOP / 2; off > 0; off >>= 1) s += __shfl_xor_sync(0xffffffffu, s, off);
     return s;
@@ -346,7 +389,7 @@ __global__ void __launch_bounds__(256) k_corr_dots_csr(LV L, int nFine, const do
         const int b = L.frs[i], e = L.frs[i + 1];
         for (int k = b + lane; k < e; k += COOP) {
             int o = L.fcn[k];
-            if (o >= 0) s += L.fupper[L.fcf[k] >> 1] * L.x[L.agg[o]];
+            if (o >= 0) s += L.fev[k] * L.x[L.agg[o]];
         }
         for (int off = COOP / 2; off > 0; off >>= 1) s += __shfl_xor_sync(0xffffffffu, s, off);
         if (live && lane == 0) {

@@ -9,6 +9,7 @@
 #include "tpp_linsolve.h"
 
 #include <map>
+#include <tuple>
 
 using namespace tpp;
 
@@ -21,10 +22,11 @@ struct Level {
     // device
     int *cf = nullptr, *cn = nullptr, *rs = nullptr, *own = nullptr, *nei = nullptr;
     int *agg = nullptr, *aggStart = nullptr, *aggRows = nullptr, *segStart = nullptr, *segFaces = nullptr;
+    double *ev = nullptr;
     double *diag = nullptr, *upper = nullptr, *rsum = nullptr, *x = nullptr, *b = nullptr, *t0 = nullptr, *t1 = nullptr, *t2 = nullptr;
     void free() {
         for (void* p : {(void*)cf, (void*)cn, (void*)rs, (void*)own, (void*)nei, (void*)agg, (void*)aggStart, (void*)aggRows, (void*)segStart, (void*)segFaces,
-                        (void*)diag, (void*)upper, (void*)rsum, (void*)x, (void*)b, (void*)t0, (void*)t1, (void*)t2})
+                        (void*)ev, (void*)diag, (void*)upper, (void*)rsum, (void*)x, (void*)b, (void*)t0, (void*)t1, (void*)t2})
             dev_free(p);
     }
 };
@@ -58,9 +60,17 @@ struct tpp_solver {
     Reducer red;
     // multigrid
     std::vector<Level> levels;  // coarse levels (level 0 = first coarse)
-    double *kr = nullptr, *kz = nullptr, *kp = nullptr, *kw = nullptr, *kt = nullptr, *kt2 = nullptr, *kt3 = nullptr, *fineRsum = nullptr, *fw0 = nullptr;
+    double *kr = nullptr, *kz = nullptr, *kp = nullptr, *kw = nullptr, *kt = nullptr, *kt2 = nullptr, *kt3 = nullptr, *fineEv = nullptr, *fineRsum = nullptr, *fw0 = nullptr;
     int *match = nullptr, *prop = nullptr, *root = nullptr;
     bool amgBuilt = false;
+    struct GraphKey {
+        const void *x, *diag; int type, precond, nv;
+        bool operator<(const GraphKey& o) const { return std::tie(x, diag, type, precond, nv) < std::tie(o.x, o.diag, o.type, o.precond, o.nv); }
+    };
+#ifndef TPP_EMU
+    struct GraphRec { cudaGraphExec_t exec; long nodes; };
+    std::map<GraphKey, GraphRec> graphs;
+#endif
     // time
     double t = 0, dt = 0, dt0 = 0, startTime = 0, Co = 0, alphaCo = 0;
     long step = 0;
@@ -276,7 +286,7 @@ struct tpp_solver {
         d.phiHbyA = AD("phiHbyA", nF); d.phig = AD("phig", nF); d.pUpper = AD("pUpper", nI); d.pCorrFlux = AD("pCorrFlux", nI);
         d.pDiag = AD("pDiag", nC); d.pSource = AD("pSource", nC); d.rec = AD("rec", nF);
         d.cellTmp = A<double>(2 * (size_t)nC);
-        kr = A<double>(nC); kz = A<double>(nC); kp = A<double>(nC); kw = A<double>(nC); kt = A<double>(nC); kt2 = A<double>(nC); kt3 = A<double>(nC); fineRsum = A<double>(nC);
+        kr = A<double>(nC); kz = A<double>(nC); kp = A<double>(nC); kw = A<double>(nC); kt = A<double>(nC); kt2 = A<double>(nC); kt3 = A<double>(nC); fineEv = A<double>((size_t)W * nCp); fineRsum = A<double>(nC);
         scal = A<double>(S_COUNT);
 #ifdef TPP_EMU
         hscal = (double*)calloc(S_COUNT, sizeof(double));
@@ -512,7 +522,7 @@ struct tpp_solver {
         memset(&L, 0, sizeof(L));
         L.n = nC; L.nf = nI; L.nCp = nCp; L.W = W; L.ell = 1;
         L.cf = d.cf; L.cn = d.cn; L.own = d.own; L.nei = d.nei;
-        L.diag = diag; L.upper = upper; L.rsum = fineRsum;
+        L.diag = diag; L.upper = upper; L.rsum = fineRsum; L.ev = fineEv;
         return L;
     }
     LV levelView(int l) {
@@ -520,14 +530,14 @@ struct tpp_solver {
         LV L;
         memset(&L, 0, sizeof(L));
         L.n = v.n; L.nf = v.nf; L.ell = 0; L.cf = v.cf; L.cn = v.cn; L.rs = v.rs; L.own = v.own; L.nei = v.nei;
-        L.diag = v.diag; L.upper = v.upper; L.rsum = v.rsum;
+        L.diag = v.diag; L.upper = v.upper; L.rsum = v.rsum; L.ev = v.ev;
         L.agg = v.agg; L.aggStart = v.aggStart; L.aggRows = v.aggRows; L.segStart = v.segStart; L.segFaces = v.segFaces;
         L.x = v.x; L.b = v.b; L.t0 = v.t0; L.t1 = v.t1; L.out = v.t2;
         return L;
     }
     static void setFine(LV& L, const LV& F) {
         L.fn = F.n; L.fnCp = F.nCp; L.fW = F.W; L.fell = F.ell; L.fcf = F.cf; L.fcn = F.cn; L.frs = F.rs;
-        L.fdiag = F.diag; L.fupper = F.upper; L.frsum = F.rsum;
+        L.fdiag = F.diag; L.fupper = F.upper; L.frsum = F.rsum; L.fev = F.ev;
     }
 
     // one pairwise matching pass on the device; returns host `root`
@@ -668,6 +678,7 @@ struct tpp_solver {
             std::vector<int> pos(aS.begin(), aS.end() - 1);
             for (int i = 0; i < g.n; i++) aR[pos[aggTot[i]]++] = i;
             v.aggStart = up(aS); v.aggRows = up(aR);
+            v.ev = dalloc<double>(std::max(2 * v.nf, 1));
             v.diag = dalloc<double>(v.n); v.upper = dalloc<double>(std::max(v.nf, 1)); v.rsum = dalloc<double>(v.n);
             v.x = dalloc<double>(v.n); v.b = dalloc<double>(v.n); v.t0 = dalloc<double>(v.n); v.t1 = dalloc<double>(v.n); v.t2 = dalloc<double>(v.n);
             levels.push_back(v);
@@ -678,12 +689,14 @@ struct tpp_solver {
     // Galerkin coefficients of every level from the fine matrix
     void galerkin(LV& F0) {
         LAUNCH(ctx, rowsum, F0, F0.n);
+        LAUNCH(ctx, fill_ev, F0, F0.n);
         LV F = F0;
         for (size_t l = 0; l < levels.size(); l++) {
             LV L = levelView((int)l);
             setFine(L, F);
             LAUNCH(ctx, coarse_upper, L, L.nf);
             LAUNCH(ctx, coarse_diag, L, L.n);
+            LAUNCH(ctx, fill_ev, L, L.n);
             F = L;
         }
     }
@@ -761,7 +774,7 @@ struct tpp_solver {
         Cn.fxw = cur;
         if (scaleCorr) {
             corrDots(Cn, L.n, rbuf, acbuf);
-            Cn.in = rbuf; Cn.out = acbuf; Cn.in2 = scal + S_TMP0;
+            Cn.in = rbuf; Cn.out = acbuf; Cn.in2 = scal + S_TMP0; Cn.omega = knobd("TPP_SCALEJ", 1.0);
             LAUNCH(ctx, scale_apply, Cn, L.n);
         } else
             LAUNCH(ctx, prolong_add, Cn, L.n);
@@ -796,7 +809,7 @@ struct tpp_solver {
         if (!amgBuilt) buildAMG();
         LV F0 = fineView(diag, upper);
         bool useAMG = !levels.empty() && !(ctl.type == 0 && ctl.precond == 0);
-        if (useAMG) galerkin(F0); else LAUNCH(ctx, rowsum, F0, F0.n);
+        if (useAMG) galerkin(F0); else { LAUNCH(ctx, rowsum, F0, F0.n); LAUNCH(ctx, fill_ev, F0, F0.n); }
         red.reduce(ctx, x, nullptr, nC, 2, scal + S_XSUM);
         initResidual(F0, x, b);
         readScal();
@@ -804,13 +817,10 @@ struct tpp_solver {
         st.r0 = st.r = hscal[S_RES] / nf;
         auto conv = [&](double r) { return r < ctl.tolerance || (ctl.rel_tol > 0 && r < ctl.rel_tol * st.r0); };
         if (conv(st.r)) return st;
+        scalSet(S_WARA, 0.0);  // WARA_OLD == 0 marks the first iteration for k_update_p
+        dev_zero(ctx, kp, nC * sizeof(double));
         do {
-            precondition(F0, ctl, kr, kz);
-            scalCopy(S_WARA_OLD, S_WARA);
-            red.reduce(ctx, kz, kr, nC, 0, scal + S_WARA);
-            updateP(st.iters == 0);
-            spmvDot(F0);
-            updateXR(x);
+            iteration(F0, ctl, x);
             readScal();
             st.r = hscal[S_RES] / nf;
             if (!(fabs(hscal[S_WAPA]) / nf >= VSMALL)) break;
@@ -818,6 +828,51 @@ struct tpp_solver {
         return st;
     }
 
+    // one PCG iteration: z = M r ; wArA ; pA ; wA = A pA ; x, r update ; |r|
+    void iterationBody(LV& F0, const tpp_solver_t& ctl, double* x) {
+        precondition(F0, ctl, kr, kz);
+        scalCopy(S_WARA_OLD, S_WARA);
+        red.reduce(ctx, kz, kr, nC, 0, scal + S_WARA);
+        updateP();
+        spmvDot(F0);
+        updateXR(x);
+    }
+    // The iteration is ~110 small launches with fixed arguments: captured once per
+    // (solver entry, solution vector) into a CUDA graph and replayed (launch-bound otherwise).
+    void iteration(LV& F0, const tpp_solver_t& ctl, double* x) {
+#ifndef TPP_EMU
+        // (the legacy default stream cannot be captured)
+        if (!ctx.prof && ctx.stream != nullptr && ctx.stream != cudaStreamLegacy && knob("TPP_GRAPH", 1)) {
+            GraphKey key{x, F0.diag, ctl.type, ctl.precond, ctl.n_vcycles};
+            auto it = graphs.find(key);
+            if (it == graphs.end()) {
+                long l0 = ctx.launches;
+                cudaGraph_t gr;
+                CUDA_CHECK(cudaStreamBeginCapture(ctx.stream, cudaStreamCaptureModeThreadLocal));
+                iterationBody(F0, ctl, x);
+                CUDA_CHECK(cudaStreamEndCapture(ctx.stream, &gr));
+                GraphRec rec;
+                CUDA_CHECK(cudaGraphInstantiate(&rec.exec, gr, 0));
+                cudaGraphDestroy(gr);
+                rec.nodes = ctx.launches - l0;
+                ctx.launches = l0;
+                it = graphs.emplace(key, rec).first;
+            }
+            CUDA_CHECK(cudaGraphLaunch(it->second.exec, ctx.stream));
+            ctx.launches += it->second.nodes;
+            return;
+        }
+#endif
+        iterationBody(F0, ctl, x);
+    }
+    void scalSet(int dst, double v) {
+#ifdef TPP_EMU
+        scal[dst] = v;
+#else
+        k_scal_set<<<1, 1, 0, ctx.stream>>>(scal, dst, v);
+#endif
+        ctx.launches++;
+    }
     void corrDots(LV& Cn, int nFine, const double* r, double* Ac) {
 #ifdef TPP_EMU
         double v = 0, w = 0;
@@ -867,13 +922,14 @@ struct tpp_solver {
         ctx.launches += 3;
 #endif
     }
-    void updateP(bool first) {
+    void updateP() {
 #ifdef TPP_EMU
+        const bool first = scal[S_WARA_OLD] == 0.0;
         double beta = first ? 0.0 : scal[S_WARA] / scal[S_WARA_OLD];
         for (int c = 0; c < nC; c++) kp[c] = first ? kz[c] : kz[c] + beta * kp[c];
 #else
         prof_begin(ctx, "update_p");
-        k_update_p<<<RED_BLOCKS, BLOCK, 0, ctx.stream>>>(nC, kp, kz, scal, first ? 1 : 0);
+        k_update_p<<<RED_BLOCKS, BLOCK, 0, ctx.stream>>>(nC, kp, kz, scal);
         prof_end(ctx);
 #endif
         ctx.launches++;
@@ -914,6 +970,7 @@ struct tpp_solver {
 #ifdef TPP_EMU
         free(hscal);
 #else
+        for (auto& g : graphs) cudaGraphExecDestroy(g.second.exec);
         if (hscal) cudaFreeHost(hscal);
         if (ctx.stream && ctx.ownStream) cudaStreamDestroy(ctx.stream);
 #endif

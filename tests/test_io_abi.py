@@ -1,0 +1,170 @@
+"""Host logic: dictionaries, polyMesh / field readers+writers, mesh generators (addressing is
+bit-exact integer work), time names, hard errors on unsupported keywords, and the C-ABI
+library's exported symbols (no compute calls: works without a GPU)."""
+import ctypes
+import os
+import re
+
+import numpy as np
+import pytest
+
+from openfoam_tpp_b200 import case as cs
+from openfoam_tpp_b200 import foamfile as ff
+from openfoam_tpp_b200 import meshgen as mg
+from openfoam_tpp_b200 import solver as sv
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+
+@pytest.mark.parametrize("binary", [True, False])
+def test_polymesh_roundtrip(tmp_path, binary):
+    m = mg.cylinder_mesh(0.004, 0.0221, 4, 3, "flat", "tet")
+    ff.write_polymesh(str(tmp_path), m, binary=binary)
+    r = ff.read_polymesh(str(tmp_path))
+    assert np.array_equal(r.owner, m.owner) and np.array_equal(r.neighbour, m.neighbour)
+    assert np.array_equal(r.face_offsets, m.face_offsets) and np.array_equal(r.face_labels, m.face_labels)
+    if binary:
+        assert np.array_equal(r.points, m.points)
+    else:
+        assert np.allclose(r.points, m.points, rtol=0, atol=0)  # repr() round-trips doubles
+    assert [(p["name"], p["type"], p["nFaces"], p["startFace"]) for p in r.patches] == [(p["name"], p["type"], p["nFaces"], p["startFace"]) for p in m.patches]
+    assert list(r.cell_zones) == ["internalMesh"] and r.cell_zones["internalMesh"].size == m.n_cells
+
+
+@pytest.mark.parametrize("gen", [
+    lambda: mg.cylinder_mesh(0.004, 0.0221, 5, 3, "flat", "tet"),
+    lambda: mg.cylinder_mesh(0.004, 0.0221, 5, 3, "cap", "prism"),
+    lambda: mg.box_mesh(3, 4, 5, cell="tet", top_patch="atmosphere"),
+    lambda: mg.sloshing_tank3d_mesh(4, 6, 6),
+])
+def test_mesh_addressing_invariants(gen):
+    """OpenFOAM ordering: owner < neighbour, upper-triangular internal faces, contiguous
+    patches; every cell closed (sum of outward Sf = 0); positive volumes."""
+    m = gen()
+    assert m.check()
+    Cf, Sf = mg.face_geometry(m)
+    C, V = mg.cell_geometry(m, Cf, Sf)
+    assert V.min() > 0
+    div = np.zeros((m.n_cells, 3))
+    np.add.at(div, m.owner, Sf)
+    np.add.at(div, m.neighbour, -Sf[: m.n_internal])
+    assert np.abs(div).max() < 1e-12 * np.abs(Sf).max()
+    # normals point from owner to neighbour
+    d = C[m.neighbour] - C[m.owner[: m.n_internal]]
+    assert np.all(np.einsum("ij,ij->i", d, Sf[: m.n_internal]) > 0)
+
+
+def test_cylinder_naming_contract():
+    """Patches walls/atmosphere, zone internalMesh (generate_mesh.py:29-51, dynamicMeshDict:25)."""
+    m = mg.cylinder_mesh(0.1, 0.02, 4, 6)
+    assert [p["name"] for p in m.patches] == ["walls", "atmosphere"]
+    Cf, Sf = mg.face_geometry(m)
+    atm = m.patch("atmosphere")
+    sl = slice(atm["startFace"], atm["startFace"] + atm["nFaces"])
+    assert np.allclose(Cf[sl, 2], 0.1) and np.all(Sf[sl, 2] > 0)
+    area = Sf[sl, 2].sum()  # inscribed 24-gon of the R = 0.01 circle
+    assert 0.97 * np.pi * 1e-4 < area < np.pi * 1e-4
+    t = mg.sloshing_tank3d_mesh(4, 6, 6)
+    assert [p["name"] for p in t.patches] == ["wall"] and list(t.cell_zones) == ["all"]
+
+
+def test_slab_meshes_tile_the_cylinder():
+    """z-slabs (the `simple` (1 1 N) decomposition) reproduce the whole mesh: same cells, and the
+    two sides of every cut hold the same faces in the same order."""
+    whole = mg.cylinder_mesh(0.02, 0.02, 3, 6)
+    a = mg.cylinder_mesh(0.02, 0.02, 3, 6, k0=0, k1=3, proc=(0, None, 1))
+    b = mg.cylinder_mesh(0.02, 0.02, 3, 6, k0=3, k1=6, proc=(1, 0, None))
+    assert a.n_cells + b.n_cells == whole.n_cells
+    pa, pb = a.patch("procBoundary0to1"), b.patch("procBoundary1to0")
+    assert pa["nFaces"] == pb["nFaces"] > 0 and pa["type"] == "processor"
+    Cfa, Sfa = mg.face_geometry(a)
+    Cfb, Sfb = mg.face_geometry(b)
+    sa = slice(pa["startFace"], pa["startFace"] + pa["nFaces"])
+    sb = slice(pb["startFace"], pb["startFace"] + pb["nFaces"])
+    assert np.allclose(Cfa[sa], Cfb[sb]) and np.allclose(Sfa[sa], -Sfb[sb])
+
+
+def test_time_names():
+    for t, s in [(0.05, "0.05"), (10.0, "10"), (20.0, "20"), (0.00119048, "0.00119048"), (1e-5, "1e-05"), (1234567.0, "1.23457e+06"), (0.1 + 0.2, "0.3")]:
+        assert ff.time_name(t) == s
+
+
+def test_set_fields_and_case_reader(tmp_path):
+    d = str(tmp_path / "case_H0.004_D0.0221_flat_R0.005_f2.0")
+    cs.setup_case(d, H=0.004, D=0.0221, R=0.005, freq=2.0, duration=1.0, n_rings=5, n_layers=4)
+    c = cs.Case(d)
+    a = c.fields["alpha.water"].internal_array(c.mesh.n_cells)
+    C, V = mg.cell_geometry(c.mesh)
+    assert set(np.unique(a)) == {0.0, 1.0} and np.array_equal(a == 1.0, C[:, 2] <= 0.002)
+    k = c.cfg
+    assert (k.n_alpha_subcycles, k.n_alpha_corr, k.n_correctors, k.n_non_orth, k.c_alpha) == (3, 1, 2, 0, 1.0)
+    assert (k.p_rgh.type, k.p_rgh.smoother, k.p_rgh.tolerance, k.p_rgh.rel_tol) == (1, 0, 1e-8, 0.01)
+    assert (k.p_rgh_final.type, k.p_rgh_final.precond, k.p_rgh_final.n_vcycles, k.p_rgh_final.n_pre_sweeps, k.p_rgh_final.max_iter) == (0, 1, 2, 2, 20)
+    assert (k.rho1, k.rho2, k.nu1, k.nu2, k.sigma) == (998.2, 1.0, 1e-6, 1.48e-5, 0.0)
+    assert k.patch_bc_u == [0, 1] and k.patch_bc_alpha == [0, 1] and k.patch_bc_p == [0, 1]
+    assert k.motion.shape == (1001, 7) and k.probes.shape == (2, 3)
+    assert c.start_name == "0"
+
+
+@pytest.mark.parametrize("path,old,new,frag", [
+    ("system/fvSchemes", "Gauss vanLeerV", "Gauss upwind", "div(rhoPhi,U)"),
+    ("system/fvSolution", "momentumPredictor no", "momentumPredictor yes", "momentumPredictor"),
+    ("system/fvSolution", "smoother        DIC;", "smoother        symGaussSeidel;", "smoother"),
+    ("constant/phaseProperties", "sigma           0", "sigma           0.07", "sigma"),
+    ("system/controlDict", "incompressibleVoF", "incompressibleFluid", "solver"),
+    ("0/U", "movingWallVelocity", "slip", "slip"),
+])
+def test_unsupported_keywords_are_hard_errors(tmp_path, path, old, new, frag):
+    """No silent defaults: the error names the file and the keyword."""
+    d = str(tmp_path / "c")
+    cs.setup_case(d, H=0.004, D=0.0221, R=0.005, freq=2.0, duration=0.1, n_rings=3, n_layers=2)
+    p = os.path.join(d, path)
+    txt = open(p).read()
+    assert old in txt
+    open(p, "w").write(txt.replace(old, new, 1))
+    with pytest.raises(ff.FoamError) as e:
+        cs.Case(d)
+    assert frag in str(e.value) and os.path.basename(path) in str(e.value)
+
+
+def _declared_symbols():
+    h = open(os.path.join(ROOT, "include", "tppvof.h")).read()
+    h = re.sub(r"/\*.*?\*/", "", h, flags=re.S)
+    return sorted(set(re.findall(r"\b(tpp_[a-z_0-9]+)\s*\(", h)))
+
+
+def test_product_library_exports_every_declared_symbol():
+    """libtppvof.so (the sm_100a build) loads without a GPU and exports the whole C-ABI."""
+    assert os.path.exists(sv.LIB_PATH), "libtppvof.so missing: run __graft_entry__.build()"
+    lib = ctypes.CDLL(sv.LIB_PATH)
+    names = _declared_symbols()
+    assert len(names) >= 20
+    for n in names:
+        assert hasattr(lib, n), f"{n} declared in include/tppvof.h but not exported"
+    lib.tpp_version.restype = ctypes.c_char_p
+    assert b"sm_100a" in lib.tpp_version()
+
+
+def test_no_cpu_fallback_in_product_path():
+    """Without a GPU the product path must fail loudly, not compute on the CPU."""
+    import torch
+
+    if torch.cuda.is_available():
+        pytest.skip("GPU present")
+    m = mg.cylinder_mesh(0.004, 0.0221, 3, 2)
+    cfg = cs.CaseConfig()
+    cfg.patch_bc_u, cfg.patch_bc_alpha, cfg.patch_bc_p = [0, 1], [0, 1], [0, 1]
+    cfg.patch_inlet_alpha, cfg.patch_p0 = [0, 0], [0, 0]
+    with pytest.raises(sv.SolverError) as e:
+        sv.Solver(m, cfg)
+    assert "no CPU path" in str(e.value) or "CUDA" in str(e.value)
+
+
+def test_product_never_references_the_oracle():
+    """Only tests/, __graft_entry__.smoke and bench.py's CPU-baseline legs may touch oracle/."""
+    pkg = os.path.join(ROOT, "openfoam-tpp_b200")
+    for dp, _, fs in os.walk(pkg):
+        for f in fs:
+            if f.endswith((".py", ".cu", ".h", ".cpp")):
+                txt = open(os.path.join(dp, f), errors="ignore").read()
+                assert "voforacle" not in txt and "import oracle" not in txt and "orc_" not in txt, f
