@@ -45,7 +45,7 @@ def mesh_for(cells_target):
     return meshgen.cylinder_mesh(CASE["H"], CASE["D"], nr, nl, "flat", "tet"), nr, nl
 
 
-def make_config(mesh):
+def make_config(mesh, freq=None):
     """The reference's numerics (case template) on the synthetic mesh, without touching disk."""
     import tempfile
 
@@ -55,7 +55,7 @@ def make_config(mesh):
 
     with tempfile.TemporaryDirectory() as tmp:
         cs.write_template(tmp, end_time=CASE["duration"], fill_z=CASE["H"] / 2)
-        rows = motion.orbital_table(CASE["R"], CASE["freq"], 3.0, CASE["dt"], CASE["ramp"])
+        rows = motion.orbital_table(CASE["R"], CASE["freq"] if freq is None else freq, 3.0, CASE["dt"], CASE["ramp"])
         motion.write_table(os.path.join(tmp, "constant", "6DoF.dat"), rows)
         cfg = cs.read_config(tmp, None)
         fields = {n: ff.read_field(os.path.join(tmp, "0", n)) for n in ("U", "alpha.water", "p_rgh")}
@@ -182,8 +182,14 @@ def main():
 
         dist.init_process_group("nccl", device_id=torch.device("cuda", local))
 
+    # N > 1: the sweep of BASELINE.json config 5 sharded one independent case per GPU (the same
+    # tank at a different shaking frequency on every rank); no data-path collective.
+    from openfoam_tpp_b200 import ensemble
+
+    freqs = ensemble.parse_range(f"{CASE['freq']}:0.04:{CASE['freq'] + 0.04 * (world - 1) + 1e-6}")
+    my_freq = ensemble.shard(freqs, world, rank)[0]
     mesh, nr, nl = mesh_for(args.cells)
-    cfg = make_config(mesh)
+    cfg = make_config(mesh, my_freq)
     nC, nI, nF = mesh.n_cells, mesh.n_internal, mesh.n_faces
     g = sv.Solver(mesh, cfg, device=local)
     # a side stream shared with the solver: CUDA events recorded here bracket its kernels, and
@@ -269,11 +275,9 @@ def main():
     barrier()
     sec_e2e = time.perf_counter() - t0
 
-    times = torch.tensor([sec, sec_e2e], dtype=torch.float64, device="cuda")
-    if world > 1:
-        dist.all_reduce(times, op=dist.ReduceOp.MAX)
-    sec, sec_e2e = times.tolist()
-    total_cells = nC * world
+    sec, sec_e2e = ensemble.max_over_ranks([sec, sec_e2e])
+    total_cells = int(ensemble.sum_over_ranks([float(nC)])[0])
+    launches = int(ensemble.sum_over_ranks([float(launches)])[0])
     value = total_cells * args.steps / sec / 1e6
     e2e = total_cells * e2e_steps / sec_e2e / 1e6
 
@@ -288,7 +292,7 @@ def main():
             "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
             "ms_per_step": sec / args.steps * 1e3, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
             "config": {"workload": f"cfg4 case_H0.208_D0.2_flat_R0.004_f1.88 tet mesh refined to {nC} cells per GPU (n_rings {nr}, n_layers {nl})",
-                       "cells_per_gpu": nC, "internal_faces_per_gpu": nI, "parallelism": "single GPU" if world == 1 else f"{world} independent replicas (halo exchange not built yet)",
+                       "cells_per_gpu": nC, "internal_faces_per_gpu": nI, "parallelism": "single GPU" if world == 1 else f"ensemble: {world} independent sweep cases (f = {freqs[0]}..{freqs[-1]} Hz), one per GPU, no halo exchange (single-case domain decomposition is not built yet)",
                        "l2": "working set (>1 kB/cell) far exceeds the 126 MB L2; no flush needed",
                        "vof_steps_per_s": args.steps / sec, "solver_iters_last_step": [int(info["it0"]), int(info["it1"])], "amg_levels": int(info["levels"])},
             "clocks": sampler.summary(), "gpu_launches": launches,

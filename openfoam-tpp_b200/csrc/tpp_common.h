@@ -48,6 +48,8 @@ struct DV {
     // geometry (current orientation)
     double *Sf, *magSf, *w, *dc, *corrVec, *dPN, *V, *gh, *ghf, *meshPhi;
     const double *Sf0, *dPN0, *corrVec0, *C0, *Cf0;  // body-frame references
+    const double* points0;                            // undisplaced points (rotating motion only)
+    const int *fOff, *fLab;                           // face -> point labels (rotating motion only)
     // fields
     double *alpha, *alpha0, *alpha_b, *U, *U_b, *U0, *U0_b, *p_rgh, *p_rgh_b, *pGrad_b, *p;
     double *rho, *rho_b, *rho0, *phi, *Uf, *Uf0, *alphaPhi, *rhoPhi;

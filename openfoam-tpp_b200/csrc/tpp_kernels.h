@@ -537,6 +537,64 @@ HD void b_p_shift(const DV& d, int c) {
 // translation: swept volume of a rigidly translated face = Sf . dT (exact)
 HD void b_meshphi_trans(const DV& d, int f) { d.meshPhi[f] = dot3(&d.Sf[3 * f], d.dT) / d.dt; }
 
+HD void rot3(const double* R, const double* v, double* out);
+HD void rigid_point(const double* R, const double* T, const double* cofg, const double* p0, double* out) {
+    double q[3] = {p0[0] - cofg[0], p0[1] - cofg[1], p0[2] - cofg[2]};
+    for (int k = 0; k < 3; k++) out[k] = (R[3 * k] * q[0] + R[3 * k + 1] * q[1] + R[3 * k + 2] * q[2]) + cofg[k] + T[k];
+}
+HD void cross3_(const double* a, const double* b, double* c) {
+    c[0] = a[1] * b[2] - a[2] * b[1];
+    c[1] = a[2] * b[0] - a[0] * b[2];
+    c[2] = a[0] * b[1] - a[1] * b[0];
+}
+// volume swept by a triangle whose vertices move linearly a->a1, b->b1, c->c1 (exact for the
+// ruled prism): mean displacement . (A0 + A1/2 + A2/3), A(s) = A0 + s A1 + s^2 A2
+HD double tri_swept(const double* a, const double* b, const double* c, const double* a1, const double* b1, const double* c1) {
+    double e1[3], e2[3], g1[3], g2[3], dm[3];
+    for (int k = 0; k < 3; k++) {
+        e1[k] = b[k] - a[k];
+        e2[k] = c[k] - a[k];
+        double da = a1[k] - a[k], db = b1[k] - b[k], dcc = c1[k] - c[k];
+        g1[k] = db - da;
+        g2[k] = dcc - da;
+        dm[k] = (1.0 / 3.0) * (da + db + dcc);
+    }
+    double A0[3], A1a[3], A1b[3], A2[3];
+    cross3_(e1, e2, A0);
+    cross3_(e1, g2, A1a);
+    cross3_(g1, e2, A1b);
+    cross3_(g1, g2, A2);
+    double s = 0;
+    for (int k = 0; k < 3; k++) s += dm[k] * (0.5 * A0[k] + 0.25 * (A1a[k] + A1b[k]) + (1.0 / 6.0) * A2[k]);
+    return s;
+}
+// general rigid motion (rotation): meshPhi = swept volume / deltaT, face fanned about its centre
+// [OF13-MEM: face::sweptVol], point positions from the old / new rigid transforms
+HD void b_meshphi_rot(const DV& d, int f) {
+    int s0 = d.fOff[f], n = d.fOff[f + 1] - s0;
+    const int* l = &d.fLab[s0];
+    double sv = 0;
+    if (n == 3) {
+        double a[3], b[3], c[3], a1[3], b1[3], c1[3];
+        rigid_point(d.Rold, d.To, d.cofg, &d.points0[3 * l[0]], a); rigid_point(d.R, d.Tn, d.cofg, &d.points0[3 * l[0]], a1);
+        rigid_point(d.Rold, d.To, d.cofg, &d.points0[3 * l[1]], b); rigid_point(d.R, d.Tn, d.cofg, &d.points0[3 * l[1]], b1);
+        rigid_point(d.Rold, d.To, d.cofg, &d.points0[3 * l[2]], c); rigid_point(d.R, d.Tn, d.cofg, &d.points0[3 * l[2]], c1);
+        sv = tri_swept(a, b, c, a1, b1, c1);
+    } else {
+        double fc0[3], fc1[3];
+        rigid_point(d.Rold, d.To, d.cofg, &d.Cf0[3 * f], fc0);
+        rigid_point(d.R, d.Tn, d.cofg, &d.Cf0[3 * f], fc1);
+        for (int i = 0; i < n; i++) {
+            int j = (i + 1) % n;
+            double b[3], c[3], b1[3], c1[3];
+            rigid_point(d.Rold, d.To, d.cofg, &d.points0[3 * l[i]], b); rigid_point(d.R, d.Tn, d.cofg, &d.points0[3 * l[i]], b1);
+            rigid_point(d.Rold, d.To, d.cofg, &d.points0[3 * l[j]], c); rigid_point(d.R, d.Tn, d.cofg, &d.points0[3 * l[j]], c1);
+            sv += tri_swept(fc0, b, c, fc1, b1, c1);
+        }
+    }
+    d.meshPhi[f] = sv / d.dt;
+}
+
 HD void rot3(const double* R, const double* v, double* out) {
     for (int k = 0; k < 3; k++) out[k] = R[3 * k] * v[0] + R[3 * k + 1] * v[1] + R[3 * k + 2] * v[2];
 }
@@ -592,6 +650,7 @@ DEF_KERNEL(Uf, DV)
 DEF_KERNEL(p, DV)
 DEF_KERNEL(p_shift, DV)
 DEF_KERNEL(meshphi_trans, DV)
+DEF_KERNEL(meshphi_rot, DV)
 DEF_KERNEL(rotate_face, DV)
 DEF_KERNEL(gh_face, DV)
 DEF_KERNEL(gh_cell, DV)

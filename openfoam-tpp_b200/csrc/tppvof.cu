@@ -269,7 +269,10 @@ struct tpp_solver {
         d.Sf = uploadD("Sf", Sf0); d.magSf = uploadD("magSf", magSf); d.w = uploadD("w", w); d.dc = uploadD("dc", dc);
         d.corrVec = uploadD("corrVec", corr); d.dPN = uploadD("dPN", dPN); d.V = uploadD("V", V);
         d.C0 = uploadD("C0", C0); d.Cf0 = uploadD("Cf0", Cf0);
-        if (hasRotation) { d.Sf0 = upload(Sf0); d.dPN0 = upload(dPN); d.corrVec0 = upload(corr); }
+        if (hasRotation) {
+            d.Sf0 = upload(Sf0); d.dPN0 = upload(dPN); d.corrVec0 = upload(corr);
+            d.points0 = upload(points0); d.fOff = upload(fOff); d.fLab = upload(fLab);
+        }
         d.gh = AD("gh", nC); d.ghf = AD("ghf", nF); d.meshPhi = AD("meshPhi", nF);
         d.alpha = AD("alpha", nC); d.alpha0 = AD("alpha0", nC); d.alpha_b = AD("alpha_b", nB);
         d.U = AD("U", 3 * (size_t)nC); d.U_b = AD("U_b", 3 * (size_t)nB); d.U0 = AD("U0", 3 * (size_t)nC); d.U0_b = AD("U0_b", 3 * (size_t)nB);
@@ -396,13 +399,9 @@ struct tpp_solver {
         memcpy(Ro, Rn, sizeof(Rn)); memcpy(To, Tn, sizeof(Tn));
         motionAt(t, Rn, Tn);
         setTransform();
-        bool rotStep = false;
-        for (int k = 0; k < 9; k++) if (Rn[k] != Ro[k]) rotStep = true;
-        if (rotStep) {
-            g_err = "rotating solid-body motion: swept-volume kernel not implemented yet";
-        }
         orientGeometry();
-        LAUNCH(ctx, meshphi_trans, d, nF);
+        if (hasRotation) LAUNCH(ctx, meshphi_rot, d, nF);
+        else LAUNCH(ctx, meshphi_trans, d, nF);
     }
     void alphaBCs() { LAUNCH(ctx, alpha_bc, d, nB); }
     void UBCs() { d.dt = dt; LAUNCH(ctx, U_bc, d, nB); }

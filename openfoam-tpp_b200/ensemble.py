@@ -1,0 +1,84 @@
+"""Parameter sweeps sharded over GPUs: one independent case per GPU, no data-path collective.
+
+The reference builds sweeps from MATLAB-style ranges (main.py:118-142), zips the lists when they
+all have the same length and takes their Cartesian product otherwise (main.py:504-534), then runs
+the cases one after another locally (main.py:599-608) or one Slurm job each.  Here the cases of a
+sweep are dealt round-robin to the ranks of a `torch.distributed` job (one process per GPU);
+ranks exchange nothing but the final timing (max over ranks).
+"""
+from __future__ import annotations
+
+import itertools
+
+
+def parse_range(s):
+    """`start:step:end`, `start:end` (step 1) or a comma list -> floats.  Inclusive end with a
+    1e-9 slack and values rounded to 6 decimals, exactly as main.py:118-142."""
+    s = s.strip()
+    if ":" in s:
+        parts = s.split(":")
+        if len(parts) == 2:
+            start, end = float(parts[0]), float(parts[1])
+            step = 1.0
+        elif len(parts) == 3:
+            start, step, end = float(parts[0]), float(parts[1]), float(parts[2])
+        else:
+            raise ValueError(f"Invalid range format: {s}")
+        vals = []
+        v = start
+        while v <= end + 1e-9:
+            vals.append(round(v, 6))
+            v += step
+        return vals
+    return [float(x.strip()) for x in s.split(",")]
+
+
+def case_name(p):
+    """main.py:163-165."""
+    return f"case_H{p['H']}_D{p['D']}_{p['geo']}_R{p['R']}_f{p['freq']}_d{p['duration']}_m{p['mesh']}"
+
+
+def build_param_sets(base, sweeps):
+    """Zip when every sweep list has the same length, Cartesian product otherwise
+    (main.py:504-534, without the interactive confirmation)."""
+    if not sweeps:
+        return [dict(base)]
+    keys = list(sweeps)
+    lengths = {len(v) for v in sweeps.values()}
+    combos = zip(*[sweeps[k] for k in keys]) if len(lengths) == 1 else itertools.product(*[sweeps[k] for k in keys])
+    out = []
+    for combo in combos:
+        p = dict(base)
+        p.update(dict(zip(keys, combo)))
+        out.append(p)
+    return out
+
+
+def shard(items, world, rank):
+    """Round-robin deal: rank r runs items r, r+world, ...  Every item lands on exactly one rank."""
+    return list(items[rank::world])
+
+
+def max_over_ranks(values, group=None):
+    """Element-wise max of a list of floats over the ranks (the job's time is its slowest rank)."""
+    import torch
+    import torch.distributed as dist
+
+    if not (dist.is_available() and dist.is_initialized()) or dist.get_world_size(group) == 1:
+        return list(values)
+    dev = "cuda" if dist.get_backend(group) == "nccl" else "cpu"
+    t = torch.tensor(values, dtype=torch.float64, device=dev)
+    dist.all_reduce(t, op=dist.ReduceOp.MAX, group=group)
+    return t.tolist()
+
+
+def sum_over_ranks(values, group=None):
+    import torch
+    import torch.distributed as dist
+
+    if not (dist.is_available() and dist.is_initialized()) or dist.get_world_size(group) == 1:
+        return list(values)
+    dev = "cuda" if dist.get_backend(group) == "nccl" else "cpu"
+    t = torch.tensor(values, dtype=torch.float64, device=dev)
+    dist.all_reduce(t, op=dist.ReduceOp.SUM, group=group)
+    return t.tolist()

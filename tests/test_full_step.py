@@ -63,6 +63,49 @@ def test_full_steps_cap_prism_gpu(tmp_path, gpu_lib):
     _full_steps(str(tmp_path / "c"), gpu_lib, 4, geo="cap", cell="prism", n_rings=10)
 
 
+def _tutorial(case_dir, lib, n_steps):
+    """sloshingTank3D6DoF (BASELINE.json config 2): closed hex tank, single `wall` patch, table
+    with rotations up to 30 degrees -> rotating geometry, swept-volume mesh flux, wall velocity
+    from the rigid transform, and the p_rgh reference cell (pRefPoint/pRefValue, fvSolution:85-86)."""
+    import oracle
+
+    cs.setup_tutorial_case(case_dir, nx=6, ny=10, nz=9)
+    c = cs.Case(case_dir)
+    _tight(c.cfg)
+    g = sv.Solver(c.mesh, c.cfg, lib_path=lib)
+    g.load_case_fields(c)
+    o = oracle.Oracle(c.mesh, c.cfg)
+    o.load_case_fields(c)
+    assert g.info()["refCell"] == o.info()["refCell"] >= 0
+    for i in range(n_steps):
+        g.step(1)
+        o.step(1)
+        assert abs(g.info()["t"] - o.info()["t"]) <= 1e-12 * o.info()["t"]
+        for nm, tol in (("meshPhi", 1e-10), ("alpha", 1e-10), ("U", 1e-9), ("p_rgh", 1e-9), ("p", 1e-9), ("phi", 1e-9)):
+            a, b = g.get(nm), o.get(nm)
+            err = np.abs(a - b).max() / max(np.abs(b).max(), 1e-300)
+            assert err <= tol, f"step {i}: {nm} differs by {err:.2e} of its scale (> {tol})"
+        assert abs(g.get("p")[int(g.info()["refCell"])] - c.cfg.p_ref_value) < 1e-6
+    # rigid motion conserves the swept volume: sum of meshPhi over each cell's faces = 0
+    nI = c.mesh.n_internal
+    mp = g.get("meshPhi")
+    div = np.zeros(c.mesh.n_cells)
+    np.add.at(div, c.mesh.owner, mp)
+    np.add.at(div, c.mesh.neighbour, -mp[:nI])
+    assert np.abs(div).max() <= 1e-9 * np.abs(mp).max()
+    g.close()
+    o.close()
+
+
+def test_tutorial_tank_rotation_emu(tmp_path, emu_lib):
+    _tutorial(str(tmp_path / "c"), emu_lib, 5)
+
+
+@pytest.mark.gpu
+def test_tutorial_tank_rotation_gpu(tmp_path, gpu_lib):
+    _tutorial(str(tmp_path / "c"), gpu_lib, 5)
+
+
 def _conservation(case_dir, lib, n_steps, n_rings, n_layers):
     """Reference tolerances.  Sum(alpha V) may change only through the boundary flux
     alphaPhi_b: |d(sum alpha V) + dt*sum_b alphaPhi_b| <= 1e-10 * sum(alpha V) per step
