@@ -47,6 +47,7 @@ typedef struct {
     const int* patch_bc_p;
     const double* patch_inlet_alpha; /* inletOutlet inletValue (0/alpha.water:27) */
     const double* patch_p0;          /* totalPressure p0 (0/p_rgh:30) */
+    const int* patch_neighb_proc;    /* processor patches: neighbour rank (boundary:neighbProcNo); may be NULL */
 } tpp_mesh_t;
 
 /* one entry of system/fvSolution:solvers (p_rgh:42-48, p_rghFinal:50-66) */
@@ -141,9 +142,23 @@ int tpp_use_stream(tpp_handle, void* cuda_stream);
 int tpp_profile(tpp_handle, int on);
 long tpp_profile_report(tpp_handle, char* buf, long cap);
 
-/* multi-GPU: NCCL communicator over the ranks that own the processor patches */
-int tpp_nccl_unique_id(char* out128);
-int tpp_comm_init(tpp_handle, int rank, int n_ranks, const char* id128);
+/* Multi-GPU, one case decomposed over ranks (one process per GPU).  The mesh passed to
+ * tpp_create is the rank's processorN mesh; its `processor` patches (BC codes -1, listed after
+ * the physical patches, faces in the neighbour's matching order as decomposePar writes them)
+ * become halo interfaces.  tpp_comm_init joins the ranks over NCCL (the library the host
+ * process already loaded: pass its path, e.g. torch's nvidia/nccl/lib/libnccl.so.2) and
+ * finishes the processor-face geometry; every stencil kernel is then preceded by a halo
+ * exchange (pack kernel + ncclSend/ncclRecv on the solver's stream) and every Krylov dot,
+ * residual norm and Courant maximum is all-reduced. */
+int tpp_nccl_unique_id(const char* nccl_path, char* out128);
+int tpp_comm_init(tpp_handle, int rank, int n_ranks, const char* id128, const char* nccl_path);
+/* the same over two host callbacks (CPU tests with gloo): exchange(user, send[nGhost*ncomp],
+ * recv[nGhost*ncomp], ncomp) in ghost order; allreduce(user, vals, n, op) with op 0 sum, 1 max */
+int tpp_comm_callbacks(tpp_handle, int rank, int n_ranks,
+                       int (*exchange)(void*, const double*, double*, int),
+                       int (*allreduce)(void*, double*, int, int), void* user);
+/* ghost layout: per processor patch the offset/count in ghost order and the neighbour rank */
+int tpp_ghost_layout(tpp_handle, int* n_ghost, int* n_patches, int* off, int* cnt, int* peer, int cap);
 
 #ifdef __cplusplus
 }

@@ -16,6 +16,7 @@ class MeshStruct(C.Structure):
         ("points", c_double_p), ("face_offsets", c_int_p), ("face_labels", c_int_p), ("owner", c_int_p), ("neighbour", c_int_p),
         ("patch_start", c_int_p), ("patch_size", c_int_p), ("patch_bc_u", c_int_p), ("patch_bc_alpha", c_int_p), ("patch_bc_p", c_int_p),
         ("patch_inlet_alpha", c_double_p), ("patch_p0", c_double_p),
+        ("patch_neighb_proc", c_int_p),  # tpp only (the oracle's struct is the prefix before this field)
     ]
 
 
@@ -77,6 +78,7 @@ def build_structs(mesh, cfg):
     m.patch_bc_p = _ip(arr(cfg.patch_bc_p, np.int32))
     m.patch_inlet_alpha = _dp(arr(cfg.patch_inlet_alpha, np.float64))
     m.patch_p0 = _dp(arr(cfg.patch_p0, np.float64))
+    m.patch_neighb_proc = _ip(arr([p.get("neighbProcNo", -1) for p in mesh.patches], np.int32))
     c = ConfigStruct()
     c.start_time, c.end_time, c.delta_t, c.write_interval = cfg.start_time, cfg.end_time, cfg.delta_t, cfg.write_interval
     c.max_co, c.max_alpha_co, c.max_delta_t, c.adjust_time_step = cfg.max_co, cfg.max_alpha_co, cfg.max_delta_t, int(cfg.adjust_time_step)

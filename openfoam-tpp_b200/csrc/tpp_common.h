@@ -60,6 +60,11 @@ struct DV {
     // pressure
     double *rAU, *HbyA, *HbyA_b, *rAUf, *phiHbyA, *phig, *pUpper, *pCorrFlux, *pDiag, *pSource, *rec;
     double *cellTmp;  // [2*nC] Courant work
+    // halo packing (domain decomposition)
+    const int* procOwner;
+    const double* xsrc;
+    double* xbuf;
+    int xnc;
     // generic scalar-gradient arguments
     const double *gs, *gsb;
     double* gout;

@@ -619,6 +619,13 @@ HD void b_gh_cell(const DV& d, int c) {
     d.gh[c] = dot3(d.g, x);
 }
 
+// halo send buffer: the owner-cell value behind every processor face, in ghost order
+HD void b_pack_halo(const DV& d, int j) {
+    int c = d.procOwner[j];
+    for (int k = 0; k < d.xnc; k++) d.xbuf[(size_t)j * d.xnc + k] = d.xsrc[(size_t)c * d.xnc + k];
+}
+
+DEF_KERNEL(pack_halo, DV)
 DEF_KERNEL(courant, DV)
 DEF_KERNEL(alpha_bc, DV)
 DEF_KERNEL(U_bc, DV)

@@ -28,7 +28,11 @@ struct LV {
     const int *cf, *cn, *rs;      // adjacency: (face<<1|side), other row; CSR row starts
     const int *own, *nei;         // [nf]
     double *diag, *upper, *rsum;  // matrix: diag, positive off-diagonal magnitude, row sums
-    double *ev;                   // off-diagonal magnitudes per adjacency entry (ELL / CSR order)
+    double *ev;                   // off-diagonal magnitudes per adjacency entry (ELL / CSR order);
+                                  // rank-local: entries towards ghost rows are 0 (block-Jacobi AMG)
+    double *ev2, *rsum2;          // fine level only: full row (with ghost couplings) for the global operator
+    int nOwn;                     // rows owned by this rank (adjacency may point at ghost rows >= nOwn)
+    double nGlob;                 // global row count (normFactor's mean)
     const double* fev;            // ... of the fine-level view
     // transfer from the next finer level
     const int *agg;               // [n_fine] fine row -> this level's row
@@ -42,7 +46,7 @@ struct LV {
     const LV* unused;
     double omega;
     // fine-level view used by transfer kernels running on the coarse grid
-    int fn, fnCp, fW, fell;
+    int fn, fnCp, fW, fell, fnOwn;
     const int *fcf, *fcn, *frs;
     const double *fdiag, *fupper, *frsum, *fx, *fb;
     double* fxw;
@@ -61,7 +65,7 @@ struct LV {
             if (e_ < 0) break;                                            \
             const int f = e_ >> 1;                                        \
             const int o = (L).cn[base_ + s_ * str_];                      \
-            if (o < 0) continue;
+            if (o < 0 || o >= (L).nOwn) continue;
 #define END_ROW }}
 
 // y = A x on a level: out = diag*in - sum upper[f]*in[o]
@@ -105,7 +109,9 @@ HD void b_fill_ev(const LV& L, int c) {
     const size_t str = L.ell ? (size_t)L.nCp : 1;
     for (int k = 0; k < cnt; k++) {
         int e = L.cf[base + k * str], o = L.cn[base + k * str];
-        L.ev[base + k * str] = (e >= 0 && o >= 0) ? L.upper[e >> 1] : 0.0;
+        double u = (e >= 0 && o >= 0) ? L.upper[e >> 1] : 0.0;
+        L.ev[base + k * str] = o < L.nOwn ? u : 0.0;
+        if (L.ev2) L.ev2[base + k * str] = u;
     }
 }
 HD void b_spmv(const LV& L, int c) { L.out[c] = row_Ax(L, c, L.in); }
@@ -118,6 +124,17 @@ HD void b_rowsum(const LV& L, int c) {
     double s = 0;
     FOR_ROW(L, c) s += L.upper[f]; END_ROW
     L.rsum[c] = L.diag[c] - s;
+    if (L.rsum2) {  // full row, ghost couplings included
+        double s2 = 0;
+        const int cnt = L.ell ? L.W : L.rs[c + 1] - L.rs[c];
+        const size_t base = L.ell ? (size_t)c : (size_t)L.rs[c];
+        const size_t str = L.ell ? (size_t)L.nCp : 1;
+        for (int k = 0; k < cnt; k++) {
+            int e = L.cf[base + k * str], o = L.cn[base + k * str];
+            if (e >= 0 && o >= 0) s2 += L.upper[e >> 1];
+        }
+        L.rsum2[c] = L.diag[c] - s2;
+    }
 }
 // Galerkin: coarse face coefficient = sum of the fine faces in its segment (fixed order)
 HD void b_coarse_upper(const LV& L, int F) {
@@ -149,12 +166,12 @@ HD double fine_row_Ac(const LV& L, int i) {
     if (L.fell) {
         for (int k = 0; k < L.fW; k++) {
             int o = L.fcn[(size_t)k * L.fnCp + i];
-            if (o >= 0) s -= L.fev[(size_t)k * L.fnCp + i] * L.x[L.agg[o]];
+            if (o >= 0 && o < L.fnOwn) s -= L.fev[(size_t)k * L.fnCp + i] * L.x[L.agg[o]];
         }
     } else
         for (int k = L.frs[i]; k < L.frs[i + 1]; k++) {
             int o = L.fcn[k];
-            if (o >= 0) s -= L.fev[k] * L.x[L.agg[o]];
+            if (o >= 0 && o < L.fnOwn) s -= L.fev[k] * L.x[L.agg[o]];
         }
     return s;
 }
@@ -314,7 +331,7 @@ __global__ void __launch_bounds__(256) k_update_p(int n, double* pA, const doubl
 __global__ void k_scal_set(double* scal, int dst, double v) { scal[dst] = v; }
 // r = b - Ax ; normFactor pieces: |Ax - xbar*sumA| + |b - xbar*sumA| ; sumA = rsum
 __global__ void __launch_bounds__(256) k_init_residual(LV L, const double* x, const double* b, double* r, const double* scal, double* partialRes, double* partialNorm) {
-    double xbar = scal[S_XSUM] / (double)L.n;
+    double xbar = scal[S_XSUM] / L.nGlob;
     double v = 0, w = 0;
     for (int c = blockIdx.x * blockDim.x + threadIdx.x; c < L.n; c += gridDim.x * blockDim.x) {
         double ax = row_Ax(L, c, x);
@@ -389,7 +406,7 @@ __global__ void __launch_bounds__(256) k_corr_dots_csr(LV L, int nFine, const do
         const int b = L.frs[i], e = L.frs[i + 1];
         for (int k = b + lane; k < e; k += COOP) {
             int o = L.fcn[k];
-            if (o >= 0) s += L.fev[k] * L.x[L.agg[o]];
+            if (o >= 0 && o < L.fnOwn) s += L.fev[k] * L.x[L.agg[o]];
         }
         for (int off = COOP / 2; off > 0; off >>= 1) s += __shfl_xor_sync(0xffffffffu, s, off);
         if (live && lane == 0) {

@@ -10,6 +10,10 @@
 
 #include <map>
 #include <tuple>
+#ifndef TPP_EMU
+#include <dlfcn.h>
+#include <nccl.h>
+#endif
 
 using namespace tpp;
 
@@ -37,6 +41,32 @@ struct SolveStats { int iters = 0; double r0 = 0, r = 0; };
 inline int knob(const char* name, int dflt) { const char* v = getenv(name); return v ? atoi(v) : dflt; }
 inline double knobd(const char* name, double dflt) { const char* v = getenv(name); return v ? atof(v) : dflt; }
 
+// Inter-rank transport.  Product: NCCL send/recv + all-reduce on the solver's stream, resolved
+// from the NCCL library the host process (torch) already loaded.  Tests / host emulation: two
+// host callbacks (gloo in the CPU tests).
+typedef int (*exchange_cb_t)(void* user, const double* send, double* recv, int ncomp);
+typedef int (*allreduce_cb_t)(void* user, double* vals, int n, int op);
+struct Comm {
+    int rank = 0, size = 1;
+    bool active = false;
+    exchange_cb_t xcb = nullptr;
+    allreduce_cb_t rcb = nullptr;
+    void* user = nullptr;
+    std::vector<double> hsend, hrecv;
+#ifndef TPP_EMU
+    void* lib = nullptr;
+    ncclComm_t nccl = nullptr;
+    ncclResult_t (*pGetUniqueId)(ncclUniqueId*) = nullptr;
+    ncclResult_t (*pCommInitRank)(ncclComm_t*, int, ncclUniqueId, int) = nullptr;
+    ncclResult_t (*pCommDestroy)(ncclComm_t) = nullptr;
+    ncclResult_t (*pSend)(const void*, size_t, ncclDataType_t, int, ncclComm_t, cudaStream_t) = nullptr;
+    ncclResult_t (*pRecv)(void*, size_t, ncclDataType_t, int, ncclComm_t, cudaStream_t) = nullptr;
+    ncclResult_t (*pAllReduce)(const void*, void*, size_t, ncclDataType_t, ncclRedOp_t, ncclComm_t, cudaStream_t) = nullptr;
+    ncclResult_t (*pGroupStart)() = nullptr;
+    ncclResult_t (*pGroupEnd)() = nullptr;
+#endif
+};
+
 }  // namespace
 
 struct tpp_solver {
@@ -60,7 +90,7 @@ struct tpp_solver {
     Reducer red;
     // multigrid
     std::vector<Level> levels;  // coarse levels (level 0 = first coarse)
-    double *kr = nullptr, *kz = nullptr, *kp = nullptr, *kw = nullptr, *kt = nullptr, *kt2 = nullptr, *kt3 = nullptr, *fineEv = nullptr, *fineRsum = nullptr, *fw0 = nullptr;
+    double *kr = nullptr, *kz = nullptr, *kp = nullptr, *kw = nullptr, *kt = nullptr, *kt2 = nullptr, *kt3 = nullptr, *fineEv = nullptr, *fineEvFull = nullptr, *fineRsumFull = nullptr, *fineRsum = nullptr, *fw0 = nullptr;
     int *match = nullptr, *prop = nullptr, *root = nullptr;
     bool amgBuilt = false;
     struct GraphKey {
@@ -71,6 +101,16 @@ struct tpp_solver {
     struct GraphRec { cudaGraphExec_t exec; long nodes; };
     std::map<GraphKey, GraphRec> graphs;
 #endif
+    // domain decomposition: processor-patch faces are renumbered as internal faces whose
+    // neighbour is a ghost cell nC + j; ghost values arrive by halo exchange
+    int nG = 0, nIloc = 0;
+    long nGlobal = 0;
+    std::vector<int> permDev2File;           // face renumbering (identity when nG == 0)
+    std::vector<int> procOwner, procOff, procCnt, procPeer;
+    int* dProcOwner = nullptr;
+    double* sendbuf = nullptr;
+    Comm comm;
+    std::vector<double> hW, hDc, hCorr, hDPN;  // kept for the processor-face geometry pass
     // time
     double t = 0, dt = 0, dt0 = 0, startTime = 0, Co = 0, alphaCo = 0;
     long step = 0;
@@ -83,7 +123,7 @@ struct tpp_solver {
     double* probeDev = nullptr;
     int* probeIdx = nullptr;
 
-    template <class T> T* A(size_t n) { T* p = dalloc<T>(n); allocs.push_back(p); return p; }
+    template <class T> T* A(size_t n) { T* p = dalloc<T>(n + 9 * (size_t)nG); allocs.push_back(p); return p; }  // room for ghost cells
     double* AD(const char* name, size_t n) { double* p = A<double>(n); reg[name] = {p, (long)n}; return p; }
 
     // ---- rigid motion (Function1s::Table linear + clamp; sixDoFMotion XYZ quaternion) --------
@@ -145,7 +185,7 @@ struct tpp_solver {
         std::vector<double> cEst(3 * nC, 0.0);
         std::vector<int> nCF(nC, 0);
         for (int f = 0; f < nF; f++) { for (int k = 0; k < 3; k++) cEst[3 * own[f] + k] += Cf0[3 * f + k]; nCF[own[f]]++; }
-        for (int f = 0; f < nI; f++) { for (int k = 0; k < 3; k++) cEst[3 * nei[f] + k] += Cf0[3 * f + k]; nCF[nei[f]]++; }
+        for (int f = 0; f < nI; f++) { if (nei[f] >= nC) continue; for (int k = 0; k < 3; k++) cEst[3 * nei[f] + k] += Cf0[3 * f + k]; nCF[nei[f]]++; }
         for (int c = 0; c < nC; c++) for (int k = 0; k < 3; k++) cEst[3 * c + k] /= nCF[c];
         C0.assign(3 * nC, 0.0); V.assign(nC, 0.0);
         for (int f = 0; f < nF; f++) {
@@ -158,6 +198,7 @@ struct tpp_solver {
         }
         for (int f = 0; f < nI; f++) {
             int n = nei[f];
+            if (n >= nC) continue;
             double dd[3];
             for (int k = 0; k < 3; k++) dd[k] = cEst[3 * n + k] - Cf0[3 * f + k];
             double pyr = Sf0[3 * f] * dd[0] + Sf0[3 * f + 1] * dd[1] + Sf0[3 * f + 2] * dd[2];
@@ -172,7 +213,9 @@ struct tpp_solver {
         for (int f = 0; f < nF; f++) {
             const double* S = &Sf0[3 * f];
             double nf[3] = {S[0] / magSf[f], S[1] / magSf[f], S[2] / magSf[f]};
-            if (f < nI) {
+            if (f < nI && nei[f] >= nC) {
+                w[f] = 0.5; dc[f] = 0.0;  // processor face: finalised once the ghost centres are known
+            } else if (f < nI) {
                 double dO[3], dN[3], dd[3];
                 for (int k = 0; k < 3; k++) {
                     dO[k] = Cf0[3 * f + k] - C0[3 * own[f] + k];
@@ -222,16 +265,49 @@ struct tpp_solver {
         cfg.motion = nullptr;
         for (int i = 0; i < cfg.n_motion; i++)
             for (int k = 4; k < 7; k++) if (motion[7 * i + k] != 0.0) hasRotation = true;
+        // processor patches (BC codes -1) must follow the physical ones, as decomposePar writes them
+        nIloc = nI;
+        {
+            bool seenProc = false;
+            for (int p = 0; p < nPatch; p++) {
+                bool isP = bcU[p] < 0 || bcA[p] < 0 || bcP[p] < 0;
+                if (isP) {
+                    seenProc = true;
+                    if (pSize[p] == 0) continue;
+                    procOff.push_back(nG); procCnt.push_back(pSize[p]);
+                    procPeer.push_back(m->patch_neighb_proc ? m->patch_neighb_proc[p] : -1);
+                    nG += pSize[p];
+                } else if (seenProc && pSize[p] > 0) { g_err = "processor patches must come after the physical patches"; return false; }
+            }
+        }
+        if (nG > 0) {
+            const int nBphys = nB - nG;
+            permDev2File.resize(nF);
+            for (int f = 0; f < nI; f++) permDev2File[f] = f;
+            for (int j = 0; j < nG; j++) permDev2File[nI + j] = nI + nBphys + j;
+            for (int b = 0; b < nBphys; b++) permDev2File[nI + nG + b] = nI + b;
+            std::vector<int> own2(nF), off2(nF + 1, 0), lab2;
+            lab2.reserve(fLab.size());
+            for (int fd = 0; fd < nF; fd++) {
+                int ff = permDev2File[fd];
+                own2[fd] = own[ff];
+                for (int k = fOff[ff]; k < fOff[ff + 1]; k++) lab2.push_back(fLab[k]);
+                off2[fd + 1] = (int)lab2.size();
+            }
+            own.swap(own2); fOff.swap(off2); fLab.swap(lab2);
+            nei.resize(nI + nG);
+            procOwner.resize(nG);
+            for (int j = 0; j < nG; j++) { nei[nI + j] = nC + j; procOwner[j] = own[nI + j]; }
+            nI += nG;
+            nB -= nG;
+        }
         // per boundary face BC tables
         std::vector<signed char> fU(nB, -1), fA(nB, -1), fP(nB, -1);
         std::vector<double> fInlet(nB, 0.0), fP0(nB, 0.0);
         for (int p = 0; p < nPatch; p++) {
-            if (bcU[p] < 0 || bcA[p] < 0 || bcP[p] < 0) {
-                if (pSize[p] > 0) { g_err = "processor patches need tpp_comm_init (multi-GPU path) - not available in this build"; return false; }
-                continue;
-            }
+            if (bcU[p] < 0 || bcA[p] < 0 || bcP[p] < 0) continue;
             for (int i = 0; i < pSize[p]; i++) {
-                int b = pStart[p] - nI + i;
+                int b = pStart[p] - nIloc + i;
                 if (b < 0 || b >= nB) { g_err = "patch range outside the boundary faces"; return false; }
                 fU[b] = (signed char)bcU[p]; fA[b] = (signed char)bcA[p]; fP[b] = (signed char)bcP[p];
                 fInlet[b] = m->patch_inlet_alpha[p]; fP0[b] = m->patch_p0[p];
@@ -241,7 +317,7 @@ struct tpp_solver {
         // ELL cell->face table, slots ascending in face index
         std::vector<int> cnt(nC, 0);
         for (int f = 0; f < nF; f++) cnt[own[f]]++;
-        for (int f = 0; f < nI; f++) cnt[nei[f]]++;
+        for (int f = 0; f < nI; f++) if (nei[f] < nC) cnt[nei[f]]++;
         W = 0;
         for (int c = 0; c < nC; c++) W = std::max(W, cnt[c]);
         nCp = (nC + 31) / 32 * 32;
@@ -252,7 +328,7 @@ struct tpp_solver {
             cf[(size_t)fill[o] * nCp + o] = f << 1;
             cn[(size_t)fill[o] * nCp + o] = f < nI ? nei[f] : -1;
             fill[o]++;
-            if (f < nI) {
+            if (f < nI && nei[f] < nC) {
                 int n = nei[f];
                 cf[(size_t)fill[n] * nCp + n] = (f << 1) | 1;
                 cn[(size_t)fill[n] * nCp + n] = o;
@@ -289,7 +365,8 @@ struct tpp_solver {
         d.phiHbyA = AD("phiHbyA", nF); d.phig = AD("phig", nF); d.pUpper = AD("pUpper", nI); d.pCorrFlux = AD("pCorrFlux", nI);
         d.pDiag = AD("pDiag", nC); d.pSource = AD("pSource", nC); d.rec = AD("rec", nF);
         d.cellTmp = A<double>(2 * (size_t)nC);
-        kr = A<double>(nC); kz = A<double>(nC); kp = A<double>(nC); kw = A<double>(nC); kt = A<double>(nC); kt2 = A<double>(nC); kt3 = A<double>(nC); fineEv = A<double>((size_t)W * nCp); fineRsum = A<double>(nC);
+        kr = A<double>(nC); kz = A<double>(nC); kp = A<double>(nC); kw = A<double>(nC); kt = A<double>(nC); kt2 = A<double>(nC); kt3 = A<double>(nC); fineEv = A<double>((size_t)W * nCp); fineEvFull = A<double>((size_t)W * nCp); fineRsumFull = A<double>(nC);
+        sendbuf = A<double>(9 * (size_t)std::max(nG, 1)); dProcOwner = upload(procOwner); d.procOwner = dProcOwner; nGlobal = nC; fineRsum = A<double>(nC);
         scal = A<double>(S_COUNT);
 #ifdef TPP_EMU
         hscal = (double*)calloc(S_COUNT, sizeof(double));
@@ -316,7 +393,8 @@ struct tpp_solver {
         d.needRef = 1;
         for (int p = 0; p < nPatch; p++) if (bcP[p] == TPP_P_TOTAL_PRESSURE && pSize[p] > 0) d.needRef = 0;
         d.refCell = -1;
-        if (d.needRef) {
+        if (d.needRef && nG > 0) d.needRef = 0;  // decided over all ranks in finalizeParallel()
+        else if (d.needRef) {
             d.refCell = findCell(cfg.p_ref_point);
             if (d.refCell < 0) { g_err = "pRefPoint is outside the mesh and p_rgh needs a reference"; return false; }
         }
@@ -356,6 +434,94 @@ struct tpp_solver {
         return best;
     }
 
+    // ---- halo exchange: owner-side values of my processor faces -> the neighbour's ghost cells
+    void X(double* field, int nc) {
+        if (!comm.active || nG == 0) return;
+        d.xsrc = field; d.xbuf = sendbuf; d.xnc = nc;
+        LAUNCH(ctx, pack_halo, d, nG);
+        double* ghost = field + (size_t)nC * nc;
+#ifndef TPP_EMU
+        if (comm.nccl) {
+            prof_begin(ctx, "halo_sendrecv");
+            comm.pGroupStart();
+            for (size_t i = 0; i < procCnt.size(); i++) {
+                comm.pSend(sendbuf + (size_t)procOff[i] * nc, (size_t)procCnt[i] * nc, ncclDouble, procPeer[i], comm.nccl, ctx.stream);
+                comm.pRecv(ghost + (size_t)procOff[i] * nc, (size_t)procCnt[i] * nc, ncclDouble, procPeer[i], comm.nccl, ctx.stream);
+            }
+            comm.pGroupEnd();
+            prof_end(ctx);
+            ctx.launches++;
+            return;
+        }
+#endif
+        comm.hsend.resize((size_t)nG * nc); comm.hrecv.resize((size_t)nG * nc);
+        d2h(ctx, comm.hsend.data(), sendbuf, (size_t)nG * nc * sizeof(double));
+        comm.xcb(comm.user, comm.hsend.data(), comm.hrecv.data(), nc);
+        h2d(ctx, ghost, comm.hrecv.data(), (size_t)nG * nc * sizeof(double));
+    }
+    // all-reduce of n device scalars scal[idx..idx+n): op 0 sum, 1 max
+    void allreduce(int idx, int n, int op) {
+        if (!comm.active) return;
+#ifndef TPP_EMU
+        if (comm.nccl) {
+            comm.pAllReduce(scal + idx, scal + idx, n, ncclDouble, op == 0 ? ncclSum : ncclMax, comm.nccl, ctx.stream);
+            ctx.launches++;
+            return;
+        }
+#endif
+        double v[8];
+        d2h(ctx, v, scal + idx, n * sizeof(double));
+        comm.rcb(comm.user, v, n, op);
+        h2d(ctx, scal + idx, v, n * sizeof(double));
+    }
+    // processor-face geometry once the neighbours' cell centres are here
+    bool finalizeParallel() {
+        {   // does any rank hold a fixed-value p_rgh patch?
+            double fixes = 0;
+            for (int p = 0; p < nPatch; p++) if (bcP[p] == TPP_P_TOTAL_PRESSURE && pSize[p] > 0) fixes = 1;
+            h2d(ctx, scal + S_TMP0, &fixes, sizeof(double));
+            allreduce(S_TMP0, 1, 1);
+            d2h(ctx, &fixes, scal + S_TMP0, sizeof(double));
+            if (fixes == 0 && comm.size > 1) { g_err = "a closed domain (p_rgh reference cell) cannot be decomposed yet"; return false; }
+        }
+        double ng = (double)nC;
+        h2d(ctx, scal + S_TMP0, &ng, sizeof(double));
+        allreduce(S_TMP0, 1, 0);
+        d2h(ctx, &ng, scal + S_TMP0, sizeof(double));
+        nGlobal = (long)(ng + 0.5);
+        if (nG == 0) return true;
+        X(const_cast<double*>(d.C0), 3);
+        std::vector<double> gc(3 * (size_t)nG);
+        d2h(ctx, gc.data(), d.C0 + 3 * (size_t)nC, gc.size() * sizeof(double));
+        std::vector<double> w(nG), dcv(nG), corr(3 * (size_t)nG), dpn(3 * (size_t)nG);
+        for (int j = 0; j < nG; j++) {
+            int f = nIloc + j, o = own[f];
+            const double* S = &Sf0[3 * f];
+            double nf[3] = {S[0] / magSf[f], S[1] / magSf[f], S[2] / magSf[f]};
+            double dO[3], dN[3], dd[3];
+            for (int k = 0; k < 3; k++) {
+                dO[k] = Cf0[3 * f + k] - C0[3 * o + k];
+                dN[k] = gc[3 * j + k] - Cf0[3 * f + k];
+                dd[k] = gc[3 * j + k] - C0[3 * o + k];
+                dpn[3 * j + k] = dd[k];
+            }
+            double so = fabs(dot3(S, dO)), sn = fabs(dot3(S, dN));
+            w[j] = sn / (so + sn);
+            dcv[j] = 1.0 / dmax(dot3(nf, dd), 0.05 * mag3(dd));
+            for (int k = 0; k < 3; k++) corr[3 * j + k] = nf[k] - dd[k] * dcv[j];
+        }
+        h2d(ctx, d.w + nIloc, w.data(), nG * sizeof(double));
+        h2d(ctx, d.dc + nIloc, dcv.data(), nG * sizeof(double));
+        h2d(ctx, d.corrVec + 3 * (size_t)nIloc, corr.data(), corr.size() * sizeof(double));
+        h2d(ctx, d.dPN + 3 * (size_t)nIloc, dpn.data(), dpn.size() * sizeof(double));
+        if (hasRotation) {
+            h2d(ctx, const_cast<double*>(d.corrVec0) + 3 * (size_t)nIloc, corr.data(), corr.size() * sizeof(double));
+            h2d(ctx, const_cast<double*>(d.dPN0) + 3 * (size_t)nIloc, dpn.data(), dpn.size() * sizeof(double));
+            orientGeometry();
+        }
+        return true;
+    }
+
     // ---- stages -------------------------------------------------------------------------------
     void readScal() { d2h(ctx, hscal, scal, S_COUNT * sizeof(double)); }
 
@@ -363,6 +529,7 @@ struct tpp_solver {
         LAUNCH(ctx, courant, d, nC);
         red.reduce(ctx, d.cellTmp, nullptr, nC, 3, scal + S_MAX0);
         red.reduce(ctx, d.cellTmp + nC, nullptr, nC, 3, scal + S_MAX1);
+        allreduce(S_MAX0, 2, 1);
         readScal();
         Co = 0.5 * hscal[S_MAX0] * dt;
         alphaCo = 0.5 * hscal[S_MAX1] * dt;
@@ -385,9 +552,9 @@ struct tpp_solver {
         dt0 = dt;
         t += dt;
         step++;
-        d2d(ctx, d.U0, d.U, 3 * (size_t)nC * sizeof(double));
+        d2d(ctx, d.U0, d.U, 3 * (size_t)(nC + nG) * sizeof(double));
         d2d(ctx, d.U0_b, d.U_b, 3 * (size_t)nB * sizeof(double));
-        d2d(ctx, d.rho0, d.rho, nC * sizeof(double));
+        d2d(ctx, d.rho0, d.rho, (size_t)(nC + nG) * sizeof(double));
         d2d(ctx, d.Uf0, d.Uf, 3 * (size_t)nF * sizeof(double));
         int wi = (int)(((t - startTime) + 0.5 * dt) / cfg.write_interval);
         if (wi > writeTimeIndex) { writeTimeIndex = wi; return true; }
@@ -414,11 +581,15 @@ struct tpp_solver {
         d.rDeltaT = 1.0 / dts;
         d2d(ctx, d.alpha0, d.alpha, nC * sizeof(double));
         alphaBCs();
+        X(d.alpha, 1);
         gradScalar(d.alpha, d.alpha_b, d.grad);
+        X(d.grad, 3);
         LAUNCH(ctx, alpha_flux, d, nF);
         LAUNCH(ctx, mules_setup, d, nC);
         for (int j = 0; j < cfg.n_limiter_iter; j++) {
             LAUNCH(ctx, mules_cell, d, nC);
+            X(d.lambdap, 1);
+            X(d.lambdam, 1);
             LAUNCH(ctx, mules_face, d, nI);
         }
         LAUNCH(ctx, mules_phipsi, d, nF);
@@ -440,12 +611,16 @@ struct tpp_solver {
             d2d(ctx, d.alphaPhi, d.alphaPhiUn, nF * sizeof(double));
         }
         mixture();
+        X(d.alpha, 1);
+        X(d.rho, 1);
         LAUNCH(ctx, rhophi, d, nF);
     }
     void momentum() {
         UBCs();
+        X(d.U, 3);
         d.rDeltaT = 1.0 / dt;
         LAUNCH(ctx, grad_U, d, nC);
+        X(d.gradU, 9);
         LAUNCH(ctx, mom_face, d, nI);
         LAUNCH(ctx, mom_bnd, d, nB);
         LAUNCH(ctx, mom_cell, d, nC);
@@ -453,23 +628,30 @@ struct tpp_solver {
     void computeHbyA() {
         LAUNCH(ctx, HbyA, d, nC);
         LAUNCH(ctx, HbyA_bnd, d, nB);
+        X(d.rAU, 1);
+        X(d.HbyA, 3);
     }
     void pcPrepare() {
         d.dt = dt; d.rDeltaT = 1.0 / dt;
         computeHbyA();
         gradScalar(d.rho, d.rho_b, d.grad);
+        X(d.grad, 3);
         LAUNCH(ctx, phiHbyA, d, nF);
     }
     void pcAssemble() {
         LAUNCH(ctx, p_total, d, nB);
+        X(d.p_rgh, 1);
         gradScalar(d.p_rgh, d.p_rgh_b, d.grad);
+        X(d.grad, 3);
         LAUNCH(ctx, p_face, d, nI);
         LAUNCH(ctx, p_cell, d, nC);
     }
     void pcFinish() {
+        X(d.p_rgh, 1);
         LAUNCH(ctx, flux, d, nF);
         LAUNCH(ctx, U_recon, d, nC);
         UBCs();
+        X(d.U, 3);
     }
     void pcEnd() {
         if (cfg.n_motion > 0) LAUNCH(ctx, Uf, d, nF);
@@ -522,6 +704,8 @@ struct tpp_solver {
         L.n = nC; L.nf = nI; L.nCp = nCp; L.W = W; L.ell = 1;
         L.cf = d.cf; L.cn = d.cn; L.own = d.own; L.nei = d.nei;
         L.diag = diag; L.upper = upper; L.rsum = fineRsum; L.ev = fineEv;
+        L.nOwn = nC; L.nGlob = (double)nGlobal;
+        if (nG > 0) { L.ev2 = fineEvFull; L.rsum2 = fineRsumFull; }
         return L;
     }
     LV levelView(int l) {
@@ -529,13 +713,13 @@ struct tpp_solver {
         LV L;
         memset(&L, 0, sizeof(L));
         L.n = v.n; L.nf = v.nf; L.ell = 0; L.cf = v.cf; L.cn = v.cn; L.rs = v.rs; L.own = v.own; L.nei = v.nei;
-        L.diag = v.diag; L.upper = v.upper; L.rsum = v.rsum; L.ev = v.ev;
+        L.diag = v.diag; L.upper = v.upper; L.rsum = v.rsum; L.ev = v.ev; L.nOwn = v.n; L.nGlob = (double)v.n;
         L.agg = v.agg; L.aggStart = v.aggStart; L.aggRows = v.aggRows; L.segStart = v.segStart; L.segFaces = v.segFaces;
         L.x = v.x; L.b = v.b; L.t0 = v.t0; L.t1 = v.t1; L.out = v.t2;
         return L;
     }
     static void setFine(LV& L, const LV& F) {
-        L.fn = F.n; L.fnCp = F.nCp; L.fW = F.W; L.fell = F.ell; L.fcf = F.cf; L.fcn = F.cn; L.frs = F.rs;
+        L.fn = F.n; L.fnCp = F.nCp; L.fW = F.W; L.fell = F.ell; L.fnOwn = F.nOwn; L.fcf = F.cf; L.fcn = F.cn; L.frs = F.rs;
         L.fdiag = F.diag; L.fupper = F.upper; L.frsum = F.rsum; L.fev = F.ev;
     }
 
@@ -543,7 +727,7 @@ struct tpp_solver {
     void matchPass(LV G, int n, const double* fwDev, std::vector<int>& rootH) {
         std::vector<int> m1(n, -1);
         h2d(ctx, match, m1.data(), n * sizeof(int));
-        G.match = match; G.prop = prop; G.root = root; G.fw = fwDev;
+        G.match = match; G.prop = prop; G.root = root; G.fw = fwDev; G.nOwn = n;
         for (int r = 0; r < knob("TPP_ROUNDS", 8); r++) {
             LAUNCH(ctx, match_propose, G, n);
             LAUNCH(ctx, match_accept, G, n);
@@ -610,8 +794,9 @@ struct tpp_solver {
         match = A<int>(nC); prop = A<int>(nC); root = A<int>(nC);
         // faceAreaPair weights |Sf/sqrt(|Sf|) * (1, 1.01, 1.02)|
         HostGraph g;
-        g.n = nC; g.nf = nI; g.own.assign(own.begin(), own.begin() + nI); g.nei = nei; g.fw.resize(nI);
-        for (int f = 0; f < nI; f++) {
+        // rank-local hierarchy: processor faces are left out (block-Jacobi multigrid)
+        g.n = nC; g.nf = nIloc; g.own.assign(own.begin(), own.begin() + nIloc); g.nei.assign(nei.begin(), nei.begin() + nIloc); g.fw.resize(nIloc);
+        for (int f = 0; f < nIloc; f++) {
             double s = sqrt(magSf[f]);
             double v[3] = {Sf0[3 * f] / s * 1.0, Sf0[3 * f + 1] / s * 1.01, Sf0[3 * f + 2] / s * 1.02};
             g.fw[f] = mag3(v);
@@ -718,7 +903,7 @@ struct tpp_solver {
     void coarseSolve(LV L) {
 #ifdef TPP_EMU
         int n = L.n;
-        std::vector<double> r(n), p(n), Ap(n);
+        std::vector<double> r(n), p(n + (size_t)nG, 0.0), Ap(n);  // p is read at ghost columns (coefficient 0)
         double rz = 0;
         for (int i = 0; i < n; i++) { L.x[i] = 0; r[i] = L.b[i]; p[i] = L.b[i] / L.diag[i]; rz += L.b[i] * p[i]; }
         double rz0 = rz;
@@ -809,8 +994,13 @@ struct tpp_solver {
         LV F0 = fineView(diag, upper);
         bool useAMG = !levels.empty() && !(ctl.type == 0 && ctl.precond == 0);
         if (useAMG) galerkin(F0); else { LAUNCH(ctx, rowsum, F0, F0.n); LAUNCH(ctx, fill_ev, F0, F0.n); }
+        LV FG = F0;  // the global operator: full rows, ghost columns filled by halo exchange
+        if (nG > 0) { FG.ev = fineEvFull; FG.rsum = fineRsumFull; }
         red.reduce(ctx, x, nullptr, nC, 2, scal + S_XSUM);
-        initResidual(F0, x, b);
+        allreduce(S_XSUM, 1, 0);
+        X(x, 1);
+        initResidual(FG, x, b);
+        allreduce(S_RES, 2, 0);
         readScal();
         double nf = hscal[S_NORM] + 1e-20;
         st.r0 = st.r = hscal[S_RES] / nf;
@@ -819,7 +1009,7 @@ struct tpp_solver {
         scalSet(S_WARA, 0.0);  // WARA_OLD == 0 marks the first iteration for k_update_p
         dev_zero(ctx, kp, nC * sizeof(double));
         do {
-            iteration(F0, ctl, x);
+            iteration(F0, FG, ctl, x);
             readScal();
             st.r = hscal[S_RES] / nf;
             if (!(fabs(hscal[S_WAPA]) / nf >= VSMALL)) break;
@@ -828,27 +1018,31 @@ struct tpp_solver {
     }
 
     // one PCG iteration: z = M r ; wArA ; pA ; wA = A pA ; x, r update ; |r|
-    void iterationBody(LV& F0, const tpp_solver_t& ctl, double* x) {
+    void iterationBody(LV& F0, LV& FG, const tpp_solver_t& ctl, double* x) {
         precondition(F0, ctl, kr, kz);
         scalCopy(S_WARA_OLD, S_WARA);
         red.reduce(ctx, kz, kr, nC, 0, scal + S_WARA);
+        allreduce(S_WARA, 1, 0);
         updateP();
-        spmvDot(F0);
+        X(kp, 1);
+        spmvDot(FG);
+        allreduce(S_WAPA, 1, 0);
         updateXR(x);
+        allreduce(S_RES, 1, 0);
     }
     // The iteration is ~110 small launches with fixed arguments: captured once per
     // (solver entry, solution vector) into a CUDA graph and replayed (launch-bound otherwise).
-    void iteration(LV& F0, const tpp_solver_t& ctl, double* x) {
+    void iteration(LV& F0, LV& FG, const tpp_solver_t& ctl, double* x) {
 #ifndef TPP_EMU
         // (the legacy default stream cannot be captured)
-        if (!ctx.prof && ctx.stream != nullptr && ctx.stream != cudaStreamLegacy && knob("TPP_GRAPH", 1)) {
+        if (!ctx.prof && ctx.stream != nullptr && ctx.stream != cudaStreamLegacy && knob("TPP_GRAPH", 1) && (!comm.active || (comm.nccl && knob("TPP_GRAPH_PAR", 1)))) {
             GraphKey key{x, F0.diag, ctl.type, ctl.precond, ctl.n_vcycles};
             auto it = graphs.find(key);
             if (it == graphs.end()) {
                 long l0 = ctx.launches;
                 cudaGraph_t gr;
                 CUDA_CHECK(cudaStreamBeginCapture(ctx.stream, cudaStreamCaptureModeThreadLocal));
-                iterationBody(F0, ctl, x);
+                iterationBody(F0, FG, ctl, x);
                 CUDA_CHECK(cudaStreamEndCapture(ctx.stream, &gr));
                 GraphRec rec;
                 CUDA_CHECK(cudaGraphInstantiate(&rec.exec, gr, 0));
@@ -862,7 +1056,7 @@ struct tpp_solver {
             return;
         }
 #endif
-        iterationBody(F0, ctl, x);
+        iterationBody(F0, FG, ctl, x);
     }
     void scalSet(int dst, double v) {
 #ifdef TPP_EMU
@@ -903,7 +1097,7 @@ struct tpp_solver {
     }
     void initResidual(LV& F0, const double* x, const double* b) {
 #ifdef TPP_EMU
-        double xbar = scal[S_XSUM] / nC, v = 0, w = 0;
+        double xbar = scal[S_XSUM] / F0.nGlob, v = 0, w = 0;
         for (int c = 0; c < nC; c++) {
             double ax = row_Ax(F0, c, x), rr = b[c] - ax;
             kr[c] = rr; v += fabs(rr);
@@ -1038,6 +1232,16 @@ long tpp_size(tpp_handle s, const char* name) {
     auto it = s->reg.find(name);
     return it == s->reg.end() ? -1 : it->second.second;
 }
+// face-sized arrays are kept in device face order (processor faces right after the internal
+// ones); callers see OpenFOAM's file order
+static int faceComp(tpp_solver* s, const char* name) {
+    static const char* f1[] = {"phi", "meshPhi", "alphaPhi", "rhoPhi", "phiBD", "alphaPhiUn", "rAUf", "phiHbyA", "phig", "rec", "ghf", "magSf", "w", "dc"};
+    static const char* f3[] = {"Uf", "Uf0", "mExpl", "Sf", "Cf0"};
+    if (s->nG == 0) return 0;
+    for (auto n : f1) if (!strcmp(n, name)) return 1;
+    for (auto n : f3) if (!strcmp(n, name)) return 3;
+    return 0;
+}
 long tpp_get(tpp_handle s, const char* name, double* out, long cap) {
     if (!strcmp(name, "points")) {
         std::vector<double> p;
@@ -1048,6 +1252,13 @@ long tpp_get(tpp_handle s, const char* name, double* out, long cap) {
     auto it = s->reg.find(name);
     if (it == s->reg.end()) { g_err = std::string("unknown array ") + name; return -1; }
     long n = std::min<long>(cap, it->second.second);
+    if (int nc = faceComp(s, name)) {
+        std::vector<double> tmp(it->second.second);
+        d2h(s->ctx, tmp.data(), it->second.first, tmp.size() * sizeof(double));
+        for (int fd = 0; fd < s->nF; fd++)
+            for (int k = 0; k < nc; k++) { long j = (long)s->permDev2File[fd] * nc + k; if (j < cap) out[j] = tmp[(size_t)fd * nc + k]; }
+        return it->second.second;
+    }
     d2h(s->ctx, out, it->second.first, n * sizeof(double));
     return it->second.second;
 }
@@ -1055,6 +1266,13 @@ long tpp_set(tpp_handle s, const char* name, const double* in, long n) {
     auto it = s->reg.find(name);
     if (it == s->reg.end()) { g_err = std::string("unknown array ") + name; return -1; }
     if (n != it->second.second) { g_err = std::string("size mismatch for ") + name; return -2; }
+    if (int nc = faceComp(s, name)) {
+        std::vector<double> tmp(n);
+        for (int fd = 0; fd < s->nF; fd++)
+            for (int k = 0; k < nc; k++) tmp[(size_t)fd * nc + k] = in[(size_t)s->permDev2File[fd] * nc + k];
+        h2d(s->ctx, it->second.first, tmp.data(), n * sizeof(double));
+        return n;
+    }
     h2d(s->ctx, it->second.first, in, n * sizeof(double));
     return n;
 }
@@ -1068,7 +1286,8 @@ int tpp_device_ptr(tpp_handle s, const char* name, void** ptr, long* n) {
 int tpp_init_fields(tpp_handle s) {
     s->alphaBCs();
     s->mixture();
-    d2d(s->ctx, s->d.rho0, s->d.rho, s->nC * sizeof(double));
+    s->X(s->d.alpha, 1); s->X(s->d.rho, 1); s->X(s->d.U, 3); s->X(s->d.p_rgh, 1);
+    d2d(s->ctx, s->d.rho0, s->d.rho, (size_t)(s->nC + s->nG) * sizeof(double));
     dev_sync(s->ctx);
     return 0;
 }
@@ -1189,6 +1408,61 @@ long tpp_profile_report(tpp_handle s, char* buf, long cap) {
     memcpy(buf, out.c_str(), out.size() + 1);
     return (long)out.size();
 }
-int tpp_nccl_unique_id(char*) { g_err = "multi-GPU halo path is not built yet"; return -1; }
-int tpp_comm_init(tpp_handle, int, int, const char*) { g_err = "multi-GPU halo path is not built yet"; return -1; }
+int tpp_ghost_layout(tpp_handle s, int* n_ghost, int* n_patches, int* off, int* cnt, int* peer, int cap) {
+    *n_ghost = s->nG;
+    *n_patches = (int)s->procCnt.size();
+    for (int i = 0; i < (int)s->procCnt.size() && i < cap; i++) { off[i] = s->procOff[i]; cnt[i] = s->procCnt[i]; peer[i] = s->procPeer[i]; }
+    return 0;
+}
+int tpp_comm_callbacks(tpp_handle s, int rank, int n_ranks, exchange_cb_t xcb, allreduce_cb_t rcb, void* user) {
+    s->comm.rank = rank; s->comm.size = n_ranks; s->comm.xcb = xcb; s->comm.rcb = rcb; s->comm.user = user;
+    s->comm.active = n_ranks > 1;
+    if (!s->finalizeParallel()) return -1;
+    dev_sync(s->ctx);
+    return 0;
+}
+#ifndef TPP_EMU
+static bool loadNccl(Comm& c, const char* path) {
+    if (c.lib) return true;
+    c.lib = dlopen(path && path[0] ? path : "libnccl.so.2", RTLD_NOW | RTLD_GLOBAL);
+    if (!c.lib) { g_err = std::string("cannot open NCCL: ") + dlerror(); return false; }
+#define SYM(field, name) *(void**)(&c.field) = dlsym(c.lib, name); if (!c.field) { g_err = std::string("NCCL symbol missing: ") + name; return false; }
+    SYM(pGetUniqueId, "ncclGetUniqueId") SYM(pCommInitRank, "ncclCommInitRank") SYM(pCommDestroy, "ncclCommDestroy")
+    SYM(pSend, "ncclSend") SYM(pRecv, "ncclRecv") SYM(pAllReduce, "ncclAllReduce") SYM(pGroupStart, "ncclGroupStart") SYM(pGroupEnd, "ncclGroupEnd")
+#undef SYM
+    return true;
+}
+#endif
+int tpp_nccl_unique_id(const char* nccl_path, char* out128) {
+#ifndef TPP_EMU
+    Comm c;
+    if (!loadNccl(c, nccl_path)) return -1;
+    ncclUniqueId id;
+    if (c.pGetUniqueId(&id) != ncclSuccess) { g_err = "ncclGetUniqueId failed"; return -2; }
+    static_assert(sizeof(id) == 128, "ncclUniqueId is 128 bytes");
+    memcpy(out128, &id, 128);
+    return 0;
+#else
+    (void)nccl_path; (void)out128;
+    g_err = "host emulation has no NCCL transport (use tpp_comm_callbacks)";
+    return -1;
+#endif
+}
+int tpp_comm_init(tpp_handle s, int rank, int n_ranks, const char* id128, const char* nccl_path) {
+#ifndef TPP_EMU
+    if (!loadNccl(s->comm, nccl_path)) return -1;
+    ncclUniqueId id;
+    memcpy(&id, id128, 128);
+    CUDA_CHECK(cudaSetDevice(s->device));
+    if (s->comm.pCommInitRank(&s->comm.nccl, n_ranks, id, rank) != ncclSuccess) { g_err = "ncclCommInitRank failed"; return -2; }
+    s->comm.rank = rank; s->comm.size = n_ranks; s->comm.active = n_ranks > 1;
+    if (!s->finalizeParallel()) return -3;
+    dev_sync(s->ctx);
+    return 0;
+#else
+    (void)s; (void)rank; (void)n_ranks; (void)id128; (void)nccl_path;
+    g_err = "host emulation has no NCCL transport (use tpp_comm_callbacks)";
+    return -1;
+#endif
+}
 }

@@ -24,6 +24,26 @@ class SolverError(RuntimeError):
     pass
 
 
+XCB = C.CFUNCTYPE(C.c_int, C.c_void_p, abi.c_double_p, abi.c_double_p, C.c_int)
+RCB = C.CFUNCTYPE(C.c_int, C.c_void_p, abi.c_double_p, C.c_int, C.c_int)
+
+
+def nccl_library_path():
+    """The libnccl the process already has loaded (torch's bundled copy), from /proc/self/maps."""
+    import torch  # noqa: F401  (loads it)
+
+    with open("/proc/self/maps") as f:
+        for line in f:
+            if "libnccl" in line:
+                return line.split()[-1]
+    import glob
+
+    hits = glob.glob(os.path.join(os.path.dirname(os.path.dirname(torch.__file__)), "nvidia", "nccl", "lib", "libnccl.so*"))
+    if hits:
+        return hits[0]
+    raise SolverError("NCCL library not found")
+
+
 def load(lib_path=None):
     path = lib_path or LIB_PATH
     if path in _LIBS:
@@ -58,6 +78,10 @@ def load(lib_path=None):
     L.tpp_profile.argtypes = [H, C.c_int]
     L.tpp_profile_report.restype = C.c_long
     L.tpp_profile_report.argtypes = [H, C.c_char_p, C.c_long]
+    L.tpp_nccl_unique_id.argtypes = [C.c_char_p, C.c_char_p]
+    L.tpp_comm_init.argtypes = [H, C.c_int, C.c_int, C.c_char_p, C.c_char_p]
+    L.tpp_comm_callbacks.argtypes = [H, C.c_int, C.c_int, XCB, RCB, C.c_void_p]
+    L.tpp_ghost_layout.argtypes = [H, abi.c_int_p, abi.c_int_p, abi.c_int_p, abi.c_int_p, abi.c_int_p, C.c_int]
     _LIBS[path] = L
     return L
 
@@ -177,6 +201,63 @@ class Solver:
             k, c, ms = line.split()
             out[k] = (int(c), float(ms))
         return out
+
+    # ---- multi-GPU: one case decomposed over the ranks of a torch.distributed job ----------------
+    def ghost_layout(self):
+        ng, npat = C.c_int(), C.c_int()
+        off, cnt, peer = (np.zeros(64, dtype=np.int32) for _ in range(3))
+        self.L.tpp_ghost_layout(self.h, C.byref(ng), C.byref(npat), off.ctypes.data_as(abi.c_int_p), cnt.ctypes.data_as(abi.c_int_p), peer.ctypes.data_as(abi.c_int_p), 64)
+        return ng.value, [(int(off[i]), int(cnt[i]), int(peer[i])) for i in range(npat.value)]
+
+    def comm_init_nccl(self):
+        """Join the ranks over NCCL (product path): rank 0 creates the unique id, torch.distributed
+        broadcasts it, every rank calls tpp_comm_init."""
+        import torch.distributed as dist
+
+        rank, world = dist.get_rank(), dist.get_world_size()
+        path = nccl_library_path().encode()
+        buf = C.create_string_buffer(128)
+        if rank == 0 and self.L.tpp_nccl_unique_id(path, buf) != 0:
+            self._err("tpp_nccl_unique_id")
+        obj = [buf.raw if rank == 0 else None]
+        dist.broadcast_object_list(obj, src=0)
+        if self.L.tpp_comm_init(self.h, rank, world, obj[0], path) != 0:
+            self._err("tpp_comm_init")
+
+    def comm_init_callbacks(self):
+        """The same exchange pattern over torch.distributed point-to-point calls on host buffers
+        (gloo): used by the CPU tests of the N > 1 path."""
+        import torch
+        import torch.distributed as dist
+
+        rank, world = dist.get_rank(), dist.get_world_size()
+        ng, patches = self.ghost_layout()
+
+        def xcb(_user, send, recv, nc):
+            s = np.ctypeslib.as_array(send, shape=(ng * nc,))
+            r = np.ctypeslib.as_array(recv, shape=(ng * nc,))
+            ops, keep = [], []
+            for off, cnt, peer in patches:
+                ts = torch.from_numpy(s[off * nc : (off + cnt) * nc].copy())
+                tr = torch.empty(cnt * nc, dtype=torch.float64)
+                keep.append((tr, off, cnt))
+                ops += [dist.P2POp(dist.isend, ts, peer), dist.P2POp(dist.irecv, tr, peer)]
+            for w in dist.batch_isend_irecv(ops):
+                w.wait()
+            for tr, off, cnt in keep:
+                r[off * nc : (off + cnt) * nc] = tr.numpy()
+            return 0
+
+        def rcb(_user, vals, n, op):
+            v = np.ctypeslib.as_array(vals, shape=(n,))
+            t = torch.from_numpy(v.copy())
+            dist.all_reduce(t, op=dist.ReduceOp.SUM if op == 0 else dist.ReduceOp.MAX)
+            v[:] = t.numpy()
+            return 0
+
+        self._cbs = (XCB(xcb), RCB(rcb))  # keep alive
+        if self.L.tpp_comm_callbacks(self.h, rank, world, self._cbs[0], self._cbs[1], None) != 0:
+            self._err("tpp_comm_callbacks")
 
     def load_case_fields(self, case):
         """Start fields from a Case (0/ or the latest time directory: restart)."""

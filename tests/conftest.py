@@ -14,6 +14,7 @@ CSRC = os.path.join(ROOT, "openfoam-tpp_b200", "csrc")
 
 def pytest_configure(config):
     config.addinivalue_line("markers", "gpu: needs a CUDA device (B200); run with -m gpu")
+    config.addinivalue_line("markers", "gpu2: needs two CUDA devices (gpurun --gpus 2); run with -m gpu2")
 
 
 def _has_gpu():
