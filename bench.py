@@ -161,6 +161,7 @@ def main():
     ap.add_argument("--cpu-cells", type=float, default=1.2e5, help="cells of the CPU-baseline sample mesh")
     ap.add_argument("--cpu-steps", type=int, default=4)
     ap.add_argument("--no-cpu", action="store_true")
+    ap.add_argument("--mode", default="decomposed", choices=["decomposed", "ensemble"], help="N > 1: one tank over N GPUs (halo exchange) or N independent sweep cases")
     args = ap.parse_args()
     if args.impl == "reference":
         return run_reference(args)
@@ -182,21 +183,39 @@ def main():
 
         dist.init_process_group("nccl", device_id=torch.device("cuda", local))
 
-    # N > 1: the sweep of BASELINE.json config 5 sharded one independent case per GPU (the same
-    # tank at a different shaking frequency on every rank); no data-path collective.
-    from openfoam_tpp_b200 import ensemble
+    from openfoam_tpp_b200 import ensemble, meshgen
 
-    freqs = ensemble.parse_range(f"{CASE['freq']}:0.04:{CASE['freq'] + 0.04 * (world - 1) + 1e-6}")
-    my_freq = ensemble.shard(freqs, world, rank)[0]
-    mesh, nr, nl = mesh_for(args.cells)
-    cfg = make_config(mesh, my_freq)
+    freqs = [CASE["freq"]]
+    if world > 1 and args.mode == "ensemble":
+        # the sweep of BASELINE.json config 5 sharded one independent case per GPU (the same tank
+        # at a different shaking frequency on every rank); no data-path collective
+        freqs = ensemble.parse_range(f"{CASE['freq']}:0.04:{CASE['freq'] + 0.04 * (world - 1) + 1e-6}")
+        mesh, nr, nl = mesh_for(args.cells)
+        cfg = make_config(mesh, ensemble.shard(freqs, world, rank)[0])
+    elif world > 1:
+        # ONE tank decomposed over the GPUs (BASELINE.json config 4): the mesh is refined so that
+        # every GPU keeps --cells cells (weak scaling), cut into z-slabs (decomposePar `simple`
+        # n = (1 1 N)); each rank builds only its slab, the cuts are `processor` patches
+        ratio = CASE["H"] / (CASE["D"] / 2)
+        nr = max(4, int(round((args.cells * world / (18.0 * ratio)) ** (1.0 / 3.0))))
+        nl = max(world, int(round(nr * ratio / world)) * world)
+        k0, k1 = rank * nl // world, (rank + 1) * nl // world
+        mesh = meshgen.cylinder_mesh(CASE["H"], CASE["D"], nr, nl, "flat", "tet", k0=k0, k1=k1,
+                                     proc=(rank, rank - 1 if rank > 0 else None, rank + 1 if rank < world - 1 else None))
+        cfg = make_config(mesh)
+    else:
+        mesh, nr, nl = mesh_for(args.cells)
+        cfg = make_config(mesh)
     nC, nI, nF = mesh.n_cells, mesh.n_internal, mesh.n_faces
     g = sv.Solver(mesh, cfg, device=local)
+    decomposed = world > 1 and args.mode != "ensemble"
     # a side stream shared with the solver: CUDA events recorded here bracket its kernels, and
     # (unlike the legacy default stream) it can be graph-captured
     stream = torch.cuda.Stream()
     torch.cuda.set_stream(stream)
     g.use_stream(stream.cuda_stream)
+    if decomposed:
+        g.comm_init_nccl()
     a0 = initial_alpha(mesh)
     g.set("alpha", a0)
     g.init_fields()
@@ -292,7 +311,7 @@ def main():
             "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
             "ms_per_step": sec / args.steps * 1e3, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
             "config": {"workload": f"cfg4 case_H0.208_D0.2_flat_R0.004_f1.88 tet mesh refined to {nC} cells per GPU (n_rings {nr}, n_layers {nl})",
-                       "cells_per_gpu": nC, "internal_faces_per_gpu": nI, "parallelism": "single GPU" if world == 1 else f"ensemble: {world} independent sweep cases (f = {freqs[0]}..{freqs[-1]} Hz), one per GPU, no halo exchange (single-case domain decomposition is not built yet)",
+                       "cells_per_gpu": nC, "internal_faces_per_gpu": nI, "parallelism": "single GPU" if world == 1 else (f"one tank decomposed into {world} z-slabs (simple (1 1 {world})), NCCL halo exchange + all-reduced Krylov dots, {total_cells} cells in total" if decomposed else f"ensemble: {world} independent sweep cases (f = {freqs[0]}..{freqs[-1]} Hz), one per GPU, no collective"),
                        "l2": "working set (>1 kB/cell) far exceeds the 126 MB L2; no flush needed",
                        "vof_steps_per_s": args.steps / sec, "solver_iters_last_step": [int(info["it0"]), int(info["it1"])], "amg_levels": int(info["levels"])},
             "clocks": sampler.summary(), "gpu_launches": launches,

@@ -336,23 +336,37 @@ HD void b_mom_bnd(const DV& d, int b) {
     }
 }
 
+// row assembly + UEqn.relax(1): fvMatrix::relax enforces diagonal dominance even with the
+// reference's relaxation factor 1 (fvSolution:89-95): D = max(|D + sum_b max|iC||, sum|offdiag|)
+// - sum_b min(iC), the difference goes to the source with the current U [OF13-MEM].  This is
+// what keeps A = D/V positive when a water-laden mass flux crosses an air cell.
 HD void b_mom_cell(const DV& d, int c) {
-    double ds = 0, src[3] = {0, 0, 0};
+    double ds = 0, so = 0, bmax = 0, bmin = 0, src[3] = {0, 0, 0};
     FOR_CELL_FACES(d, c)
         if (f < d.nI) {
             if (isN) {
                 ds -= d.mUpper[f];
+                so += fabs(d.mLower[f]);
                 for (int k = 0; k < 3; k++) src[k] -= d.mExpl[3 * f + k];
             } else {
                 ds -= d.mLower[f];
+                so += fabs(d.mUpper[f]);
                 for (int k = 0; k < 3; k++) src[k] += d.mExpl[3 * f + k];
             }
-        } else
+        } else {
+            const double* iC = &d.mBIC[3 * (f - d.nI)];
+            bmax += dmax(fabs(iC[0]), dmax(fabs(iC[1]), fabs(iC[2])));
+            bmin += dmin(iC[0], dmin(iC[1], iC[2]));
             for (int k = 0; k < 3; k++) src[k] += d.mExpl[3 * f + k];
+        }
     END_CELL_FACES
     double V = d.V[c];
-    d.mDiag[c] = d.rDeltaT * d.rho[c] * V + ds;
-    for (int k = 0; k < 3; k++) d.mSource[3 * c + k] = d.rDeltaT * d.rho0[c] * d.U0[3 * c + k] * V + src[k];
+    double D0 = d.rDeltaT * d.rho[c] * V + ds;
+    double D = D0 + bmax;
+    D = dmax(fabs(D), so);
+    D = D - bmin;
+    d.mDiag[c] = D;
+    for (int k = 0; k < 3; k++) d.mSource[3 * c + k] = (d.rDeltaT * d.rho0[c] * d.U0[3 * c + k] * V + src[k]) + (D - D0) * d.U[3 * c + k];
 }
 
 // ---- S5 pressure corrector ---------------------------------------------------------------------

@@ -552,6 +552,7 @@ struct tpp_solver {
         dt0 = dt;
         t += dt;
         step++;
+        X(d.U, 3);  // ghosts may be stale after a tpp_set
         d2d(ctx, d.U0, d.U, 3 * (size_t)(nC + nG) * sizeof(double));
         d2d(ctx, d.U0_b, d.U_b, 3 * (size_t)nB * sizeof(double));
         d2d(ctx, d.rho0, d.rho, (size_t)(nC + nG) * sizeof(double));

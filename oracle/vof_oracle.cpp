@@ -1095,9 +1095,28 @@ struct orc_state {
                 src[3 * P + j] += dev;
             }
         }
+        // UEqn.relax() with the reference's relaxation factor 1 (fvSolution:89-95) is not a no-op:
+        // fvMatrix::relax enforces diagonal dominance, D = max(|D + sum_b max|iC||, sum|offdiag|)
+        // - sum_b min(iC), and moves the difference to the source with the current U [OF13-MEM].
+        dvec sumOff(nC, 0.0), bMax(nC, 0.0), bMin(nC, 0.0);
+        for (int f = 0; f < nI; f++) {
+            sumOff[own[f]] += std::fabs(mUpper[f]);
+            sumOff[nei[f]] += std::fabs(mLower[f]);
+        }
+        for (int b = 0; b < nB; b++) {
+            int P = own[nI + b];
+            const double* iC = &mBIC[3 * b];
+            bMax[P] += std::max(std::fabs(iC[0]), std::max(std::fabs(iC[1]), std::fabs(iC[2])));
+            bMin[P] += std::min(iC[0], std::min(iC[1], iC[2]));
+        }
         for (int c = 0; c < nC; c++) {
-            mDiag[c] = rDeltaT * rho[c] * V[c] + diagSum[c];
-            for (int k = 0; k < 3; k++) mSource[3 * c + k] = rDeltaT * rho0[c] * U0[3 * c + k] * V0[c] + src[3 * c + k];
+            double D0 = rDeltaT * rho[c] * V[c] + diagSum[c];
+            double D = D0 + bMax[c];
+            D = std::max(std::fabs(D), sumOff[c]);
+            D = D - bMin[c];
+            mDiag[c] = D;
+            for (int k = 0; k < 3; k++)
+                mSource[3 * c + k] = (rDeltaT * rho0[c] * U0[3 * c + k] * V0[c] + src[3 * c + k]) + (D - D0) * U[3 * c + k];
         }
     }
 
