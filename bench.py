@@ -4,7 +4,7 @@
 Workload (BASELINE.json configs[3], the configuration the metric is quoted on): the
 D = 0.2 m, H = 0.208 m flat-bottom tank, orbital shaking R = 4 mm at 1.88 Hz
 (case_H0.208_D0.2_flat_R0.004_f1.88_d20.0_m0.009), tet mesh synthetically refined to
---cells per GPU (default ~2.1 M; the 8-GPU run of the ~50 M-cell case is 6.2 M per GPU).
+--cells per GPU (default 6.2 M: the ~50 M-cell case of BASELINE.json over 8 GPUs).
 A "step" is one full time step: Courant -> deltaT -> mesh motion -> 3 MULES sub-cycles ->
 momentum assembly -> 2 pressure correctors (GAMG-PCG solves).
 
@@ -91,6 +91,21 @@ ALG_BYTES = {
 }
 
 
+class stdout_to_stderr:
+    """fd-level redirect: NCCL prints its version banner on stdout at communicator creation, and
+    the bench contract is ONE JSON line on stdout."""
+
+    def __enter__(self):
+        sys.stdout.flush()
+        self.saved = os.dup(1)
+        os.dup2(2, 1)
+
+    def __exit__(self, *a):
+        sys.stdout.flush()
+        os.dup2(self.saved, 1)
+        os.close(self.saved)
+
+
 class ClockSampler(threading.Thread):
     def __init__(self, index=0):
         super().__init__(daemon=True)
@@ -157,7 +172,7 @@ def main():
     ap.add_argument("--steps", type=int, default=10)
     ap.add_argument("--warmup", type=int, default=5)
     ap.add_argument("--impl", default="ours")
-    ap.add_argument("--cells", type=float, default=2.1e6, help="target cells per GPU")
+    ap.add_argument("--cells", type=float, default=6.2e6, help="target cells per GPU (6.2 M = the ~50 M-cell tank of BASELINE config 4 over 8 GPUs)")
     ap.add_argument("--cpu-cells", type=float, default=1.2e5, help="cells of the CPU-baseline sample mesh")
     ap.add_argument("--cpu-steps", type=int, default=4)
     ap.add_argument("--no-cpu", action="store_true")
@@ -181,7 +196,9 @@ def main():
     if world > 1:
         import torch.distributed as dist
 
-        dist.init_process_group("nccl", device_id=torch.device("cuda", local))
+        with stdout_to_stderr():
+            dist.init_process_group("nccl", device_id=torch.device("cuda", local))
+            dist.barrier()
 
     from openfoam_tpp_b200 import ensemble, meshgen
 
@@ -215,7 +232,9 @@ def main():
     torch.cuda.set_stream(stream)
     g.use_stream(stream.cuda_stream)
     if decomposed:
-        g.comm_init_nccl()
+        with stdout_to_stderr():
+            g.comm_init_nccl()
+            torch.cuda.synchronize()
     a0 = initial_alpha(mesh)
     g.set("alpha", a0)
     g.init_fields()

@@ -639,7 +639,20 @@ HD void b_pack_halo(const DV& d, int j) {
     for (int k = 0; k < d.xnc; k++) d.xbuf[(size_t)j * d.xnc + k] = d.xsrc[(size_t)c * d.xnc + k];
 }
 
+// face arrays between device order (processor faces after the internal ones) and file order;
+// procOwner temporarily carries the permutation dev -> file
+HD void b_face_to_file(const DV& d, int fd) {
+    int ff = d.procOwner[fd];
+    for (int k = 0; k < d.xnc; k++) d.xbuf[(size_t)ff * d.xnc + k] = d.xsrc[(size_t)fd * d.xnc + k];
+}
+HD void b_file_to_face(const DV& d, int fd) {
+    int ff = d.procOwner[fd];
+    for (int k = 0; k < d.xnc; k++) d.xbuf[(size_t)fd * d.xnc + k] = d.xsrc[(size_t)ff * d.xnc + k];
+}
+
 DEF_KERNEL(pack_halo, DV)
+DEF_KERNEL(face_to_file, DV)
+DEF_KERNEL(file_to_face, DV)
 DEF_KERNEL(courant, DV)
 DEF_KERNEL(alpha_bc, DV)
 DEF_KERNEL(U_bc, DV)

@@ -364,7 +364,8 @@ __global__ void __launch_bounds__(256) k_corr_dots(LV L, int nFine, const double
 // ---- coarse (CSR) levels: COOP lanes per row, fixed-order shuffle reduction ---------------------
 // A thread per row is latency-bound on the coarse levels (rows of 10-30 entries, few rows);
 // eight lanes per row walk the row together.
-constexpr int COOP = 8;
+// COOP lanes per row (4 for short rows, 8 otherwise), chosen per level from the mean row length.
+template <int COOP>
 DEV double coop_offdiag(const LV& L, int c, const double* x, int lane) {
     double s = 0;
     const int b = L.rs[c], e = L.rs[c + 1];
@@ -372,16 +373,18 @@ DEV double coop_offdiag(const LV& L, int c, const double* x, int lane) {
         int o = L.cn[k];
         if (o >= 0) s += L.ev[k] * x[o];
     }
+#pragma unroll
     for (int off = COOP / 2; off > 0; off >>= 1) s += __shfl_xor_sync(0xffffffffu, s, off);
     return s;
 }
 // mode 0: out = in + omega (b - A in)/diag ; 1: out = b - A in ; 2: out = A in
+template <int COOP>
 __global__ void __launch_bounds__(256) k_csr_row_op(const LV L, int mode) {
     int gid = blockIdx.x * blockDim.x + threadIdx.x;
     int c = gid / COOP, lane = gid % COOP;
     bool live = c < L.n;
     int cc = live ? c : L.n - 1;
-    double off = coop_offdiag(L, cc, L.in, lane);
+    double off = coop_offdiag<COOP>(L, cc, L.in, lane);
     if (live && lane == 0) {
         double ax = L.diag[c] * L.in[c] - off;
         if (mode == 0) L.out[c] = L.in[c] + L.omega * (L.b[c] - ax) / L.diag[c];
@@ -390,6 +393,7 @@ __global__ void __launch_bounds__(256) k_csr_row_op(const LV L, int mode) {
     }
 }
 // A c for the prolonged correction on a CSR fine level (L = coarse level with fine view), COOP lanes
+template <int COOP>
 __global__ void __launch_bounds__(256) k_corr_dots_csr(LV L, int nFine, const double* r, double* Ac, double* partialNum, double* partialDen) {
     double v = 0, w = 0;
     const int lane = threadIdx.x % COOP;
@@ -408,6 +412,7 @@ __global__ void __launch_bounds__(256) k_corr_dots_csr(LV L, int nFine, const do
             int o = L.fcn[k];
             if (o >= 0 && o < L.fnOwn) s += L.fev[k] * L.x[L.agg[o]];
         }
+#pragma unroll
         for (int off = COOP / 2; off > 0; off >>= 1) s += __shfl_xor_sync(0xffffffffu, s, off);
         if (live && lane == 0) {
             double c = L.x[L.agg[i]];

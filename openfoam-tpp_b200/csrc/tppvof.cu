@@ -110,6 +110,13 @@ struct tpp_solver {
     int* dProcOwner = nullptr;
     double* sendbuf = nullptr;
     Comm comm;
+    double* permBuf = nullptr;
+    int* dPerm = nullptr;
+    void ensurePermBuf() {
+        if (permBuf) return;
+        permBuf = A<double>(3 * (size_t)nF);
+        dPerm = upload(permDev2File);
+    }
     std::vector<double> hW, hDc, hCorr, hDPN;  // kept for the processor-face geometry pass
     // time
     double t = 0, dt = 0, dt0 = 0, startTime = 0, Co = 0, alphaCo = 0;
@@ -891,7 +898,8 @@ struct tpp_solver {
 #ifndef TPP_EMU
         if (!L.ell) {
             prof_begin(ctx, mode == 0 ? "jacobi_csr" : (mode == 1 ? "residual_csr" : "spmv_csr"));
-            k_csr_row_op<<<(L.n * COOP + 255) / 256, 256, 0, ctx.stream>>>(L, mode);
+            if (2 * L.nf <= 10 * (long)L.n) k_csr_row_op<4><<<(L.n * 4 + 255) / 256, 256, 0, ctx.stream>>>(L, mode);
+            else k_csr_row_op<8><<<(L.n * 8 + 255) / 256, 256, 0, ctx.stream>>>(L, mode);
             prof_end(ctx);
             ctx.launches++;
             return;
@@ -958,7 +966,7 @@ struct tpp_solver {
         vcycle(l + 1, F0, cvp->b, cvp->x, cvp->t0, true, nPre, nPost);
         Cn.fxw = cur;
         if (scaleCorr) {
-            corrDots(Cn, L.n, rbuf, acbuf);
+            corrDots(Cn, L.n, rbuf, acbuf, L.nf);
             Cn.in = rbuf; Cn.out = acbuf; Cn.in2 = scal + S_TMP0; Cn.omega = knobd("TPP_SCALEJ", 1.0);
             LAUNCH(ctx, scale_apply, Cn, L.n);
         } else
@@ -1067,7 +1075,7 @@ struct tpp_solver {
 #endif
         ctx.launches++;
     }
-    void corrDots(LV& Cn, int nFine, const double* r, double* Ac) {
+    void corrDots(LV& Cn, int nFine, const double* r, double* Ac, int fineNf = 0) {
 #ifdef TPP_EMU
         double v = 0, w = 0;
         for (int i = 0; i < nFine; i++) {
@@ -1077,10 +1085,13 @@ struct tpp_solver {
         scal[S_TMP0] = v; scal[S_TMP1] = w;
 #else
         prof_begin(ctx, Cn.fell ? "corr_dots" : "corr_dots_csr");
+        const bool shortRows = !Cn.fell && 2 * (long)fineNf <= 10 * (long)nFine;
+        const int lanes = shortRows ? 4 : 8;
+        int nb = Cn.fell ? RED_BLOCKS : std::min(RED_BLOCKS, (nFine * lanes + 255) / 256);
         if (Cn.fell) k_corr_dots<<<RED_BLOCKS, BLOCK, 0, ctx.stream>>>(Cn, nFine, r, Ac, red.partial, red.partial2);
-        else k_corr_dots_csr<<<std::min(RED_BLOCKS, (nFine * COOP + 255) / 256), BLOCK, 0, ctx.stream>>>(Cn, nFine, r, Ac, red.partial, red.partial2);
+        else if (shortRows) k_corr_dots_csr<4><<<nb, BLOCK, 0, ctx.stream>>>(Cn, nFine, r, Ac, red.partial, red.partial2);
+        else k_corr_dots_csr<8><<<nb, BLOCK, 0, ctx.stream>>>(Cn, nFine, r, Ac, red.partial, red.partial2);
         {
-            int nb = Cn.fell ? RED_BLOCKS : std::min(RED_BLOCKS, (nFine * COOP + 255) / 256);
             k_reduce_final<<<1, BLOCK, 0, ctx.stream>>>(red.partial, nb, 2, scal + S_TMP0);
             k_reduce_final<<<1, BLOCK, 0, ctx.stream>>>(red.partial2, nb, 2, scal + S_TMP1);
         }
@@ -1253,11 +1264,12 @@ long tpp_get(tpp_handle s, const char* name, double* out, long cap) {
     auto it = s->reg.find(name);
     if (it == s->reg.end()) { g_err = std::string("unknown array ") + name; return -1; }
     long n = std::min<long>(cap, it->second.second);
-    if (int nc = faceComp(s, name)) {
-        std::vector<double> tmp(it->second.second);
-        d2h(s->ctx, tmp.data(), it->second.first, tmp.size() * sizeof(double));
-        for (int fd = 0; fd < s->nF; fd++)
-            for (int k = 0; k < nc; k++) { long j = (long)s->permDev2File[fd] * nc + k; if (j < cap) out[j] = tmp[(size_t)fd * nc + k]; }
+    if (int nc = faceComp(s, name)) {  // device order -> OpenFOAM file order, on the device
+        s->ensurePermBuf();
+        s->d.xsrc = it->second.first; s->d.xbuf = s->permBuf; s->d.xnc = nc; s->d.procOwner = s->dPerm;
+        LAUNCH(s->ctx, face_to_file, s->d, s->nF);
+        s->d.procOwner = s->dProcOwner;
+        d2h(s->ctx, out, s->permBuf, n * sizeof(double));
         return it->second.second;
     }
     d2h(s->ctx, out, it->second.first, n * sizeof(double));
@@ -1268,10 +1280,12 @@ long tpp_set(tpp_handle s, const char* name, const double* in, long n) {
     if (it == s->reg.end()) { g_err = std::string("unknown array ") + name; return -1; }
     if (n != it->second.second) { g_err = std::string("size mismatch for ") + name; return -2; }
     if (int nc = faceComp(s, name)) {
-        std::vector<double> tmp(n);
-        for (int fd = 0; fd < s->nF; fd++)
-            for (int k = 0; k < nc; k++) tmp[(size_t)fd * nc + k] = in[(size_t)s->permDev2File[fd] * nc + k];
-        h2d(s->ctx, it->second.first, tmp.data(), n * sizeof(double));
+        s->ensurePermBuf();
+        h2d(s->ctx, s->permBuf, in, n * sizeof(double));
+        s->d.xsrc = s->permBuf; s->d.xbuf = it->second.first; s->d.xnc = nc; s->d.procOwner = s->dPerm;
+        LAUNCH(s->ctx, file_to_face, s->d, s->nF);
+        s->d.procOwner = s->dProcOwner;
+        dev_sync(s->ctx);
         return n;
     }
     h2d(s->ctx, it->second.first, in, n * sizeof(double));
