@@ -76,6 +76,9 @@ ALG_BYTES = {
     # label 4 B; C cells, F internal faces)
     "jacobi": lambda C, F: 32 * C + 16 * F,            # x, b, diag in; x out; upper + addressing
     "spmv_dot": lambda C, F: 24 * C + 16 * F,
+    "corr_dots": lambda C, F: 32 * C + 16 * F,           # r, diag, agg/x_c in; A c out; upper + addressing
+    "residual": lambda C, F: 32 * C + 16 * F,
+    "scale_apply": lambda C, F: 40 * C,
     "restrict_residual": lambda C, F: 24 * C + 16 * F + 8 * C / 4,
     "grad_scalar": lambda C, F: 32 * C + 40 * F,
     "alpha_flux": lambda C, F: 56 * C + 56 * F,
@@ -268,17 +271,36 @@ def main():
     g.profile(False)
     tot_ms = sum(v[1] for v in prof.values())
     top = sorted(prof.items(), key=lambda kv: -kv[1][1])
-    dom, (dom_n, dom_ms) = top[0]
     peaks = {}
     pk = os.path.join(ROOT, "MEASURED_PEAKS.json")
     if os.path.exists(pk):
         peaks = json.load(open(pk))
     peak = float(peaks.get("hbm_gbs", 6650.0))
-    alg = ALG_BYTES.get(dom)
-    achieved = alg(nC, nI) / (dom_ms / dom_n * 1e-3) / 1e9 if alg else None
+    levels = g.amg_levels()
+    coarse = levels[1:-1] if len(levels) > 2 else levels[1:]  # CSR levels that are smoothed (the coarsest is solved by coarse_cg)
+
+    def alg_bytes(name, launches):
+        """algorithmic bytes of ALL launches of a kernel in the profiled window"""
+        if name in ALG_BYTES:
+            return ALG_BYTES[name](nC, mesh.n_internal) * launches
+        per_row = {"jacobi_csr": 32, "residual_csr": 24, "corr_dots_csr": 32}.get(name)
+        if per_row and coarse:  # one launch per coarse level and sweep: bytes summed over the levels
+            sweep = sum(per_row * n + 16 * f for n, f in coarse)
+            return sweep * launches / len(coarse)
+        return None
+
+    rated = [(k, v) for k, v in top if alg_bytes(k, v[0])]
+    dom, (dom_n, dom_ms) = rated[0] if rated else top[0]
+    ab = alg_bytes(dom, dom_n)
+    achieved = ab / (dom_ms * 1e-3) / 1e9 if ab else None
+    table = []
+    for k, v in top[:10]:
+        b = alg_bytes(k, v[0])
+        table.append([k, v[0], round(v[1], 3), round(b / (v[1] * 1e-3) / 1e9, 1) if b else None])
     roofline = {"bound": "hbm", "kernel": f"k_{dom}", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak if achieved else None,
                 "traffic": None, "peak_source": "measured (MEASURED_PEAKS.json)" if peaks else "fallback",
-                "share_of_step": dom_ms / tot_ms, "top": [[k, v[0], round(v[1], 3)] for k, v in top[:8]]}
+                "share_of_step": dom_ms / tot_ms, "amg_levels_rows_faces": levels,
+                "top_kernels_launches_ms_GBps": table}
 
     # ---- end to end: pinned host state in, one step, host state out, every step ---------------
     names_in = ["alpha", "U", "p_rgh", "phi", "Uf"]

@@ -134,6 +134,10 @@ int tpp_set_probes(tpp_handle, int n, const int* cells);
 long tpp_probe_log(tpp_handle, double* out, long cap_rows); /* rows (t, v0..); drains */
 int tpp_find_cell(tpp_handle, const double* xyz);
 
+/* multigrid hierarchy: rows / faces of the fine level and of every coarse level; returns the
+ * number of levels (fine included) */
+int tpp_amg_levels(tpp_handle, int* n_rows, int* n_faces, int cap);
+
 /* run on the caller's CUDA stream (e.g. torch.cuda.current_stream().cuda_stream) instead
  * of the handle's own, so the caller's CUDA events bracket the solver's kernels */
 int tpp_use_stream(tpp_handle, void* cuda_stream);

@@ -7,6 +7,7 @@
 #include "../../include/tppvof.h"
 #include "tpp_kernels.h"
 #include "tpp_linsolve.h"
+#include "tpp_vcycle.h"
 
 #include <map>
 #include <tuple>
@@ -893,92 +894,165 @@ struct tpp_solver {
         }
     }
 
-    // out = op(in) on level L: ELL fine level -> one thread per row; CSR levels -> COOP lanes per row
-    void rowOp(LV& L, int mode) {
+    // ---- V-cycle in precision R (tpp_vcycle.h): per-level storage, conversion, cycle, preconditioner
+    template <class R> struct VStore {
+        std::vector<R*> diag, ev, x, b, t0, r, Ac;  // index 0 = fine level, 1.. = coarse levels
+        bool ready = false;
+    };
+    VStore<float> vsF;
+    VStore<double> vsD;
+    template <class R> VStore<R>& vstore();
+    int vLevels() const { return 1 + (int)levels.size(); }
+    int vRows(int lv) const { return lv == 0 ? nC : levels[lv - 1].n; }
+    size_t vEntries(int lv) const { return lv == 0 ? (size_t)W * nCp : (size_t)std::max(2 * levels[lv - 1].nf, 1); }
+    template <class R> void ensureVStore() {
+        VStore<R>& v = vstore<R>();
+        if (v.ready) return;
+        for (int lv = 0; lv < vLevels(); lv++) {
+            size_t n = (size_t)vRows(lv) + (lv == 0 ? (size_t)nG : 0);
+            v.diag.push_back(A<R>(n)); v.ev.push_back(A<R>(vEntries(lv)));
+            v.x.push_back(A<R>(n)); v.b.push_back(A<R>(n)); v.t0.push_back(A<R>(n)); v.r.push_back(A<R>(n)); v.Ac.push_back(A<R>(n));
+        }
+        v.ready = true;
+    }
+    template <class R> VL<R> vview(int lv) {
+        VStore<R>& v = vstore<R>();
+        VL<R> L;
+        memset(&L, 0, sizeof(L));
+        if (lv == 0) { L.n = nC; L.nf = nIloc; L.nCp = nCp; L.W = W; L.ell = 1; L.cn = d.cn; L.nOwn = nC; }
+        else { Level& c = levels[lv - 1]; L.n = c.n; L.nf = c.nf; L.ell = 0; L.cn = c.cn; L.rs = c.rs; L.nOwn = c.n; L.agg = c.agg; L.aggStart = c.aggStart; L.aggRows = c.aggRows; }
+        L.diag = v.diag[lv]; L.ev = v.ev[lv];
+        return L;
+    }
+    // matrix values of every level in precision R (after galerkin(), once per solve)
+    template <class R> void convertLevels(LV& F0) {
+        VStore<R>& v = vstore<R>();
+        for (int lv = 0; lv < vLevels(); lv++) {
+            const double* dg = lv == 0 ? F0.diag : levels[lv - 1].diag;
+            const double* ev = lv == 0 ? F0.ev : levels[lv - 1].ev;
+            CastArgs<R> a;
+            memset(&a, 0, sizeof(a));
+            a.src = dg; a.dst = v.diag[lv];
+            VLAUNCH(ctx, cast_in, a, vRows(lv));
+            a.src = ev; a.dst = v.ev[lv];
+            VLAUNCH(ctx, cast_in, a, (int)vEntries(lv));
+        }
+    }
+    template <class R> void vRowOp(VL<R>& L, int mode) {  // 0 Jacobi sweep, 1 residual
 #ifndef TPP_EMU
         if (!L.ell) {
-            prof_begin(ctx, mode == 0 ? "jacobi_csr" : (mode == 1 ? "residual_csr" : "spmv_csr"));
-            if (2 * L.nf <= 10 * (long)L.n) k_csr_row_op<4><<<(L.n * 4 + 255) / 256, 256, 0, ctx.stream>>>(L, mode);
-            else k_csr_row_op<8><<<(L.n * 8 + 255) / 256, 256, 0, ctx.stream>>>(L, mode);
+            prof_begin(ctx, mode == 0 ? "v_jacobi_csr" : "v_residual_csr");
+            if (2 * (long)L.nf <= 10 * (long)L.n) vk_csr_row_op<R, 4><<<(L.n * 4 + 255) / 256, 256, 0, ctx.stream>>>(L, mode);
+            else vk_csr_row_op<R, 8><<<(L.n * 8 + 255) / 256, 256, 0, ctx.stream>>>(L, mode);
             prof_end(ctx);
             ctx.launches++;
             return;
         }
 #endif
-        if (mode == 0) LAUNCH(ctx, jacobi, L, L.n);
-        else if (mode == 1) LAUNCH(ctx, residual, L, L.n);
-        else LAUNCH(ctx, spmv, L, L.n);
+        if (mode == 0) VLAUNCH(ctx, jacobi, L, L.n);
+        else VLAUNCH(ctx, residual, L, L.n);
     }
-    void coarseSolve(LV L) {
+    // out = A in ; scal[S_TMP0] = r.in ; scal[S_TMP1] = in.out
+    template <class R> void vSpmvDot2(VL<R>& L) {
+#ifdef TPP_EMU
+        double v = 0, w = 0;
+        for (int c = 0; c < L.n; c++) { R y = vl_Ax(L, c, L.in); L.out[c] = y; v += (double)L.r[c] * (double)L.in[c]; w += (double)y * (double)L.in[c]; }
+        scal[S_TMP0] = v; scal[S_TMP1] = w;
+#else
+        prof_begin(ctx, L.ell ? "v_spmv_dot2" : "v_spmv_dot2_csr");
+        int nb = RED_BLOCKS;
+        if (L.ell) vk_spmv_dot2<R><<<nb, BLOCK, 0, ctx.stream>>>(L, red.partial, red.partial2);
+        else {
+            const bool shortRows = 2 * (long)L.nf <= 10 * (long)L.n;
+            nb = std::min(RED_BLOCKS, (L.n * (shortRows ? 4 : 8) + 255) / 256);
+            if (shortRows) vk_csr_spmv_dot2<R, 4><<<nb, BLOCK, 0, ctx.stream>>>(L, red.partial, red.partial2);
+            else vk_csr_spmv_dot2<R, 8><<<nb, BLOCK, 0, ctx.stream>>>(L, red.partial, red.partial2);
+        }
+        k_reduce_final<<<1, BLOCK, 0, ctx.stream>>>(red.partial, nb, 2, scal + S_TMP0);
+        k_reduce_final<<<1, BLOCK, 0, ctx.stream>>>(red.partial2, nb, 2, scal + S_TMP1);
+        prof_end(ctx);
+#endif
+        ctx.launches += 3;
+    }
+    template <class R> void vCoarseSolve(VL<R>& L, R* r, R* p, R* Ap) {  // L.b -> L.out
+        const int maxIt = knob("TPP_CITER", 16);
+        const double tol = knobd("TPP_CTOL", 0.05);
 #ifdef TPP_EMU
         int n = L.n;
-        std::vector<double> r(n), p(n + (size_t)nG, 0.0), Ap(n);  // p is read at ghost columns (coefficient 0)
+        R* x = L.out;
         double rz = 0;
-        for (int i = 0; i < n; i++) { L.x[i] = 0; r[i] = L.b[i]; p[i] = L.b[i] / L.diag[i]; rz += L.b[i] * p[i]; }
+        for (int i = 0; i < n; i++) { x[i] = 0; r[i] = L.b[i]; p[i] = L.b[i] / L.diag[i]; rz += (double)L.b[i] * (double)p[i]; }
         double rz0 = rz;
         if (rz > 0)
-            for (int it = 0; it < knob("TPP_CITER", 16); it++) {
+            for (int it = 0; it < maxIt; it++) {
                 double pAp = 0;
-                for (int i = 0; i < n; i++) { Ap[i] = row_Ax(L, i, p.data()); pAp += Ap[i] * p[i]; }
-                double alpha = rz / pAp, rzn = 0;
-                for (int i = 0; i < n; i++) { L.x[i] += alpha * p[i]; r[i] -= alpha * Ap[i]; rzn += r[i] * r[i] / L.diag[i]; }
-                { double ct = knobd("TPP_CTOL", 0.05); if (rzn <= ct * ct * rz0) break; }
-                double beta = rzn / rz;
+                for (int i = 0; i < n; i++) { Ap[i] = vl_Ax(L, i, (const R*)p); pAp += (double)Ap[i] * (double)p[i]; }
+                R alpha = (R)(rz / pAp);
+                double rzn = 0;
+                for (int i = 0; i < n; i++) { x[i] += alpha * p[i]; r[i] -= alpha * Ap[i]; rzn += (double)r[i] * (double)r[i] / (double)L.diag[i]; }
+                if (rzn <= tol * tol * rz0) break;
+                R beta = (R)(rzn / rz);
                 rz = rzn;
                 for (int i = 0; i < n; i++) p[i] = r[i] / L.diag[i] + beta * p[i];
             }
-        ctx.launches++;
 #else
-        prof_begin(ctx, "coarse_cg");
-        k_coarse_cg<<<1, 1024, 0, ctx.stream>>>(L, knob("TPP_CITER", 16), knobd("TPP_CTOL", 0.05));
+        prof_begin(ctx, "v_coarse_cg");
+        vk_coarse_cg<R><<<1, 1024, 0, ctx.stream>>>(L, r, p, Ap, maxIt, tol);
         prof_end(ctx);
-        ctx.launches++;
 #endif
+        ctx.launches++;
     }
-
-    // x (output) ~= A^-1 b on level l (l = -1: fine).  zeroGuess: x is overwritten.
-    void vcycle(int l, LV& F0, const double* b, double* x, double* tmp, bool zeroGuess, int nPre, int nPost) {
-        LV L = l < 0 ? F0 : levelView(l);
-        const double omega = knobd("TPP_OMEGA", 0.8);
-        const bool scaleCorr = knob("TPP_SCALE", 1) != 0;
-        if (l == (int)levels.size() - 1 && l >= 0) {
-            L.b = const_cast<double*>(b); L.x = x;
-            coarseSolve(L);
+    // x ~= A^-1 b on level lv (0 = fine); x, b are the level's own buffers unless given
+    template <class R> void vcycleT(int lv, const R* b, R* x, bool zeroGuess, int nPre, int nPost) {
+        VStore<R>& v = vstore<R>();
+        VL<R> L = vview<R>(lv);
+        const R omega = (R)knobd("TPP_OMEGA", 0.8);
+        if (lv == vLevels() - 1) {  // coarsest (or the only) level: one-CTA CG
+            L.b = b; L.out = x;
+            vCoarseSolve(L, v.r[lv], v.t0[lv], v.Ac[lv]);
             return;
         }
-        L.omega = omega; L.b = const_cast<double*>(b);
-        double *cur = x, *oth = tmp;
-        int sweeps = std::max(nPre, 1);
-        for (int s = 0; s < sweeps; s++) {
-            if (s == 0 && zeroGuess) { L.out = cur; LAUNCH(ctx, jacobi0, L, L.n); }
-            else { L.in = cur; L.out = oth; rowOp(L, 0); std::swap(cur, oth); }
+        L.omega = omega; L.b = b;
+        R *cur = x, *oth = v.t0[lv];
+        for (int s = 0; s < std::max(nPre, 1); s++) {
+            if (s == 0 && zeroGuess) { L.out = cur; VLAUNCH(ctx, jacobi0, L, L.n); }
+            else { L.in = cur; L.out = oth; vRowOp(L, 0); std::swap(cur, oth); }
         }
-        // residual, restriction, coarse solve, scaled correction (GAMGSolver::scale)
-        Level* cvp = &levels[l + 1];
-        double* rbuf = l < 0 ? kt2 : levels[l].t1;
-        double* acbuf = l < 0 ? kt3 : levels[l].t2;
-        L.in = cur; L.out = rbuf;
-        rowOp(L, 1);
-        LV Cn = levelView(l + 1);
-        setFine(Cn, L);
-        Cn.in = rbuf;
-        LAUNCH(ctx, restrict_sum, Cn, Cn.n);
-        vcycle(l + 1, F0, cvp->b, cvp->x, cvp->t0, true, nPre, nPost);
-        Cn.fxw = cur;
-        if (scaleCorr) {
-            corrDots(Cn, L.n, rbuf, acbuf, L.nf);
-            Cn.in = rbuf; Cn.out = acbuf; Cn.in2 = scal + S_TMP0; Cn.omega = knobd("TPP_SCALEJ", 1.0);
-            LAUNCH(ctx, scale_apply, Cn, L.n);
-        } else
-            LAUNCH(ctx, prolong_add, Cn, L.n);
+        L.in = cur; L.out = v.r[lv];
+        vRowOp(L, 1);
+        VL<R> Cn = vview<R>(lv + 1);
+        Cn.r = v.r[lv]; Cn.out = v.b[lv + 1];
+        VLAUNCH(ctx, restrict, Cn, Cn.n);
+        vcycleT<R>(lv + 1, v.b[lv + 1], v.x[lv + 1], true, nPre, nPost);
+        // prolonged correction c = P x_c in `oth`, A c, scaling, x += ...
+        VL<R> Pn = vview<R>(lv + 1);
+        Pn.xc = v.x[lv + 1]; Pn.out = oth;
+        VLAUNCH(ctx, prolong, Pn, L.n);
+        L.in = oth; L.out = v.Ac[lv]; L.r = v.r[lv];
+        vSpmvDot2(L);
+        L.c = oth; L.Ac = v.Ac[lv]; L.r = v.r[lv]; L.out = cur; L.sf = scal + S_TMP0; L.omega = (R)knobd("TPP_SCALEJ", 1.0);
+        VLAUNCH(ctx, scale_apply, L, L.n);
+        L.omega = omega;
         for (int s = 0; s < std::max(nPost, 1); s++) {
             L.in = cur; L.out = oth;
-            rowOp(L, 0);
+            vRowOp(L, 0);
             std::swap(cur, oth);
         }
-        if (cur != x) d2d(ctx, x, cur, L.n * sizeof(double));
+        if (cur != x) d2d(ctx, x, cur, L.n * sizeof(R));
     }
-
+    template <class R> void preconditionT(const tpp_solver_t& ctl, const double* r, double* z) {
+        VStore<R>& v = vstore<R>();
+        CastArgs<R> a;
+        memset(&a, 0, sizeof(a));
+        a.src = r; a.dst = v.b[0];
+        VLAUNCH(ctx, cast_in, a, nC);
+        int nv = ctl.type == 1 ? 1 : std::max(ctl.n_vcycles, 1);
+        int nPre = knob("TPP_NPRE", 2), nPost = knob("TPP_NPOST", 2);
+        for (int cyc = 0; cyc < nv; cyc++) vcycleT<R>(0, v.b[0], v.x[0], cyc == 0, nPre, nPost);
+        a.rsrc = v.x[0]; a.ddst = z;
+        VLAUNCH(ctx, cast_out, a, nC);
+    }
+    bool useFp32() const { return knob("TPP_FP32", 1) != 0; }
     void precondition(LV& F0, const tpp_solver_t& ctl, const double* r, double* z) {
         if (ctl.type == 0 && ctl.precond == 0) {  // PCG + DIC requested: diagonal preconditioning
             LV L = F0;
@@ -986,23 +1060,22 @@ struct tpp_solver {
             LAUNCH(ctx, jacobi0, L, L.n);
             return;
         }
-        if (levels.empty()) {  // mesh no larger than a coarsest level: one-CTA CG is the "multigrid"
-            LV L = F0;
-            L.b = const_cast<double*>(r); L.x = z; L.t0 = kt; L.t1 = kt2; L.out = kt3;
-            coarseSolve(L);
-            return;
-        }
-        int nv = ctl.type == 1 ? 1 : std::max(ctl.n_vcycles, 1);
-        int nPre = knob("TPP_NPRE", 2), nPost = knob("TPP_NPOST", 2);
-        for (int cyc = 0; cyc < nv; cyc++) vcycle(-1, F0, r, z, kt, cyc == 0, nPre, nPost);
+        if (useFp32()) preconditionT<float>(ctl, r, z);
+        else preconditionT<double>(ctl, r, z);
     }
+
 
     SolveStats solve(const tpp_solver_t& ctl, double* diag, double* upper, const double* b, double* x) {
         SolveStats st;
         if (!amgBuilt) buildAMG();
         LV F0 = fineView(diag, upper);
         bool useAMG = !levels.empty() && !(ctl.type == 0 && ctl.precond == 0);
+        const bool jacobiOnly = ctl.type == 0 && ctl.precond == 0;
         if (useAMG) galerkin(F0); else { LAUNCH(ctx, rowsum, F0, F0.n); LAUNCH(ctx, fill_ev, F0, F0.n); }
+        if (!jacobiOnly) {
+            if (useFp32()) { ensureVStore<float>(); convertLevels<float>(F0); }
+            else { ensureVStore<double>(); convertLevels<double>(F0); }
+        }
         LV FG = F0;  // the global operator: full rows, ghost columns filled by halo exchange
         if (nG > 0) { FG.ev = fineEvFull; FG.rsum = fineRsumFull; }
         red.reduce(ctx, x, nullptr, nC, 2, scal + S_XSUM);
@@ -1074,30 +1147,6 @@ struct tpp_solver {
         k_scal_set<<<1, 1, 0, ctx.stream>>>(scal, dst, v);
 #endif
         ctx.launches++;
-    }
-    void corrDots(LV& Cn, int nFine, const double* r, double* Ac, int fineNf = 0) {
-#ifdef TPP_EMU
-        double v = 0, w = 0;
-        for (int i = 0; i < nFine; i++) {
-            double c = Cn.x[Cn.agg[i]], a = fine_row_Ac(Cn, i);
-            Ac[i] = a; v += r[i] * c; w += a * c;
-        }
-        scal[S_TMP0] = v; scal[S_TMP1] = w;
-#else
-        prof_begin(ctx, Cn.fell ? "corr_dots" : "corr_dots_csr");
-        const bool shortRows = !Cn.fell && 2 * (long)fineNf <= 10 * (long)nFine;
-        const int lanes = shortRows ? 4 : 8;
-        int nb = Cn.fell ? RED_BLOCKS : std::min(RED_BLOCKS, (nFine * lanes + 255) / 256);
-        if (Cn.fell) k_corr_dots<<<RED_BLOCKS, BLOCK, 0, ctx.stream>>>(Cn, nFine, r, Ac, red.partial, red.partial2);
-        else if (shortRows) k_corr_dots_csr<4><<<nb, BLOCK, 0, ctx.stream>>>(Cn, nFine, r, Ac, red.partial, red.partial2);
-        else k_corr_dots_csr<8><<<nb, BLOCK, 0, ctx.stream>>>(Cn, nFine, r, Ac, red.partial, red.partial2);
-        {
-            k_reduce_final<<<1, BLOCK, 0, ctx.stream>>>(red.partial, nb, 2, scal + S_TMP0);
-            k_reduce_final<<<1, BLOCK, 0, ctx.stream>>>(red.partial2, nb, 2, scal + S_TMP1);
-        }
-        prof_end(ctx);
-#endif
-        ctx.launches += 3;
     }
     void scalCopy(int dst, int src) {
 #ifdef TPP_EMU
@@ -1181,6 +1230,9 @@ struct tpp_solver {
 #endif
     }
 };
+
+template <> tpp_solver::VStore<float>& tpp_solver::vstore<float>() { return vsF; }
+template <> tpp_solver::VStore<double>& tpp_solver::vstore<double>() { return vsD; }
 
 // ------------------------------------------------------------------------------------
 // C-ABI
@@ -1422,6 +1474,13 @@ long tpp_profile_report(tpp_handle s, char* buf, long cap) {
     if ((long)out.size() + 1 > cap) return -(long)out.size() - 1;
     memcpy(buf, out.c_str(), out.size() + 1);
     return (long)out.size();
+}
+int tpp_amg_levels(tpp_handle s, int* n_rows, int* n_faces, int cap) {
+    int k = 0;
+    if (k < cap) { n_rows[k] = s->nC; n_faces[k] = s->nIloc; }
+    k++;
+    for (auto& l : s->levels) { if (k < cap) { n_rows[k] = l.n; n_faces[k] = l.nf; } k++; }
+    return k;
 }
 int tpp_ghost_layout(tpp_handle s, int* n_ghost, int* n_patches, int* off, int* cnt, int* peer, int cap) {
     *n_ghost = s->nG;

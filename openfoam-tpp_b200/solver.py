@@ -81,6 +81,7 @@ def load(lib_path=None):
     L.tpp_nccl_unique_id.argtypes = [C.c_char_p, C.c_char_p]
     L.tpp_comm_init.argtypes = [H, C.c_int, C.c_int, C.c_char_p, C.c_char_p]
     L.tpp_comm_callbacks.argtypes = [H, C.c_int, C.c_int, XCB, RCB, C.c_void_p]
+    L.tpp_amg_levels.argtypes = [H, abi.c_int_p, abi.c_int_p, C.c_int]
     L.tpp_ghost_layout.argtypes = [H, abi.c_int_p, abi.c_int_p, abi.c_int_p, abi.c_int_p, abi.c_int_p, C.c_int]
     _LIBS[path] = L
     return L
@@ -185,6 +186,12 @@ class Solver:
     def find_cell(self, xyz):
         a = np.ascontiguousarray(xyz, dtype=np.float64)
         return self.L.tpp_find_cell(self.h, a.ctypes.data_as(abi.c_double_p))
+
+    def amg_levels(self):
+        """[(rows, faces)] of the fine level and every coarse level of the cached hierarchy."""
+        n, f = np.zeros(32, dtype=np.int32), np.zeros(32, dtype=np.int32)
+        k = self.L.tpp_amg_levels(self.h, n.ctypes.data_as(abi.c_int_p), f.ctypes.data_as(abi.c_int_p), 32)
+        return [(int(n[i]), int(f[i])) for i in range(k)]
 
     def use_stream(self, cuda_stream):
         self.L.tpp_use_stream(self.h, C.c_void_p(cuda_stream))
