@@ -71,15 +71,15 @@ def initial_alpha(mesh):
     return (C[:, 2] <= CASE["H"] / 2).astype(np.float64)
 
 
+VB = 4  # bytes per value inside the multigrid V-cycle (FP32 preconditioner; TPP_FP32=0 -> 8)
 ALG_BYTES = {
     # algorithmic bytes per launch (SURVEY.md §8d convention: each distinct array once; FP64 8 B,
-    # label 4 B; C cells, F internal faces)
-    "jacobi": lambda C, F: 32 * C + 16 * F,            # x, b, diag in; x out; upper + addressing
+    # label 4 B; C cells, F internal faces).  V-cycle kernels (v_*) move VB-byte values.
+    "v_jacobi": lambda C, F: 4 * VB * C + (VB + 8) * F,      # x, b, diag in; x out; upper + addressing
+    "v_residual": lambda C, F: 4 * VB * C + (VB + 8) * F,
+    "v_spmv_dot2": lambda C, F: 4 * VB * C + (VB + 8) * F,   # c, r, diag in; A c out
+    "v_scale_apply": lambda C, F: 6 * VB * C,
     "spmv_dot": lambda C, F: 24 * C + 16 * F,
-    "corr_dots": lambda C, F: 32 * C + 16 * F,           # r, diag, agg/x_c in; A c out; upper + addressing
-    "residual": lambda C, F: 32 * C + 16 * F,
-    "scale_apply": lambda C, F: 40 * C,
-    "restrict_residual": lambda C, F: 24 * C + 16 * F + 8 * C / 4,
     "grad_scalar": lambda C, F: 32 * C + 40 * F,
     "alpha_flux": lambda C, F: 56 * C + 56 * F,
     "mules_setup": lambda C, F: 40 * C + 32 * F,
@@ -170,6 +170,8 @@ def run_reference(args):
 
 
 def main():
+    global VB
+    VB = 8 if os.environ.get("TPP_FP32", "1") == "0" else 4
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
     ap.add_argument("--steps", type=int, default=10)
@@ -283,9 +285,9 @@ def main():
         """algorithmic bytes of ALL launches of a kernel in the profiled window"""
         if name in ALG_BYTES:
             return ALG_BYTES[name](nC, mesh.n_internal) * launches
-        per_row = {"jacobi_csr": 32, "residual_csr": 24, "corr_dots_csr": 32}.get(name)
+        per_row = {"v_jacobi_csr": 4 * VB, "v_residual_csr": 4 * VB, "v_spmv_dot2_csr": 4 * VB}.get(name)
         if per_row and coarse:  # one launch per coarse level and sweep: bytes summed over the levels
-            sweep = sum(per_row * n + 16 * f for n, f in coarse)
+            sweep = sum(per_row * n + (VB + 8) * f for n, f in coarse)
             return sweep * launches / len(coarse)
         return None
 
@@ -354,7 +356,8 @@ def main():
             "config": {"workload": f"cfg4 case_H0.208_D0.2_flat_R0.004_f1.88 tet mesh refined to {nC} cells per GPU (n_rings {nr}, n_layers {nl})",
                        "cells_per_gpu": nC, "internal_faces_per_gpu": nI, "parallelism": "single GPU" if world == 1 else (f"one tank decomposed into {world} z-slabs (simple (1 1 {world})), NCCL halo exchange + all-reduced Krylov dots, {total_cells} cells in total" if decomposed else f"ensemble: {world} independent sweep cases (f = {freqs[0]}..{freqs[-1]} Hz), one per GPU, no collective"),
                        "l2": "working set (>1 kB/cell) far exceeds the 126 MB L2; no flush needed",
-                       "vof_steps_per_s": args.steps / sec, "solver_iters_last_step": [int(info["it0"]), int(info["it1"])], "amg_levels": int(info["levels"])},
+                       "vof_steps_per_s": args.steps / sec, "solver_iters_last_step": [int(info["it0"]), int(info["it1"])], "amg_levels": int(info["levels"]),
+                       "precision": "FP64 fields, operators, Krylov iteration and residuals; multigrid preconditioner in " + ("FP64" if VB == 8 else "FP32")},
             "clocks": sampler.summary(), "gpu_launches": launches,
             "e2e": {"value": e2e, "unit": UNIT, "h2d_bytes_per_step": h2d_b, "d2h_bytes_per_step": d2h_b + (host_in["phi"].numel() + host_in["Uf"].numel()) * 8, "steps": e2e_steps},
             "roofline": roofline, "cpu_baseline": cpu,
