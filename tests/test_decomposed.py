@@ -84,6 +84,11 @@ def test_three_rank_decomposition_gloo(tmp_path, emu_lib):
     _run(tmp_path, emu_lib, nr=4, nl=9, steps=3, port=29632, nproc=3)
 
 
+@pytest.mark.gpu
 @pytest.mark.gpu2
 def test_two_rank_decomposition_matches_single_rank_nccl(tmp_path, gpu_lib):
+    import torch
+
+    if torch.cuda.device_count() < 2:
+        pytest.skip("needs two CUDA devices (gpurun --gpus 2)")
     _run(tmp_path, None, nr=12, nl=24, steps=4, port=29633)
