@@ -279,7 +279,8 @@ def main():
         peaks = json.load(open(pk))
     peak = float(peaks.get("hbm_gbs", 6650.0))
     levels = g.amg_levels()
-    coarse = levels[1:-1] if len(levels) > 2 else levels[1:]  # CSR levels that are smoothed (the coarsest is solved by coarse_cg)
+    layout = g.amg_layout()
+    coarse = levels[1:layout["kernel_levels"]]  # CSR levels smoothed kernel by kernel (the rest live in the tail kernel)
 
     def alg_bytes(name, launches):
         """algorithmic bytes of ALL launches of a kernel in the profiled window"""
@@ -301,7 +302,7 @@ def main():
         table.append([k, v[0], round(v[1], 3), round(b / (v[1] * 1e-3) / 1e9, 1) if b else None])
     roofline = {"bound": "hbm", "kernel": f"k_{dom}", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak if achieved else None,
                 "traffic": None, "peak_source": "measured (MEASURED_PEAKS.json)" if peaks else "fallback",
-                "share_of_step": dom_ms / tot_ms, "amg_levels_rows_faces": levels,
+                "share_of_step": dom_ms / tot_ms, "amg_levels_rows_faces": levels, "amg_layout": layout,
                 "top_kernels_launches_ms_GBps": table}
 
     # ---- end to end: pinned host state in, one step, host state out, every step ---------------

@@ -137,6 +137,10 @@ int tpp_find_cell(tpp_handle, const double* xyz);
 /* multigrid hierarchy: rows / faces of the fine level and of every coarse level; returns the
  * number of levels (fine included) */
 int tpp_amg_levels(tpp_handle, int* n_rows, int* n_faces, int cap);
+/* out4: levels smoothed kernel by kernel (mesh included; rows distributed over the ranks),
+ * levels of the tail (gathered onto every rank, one persistent kernel), rows of the first tail
+ * level, CTAs of the tail kernel */
+int tpp_amg_layout(tpp_handle, int* out4);
 
 /* run on the caller's CUDA stream (e.g. torch.cuda.current_stream().cuda_stream) instead
  * of the handle's own, so the caller's CUDA events bracket the solver's kernels */

@@ -9,9 +9,13 @@
 //   * agglomeration: pairwise handshake matching on the faceAreaPair weights (the weights
 //     OpenFOAM's faceAreaPair agglomerator uses), two matching passes merged per level
 //     (the equivalent of mergeLevels 2), built once and cached (the mesh moves rigidly);
+//     aggregates never cross a rank boundary, processor faces are agglomerated into coarse
+//     processor faces (OpenFOAM's GAMG processor-interface agglomeration), so every level
+//     keeps its inter-rank couplings and its own halo exchange;
 //   * Galerkin coarse operators re-summed every solve by segment gathers (no atomics);
-//   * damped-Jacobi pre/post smoothing (symmetric V-cycle), single-CTA CG on the coarsest
-//     level;
+//   * the V-cycle itself (tpp_vcycle.h): damped Jacobi, scaled corrections; the large levels
+//     run one kernel per operation, the small ones ("tail": gathered onto every rank) run
+//     inside ONE persistent cooperative kernel with grid barriers;
 //   * SpMV is cell-gathered over the ELL table (fine level) / CSR rows (coarse levels);
 //     dot products are two-stage with a fixed grid, so every sum has a fixed order.
 #pragma once
@@ -22,34 +26,25 @@
 
 namespace tpp {
 
-// One multigrid level (also used for the finest level, aliasing the solver's arrays).
+// One multigrid level in FP64 (Galerkin assembly, matching, the outer Krylov operator); the
+// finest level aliases the solver's arrays.  Rows [0,n) are owned, columns [n,nOwn) are ghost
+// rows behind processor faces (filled by the level's halo exchange).
 struct LV {
     int n, nf, nCp, W, ell;       // rows, faces, ELL stride/width, ell=1: ELL, 0: CSR
     const int *cf, *cn, *rs;      // adjacency: (face<<1|side), other row; CSR row starts
     const int *own, *nei;         // [nf]
     double *diag, *upper, *rsum;  // matrix: diag, positive off-diagonal magnitude, row sums
-    double *ev;                   // off-diagonal magnitudes per adjacency entry (ELL / CSR order);
-                                  // rank-local: entries towards ghost rows are 0 (block-Jacobi AMG)
-    double *ev2, *rsum2;          // fine level only: full row (with ghost couplings) for the global operator
-    int nOwn;                     // rows owned by this rank (adjacency may point at ghost rows >= nOwn)
+    double *ev;                   // off-diagonal magnitudes per adjacency entry (ELL / CSR order)
+    int nOwn;                     // valid columns: n + ghosts (n alone while matching: ghosts never pair)
     double nGlob;                 // global row count (normFactor's mean)
-    const double* fev;            // ... of the fine-level view
     // transfer from the next finer level
-    const int *agg;               // [n_fine] fine row -> this level's row
     const int *aggStart, *aggRows;   // CSR: members of each row of this level
     const int *segStart, *segFaces;  // CSR: fine faces summed into each face of this level
-    // work vectors
-    double *x, *b, *t0, *t1;
+    const double *fupper, *frsum;    // the finer level's coefficients
     // kernel arguments
-    const double *in, *in2;
+    const double *in, *b;
     double* out;
-    const LV* unused;
     double omega;
-    // fine-level view used by transfer kernels running on the coarse grid
-    int fn, fnCp, fW, fell, fnOwn;
-    const int *fcf, *fcn, *frs;
-    const double *fdiag, *fupper, *frsum, *fx, *fb;
-    double* fxw;
     // matching work
     int *match, *prop, *root;
     const double* fw;  // face weights
@@ -109,32 +104,17 @@ HD void b_fill_ev(const LV& L, int c) {
     const size_t str = L.ell ? (size_t)L.nCp : 1;
     for (int k = 0; k < cnt; k++) {
         int e = L.cf[base + k * str], o = L.cn[base + k * str];
-        double u = (e >= 0 && o >= 0) ? L.upper[e >> 1] : 0.0;
-        L.ev[base + k * str] = o < L.nOwn ? u : 0.0;
-        if (L.ev2) L.ev2[base + k * str] = u;
+        L.ev[base + k * str] = (e >= 0 && o >= 0 && o < L.nOwn) ? L.upper[e >> 1] : 0.0;
     }
 }
-HD void b_spmv(const LV& L, int c) { L.out[c] = row_Ax(L, c, L.in); }
-// out = in + omega*(b - A in)/diag   (damped Jacobi, in != out)
-HD void b_jacobi(const LV& L, int c) { L.out[c] = L.in[c] + L.omega * (L.b[c] - row_Ax(L, c, L.in)) / L.diag[c]; }
-// first sweep from a zero guess: out = omega*b/diag
+// first sweep from a zero guess: out = omega*b/diag  (also the diagonal preconditioner)
 HD void b_jacobi0(const LV& L, int c) { L.out[c] = L.omega * L.b[c] / L.diag[c]; }
-// rsum = diag - sum upper  (what is left of the row after the Laplacian part: boundary terms)
+// rsum = diag - sum upper  (what is left of the row after the Laplacian part: boundary terms);
+// couplings to ghost rows are part of the row
 HD void b_rowsum(const LV& L, int c) {
     double s = 0;
     FOR_ROW(L, c) s += L.upper[f]; END_ROW
     L.rsum[c] = L.diag[c] - s;
-    if (L.rsum2) {  // full row, ghost couplings included
-        double s2 = 0;
-        const int cnt = L.ell ? L.W : L.rs[c + 1] - L.rs[c];
-        const size_t base = L.ell ? (size_t)c : (size_t)L.rs[c];
-        const size_t str = L.ell ? (size_t)L.nCp : 1;
-        for (int k = 0; k < cnt; k++) {
-            int e = L.cf[base + k * str], o = L.cn[base + k * str];
-            if (e >= 0 && o >= 0) s2 += L.upper[e >> 1];
-        }
-        L.rsum2[c] = L.diag[c] - s2;
-    }
 }
 // Galerkin: coarse face coefficient = sum of the fine faces in its segment (fixed order)
 HD void b_coarse_upper(const LV& L, int F) {
@@ -151,41 +131,6 @@ HD void b_coarse_diag(const LV& L, int I) {
     FOR_ROW(L, I) s += L.upper[f]; END_ROW
     L.diag[I] = r + s;
 }
-// fine residual out = b - A in  (runs over the rows of L)
-HD void b_residual(const LV& L, int c) { L.out[c] = L.b[c] - row_Ax(L, c, L.in); }
-// restriction: b_c[I] = sum of the fine residual over the members of I (fixed order)
-HD void b_restrict_sum(const LV& L, int I) {
-    double r = 0;
-    for (int k = L.aggStart[I]; k < L.aggStart[I + 1]; k++) r += L.in[L.aggRows[k]];
-    L.b[I] = r;
-}
-// row i of A applied to the prolonged coarse correction c = x_c[agg]  (L = coarse level with
-// its fine view): returns (A c)_i
-HD double fine_row_Ac(const LV& L, int i) {
-    double s = L.fdiag[i] * L.x[L.agg[i]];
-    if (L.fell) {
-        for (int k = 0; k < L.fW; k++) {
-            int o = L.fcn[(size_t)k * L.fnCp + i];
-            if (o >= 0 && o < L.fnOwn) s -= L.fev[(size_t)k * L.fnCp + i] * L.x[L.agg[o]];
-        }
-    } else
-        for (int k = L.frs[i]; k < L.frs[i + 1]; k++) {
-            int o = L.fcn[k];
-            if (o >= 0 && o < L.fnOwn) s -= L.fev[k] * L.x[L.agg[o]];
-        }
-    return s;
-}
-// GAMGSolver::scale: x += sf*c + (r - sf*A c)/diag with sf = (r.c)/(c.Ac) read from the device
-// scalars in2[0], in2[1]; in = r, out = A c (runs over fine rows; L = coarse level)
-HD void b_scale_apply(const LV& L, int i) {
-    double den = L.in2[1];
-    double sf = L.in2[0] / (fabs(den) < VSMALL ? (den >= 0 ? VSMALL : -VSMALL) : den);
-    double c = L.x[L.agg[i]];
-    L.fxw[i] += sf * c + L.omega * (L.in[i] - sf * L.out[i]) / L.fdiag[i];
-}
-// prolongation: fine x += coarse x[agg]   (runs over fine rows; L = coarse level)
-HD void b_prolong_add(const LV& L, int i) { L.fxw[i] += L.x[L.agg[i]]; }
-
 // ---- pairwise matching (handshake) on face weights --------------------------------------------
 // Exact weight ties are the rule on extruded meshes; breaking them by cell index makes the
 // handshake degenerate into chains (one pair per round).  A symmetric hash of the edge gives
@@ -232,17 +177,11 @@ HD void b_match_root(const LV& L, int c) {
     else { int bm = L.match[best]; L.root[c] = best < bm ? best : bm; }
 }
 
-DEF_KERNEL(spmv, LV)
 DEF_KERNEL(fill_ev, LV)
-DEF_KERNEL(jacobi, LV)
 DEF_KERNEL(jacobi0, LV)
 DEF_KERNEL(rowsum, LV)
 DEF_KERNEL(coarse_upper, LV)
 DEF_KERNEL(coarse_diag, LV)
-DEF_KERNEL(residual, LV)
-DEF_KERNEL(restrict_sum, LV)
-DEF_KERNEL(scale_apply, LV)
-DEF_KERNEL(prolong_add, LV)
 DEF_KERNEL(match_propose, LV)
 DEF_KERNEL(match_accept, LV)
 DEF_KERNEL(match_root, LV)
@@ -298,6 +237,14 @@ __global__ void __launch_bounds__(256) k_reduce_final(const double* partial, int
     v = mode == 3 ? block_max(v) : block_sum(v);
     if (threadIdx.x == 0) *out = v;
 }
+// two final reductions (sums) in one launch: CTA 0 -> out0, CTA 1 -> out1
+__global__ void __launch_bounds__(256) k_reduce_final2(const double* p0, const double* p1, int np, double* out0, double* out1) {
+    const double* partial = blockIdx.x == 0 ? p0 : p1;
+    double v = 0;
+    for (int i = threadIdx.x; i < np; i += blockDim.x) v += partial[i];
+    v = block_sum(v);
+    if (threadIdx.x == 0) *(blockIdx.x == 0 ? out0 : out1) = v;
+}
 // wA = A pA fused with partial sums of wA.pA
 __global__ void __launch_bounds__(256) k_spmv_dot(LV L, double* partial) {
     double v = 0;
@@ -346,125 +293,8 @@ __global__ void __launch_bounds__(256) k_init_residual(LV L, const double* x, co
     w = block_sum(w);
     if (threadIdx.x == 0) { partialRes[blockIdx.x] = v; partialNorm[blockIdx.x] = w; }
 }
-// A c for the prolonged coarse correction fused with the partial sums of r.c and c.Ac
-__global__ void __launch_bounds__(256) k_corr_dots(LV L, int nFine, const double* r, double* Ac, double* partialNum, double* partialDen) {
-    double v = 0, w = 0;
-    for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < nFine; i += gridDim.x * blockDim.x) {
-        double c = L.x[L.agg[i]];
-        double a = fine_row_Ac(L, i);
-        Ac[i] = a;
-        v += r[i] * c;
-        w += a * c;
-    }
-    v = block_sum(v);
-    __syncthreads();
-    w = block_sum(w);
-    if (threadIdx.x == 0) { partialNum[blockIdx.x] = v; partialDen[blockIdx.x] = w; }
-}
-// ---- coarse (CSR) levels: COOP lanes per row, fixed-order shuffle reduction ---------------------
-// A thread per row is latency-bound on the coarse levels (rows of 10-30 entries, few rows);
-// eight lanes per row walk the row together.
-// COOP lanes per row (4 for short rows, 8 otherwise), chosen per level from the mean row length.
-template <int COOP>
-DEV double coop_offdiag(const LV& L, int c, const double* x, int lane) {
-    double s = 0;
-    const int b = L.rs[c], e = L.rs[c + 1];
-    for (int k = b + lane; k < e; k += COOP) {
-        int o = L.cn[k];
-        if (o >= 0) s += L.ev[k] * x[o];
-    }
-#pragma unroll
-    for (int off = COOP / 2; off > 0; off >>= 1) s += __shfl_xor_sync(0xffffffffu, s, off);
-    return s;
-}
-// mode 0: out = in + omega (b - A in)/diag ; 1: out = b - A in ; 2: out = A in
-template <int COOP>
-__global__ void __launch_bounds__(256) k_csr_row_op(const LV L, int mode) {
-    int gid = blockIdx.x * blockDim.x + threadIdx.x;
-    int c = gid / COOP, lane = gid % COOP;
-    bool live = c < L.n;
-    int cc = live ? c : L.n - 1;
-    double off = coop_offdiag<COOP>(L, cc, L.in, lane);
-    if (live && lane == 0) {
-        double ax = L.diag[c] * L.in[c] - off;
-        if (mode == 0) L.out[c] = L.in[c] + L.omega * (L.b[c] - ax) / L.diag[c];
-        else if (mode == 1) L.out[c] = L.b[c] - ax;
-        else L.out[c] = ax;
-    }
-}
-// A c for the prolonged correction on a CSR fine level (L = coarse level with fine view), COOP lanes
-template <int COOP>
-__global__ void __launch_bounds__(256) k_corr_dots_csr(LV L, int nFine, const double* r, double* Ac, double* partialNum, double* partialDen) {
-    double v = 0, w = 0;
-    const int lane = threadIdx.x % COOP;
-    const int sub = (threadIdx.x % 32) / COOP;  // row within the warp
-    const int rowsPerWarp = 32 / COOP;
-    const int warpId = (blockIdx.x * blockDim.x + threadIdx.x) / 32;
-    const int nWarps = gridDim.x * blockDim.x / 32;
-    // warp-uniform loop: every lane of a warp runs the same number of trips (shuffles inside)
-    for (int base = warpId * rowsPerWarp; base < nFine; base += nWarps * rowsPerWarp) {
-        int i0 = base + sub;
-        bool live = i0 < nFine;
-        int i = live ? i0 : nFine - 1;
-        double s = 0;
-        const int b = L.frs[i], e = L.frs[i + 1];
-        for (int k = b + lane; k < e; k += COOP) {
-            int o = L.fcn[k];
-            if (o >= 0 && o < L.fnOwn) s += L.fev[k] * L.x[L.agg[o]];
-        }
-#pragma unroll
-        for (int off = COOP / 2; off > 0; off >>= 1) s += __shfl_xor_sync(0xffffffffu, s, off);
-        if (live && lane == 0) {
-            double c = L.x[L.agg[i]];
-            double a = L.fdiag[i] * c - s;
-            Ac[i] = a;
-            v += r[i] * c;
-            w += a * c;
-        }
-    }
-    v = block_sum(v);
-    __syncthreads();
-    w = block_sum(w);
-    if (threadIdx.x == 0) { partialNum[blockIdx.x] = v; partialDen[blockIdx.x] = w; }
-}
 __global__ void k_scal_copy(double* scal, int dst, int src) { scal[dst] = scal[src]; }
 
-// Jacobi-preconditioned CG on the coarsest level, one CTA (n is a few thousand at most).
-__global__ void __launch_bounds__(1024) k_coarse_cg(LV L, int maxIter, double relTol) {
-    __shared__ double red[1024];
-    __shared__ double s_rz, s_pAp, s_rz0;
-    const int n = L.n, t = threadIdx.x, T = blockDim.x;
-    double* x = L.x; const double* b = L.b; double *r = L.t0, *p = L.t1, *Ap = L.out;
-    auto bsum = [&](double v) {
-        red[t] = v;
-        __syncthreads();
-        for (int s = T / 2; s > 0; s >>= 1) { if (t < s) red[t] += red[t + s]; __syncthreads(); }
-        double o = red[0];
-        __syncthreads();
-        return o;
-    };
-    double loc = 0;
-    for (int i = t; i < n; i += T) { x[i] = 0; r[i] = b[i]; double z = b[i] / L.diag[i]; p[i] = z; loc += b[i] * z; }
-    double rz = bsum(loc);
-    if (t == 0) { s_rz = rz; s_rz0 = rz; }
-    __syncthreads();
-    if (rz <= 0) return;
-    for (int it = 0; it < maxIter; it++) {
-        loc = 0;
-        for (int i = t; i < n; i += T) { double y = row_Ax(L, i, p); Ap[i] = y; loc += y * p[i]; }
-        double pAp = bsum(loc);
-        double alpha = s_rz / pAp;
-        loc = 0;
-        for (int i = t; i < n; i += T) { x[i] += alpha * p[i]; double rr = r[i] - alpha * Ap[i]; r[i] = rr; loc += rr * rr / L.diag[i]; }
-        double rzn = bsum(loc);
-        if (rzn <= relTol * relTol * s_rz0) break;
-        double beta = rzn / s_rz;
-        __syncthreads();
-        if (t == 0) s_rz = rzn;
-        for (int i = t; i < n; i += T) p[i] = r[i] / L.diag[i] + beta * p[i];
-        __syncthreads();
-    }
-}
 #endif
 
 struct Reducer {

@@ -1,10 +1,18 @@
 // The multigrid V-cycle used as the PCG preconditioner, templated on the value type R.
 //
-// The cycle is pure HBM traffic (Jacobi sweeps, residuals, transfers) and is applied ~40 times
+// The cycle is pure HBM traffic (Jacobi sweeps, residuals, transfers) and is applied ~30 times
 // per time step, so it runs in FP32 by default: the outer PCG (operator, dot products,
 // residual norms, convergence test) stays FP64 and reaches the same tolerance; the
 // preconditioner only has to be a good approximate inverse.  R = double is kept (TPP_FP32=0).
 // Sums inside a row are accumulated in R, global reductions (the scaling factor) in double.
+//
+// Two regimes:
+//   * large levels (bandwidth-bound): one kernel per operation (vk_*), rows distributed over
+//     the ranks with one halo exchange per operator application;
+//   * the tail (every level below TPP_TAIL_ROWS rows, gathered onto every rank): these levels
+//     live in L2 and are launch/latency-bound, so the whole sub-cycle - smoothing, residual,
+//     restriction, coarsest-level CG, prolongation, correction scaling - is ONE persistent
+//     cooperative kernel (vk_tail) with grid barriers between the phases.
 #pragma once
 #include "tpp_linsolve.h"
 
@@ -14,7 +22,7 @@ template <class R>
 struct VL {
     int n, nf, nCp, W, ell, nOwn;
     const int *cn, *rs;  // adjacency: other row (ELL slot-major / CSR), CSR row starts
-    const R *diag, *ev;  // matrix values (ev: off-diagonal magnitude per adjacency entry, 0 towards ghosts)
+    const R *diag, *ev;  // matrix values (ev: off-diagonal magnitude per adjacency entry)
     // transfer (set on the level being restricted to / prolonged from)
     const int *agg, *aggStart, *aggRows;
     // kernel arguments
@@ -74,6 +82,9 @@ template <class R> HD void vb_scale_apply(const VL<R>& L, int i) {
 template <class R> struct CastArgs { const double* src; R* dst; const R* rsrc; double* ddst; };
 template <class R> HD void vb_cast_in(const CastArgs<R>& a, int i) { a.dst[i] = (R)a.src[i]; }
 template <class R> HD void vb_cast_out(const CastArgs<R>& a, int i) { a.ddst[i] = (double)a.rsrc[i]; }
+// halo send buffer of a level: the owned row behind every processor face, in ghost order
+template <class R> struct PackArgs { const int* owner; const R* src; R* dst; };
+template <class R> HD void vb_pack(const PackArgs<R>& a, int j) { a.dst[j] = a.src[a.owner[j]]; }
 
 #ifdef TPP_EMU
 #define DEF_VKERNEL(name, VIEW) \
@@ -96,8 +107,212 @@ DEF_VKERNEL(prolong, VL)
 DEF_VKERNEL(scale_apply, VL)
 DEF_VKERNEL(cast_in, CastArgs)
 DEF_VKERNEL(cast_out, CastArgs)
+DEF_VKERNEL(pack, PackArgs)
+
+// ---- the tail: all small levels in one persistent kernel ---------------------------------------
+constexpr int TAIL_MAXLV = 12;
+constexpr int TAIL_THREADS = 1024;
+template <class R>
+struct TLv {
+    int n, coop;                    // rows; lanes that walk one row together (4, 8 or 16)
+    const int *rs, *cn;             // CSR (global numbering: the tail has no ghost rows)
+    const R *ev, *diag;
+    const int* agg;                 // [n] row of the next (coarser) tail level; unused on the last
+    const int *aggStart, *aggRows;  // members (rows of the previous tail level) of each row; unused on level 0
+    R *x, *y, *b, *r;               // work vectors [n]; level 0: b = input, x = output
+};
+template <class R>
+struct TailArgs {
+    int T;  // tail levels
+    TLv<R> lv[TAIL_MAXLV];
+    unsigned* bar;    // grid-barrier counter, zeroed before every launch
+    int* err;         // set if a barrier timed out (never in a healthy launch)
+    double* partial;  // [2 * gridDim.x] block partials of the scaling dots
+    R omega, scaleJ;
+    int nPre, nPost, cgIter;
+    double cgTol;
+    R *cgR, *cgP, *cgAp;  // coarsest-level CG scratch
+};
+// the buffer (x or y) that holds a level's iterate after `swaps` Jacobi sweeps when the final
+// iterate has to land in x
+template <class R> HD R* tail_start(const TLv<R>& L, int swaps) { return (swaps & 1) ? L.y : L.x; }
 
 #ifndef TPP_EMU
+struct GridBar {
+    unsigned* ctr;
+    unsigned nb, gen;
+    int* err;
+};
+// all CTAs of the (cooperatively launched, hence co-resident) grid; bounded spin
+DEV void gsync(GridBar& g) {
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        g.gen += g.nb;
+        __threadfence();
+        atomicAdd(g.ctr, 1u);
+        unsigned v;
+        long spins = 0;
+        do {
+            asm volatile("ld.acquire.gpu.u32 %0, [%1];" : "=r"(v) : "l"(g.ctr) : "memory");
+            if (v >= g.gen) break;
+            if ((++spins & 1023) == 0 && (*(volatile int*)g.err != 0 || spins > (1L << 24))) { *(volatile int*)g.err = 1; break; }
+        } while (true);
+        __threadfence();
+    }
+    __syncthreads();
+}
+// sum_k ev[k] * x[col(k)] over a row walked by `coop` lanes; col = cn[k] or, through the
+// aggregate map, map[cn[k]] (a prolonged coarse vector, never stored)
+template <class R>
+DEV R tail_row(const TLv<R>& L, int row, const R* x, const int* map, int lane, int coop) {
+    R s = 0;
+    const int e = L.rs[row + 1];
+    for (int k = L.rs[row] + lane; k < e; k += coop) {
+        int o = L.cn[k];
+        s += L.ev[k] * x[map ? map[o] : o];
+    }
+    for (int off = coop >> 1; off > 0; off >>= 1) s += __shfl_xor_sync(0xffffffffu, s, off);
+    return s;
+}
+DEV double tail_block_sum(double v, double* sh) {  // blockDim = TAIL_THREADS; result in every thread
+    for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+    __syncthreads();
+    if ((threadIdx.x & 31) == 0) sh[threadIdx.x >> 5] = v;
+    __syncthreads();
+    double s = 0;
+    for (int k = 0; k < TAIL_THREADS / 32; k++) s += sh[k];  // the same 32 values in the same order everywhere
+    return s;
+}
+// Jacobi-preconditioned CG on the coarsest tail level by ONE CTA (zero initial guess)
+template <class R>
+DEV void tail_coarse_cg(const TLv<R>& L, R* r, R* p, R* Ap, int maxIter, double relTol, double* sh) {
+    const int n = L.n, t = threadIdx.x, T = blockDim.x;
+    R* x = L.x;
+    const R* b = L.b;
+    double loc = 0;
+    for (int i = t; i < n; i += T) { x[i] = 0; r[i] = b[i]; R z = b[i] / L.diag[i]; p[i] = z; loc += (double)b[i] * (double)z; }
+    double rz = tail_block_sum(loc, sh);
+    const double rz0 = rz;
+    if (!(rz > 0)) return;
+    for (int it = 0; it < maxIter; it++) {
+        loc = 0;
+        __syncthreads();
+        for (int i = t; i < n; i += T) {
+            R s = 0;
+            for (int k = L.rs[i]; k < L.rs[i + 1]; k++) s += L.ev[k] * p[L.cn[k]];
+            R y = L.diag[i] * p[i] - s;
+            Ap[i] = y;
+            loc += (double)y * (double)p[i];
+        }
+        double pAp = tail_block_sum(loc, sh);
+        R alpha = (R)(rz / pAp);
+        loc = 0;
+        for (int i = t; i < n; i += T) { x[i] += alpha * p[i]; R rr = r[i] - alpha * Ap[i]; r[i] = rr; loc += (double)rr * (double)rr / (double)L.diag[i]; }
+        double rzn = tail_block_sum(loc, sh);
+        if (rzn <= relTol * relTol * rz0) break;
+        R beta = (R)(rzn / rz);
+        rz = rzn;
+        for (int i = t; i < n; i += T) p[i] = r[i] / L.diag[i] + beta * p[i];
+    }
+}
+// The V-cycle over the tail levels lv[0..T-1]: lv[0].b -> lv[0].x.  Same cycle as the
+// per-kernel levels (damped Jacobi from a zero guess, residual, restriction; coarsest CG;
+// prolongation with GAMG's energy-minimising correction scaling, post-smoothing).
+template <class R>
+__global__ void __launch_bounds__(TAIL_THREADS, 1) vk_tail(const TailArgs<R> A) {
+    __shared__ double sh[TAIL_THREADS / 32];
+    __shared__ double s_sf[2];
+    GridBar gb{A.bar, gridDim.x, 0u, A.err};
+    const int tid = blockIdx.x * blockDim.x + threadIdx.x, nth = gridDim.x * blockDim.x;
+    const int swaps = (A.nPre > 1 ? A.nPre - 1 : 0) + (A.nPost > 1 ? A.nPost : 1);
+    for (int t = 0; t < A.T - 1; t++) {
+        const TLv<R>& L = A.lv[t];
+        const int coop = L.coop, lane = tid % coop, rpp = nth / coop;
+        R* cur = tail_start(L, swaps);
+        R* oth = cur == L.x ? L.y : L.x;
+        for (int i = tid; i < L.n; i += nth) cur[i] = A.omega * L.b[i] / L.diag[i];
+        gsync(gb);
+        for (int s = 1; s < A.nPre; s++) {
+            for (int base = 0; base < L.n; base += rpp) {
+                int row = base + tid / coop;
+                bool live = row < L.n;
+                int rr = live ? row : L.n - 1;
+                R off = tail_row(L, rr, cur, (const int*)nullptr, lane, coop);
+                if (live && lane == 0) oth[rr] = cur[rr] + A.omega * (L.b[rr] - (L.diag[rr] * cur[rr] - off)) / L.diag[rr];
+            }
+            R* tmp = cur; cur = oth; oth = tmp;
+            gsync(gb);
+        }
+        for (int base = 0; base < L.n; base += rpp) {
+            int row = base + tid / coop;
+            bool live = row < L.n;
+            int rr = live ? row : L.n - 1;
+            R off = tail_row(L, rr, cur, (const int*)nullptr, lane, coop);
+            if (live && lane == 0) L.r[rr] = L.b[rr] - (L.diag[rr] * cur[rr] - off);
+        }
+        gsync(gb);
+        const TLv<R>& C = A.lv[t + 1];
+        for (int I = tid; I < C.n; I += nth) {
+            R s = 0;
+            for (int k = C.aggStart[I]; k < C.aggStart[I + 1]; k++) s += L.r[C.aggRows[k]];
+            C.b[I] = s;
+        }
+        gsync(gb);
+    }
+    if (blockIdx.x == 0) tail_coarse_cg(A.lv[A.T - 1], A.cgR, A.cgP, A.cgAp, A.cgIter, A.cgTol, sh);
+    gsync(gb);
+    for (int t = A.T - 2; t >= 0; t--) {
+        const TLv<R>& L = A.lv[t];
+        const R* xc = A.lv[t + 1].x;
+        const int coop = L.coop, lane = tid % coop, rpp = nth / coop;
+        R* cur = tail_start(L, swaps);
+        R* oth = cur == L.x ? L.y : L.x;
+        if ((A.nPre > 1 ? A.nPre - 1 : 0) & 1) { R* tmp = cur; cur = oth; oth = tmp; }
+        // A c for the prolonged correction c = xc[agg], with the dots r.c and c.Ac
+        double v = 0, w = 0;
+        for (int base = 0; base < L.n; base += rpp) {
+            int row = base + tid / coop;
+            bool live = row < L.n;
+            int rr = live ? row : L.n - 1;
+            R off = tail_row(L, rr, xc, L.agg, lane, coop);
+            if (live && lane == 0) {
+                R c = xc[L.agg[rr]];
+                R ac = L.diag[rr] * c - off;
+                oth[rr] = ac;
+                v += (double)L.r[rr] * (double)c;
+                w += (double)ac * (double)c;
+            }
+        }
+        v = tail_block_sum(v, sh);
+        w = tail_block_sum(w, sh);
+        if (threadIdx.x == 0) { A.partial[blockIdx.x] = v; A.partial[gridDim.x + blockIdx.x] = w; }
+        gsync(gb);
+        if (threadIdx.x < 32) {  // every CTA sums the partials in the same order
+            double a = 0, b = 0;
+            for (int k = threadIdx.x; k < (int)gridDim.x; k += 32) { a += A.partial[k]; b += A.partial[gridDim.x + k]; }
+            for (int o = 16; o > 0; o >>= 1) { a += __shfl_xor_sync(0xffffffffu, a, o); b += __shfl_xor_sync(0xffffffffu, b, o); }
+            if (threadIdx.x == 0) { s_sf[0] = a; s_sf[1] = b; }
+        }
+        __syncthreads();
+        const double den = s_sf[1];
+        const R sf = (R)(s_sf[0] / (fabs(den) < VSMALL ? (den >= 0 ? VSMALL : -VSMALL) : den));
+        for (int i = tid; i < L.n; i += nth) cur[i] += sf * xc[L.agg[i]] + A.scaleJ * (L.r[i] - sf * oth[i]) / L.diag[i];
+        gsync(gb);
+        const int nPost = A.nPost > 1 ? A.nPost : 1;
+        for (int s = 0; s < nPost; s++) {
+            for (int base = 0; base < L.n; base += rpp) {
+                int row = base + tid / coop;
+                bool live = row < L.n;
+                int rr = live ? row : L.n - 1;
+                R off = tail_row(L, rr, cur, (const int*)nullptr, lane, coop);
+                if (live && lane == 0) oth[rr] = cur[rr] + A.omega * (L.b[rr] - (L.diag[rr] * cur[rr] - off)) / L.diag[rr];
+            }
+            R* tmp = cur; cur = oth; oth = tmp;
+            if (s + 1 < nPost || t > 0) gsync(gb);
+        }
+    }
+}
+
 // ---- CSR levels: COOP lanes per row ---------------------------------------------------------
 template <class R, int COOP>
 DEV R vl_coop_off(const VL<R>& L, int c, const R* x, int lane) {
@@ -167,8 +382,8 @@ __global__ void __launch_bounds__(256) vk_csr_spmv_dot2(const VL<R> L, double* p
     w = block_sum(w);
     if (threadIdx.x == 0) { partialNum[blockIdx.x] = v; partialDen[blockIdx.x] = w; }
 }
-// Jacobi-preconditioned CG on the coarsest level, one CTA; vectors in R, reductions in double.
-// out = x, b = rhs; scratch: r -> (R*)L.r, p -> (R*)L.c, Ap -> (R*)L.Ac (writable aliases)
+// Jacobi-preconditioned CG on a whole (tiny) mesh without any coarse level, one CTA; vectors
+// in R, reductions in double.  out = x, b = rhs
 template <class R>
 __global__ void __launch_bounds__(1024) vk_coarse_cg(const VL<R> L, R* r, R* p, R* Ap, int maxIter, double relTol) {
     __shared__ double red[32];
@@ -205,6 +420,76 @@ __global__ void __launch_bounds__(1024) vk_coarse_cg(const VL<R> L, R* r, R* p, 
         if (t == 0) s_rz = rzn;
         for (int i = t; i < n; i += T) p[i] = r[i] / L.diag[i] + beta * p[i];
         __syncthreads();
+    }
+}
+#else
+// ---- host emulation of the tail (tests of the launch logic only) --------------------------------
+template <class R>
+inline void tail_host(const TailArgs<R>& A) {
+    const int swaps = (A.nPre > 1 ? A.nPre - 1 : 0) + (A.nPost > 1 ? A.nPost : 1);
+    auto off = [](const TLv<R>& L, int row, const R* x, const int* map) {
+        R s = 0;
+        for (int k = L.rs[row]; k < L.rs[row + 1]; k++) { int o = L.cn[k]; s += L.ev[k] * x[map ? map[o] : o]; }
+        return s;
+    };
+    for (int t = 0; t < A.T - 1; t++) {
+        const TLv<R>& L = A.lv[t];
+        R* cur = tail_start(L, swaps);
+        R* oth = cur == L.x ? L.y : L.x;
+        for (int i = 0; i < L.n; i++) cur[i] = A.omega * L.b[i] / L.diag[i];
+        for (int s = 1; s < A.nPre; s++) {
+            for (int i = 0; i < L.n; i++) oth[i] = cur[i] + A.omega * (L.b[i] - (L.diag[i] * cur[i] - off(L, i, cur, nullptr))) / L.diag[i];
+            std::swap(cur, oth);
+        }
+        for (int i = 0; i < L.n; i++) L.r[i] = L.b[i] - (L.diag[i] * cur[i] - off(L, i, cur, nullptr));
+        const TLv<R>& C = A.lv[t + 1];
+        for (int I = 0; I < C.n; I++) {
+            R s = 0;
+            for (int k = C.aggStart[I]; k < C.aggStart[I + 1]; k++) s += L.r[C.aggRows[k]];
+            C.b[I] = s;
+        }
+    }
+    {
+        const TLv<R>& L = A.lv[A.T - 1];
+        const int n = L.n;
+        R *x = L.x, *r = A.cgR, *p = A.cgP, *Ap = A.cgAp;
+        double rz = 0;
+        for (int i = 0; i < n; i++) { x[i] = 0; r[i] = L.b[i]; p[i] = L.b[i] / L.diag[i]; rz += (double)L.b[i] * (double)p[i]; }
+        const double rz0 = rz;
+        if (rz > 0)
+            for (int it = 0; it < A.cgIter; it++) {
+                double pAp = 0;
+                for (int i = 0; i < n; i++) { Ap[i] = L.diag[i] * p[i] - off(L, i, p, nullptr); pAp += (double)Ap[i] * (double)p[i]; }
+                R alpha = (R)(rz / pAp);
+                double rzn = 0;
+                for (int i = 0; i < n; i++) { x[i] += alpha * p[i]; r[i] -= alpha * Ap[i]; rzn += (double)r[i] * (double)r[i] / (double)L.diag[i]; }
+                if (rzn <= A.cgTol * A.cgTol * rz0) break;
+                R beta = (R)(rzn / rz);
+                rz = rzn;
+                for (int i = 0; i < n; i++) p[i] = r[i] / L.diag[i] + beta * p[i];
+            }
+    }
+    for (int t = A.T - 2; t >= 0; t--) {
+        const TLv<R>& L = A.lv[t];
+        const R* xc = A.lv[t + 1].x;
+        R* cur = tail_start(L, swaps);
+        R* oth = cur == L.x ? L.y : L.x;
+        if ((A.nPre > 1 ? A.nPre - 1 : 0) & 1) std::swap(cur, oth);
+        double v = 0, w = 0;
+        for (int i = 0; i < L.n; i++) {
+            R c = xc[L.agg[i]];
+            R ac = L.diag[i] * c - off(L, i, xc, L.agg);
+            oth[i] = ac;
+            v += (double)L.r[i] * (double)c;
+            w += (double)ac * (double)c;
+        }
+        const R sf = (R)(v / (std::fabs(w) < VSMALL ? (w >= 0 ? VSMALL : -VSMALL) : w));
+        for (int i = 0; i < L.n; i++) cur[i] += sf * xc[L.agg[i]] + A.scaleJ * (L.r[i] - sf * oth[i]) / L.diag[i];
+        const int nPost = A.nPost > 1 ? A.nPost : 1;
+        for (int s = 0; s < nPost; s++) {
+            for (int i = 0; i < L.n; i++) oth[i] = cur[i] + A.omega * (L.b[i] - (L.diag[i] * cur[i] - off(L, i, cur, nullptr))) / L.diag[i];
+            std::swap(cur, oth);
+        }
     }
 }
 #endif

@@ -9,6 +9,7 @@
 #include "tpp_linsolve.h"
 #include "tpp_vcycle.h"
 
+#include <array>
 #include <map>
 #include <tuple>
 #ifndef TPP_EMU
@@ -23,15 +24,17 @@ namespace {
 std::string g_err;
 
 struct Level {
-    int n = 0, nf = 0;
+    int n = 0, nf = 0, nfLoc = 0, nG = 0, nnz = 0;  // rows, faces (local + processor), ghost rows, CSR entries
+    double nGlob = 0;
+    // halo patches of this level (offset / count in ghost order, neighbour rank)
+    std::vector<int> poff, pcnt, ppeer;
     // device
-    int *cf = nullptr, *cn = nullptr, *rs = nullptr, *own = nullptr, *nei = nullptr;
+    int *cf = nullptr, *cn = nullptr, *rs = nullptr, *own = nullptr, *nei = nullptr, *dOwner = nullptr;
     int *agg = nullptr, *aggStart = nullptr, *aggRows = nullptr, *segStart = nullptr, *segFaces = nullptr;
-    double *ev = nullptr;
-    double *diag = nullptr, *upper = nullptr, *rsum = nullptr, *x = nullptr, *b = nullptr, *t0 = nullptr, *t1 = nullptr, *t2 = nullptr;
+    double *ev = nullptr, *diag = nullptr, *upper = nullptr, *rsum = nullptr;
     void free() {
-        for (void* p : {(void*)cf, (void*)cn, (void*)rs, (void*)own, (void*)nei, (void*)agg, (void*)aggStart, (void*)aggRows, (void*)segStart, (void*)segFaces,
-                        (void*)ev, (void*)diag, (void*)upper, (void*)rsum, (void*)x, (void*)b, (void*)t0, (void*)t1, (void*)t2})
+        for (void* p : {(void*)cf, (void*)cn, (void*)rs, (void*)own, (void*)nei, (void*)dOwner, (void*)agg, (void*)aggStart, (void*)aggRows, (void*)segStart, (void*)segFaces,
+                        (void*)ev, (void*)diag, (void*)upper, (void*)rsum})
             dev_free(p);
     }
 };
@@ -90,8 +93,14 @@ struct tpp_solver {
     double* hscal = nullptr;      // pinned host mirror
     Reducer red;
     // multigrid
-    std::vector<Level> levels;  // coarse levels (level 0 = first coarse)
-    double *kr = nullptr, *kz = nullptr, *kp = nullptr, *kw = nullptr, *kt = nullptr, *kt2 = nullptr, *kt3 = nullptr, *fineEv = nullptr, *fineEvFull = nullptr, *fineRsumFull = nullptr, *fineRsum = nullptr, *fw0 = nullptr;
+    std::vector<Level> levels;  // distributed coarse levels (levels[0] = first coarse); the last one is gathered
+    std::vector<Level> tail;    // tail[0] = levels[gatherLevel] over all ranks, then the replicated coarser levels
+    int gatherLevel = -1, tailRowOff = 0, tailFaceOff = 0, tailGrid = 1;
+    std::vector<std::array<int, 3>> tailCopy;  // processor-face coefficient ranges (src face, count, dst face) of the gather
+    unsigned* tailBar = nullptr;
+    int* tailErr = nullptr;
+    double* tailPartial = nullptr;
+    double *kr = nullptr, *kz = nullptr, *kp = nullptr, *kw = nullptr, *fineEv = nullptr, *fineRsum = nullptr;
     int *match = nullptr, *prop = nullptr, *root = nullptr;
     bool amgBuilt = false;
     struct GraphKey {
@@ -373,7 +382,7 @@ struct tpp_solver {
         d.phiHbyA = AD("phiHbyA", nF); d.phig = AD("phig", nF); d.pUpper = AD("pUpper", nI); d.pCorrFlux = AD("pCorrFlux", nI);
         d.pDiag = AD("pDiag", nC); d.pSource = AD("pSource", nC); d.rec = AD("rec", nF);
         d.cellTmp = A<double>(2 * (size_t)nC);
-        kr = A<double>(nC); kz = A<double>(nC); kp = A<double>(nC); kw = A<double>(nC); kt = A<double>(nC); kt2 = A<double>(nC); kt3 = A<double>(nC); fineEv = A<double>((size_t)W * nCp); fineEvFull = A<double>((size_t)W * nCp); fineRsumFull = A<double>(nC);
+        kr = A<double>(nC); kz = A<double>(nC); kp = A<double>(nC); kw = A<double>(nC); fineEv = A<double>((size_t)W * nCp);
         sendbuf = A<double>(9 * (size_t)std::max(nG, 1)); dProcOwner = upload(procOwner); d.procOwner = dProcOwner; nGlobal = nC; fineRsum = A<double>(nC);
         scal = A<double>(S_COUNT);
 #ifdef TPP_EMU
@@ -707,36 +716,107 @@ struct tpp_solver {
     }
 
     // ---- multigrid hierarchy (cached: the mesh only moves rigidly) ------------------------------
+    // Levels: 0 = the mesh (ELL), levels[l] = hierarchy level l + 1 (CSR).  levels[0..gatherLevel)
+    // are smoothed where they live (rows distributed over the ranks, halo exchange per operator
+    // application); levels[gatherLevel] is assembled distributed, then gathered onto every rank
+    // as tail[0]; tail[1..] continue the coarsening on the gathered graph (replicated).
     LV fineView(double* diag, double* upper) {
         LV L;
         memset(&L, 0, sizeof(L));
         L.n = nC; L.nf = nI; L.nCp = nCp; L.W = W; L.ell = 1;
         L.cf = d.cf; L.cn = d.cn; L.own = d.own; L.nei = d.nei;
         L.diag = diag; L.upper = upper; L.rsum = fineRsum; L.ev = fineEv;
-        L.nOwn = nC; L.nGlob = (double)nGlobal;
-        if (nG > 0) { L.ev2 = fineEvFull; L.rsum2 = fineRsumFull; }
+        L.nOwn = nC + nG; L.nGlob = (double)nGlobal;
         return L;
     }
-    LV levelView(int l) {
-        Level& v = levels[l];
+    static LV viewOf(Level& v) {
         LV L;
         memset(&L, 0, sizeof(L));
         L.n = v.n; L.nf = v.nf; L.ell = 0; L.cf = v.cf; L.cn = v.cn; L.rs = v.rs; L.own = v.own; L.nei = v.nei;
-        L.diag = v.diag; L.upper = v.upper; L.rsum = v.rsum; L.ev = v.ev; L.nOwn = v.n; L.nGlob = (double)v.n;
-        L.agg = v.agg; L.aggStart = v.aggStart; L.aggRows = v.aggRows; L.segStart = v.segStart; L.segFaces = v.segFaces;
-        L.x = v.x; L.b = v.b; L.t0 = v.t0; L.t1 = v.t1; L.out = v.t2;
+        L.diag = v.diag; L.upper = v.upper; L.rsum = v.rsum; L.ev = v.ev; L.nOwn = v.n + v.nG; L.nGlob = v.nGlob;
+        L.aggStart = v.aggStart; L.aggRows = v.aggRows; L.segStart = v.segStart; L.segFaces = v.segFaces;
         return L;
     }
-    static void setFine(LV& L, const LV& F) {
-        L.fn = F.n; L.fnCp = F.nCp; L.fW = F.W; L.fell = F.ell; L.fnOwn = F.nOwn; L.fcf = F.cf; L.fcn = F.cn; L.frs = F.rs;
-        L.fdiag = F.diag; L.fupper = F.upper; L.frsum = F.rsum; L.fev = F.ev;
+
+    // ---- host-side collectives used while the hierarchy is built ------------------------------
+    // neighbour exchange of one double per processor face of a (coarse) level's halo
+    void hostExchange(const std::vector<int>& poff, const std::vector<int>& pcnt, const std::vector<int>& ppeer, const std::vector<double>& send, std::vector<double>& recv) {
+        recv.assign(send.size(), 0.0);
+        if (!comm.active || send.empty()) return;
+#ifndef TPP_EMU
+        if (comm.nccl) {
+            double* ds = dalloc<double>(send.size());
+            double* dr = dalloc<double>(send.size());
+            h2d(ctx, ds, send.data(), send.size() * sizeof(double));
+            comm.pGroupStart();
+            for (size_t i = 0; i < pcnt.size(); i++) {
+                if (pcnt[i] == 0) continue;
+                comm.pSend(ds + poff[i], (size_t)pcnt[i], ncclDouble, ppeer[i], comm.nccl, ctx.stream);
+                comm.pRecv(dr + poff[i], (size_t)pcnt[i], ncclDouble, ppeer[i], comm.nccl, ctx.stream);
+            }
+            comm.pGroupEnd();
+            d2h(ctx, recv.data(), dr, send.size() * sizeof(double));
+            dev_free(ds); dev_free(dr);
+            return;
+        }
+#endif
+        // callback transport: it knows the mesh-level ghost layout only; a coarse patch never has
+        // more faces than the mesh-level patch it agglomerates, so it rides in that patch's slots
+        std::vector<double> fs((size_t)nG, 0.0), fr((size_t)nG, 0.0);
+        for (size_t i = 0; i < pcnt.size(); i++) for (int k = 0; k < pcnt[i]; k++) fs[procOff[i] + k] = send[poff[i] + k];
+        comm.xcb(comm.user, fs.data(), fr.data(), 1);
+        for (size_t i = 0; i < pcnt.size(); i++) for (int k = 0; k < pcnt[i]; k++) recv[poff[i] + k] = fr[procOff[i] + k];
+    }
+    void hostAllreduce(std::vector<double>& v, int op) {
+        if (!comm.active || v.empty()) return;
+#ifndef TPP_EMU
+        if (comm.nccl) {
+            double* dv = dalloc<double>(v.size());
+            h2d(ctx, dv, v.data(), v.size() * sizeof(double));
+            comm.pAllReduce(dv, dv, v.size(), ncclDouble, op == 0 ? ncclSum : ncclMax, comm.nccl, ctx.stream);
+            d2h(ctx, v.data(), dv, v.size() * sizeof(double));
+            dev_free(dv);
+            return;
+        }
+#endif
+        comm.rcb(comm.user, v.data(), (int)v.size(), op);
+    }
+    double globalCount(double n) {
+        std::vector<double> v(1, n);
+        hostAllreduce(v, 0);
+        return v[0];
+    }
+    // device vectors: sum over the ranks, in place
+    template <class R> void allreduceDev(R* p, size_t n) {
+        if (!comm.active || n == 0) return;
+#ifndef TPP_EMU
+        if (comm.nccl) {
+            prof_begin(ctx, "tail_allreduce");
+            comm.pAllReduce(p, p, n, sizeof(R) == 4 ? ncclFloat : ncclDouble, ncclSum, comm.nccl, ctx.stream);
+            prof_end(ctx);
+            ctx.launches++;
+            return;
+        }
+#endif
+        std::vector<R> h(n);
+        d2h(ctx, h.data(), p, n * sizeof(R));
+        std::vector<double> v(h.begin(), h.end());
+        comm.rcb(comm.user, v.data(), (int)n, 0);
+        for (size_t i = 0; i < n; i++) h[i] = (R)v[i];
+        h2d(ctx, p, h.data(), n * sizeof(R));
     }
 
     // one pairwise matching pass on the device; returns host `root`
+    int matchCap = 0;
     void matchPass(LV G, int n, const double* fwDev, std::vector<int>& rootH) {
+        if (n > matchCap) {
+            dev_free(match); dev_free(prop); dev_free(root);
+            matchCap = n;
+            match = dalloc<int>(n); prop = dalloc<int>(n); root = dalloc<int>(n);
+        }
         std::vector<int> m1(n, -1);
         h2d(ctx, match, m1.data(), n * sizeof(int));
-        G.match = match; G.prop = prop; G.root = root; G.fw = fwDev; G.nOwn = n;
+        G.match = match; G.prop = prop; G.root = root; G.fw = fwDev; G.nOwn = n;  // ghost rows never pair
         for (int r = 0; r < knob("TPP_ROUNDS", 8); r++) {
             LAUNCH(ctx, match_propose, G, n);
             LAUNCH(ctx, match_accept, G, n);
@@ -746,137 +826,272 @@ struct tpp_solver {
         d2h(ctx, rootH.data(), root, n * sizeof(int));
     }
 
+    // a level's graph on the host: faces [0,nfLoc) join two owned rows, faces [nfLoc,nf) are
+    // processor faces whose neighbour is the ghost row n + j (j in halo order)
     struct HostGraph {
-        int n = 0, nf = 0;
+        int n = 0, nf = 0, nfLoc = 0;
+        double nGlob = 0;
         std::vector<int> own, nei;
         std::vector<double> fw;
+        std::vector<int> poff, pcnt, ppeer;  // halo patches
+        std::vector<int> ghostRow;           // the peer's row behind each processor face
+        int nG() const { return nf - nfLoc; }
     };
     // CSR rows (neighbour-side faces then owner-side faces: ascending face index)
     static void csrOf(const HostGraph& g, std::vector<int>& rs, std::vector<int>& cf, std::vector<int>& cn) {
         rs.assign(g.n + 1, 0);
-        for (int f = 0; f < g.nf; f++) { rs[g.own[f] + 1]++; rs[g.nei[f] + 1]++; }
+        for (int f = 0; f < g.nf; f++) { rs[g.own[f] + 1]++; if (f < g.nfLoc) rs[g.nei[f] + 1]++; }
         for (int c = 0; c < g.n; c++) rs[c + 1] += rs[c];
-        cf.assign(2 * (size_t)g.nf, -1); cn.assign(2 * (size_t)g.nf, -1);
+        cf.assign((size_t)rs[g.n], -1); cn.assign((size_t)rs[g.n], -1);
         std::vector<int> cur(rs.begin(), rs.end() - 1);
         for (int f = 0; f < g.nf; f++) {
             int o = g.own[f], n = g.nei[f];
             cf[cur[o]] = f << 1; cn[cur[o]] = n; cur[o]++;
-            cf[cur[n]] = (f << 1) | 1; cn[cur[n]] = o; cur[n]++;
+            if (f < g.nfLoc) { cf[cur[n]] = (f << 1) | 1; cn[cur[n]] = o; cur[n]++; }
         }
     }
-    // aggregate `g` by `root`; returns the coarse graph, the map and, per coarse face, its fine faces
-    static void coarsen(const HostGraph& g, const std::vector<int>& root, HostGraph& c, std::vector<int>& agg, std::vector<int>& segStart, std::vector<int>& segFaces) {
-        std::vector<int> rank(g.n, -1);
-        int nc = 0;
-        for (int i = 0; i < g.n; i++) if (root[i] == i) rank[i] = nc++;
-        agg.resize(g.n);
-        for (int i = 0; i < g.n; i++) agg[i] = rank[root[i]];
-        std::vector<std::pair<unsigned long long, int>> keys;
-        keys.reserve(g.nf);
-        for (int f = 0; f < g.nf; f++) {
+    // aggregate `g` by the map agg (nc aggregates; ghostAgg = the peers' aggregates behind the
+    // processor faces): coarse graph and, per coarse face, the fine faces summed into it.
+    // Coarse processor faces are the distinct (my aggregate, peer aggregate) pairs of a patch in
+    // the order of (aggregate on the lower rank, aggregate on the higher rank): both sides of an
+    // interface enumerate them identically, as OpenFOAM's GAMG interface agglomeration does.
+    void coarsen(const HostGraph& g, const std::vector<int>& agg, int nc, const std::vector<int>& ghostAgg, HostGraph& c, std::vector<int>& segStart, std::vector<int>& segFaces) {
+        typedef std::pair<unsigned long long, int> KF;
+        std::vector<KF> keys;
+        keys.reserve(g.nfLoc);
+        for (int f = 0; f < g.nfLoc; f++) {
             int a = agg[g.own[f]], b = agg[g.nei[f]];
             if (a != b) keys.push_back({((unsigned long long)std::min(a, b) << 32) | (unsigned)std::max(a, b), f});
         }
         std::sort(keys.begin(), keys.end());
-        c.n = nc; c.own.clear(); c.nei.clear(); c.fw.clear();
-        segStart.clear(); segFaces.resize(keys.size());
+        c = HostGraph();
+        c.n = nc;
+        segStart.clear(); segFaces.clear(); segFaces.reserve(keys.size() + g.nG());
         unsigned long long last = ~0ull;
         for (size_t k = 0; k < keys.size(); k++) {
             if (keys[k].first != last) {
                 c.own.push_back((int)(keys[k].first >> 32));
                 c.nei.push_back((int)(keys[k].first & 0xffffffffu));
                 c.fw.push_back(0.0);
-                segStart.push_back((int)k);
+                segStart.push_back((int)segFaces.size());
                 last = keys[k].first;
             }
-            segFaces[k] = keys[k].second;
+            segFaces.push_back(keys[k].second);
             c.fw.back() += g.fw[keys[k].second];
         }
-        segStart.push_back((int)keys.size());
+        c.nfLoc = (int)c.own.size();
+        for (size_t p = 0; p < g.pcnt.size(); p++) {
+            const bool low = comm.rank < g.ppeer[p];
+            keys.clear();
+            for (int k = 0; k < g.pcnt[p]; k++) {
+                int j = g.poff[p] + k, f = g.nfLoc + j;
+                unsigned a = (unsigned)agg[g.own[f]], b = (unsigned)ghostAgg[j];
+                keys.push_back({low ? ((unsigned long long)a << 32) | b : ((unsigned long long)b << 32) | a, f});
+            }
+            std::sort(keys.begin(), keys.end());
+            c.poff.push_back((int)c.own.size() - c.nfLoc);
+            c.ppeer.push_back(g.ppeer[p]);
+            last = ~0ull;
+            int cnt = 0;
+            for (size_t k = 0; k < keys.size(); k++) {
+                if (keys[k].first != last) {
+                    unsigned hi = (unsigned)(keys[k].first >> 32), lo = (unsigned)(keys[k].first & 0xffffffffu);
+                    c.own.push_back((int)(low ? hi : lo));
+                    c.ghostRow.push_back((int)(low ? lo : hi));
+                    c.nei.push_back(nc + (int)c.own.size() - 1 - c.nfLoc);
+                    c.fw.push_back(0.0);
+                    segStart.push_back((int)segFaces.size());
+                    last = keys[k].first;
+                    cnt++;
+                }
+                segFaces.push_back(keys[k].second);
+                c.fw.back() += g.fw[keys[k].second];
+            }
+            c.pcnt.push_back(cnt);
+        }
+        segStart.push_back((int)segFaces.size());
         c.nf = (int)c.own.size();
+    }
+    template <class T> static T* upNew(Ctx& ctx, const std::vector<T>& h) {
+        T* p = dalloc<T>(std::max<size_t>(h.size(), 1));
+        if (!h.empty()) h2d(ctx, p, h.data(), h.size() * sizeof(T));
+        return p;
+    }
+    // one hierarchy level below `g`: `passes` matching passes merged (mergeLevels); g becomes the
+    // coarse graph.  dist: rows are distributed (halo patches, global decisions).  Returns false
+    // when the coarsening has stalled.
+    bool makeLevel(HostGraph& g, bool fineEll, bool dist, int stopRows, Level& v) {
+        std::vector<int> aggTot, segS, segF;
+        HostGraph cur = g, nxt;
+        bool first = true;
+        double* fwDev = dalloc<double>(std::max(g.nf, 1));
+        for (int pass = 0; pass < knob("TPP_PASSES", 2); pass++) {
+            h2d(ctx, fwDev, cur.fw.data(), cur.nf * sizeof(double));
+            LV M;
+            std::vector<int> rs, cf, cn;
+            int *drs = nullptr, *dcf = nullptr, *dcn = nullptr;
+            if (first && fineEll) M = fineView(nullptr, nullptr);
+            else {
+                csrOf(cur, rs, cf, cn);
+                drs = upNew(ctx, rs); dcf = upNew(ctx, cf); dcn = upNew(ctx, cn);
+                memset(&M, 0, sizeof(M));
+                M.n = cur.n; M.nf = cur.nf; M.ell = 0; M.rs = drs; M.cf = dcf; M.cn = dcn;
+            }
+            std::vector<int> rootH;
+            matchPass(M, cur.n, fwDev, rootH);
+            dev_sync(ctx);
+            dev_free(drs); dev_free(dcf); dev_free(dcn);
+            std::vector<int> rank(cur.n, -1), agg(cur.n);
+            int nc = 0;
+            for (int i = 0; i < cur.n; i++) if (rootH[i] == i) rank[i] = nc++;
+            for (int i = 0; i < cur.n; i++) agg[i] = rank[rootH[i]];
+            std::vector<int> ghostAgg(cur.nG(), 0);
+            if (dist && comm.active) {
+                std::vector<double> snd(cur.nG()), rcv;
+                for (int j = 0; j < cur.nG(); j++) snd[j] = (double)agg[cur.own[cur.nfLoc + j]];
+                hostExchange(cur.poff, cur.pcnt, cur.ppeer, snd, rcv);
+                for (int j = 0; j < cur.nG(); j++) ghostAgg[j] = (int)(rcv[j] + 0.5);
+            }
+            std::vector<int> sS, sF;
+            coarsen(cur, agg, nc, ghostAgg, nxt, sS, sF);
+            nxt.nGlob = dist ? globalCount((double)nxt.n) : (double)nxt.n;
+            if (knob("TPP_VERBOSE", 0)) fprintf(stderr, "amg pass%s: n %d nf %d (+%d proc) -> n %d nf %d (+%d proc), avg degree %.1f, global rows %.0f\n", dist ? "" : " (tail)", cur.n, cur.nfLoc, cur.nG(), nxt.n, nxt.nfLoc, nxt.nG(), 2.0 * nxt.nfLoc / std::max(nxt.n, 1), nxt.nGlob);
+            if (first) { aggTot = agg; segS = sS; segF = sF; first = false; }
+            else {
+                for (auto& a : aggTot) a = agg[a];
+                // flatten: coarse face -> intermediate faces -> fine faces
+                std::vector<int> nS(1, 0), nF2;
+                for (int F = 0; F < nxt.nf; F++) {
+                    for (int k = sS[F]; k < sS[F + 1]; k++) {
+                        int mid = sF[k];
+                        for (int q = segS[mid]; q < segS[mid + 1]; q++) nF2.push_back(segF[q]);
+                    }
+                    nS.push_back((int)nF2.size());
+                }
+                segS.swap(nS); segF.swap(nF2);
+            }
+            cur = nxt;
+            if (cur.nGlob <= stopRows) break;
+        }
+        dev_free(fwDev);
+        if (cur.nGlob >= 0.9 * g.nGlob) return false;  // stalled
+        v = Level();
+        v.n = cur.n; v.nf = cur.nf; v.nfLoc = cur.nfLoc; v.nG = cur.nG(); v.nGlob = cur.nGlob;
+        v.poff = cur.poff; v.pcnt = cur.pcnt; v.ppeer = cur.ppeer;
+        std::vector<int> rs, cf, cn;
+        csrOf(cur, rs, cf, cn);
+        v.nnz = rs[cur.n];
+        v.rs = upNew(ctx, rs); v.cf = upNew(ctx, cf); v.cn = upNew(ctx, cn); v.own = upNew(ctx, cur.own); v.nei = upNew(ctx, cur.nei);
+        v.agg = upNew(ctx, aggTot); v.segStart = upNew(ctx, segS); v.segFaces = upNew(ctx, segF);
+        std::vector<int> howner(cur.own.begin() + cur.nfLoc, cur.own.end());
+        v.dOwner = upNew(ctx, howner);
+        // members of each aggregate, ascending fine index
+        std::vector<int> aS(cur.n + 1, 0), aR(g.n);
+        for (int i = 0; i < g.n; i++) aS[aggTot[i] + 1]++;
+        for (int c = 0; c < cur.n; c++) aS[c + 1] += aS[c];
+        std::vector<int> pos(aS.begin(), aS.end() - 1);
+        for (int i = 0; i < g.n; i++) aR[pos[aggTot[i]]++] = i;
+        v.aggStart = upNew(ctx, aS); v.aggRows = upNew(ctx, aR);
+        v.ev = dalloc<double>(std::max(v.nnz, 1));
+        v.diag = dalloc<double>(v.n); v.upper = dalloc<double>(std::max(v.nf, 1)); v.rsum = dalloc<double>(v.n);
+        g = cur;
+        return true;
+    }
+    // the gather level's graph over all ranks: rows and faces rank by rank (a rank's local
+    // faces, then its processor faces towards higher ranks)
+    void gatherGraph(const HostGraph& g, HostGraph& G) {
+        const int me = comm.active ? comm.rank : 0, world = comm.active ? comm.size : 1;
+        std::vector<double> cnt(3 * (size_t)world, 0.0);
+        int nUp = 0;
+        for (size_t p = 0; p < g.pcnt.size(); p++) if (g.ppeer[p] > me) nUp += g.pcnt[p];
+        cnt[3 * me] = g.n; cnt[3 * me + 1] = g.nfLoc; cnt[3 * me + 2] = nUp;
+        hostAllreduce(cnt, 0);
+        std::vector<int> rowOff(world + 1, 0), faceOff(world + 1, 0);
+        for (int r = 0; r < world; r++) {
+            rowOff[r + 1] = rowOff[r] + (int)(cnt[3 * r] + 0.5);
+            faceOff[r + 1] = faceOff[r] + (int)(cnt[3 * r + 1] + 0.5) + (int)(cnt[3 * r + 2] + 0.5);
+        }
+        G = HostGraph();
+        G.n = rowOff[world]; G.nf = G.nfLoc = faceOff[world]; G.nGlob = G.n;
+        std::vector<double> own(G.nf, 0.0), nei(G.nf, 0.0), fw(G.nf, 0.0);
+        tailRowOff = rowOff[me]; tailFaceOff = faceOff[me];
+        tailCopy.clear();
+        int at = faceOff[me];
+        for (int f = 0; f < g.nfLoc; f++, at++) { own[at] = g.own[f] + rowOff[me]; nei[at] = g.nei[f] + rowOff[me]; fw[at] = g.fw[f]; }
+        for (size_t p = 0; p < g.pcnt.size(); p++) {
+            if (g.ppeer[p] <= me || g.pcnt[p] == 0) continue;
+            tailCopy.push_back({g.nfLoc + g.poff[p], g.pcnt[p], at});
+            for (int k = 0; k < g.pcnt[p]; k++, at++) {
+                int j = g.poff[p] + k, f = g.nfLoc + j;
+                own[at] = g.own[f] + rowOff[me];
+                nei[at] = g.ghostRow[j] + rowOff[g.ppeer[p]];
+                fw[at] = g.fw[f];
+            }
+        }
+        hostAllreduce(own, 0); hostAllreduce(nei, 0); hostAllreduce(fw, 0);
+        G.own.resize(G.nf); G.nei.resize(G.nf); G.fw = fw;
+        for (int f = 0; f < G.nf; f++) { G.own[f] = (int)(own[f] + 0.5); G.nei[f] = (int)(nei[f] + 0.5); }
     }
 
     void buildAMG() {
         amgBuilt = true;
         const int coarsestTarget = knob("TPP_COARSEST", 1500), maxLevels = 24;
-        if (nC <= coarsestTarget) return;
-        match = A<int>(nC); prop = A<int>(nC); root = A<int>(nC);
+        const int tailRows = std::max(knob("TPP_TAIL_ROWS", 300000), coarsestTarget);
+        if (nGlobal <= coarsestTarget) return;
         // faceAreaPair weights |Sf/sqrt(|Sf|) * (1, 1.01, 1.02)|
         HostGraph g;
-        // rank-local hierarchy: processor faces are left out (block-Jacobi multigrid)
-        g.n = nC; g.nf = nIloc; g.own.assign(own.begin(), own.begin() + nIloc); g.nei.assign(nei.begin(), nei.begin() + nIloc); g.fw.resize(nIloc);
-        for (int f = 0; f < nIloc; f++) {
+        g.n = nC; g.nf = nI; g.nfLoc = nIloc; g.nGlob = (double)nGlobal;
+        g.own.assign(own.begin(), own.begin() + nI); g.nei.assign(nei.begin(), nei.begin() + nI); g.fw.resize(nI);
+        g.poff = procOff; g.pcnt = procCnt; g.ppeer = procPeer;
+        for (int f = 0; f < nI; f++) {
             double s = sqrt(magSf[f]);
             double v[3] = {Sf0[3 * f] / s * 1.0, Sf0[3 * f + 1] / s * 1.01, Sf0[3 * f + 2] / s * 1.02};
             g.fw[f] = mag3(v);
         }
-        double* fwDev = A<double>(nI);
-        LV G = fineView(nullptr, nullptr);
-        while ((int)levels.size() < maxLevels && g.n > coarsestTarget) {
-            // two matching passes merged into one level
-            std::vector<int> aggTot, segS, segF;
-            HostGraph cur = g, nxt;
-            bool first = true;
-            int passes = 0;
-            for (int pass = 0; pass < knob("TPP_PASSES", 2); pass++) {
-                h2d(ctx, fwDev, cur.fw.data(), cur.nf * sizeof(double));
-                LV M;
-                std::vector<int> rs, cf, cn;
-                int *drs = nullptr, *dcf = nullptr, *dcn = nullptr;
-                if (first && levels.empty()) M = G;
-                else {
-                    csrOf(cur, rs, cf, cn);
-                    drs = dalloc<int>(rs.size()); dcf = dalloc<int>(cf.size()); dcn = dalloc<int>(cn.size());
-                    h2d(ctx, drs, rs.data(), rs.size() * sizeof(int));
-                    if (!cf.empty()) { h2d(ctx, dcf, cf.data(), cf.size() * sizeof(int)); h2d(ctx, dcn, cn.data(), cn.size() * sizeof(int)); }
-                    memset(&M, 0, sizeof(M));
-                    M.n = cur.n; M.nf = cur.nf; M.ell = 0; M.rs = drs; M.cf = dcf; M.cn = dcn;
-                }
-                std::vector<int> rootH, agg, sS, sF;
-                matchPass(M, cur.n, fwDev, rootH);
-                dev_sync(ctx);
-                dev_free(drs); dev_free(dcf); dev_free(dcn);
-                coarsen(cur, rootH, nxt, agg, sS, sF);
-                if (knob("TPP_VERBOSE", 0)) { int nm = 0, ns = 0; for (int i = 0; i < cur.n; i++) { if (rootH[i] == i) ns++; } fprintf(stderr, "amg pass: n %d nf %d -> n %d nf %d (avg degree %.1f)\n", cur.n, cur.nf, nxt.n, nxt.nf, 2.0 * nxt.nf / std::max(nxt.n, 1)); (void)nm; }
-                passes++;
-                if (first) { aggTot = agg; segS = sS; segF = sF; first = false; }
-                else {
-                    for (auto& a : aggTot) a = agg[a];
-                    // flatten: coarse face -> intermediate faces -> fine faces
-                    std::vector<int> nS(1, 0), nF2;
-                    for (int F = 0; F < nxt.nf; F++) {
-                        for (int k = sS[F]; k < sS[F + 1]; k++) {
-                            int mid = sF[k];
-                            for (int q = segS[mid]; q < segS[mid + 1]; q++) nF2.push_back(segF[q]);
-                        }
-                        nS.push_back((int)nF2.size());
-                    }
-                    segS.swap(nS); segF.swap(nF2);
-                }
-                cur = nxt;
-                if (cur.n <= coarsestTarget) break;
-            }
-            if (cur.n >= 0.9 * g.n) break;  // stalled
+        // distributed levels, down to the first one small enough to be gathered onto every rank
+        while ((int)levels.size() < maxLevels) {
             Level v;
-            v.n = cur.n; v.nf = cur.nf;
-            std::vector<int> rs, cf, cn;
-            csrOf(cur, rs, cf, cn);
-            auto up = [&](const std::vector<int>& h) { int* p = dalloc<int>(h.size()); if (!h.empty()) h2d(ctx, p, h.data(), h.size() * sizeof(int)); return p; };
-            v.rs = up(rs); v.cf = up(cf); v.cn = up(cn); v.own = up(cur.own); v.nei = up(cur.nei);
-            v.agg = up(aggTot); v.segStart = up(segS); v.segFaces = up(segF);
-            // members of each aggregate, ascending fine index
-            std::vector<int> aS(cur.n + 1, 0), aR(g.n);
-            for (int i = 0; i < g.n; i++) aS[aggTot[i] + 1]++;
-            for (int c = 0; c < cur.n; c++) aS[c + 1] += aS[c];
-            std::vector<int> pos(aS.begin(), aS.end() - 1);
-            for (int i = 0; i < g.n; i++) aR[pos[aggTot[i]]++] = i;
-            v.aggStart = up(aS); v.aggRows = up(aR);
-            v.ev = dalloc<double>(std::max(2 * v.nf, 1));
-            v.diag = dalloc<double>(v.n); v.upper = dalloc<double>(std::max(v.nf, 1)); v.rsum = dalloc<double>(v.n);
-            v.x = dalloc<double>(v.n); v.b = dalloc<double>(v.n); v.t0 = dalloc<double>(v.n); v.t1 = dalloc<double>(v.n); v.t2 = dalloc<double>(v.n);
+            if (!makeLevel(g, levels.empty(), true, coarsestTarget, v)) break;
             levels.push_back(v);
-            g = cur;
+            if (g.nGlob <= tailRows) break;
         }
+        if (levels.empty()) return;
+        gatherLevel = (int)levels.size() - 1;
+        HostGraph G;
+        gatherGraph(g, G);
+        {
+            Level t;
+            t.n = G.n; t.nf = t.nfLoc = G.nf; t.nG = 0; t.nGlob = G.n;
+            std::vector<int> rs, cf, cn;
+            csrOf(G, rs, cf, cn);
+            t.nnz = rs[G.n];
+            t.rs = upNew(ctx, rs); t.cf = upNew(ctx, cf); t.cn = upNew(ctx, cn); t.own = upNew(ctx, G.own); t.nei = upNew(ctx, G.nei);
+            t.ev = dalloc<double>(std::max(t.nnz, 1));
+            t.diag = dalloc<double>(t.n); t.upper = dalloc<double>(std::max(t.nf, 1)); t.rsum = dalloc<double>(t.n);
+            tail.push_back(t);
+        }
+        while ((int)tail.size() < TAIL_MAXLV && G.n > coarsestTarget) {
+            Level v;
+            if (!makeLevel(G, false, false, coarsestTarget, v)) break;
+            tail.push_back(v);
+        }
+        tailBar = (unsigned*)dev_alloc(64);
+        tailErr = (int*)dev_alloc(64);
+        tailPartial = dalloc<double>(2 * 1024);
+#ifndef TPP_EMU
+        {
+            int dev = 0, sms = 0, perSm = 0;
+            cudaGetDevice(&dev);
+            cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
+            if (knob("TPP_FP32", 1)) cudaOccupancyMaxActiveBlocksPerMultiprocessor(&perSm, vk_tail<float>, TAIL_THREADS, 0);
+            else cudaOccupancyMaxActiveBlocksPerMultiprocessor(&perSm, vk_tail<double>, TAIL_THREADS, 0);
+            tailGrid = std::min(sms * std::max(perSm, 1), 1024);
+            if (perSm < 1) { fprintf(stderr, "tppvof: vk_tail does not fit an SM\n"); abort(); }
+            // small tails do not need every SM: fewer CTAs make the grid barrier cheaper
+            int need = (tail[0].n * 4 + TAIL_THREADS - 1) / TAIL_THREADS;
+            tailGrid = std::max(1, std::min(tailGrid, need));
+        }
+#endif
     }
 
     // Galerkin coefficients of every level from the fine matrix
@@ -884,9 +1099,31 @@ struct tpp_solver {
         LAUNCH(ctx, rowsum, F0, F0.n);
         LAUNCH(ctx, fill_ev, F0, F0.n);
         LV F = F0;
-        for (size_t l = 0; l < levels.size(); l++) {
-            LV L = levelView((int)l);
-            setFine(L, F);
+        for (int l = 0; l <= gatherLevel; l++) {
+            LV L = viewOf(levels[l]);
+            L.fupper = F.upper; L.frsum = F.rsum;
+            LAUNCH(ctx, coarse_upper, L, L.nf);
+            LAUNCH(ctx, coarse_diag, L, L.n);
+            if (l < gatherLevel) LAUNCH(ctx, fill_ev, L, L.n);
+            F = L;
+        }
+        if (tail.empty()) return;
+        // gather: every rank's slice of the gather level's diagonal and face coefficients
+        Level& S = levels[gatherLevel];
+        Level& T0 = tail[0];
+        if (comm.active) { dev_zero(ctx, T0.diag, T0.n * sizeof(double)); dev_zero(ctx, T0.upper, T0.nf * sizeof(double)); }
+        d2d(ctx, T0.diag + tailRowOff, S.diag, S.n * sizeof(double));
+        if (S.nfLoc) d2d(ctx, T0.upper + tailFaceOff, S.upper, S.nfLoc * sizeof(double));
+        for (auto& c : tailCopy) d2d(ctx, T0.upper + c[2], S.upper + c[0], c[1] * sizeof(double));
+        allreduceDev(T0.diag, (size_t)T0.n);
+        allreduceDev(T0.upper, (size_t)T0.nf);
+        LV L0 = viewOf(T0);
+        LAUNCH(ctx, rowsum, L0, L0.n);
+        LAUNCH(ctx, fill_ev, L0, L0.n);
+        F = L0;
+        for (size_t t = 1; t < tail.size(); t++) {
+            LV L = viewOf(tail[t]);
+            L.fupper = F.upper; L.frsum = F.rsum;
             LAUNCH(ctx, coarse_upper, L, L.nf);
             LAUNCH(ctx, coarse_diag, L, L.n);
             LAUNCH(ctx, fill_ev, L, L.n);
@@ -896,22 +1133,38 @@ struct tpp_solver {
 
     // ---- V-cycle in precision R (tpp_vcycle.h): per-level storage, conversion, cycle, preconditioner
     template <class R> struct VStore {
-        std::vector<R*> diag, ev, x, b, t0, r, Ac;  // index 0 = fine level, 1.. = coarse levels
+        std::vector<R*> diag, ev, x, b, t0, r, Ac, send;  // index 0 = fine level, 1.. = distributed coarse levels
+        std::vector<R*> tdiag, tev, tx, ty, tb, tr;       // tail levels
+        R *cgR = nullptr, *cgP = nullptr, *cgAp = nullptr;
         bool ready = false;
     };
     VStore<float> vsF;
     VStore<double> vsD;
     template <class R> VStore<R>& vstore();
-    int vLevels() const { return 1 + (int)levels.size(); }
+    int vLevels() const { return 1 + std::max(gatherLevel, 0); }  // levels smoothed kernel by kernel
     int vRows(int lv) const { return lv == 0 ? nC : levels[lv - 1].n; }
-    size_t vEntries(int lv) const { return lv == 0 ? (size_t)W * nCp : (size_t)std::max(2 * levels[lv - 1].nf, 1); }
+    int vGhosts(int lv) const { return lv == 0 ? nG : levels[lv - 1].nG; }
+    size_t vEntries(int lv) const { return lv == 0 ? (size_t)W * nCp : (size_t)std::max(levels[lv - 1].nnz, 1); }
     template <class R> void ensureVStore() {
         VStore<R>& v = vstore<R>();
         if (v.ready) return;
         for (int lv = 0; lv < vLevels(); lv++) {
-            size_t n = (size_t)vRows(lv) + (lv == 0 ? (size_t)nG : 0);
-            v.diag.push_back(A<R>(n)); v.ev.push_back(A<R>(vEntries(lv)));
-            v.x.push_back(A<R>(n)); v.b.push_back(A<R>(n)); v.t0.push_back(A<R>(n)); v.r.push_back(A<R>(n)); v.Ac.push_back(A<R>(n));
+            size_t n = (size_t)vRows(lv) + (size_t)vGhosts(lv);
+            v.diag.push_back(dalloc<R>(n)); v.ev.push_back(dalloc<R>(vEntries(lv)));
+            v.x.push_back(dalloc<R>(n)); v.b.push_back(dalloc<R>(n)); v.t0.push_back(dalloc<R>(n)); v.r.push_back(dalloc<R>(n)); v.Ac.push_back(dalloc<R>(n));
+            v.send.push_back(dalloc<R>(std::max(vGhosts(lv), 1)));
+        }
+        for (auto* vec : {&v.diag, &v.ev, &v.x, &v.b, &v.t0, &v.r, &v.Ac, &v.send}) for (R* p : *vec) allocs.push_back(p);
+        for (size_t t = 0; t < tail.size(); t++) {
+            size_t n = (size_t)tail[t].n;
+            v.tdiag.push_back(dalloc<R>(n)); v.tev.push_back(dalloc<R>(std::max(tail[t].nnz, 1)));
+            v.tx.push_back(dalloc<R>(n)); v.ty.push_back(dalloc<R>(n)); v.tb.push_back(dalloc<R>(n)); v.tr.push_back(dalloc<R>(n));
+        }
+        for (auto* vec : {&v.tdiag, &v.tev, &v.tx, &v.ty, &v.tb, &v.tr}) for (R* p : *vec) allocs.push_back(p);
+        if (!tail.empty()) {
+            size_t n = (size_t)tail.back().n;
+            v.cgR = dalloc<R>(n); v.cgP = dalloc<R>(n); v.cgAp = dalloc<R>(n);
+            allocs.push_back(v.cgR); allocs.push_back(v.cgP); allocs.push_back(v.cgAp);
         }
         v.ready = true;
     }
@@ -919,24 +1172,63 @@ struct tpp_solver {
         VStore<R>& v = vstore<R>();
         VL<R> L;
         memset(&L, 0, sizeof(L));
-        if (lv == 0) { L.n = nC; L.nf = nIloc; L.nCp = nCp; L.W = W; L.ell = 1; L.cn = d.cn; L.nOwn = nC; }
-        else { Level& c = levels[lv - 1]; L.n = c.n; L.nf = c.nf; L.ell = 0; L.cn = c.cn; L.rs = c.rs; L.nOwn = c.n; L.agg = c.agg; L.aggStart = c.aggStart; L.aggRows = c.aggRows; }
-        L.diag = v.diag[lv]; L.ev = v.ev[lv];
+        if (lv == 0) { L.n = nC; L.nf = nI; L.nCp = nCp; L.W = W; L.ell = 1; L.cn = d.cn; L.nOwn = levels.empty() ? nC : nC + nG; }
+        else { Level& c = levels[lv - 1]; L.n = c.n; L.nf = c.nf; L.ell = 0; L.cn = c.cn; L.rs = c.rs; L.nOwn = c.n + c.nG; L.agg = c.agg; L.aggStart = c.aggStart; L.aggRows = c.aggRows; }
+        if (lv < vLevels()) { L.diag = v.diag[lv]; L.ev = v.ev[lv]; }
         return L;
     }
     // matrix values of every level in precision R (after galerkin(), once per solve)
     template <class R> void convertLevels(LV& F0) {
         VStore<R>& v = vstore<R>();
+        CastArgs<R> a;
+        memset(&a, 0, sizeof(a));
         for (int lv = 0; lv < vLevels(); lv++) {
-            const double* dg = lv == 0 ? F0.diag : levels[lv - 1].diag;
-            const double* ev = lv == 0 ? F0.ev : levels[lv - 1].ev;
-            CastArgs<R> a;
-            memset(&a, 0, sizeof(a));
-            a.src = dg; a.dst = v.diag[lv];
+            a.src = lv == 0 ? F0.diag : levels[lv - 1].diag; a.dst = v.diag[lv];
             VLAUNCH(ctx, cast_in, a, vRows(lv));
-            a.src = ev; a.dst = v.ev[lv];
+            a.src = lv == 0 ? F0.ev : levels[lv - 1].ev; a.dst = v.ev[lv];
             VLAUNCH(ctx, cast_in, a, (int)vEntries(lv));
         }
+        for (size_t t = 0; t < tail.size(); t++) {
+            a.src = tail[t].diag; a.dst = v.tdiag[t];
+            VLAUNCH(ctx, cast_in, a, tail[t].n);
+            a.src = tail[t].ev; a.dst = v.tev[t];
+            VLAUNCH(ctx, cast_in, a, std::max(tail[t].nnz, 1));
+        }
+    }
+    // halo exchange of a V-cycle vector on level lv (0 = mesh): owned rows behind my processor
+    // faces -> the neighbours' ghost rows [n, n + nG)
+    template <class R> void XL(int lv, R* vec) {
+        const int ng = vGhosts(lv);
+        if (!comm.active || ng == 0 || levels.empty()) return;
+        VStore<R>& v = vstore<R>();
+        const std::vector<int>& off = lv == 0 ? procOff : levels[lv - 1].poff;
+        const std::vector<int>& cnt = lv == 0 ? procCnt : levels[lv - 1].pcnt;
+        const std::vector<int>& peer = lv == 0 ? procPeer : levels[lv - 1].ppeer;
+        PackArgs<R> a;
+        a.owner = lv == 0 ? dProcOwner : levels[lv - 1].dOwner; a.src = vec; a.dst = v.send[lv];
+        VLAUNCH(ctx, pack, a, ng);
+        R* ghost = vec + vRows(lv);
+#ifndef TPP_EMU
+        if (comm.nccl) {
+            prof_begin(ctx, "v_halo_sendrecv");
+            comm.pGroupStart();
+            for (size_t i = 0; i < cnt.size(); i++) {
+                if (cnt[i] == 0) continue;
+                comm.pSend(v.send[lv] + off[i], (size_t)cnt[i], sizeof(R) == 4 ? ncclFloat : ncclDouble, peer[i], comm.nccl, ctx.stream);
+                comm.pRecv(ghost + off[i], (size_t)cnt[i], sizeof(R) == 4 ? ncclFloat : ncclDouble, peer[i], comm.nccl, ctx.stream);
+            }
+            comm.pGroupEnd();
+            prof_end(ctx);
+            ctx.launches++;
+            return;
+        }
+#endif
+        std::vector<R> hs(ng), hr(ng);
+        d2h(ctx, hs.data(), v.send[lv], ng * sizeof(R));
+        std::vector<double> s(hs.begin(), hs.end()), r;
+        hostExchange(off, cnt, peer, s, r);
+        for (int j = 0; j < ng; j++) hr[j] = (R)r[j];
+        h2d(ctx, ghost, hr.data(), ng * sizeof(R));
     }
     template <class R> void vRowOp(VL<R>& L, int mode) {  // 0 Jacobi sweep, 1 residual
 #ifndef TPP_EMU
@@ -952,7 +1244,7 @@ struct tpp_solver {
         if (mode == 0) VLAUNCH(ctx, jacobi, L, L.n);
         else VLAUNCH(ctx, residual, L, L.n);
     }
-    // out = A in ; scal[S_TMP0] = r.in ; scal[S_TMP1] = in.out
+    // out = A in ; scal[S_TMP0] = r.in ; scal[S_TMP1] = in.out  (summed over the ranks)
     template <class R> void vSpmvDot2(VL<R>& L) {
 #ifdef TPP_EMU
         double v = 0, w = 0;
@@ -968,13 +1260,13 @@ struct tpp_solver {
             if (shortRows) vk_csr_spmv_dot2<R, 4><<<nb, BLOCK, 0, ctx.stream>>>(L, red.partial, red.partial2);
             else vk_csr_spmv_dot2<R, 8><<<nb, BLOCK, 0, ctx.stream>>>(L, red.partial, red.partial2);
         }
-        k_reduce_final<<<1, BLOCK, 0, ctx.stream>>>(red.partial, nb, 2, scal + S_TMP0);
-        k_reduce_final<<<1, BLOCK, 0, ctx.stream>>>(red.partial2, nb, 2, scal + S_TMP1);
+        k_reduce_final2<<<2, BLOCK, 0, ctx.stream>>>(red.partial, red.partial2, nb, scal + S_TMP0, scal + S_TMP1);
         prof_end(ctx);
 #endif
-        ctx.launches += 3;
+        ctx.launches += 2;
+        allreduce(S_TMP0, 2, 0);
     }
-    template <class R> void vCoarseSolve(VL<R>& L, R* r, R* p, R* Ap) {  // L.b -> L.out
+    template <class R> void vCoarseSolve(VL<R>& L, R* r, R* p, R* Ap) {  // L.b -> L.out (a mesh without coarse levels)
         const int maxIt = knob("TPP_CITER", 16);
         const double tol = knobd("TPP_CTOL", 0.05);
 #ifdef TPP_EMU
@@ -1002,12 +1294,45 @@ struct tpp_solver {
 #endif
         ctx.launches++;
     }
+    // the tail sub-cycle: tb[0] (restricted residual, gathered) -> tx[0]
+    template <class R> void runTail(int nPre, int nPost) {
+        VStore<R>& v = vstore<R>();
+        TailArgs<R> A;
+        memset(&A, 0, sizeof(A));
+        A.T = (int)tail.size();
+        for (int t = 0; t < A.T; t++) {
+            Level& c = tail[t];
+            TLv<R>& L = A.lv[t];
+            L.n = c.n;
+            double deg = (double)c.nnz / std::max(c.n, 1);
+            L.coop = deg <= 6 ? 4 : deg <= 14 ? 8 : 16;
+            L.rs = c.rs; L.cn = c.cn; L.ev = v.tev[t]; L.diag = v.tdiag[t];
+            if (t + 1 < A.T) L.agg = tail[t + 1].agg;
+            if (t > 0) { L.aggStart = c.aggStart; L.aggRows = c.aggRows; }
+            L.x = v.tx[t]; L.y = v.ty[t]; L.b = v.tb[t]; L.r = v.tr[t];
+        }
+        A.bar = tailBar; A.err = tailErr; A.partial = tailPartial;
+        A.omega = (R)knobd("TPP_OMEGA", 0.8); A.scaleJ = (R)knobd("TPP_SCALEJ", 1.0);
+        A.nPre = nPre; A.nPost = nPost; A.cgIter = knob("TPP_CITER", 16); A.cgTol = knobd("TPP_CTOL", 0.05);
+        A.cgR = v.cgR; A.cgP = v.cgP; A.cgAp = v.cgAp;
+        prof_begin(ctx, "v_tail");
+#ifdef TPP_EMU
+        tail_host(A);
+#else
+        CUDA_CHECK(cudaMemsetAsync(tailBar, 0, sizeof(unsigned), ctx.stream));
+        void* args[] = {&A};
+        if (knob("TPP_TAIL_COOP", 1)) CUDA_CHECK(cudaLaunchCooperativeKernel((void*)vk_tail<R>, dim3(tailGrid), dim3(TAIL_THREADS), args, 0, ctx.stream));
+        else vk_tail<R><<<tailGrid, TAIL_THREADS, 0, ctx.stream>>>(A);
+#endif
+        prof_end(ctx);
+        ctx.launches += 2;
+    }
     // x ~= A^-1 b on level lv (0 = fine); x, b are the level's own buffers unless given
     template <class R> void vcycleT(int lv, const R* b, R* x, bool zeroGuess, int nPre, int nPost) {
         VStore<R>& v = vstore<R>();
         VL<R> L = vview<R>(lv);
         const R omega = (R)knobd("TPP_OMEGA", 0.8);
-        if (lv == vLevels() - 1) {  // coarsest (or the only) level: one-CTA CG
+        if (levels.empty()) {  // a mesh too small for a hierarchy: one-CTA CG on the rank's own rows
             L.b = b; L.out = x;
             vCoarseSolve(L, v.r[lv], v.t0[lv], v.Ac[lv]);
             return;
@@ -1016,24 +1341,35 @@ struct tpp_solver {
         R *cur = x, *oth = v.t0[lv];
         for (int s = 0; s < std::max(nPre, 1); s++) {
             if (s == 0 && zeroGuess) { L.out = cur; VLAUNCH(ctx, jacobi0, L, L.n); }
-            else { L.in = cur; L.out = oth; vRowOp(L, 0); std::swap(cur, oth); }
+            else { XL<R>(lv, cur); L.in = cur; L.out = oth; vRowOp(L, 0); std::swap(cur, oth); }
         }
+        XL<R>(lv, cur);
         L.in = cur; L.out = v.r[lv];
         vRowOp(L, 1);
+        const bool toTail = lv + 1 == vLevels();
         VL<R> Cn = vview<R>(lv + 1);
-        Cn.r = v.r[lv]; Cn.out = v.b[lv + 1];
+        Cn.r = v.r[lv];
+        if (toTail) {
+            if (comm.active) dev_zero(ctx, v.tb[0], tail[0].n * sizeof(R));
+            Cn.out = v.tb[0] + tailRowOff;
+        } else Cn.out = v.b[lv + 1];
         VLAUNCH(ctx, restrict, Cn, Cn.n);
-        vcycleT<R>(lv + 1, v.b[lv + 1], v.x[lv + 1], true, nPre, nPost);
+        if (toTail) {
+            allreduceDev(v.tb[0], (size_t)tail[0].n);
+            runTail<R>(nPre, nPost);
+        } else vcycleT<R>(lv + 1, v.b[lv + 1], v.x[lv + 1], true, nPre, nPost);
         // prolonged correction c = P x_c in `oth`, A c, scaling, x += ...
         VL<R> Pn = vview<R>(lv + 1);
-        Pn.xc = v.x[lv + 1]; Pn.out = oth;
+        Pn.xc = toTail ? v.tx[0] + tailRowOff : v.x[lv + 1]; Pn.out = oth;
         VLAUNCH(ctx, prolong, Pn, L.n);
+        XL<R>(lv, oth);
         L.in = oth; L.out = v.Ac[lv]; L.r = v.r[lv];
         vSpmvDot2(L);
         L.c = oth; L.Ac = v.Ac[lv]; L.r = v.r[lv]; L.out = cur; L.sf = scal + S_TMP0; L.omega = (R)knobd("TPP_SCALEJ", 1.0);
         VLAUNCH(ctx, scale_apply, L, L.n);
         L.omega = omega;
         for (int s = 0; s < std::max(nPost, 1); s++) {
+            XL<R>(lv, cur);
             L.in = cur; L.out = oth;
             vRowOp(L, 0);
             std::swap(cur, oth);
@@ -1077,7 +1413,6 @@ struct tpp_solver {
             else { ensureVStore<double>(); convertLevels<double>(F0); }
         }
         LV FG = F0;  // the global operator: full rows, ghost columns filled by halo exchange
-        if (nG > 0) { FG.ev = fineEvFull; FG.rsum = fineRsumFull; }
         red.reduce(ctx, x, nullptr, nC, 2, scal + S_XSUM);
         allreduce(S_XSUM, 1, 0);
         X(x, 1);
@@ -1096,6 +1431,11 @@ struct tpp_solver {
             st.r = hscal[S_RES] / nf;
             if (!(fabs(hscal[S_WAPA]) / nf >= VSMALL)) break;
         } while (++st.iters < ctl.max_iter && !conv(st.r));
+        if (!tail.empty()) {  // a grid barrier of the tail kernel that timed out is a hard error
+            int e = 0;
+            d2h(ctx, &e, tailErr, sizeof(int));
+            if (e) { ctx.err = "vk_tail: grid barrier timed out (the cooperative grid was not co-resident?)"; fprintf(stderr, "tppvof: %s\n", ctx.err.c_str()); }
+        }
         return st;
     }
 
@@ -1222,6 +1562,9 @@ struct tpp_solver {
     void destroy() {
         for (void* p : allocs) dev_free(p);
         for (auto& l : levels) l.free();
+        for (auto& l : tail) l.free();
+        dev_free(match); dev_free(prop); dev_free(root);
+        dev_free(tailBar); dev_free(tailErr); dev_free(tailPartial);
         red.free();
 #ifdef TPP_EMU
         free(hscal);
@@ -1374,6 +1717,7 @@ int tpp_set_time(tpp_handle s, double t, double dt) {
 int tpp_step(tpp_handle s, int n) {
     for (int i = 0; i < n; i++) s->oneStep();
     dev_sync(s->ctx);
+    if (!s->ctx.err.empty()) { g_err = s->ctx.err; return -1; }
     return 0;
 }
 int tpp_run_to_write(tpp_handle s, long max_steps) {
@@ -1481,8 +1825,16 @@ int tpp_amg_levels(tpp_handle s, int* n_rows, int* n_faces, int cap) {
     int k = 0;
     if (k < cap) { n_rows[k] = s->nC; n_faces[k] = s->nIloc; }
     k++;
-    for (auto& l : s->levels) { if (k < cap) { n_rows[k] = l.n; n_faces[k] = l.nf; } k++; }
+    for (auto& l : s->levels) { if (k < cap) { n_rows[k] = l.n; n_faces[k] = l.nfLoc; } k++; }
+    for (size_t t = 1; t < s->tail.size(); t++) { if (k < cap) { n_rows[k] = s->tail[t].n; n_faces[k] = s->tail[t].nf; } k++; }
     return k;
+}
+int tpp_amg_layout(tpp_handle s, int* out4) {
+    out4[0] = s->levels.empty() ? 0 : s->vLevels();
+    out4[1] = (int)s->tail.size();
+    out4[2] = s->tail.empty() ? 0 : s->tail[0].n;
+    out4[3] = s->tailGrid;
+    return 0;
 }
 int tpp_ghost_layout(tpp_handle s, int* n_ghost, int* n_patches, int* off, int* cnt, int* peer, int cap) {
     *n_ghost = s->nG;

@@ -82,6 +82,7 @@ def load(lib_path=None):
     L.tpp_comm_init.argtypes = [H, C.c_int, C.c_int, C.c_char_p, C.c_char_p]
     L.tpp_comm_callbacks.argtypes = [H, C.c_int, C.c_int, XCB, RCB, C.c_void_p]
     L.tpp_amg_levels.argtypes = [H, abi.c_int_p, abi.c_int_p, C.c_int]
+    L.tpp_amg_layout.argtypes = [H, abi.c_int_p]
     L.tpp_ghost_layout.argtypes = [H, abi.c_int_p, abi.c_int_p, abi.c_int_p, abi.c_int_p, abi.c_int_p, C.c_int]
     _LIBS[path] = L
     return L
@@ -192,6 +193,13 @@ class Solver:
         n, f = np.zeros(32, dtype=np.int32), np.zeros(32, dtype=np.int32)
         k = self.L.tpp_amg_levels(self.h, n.ctypes.data_as(abi.c_int_p), f.ctypes.data_as(abi.c_int_p), 32)
         return [(int(n[i]), int(f[i])) for i in range(k)]
+
+    def amg_layout(self):
+        """levels smoothed kernel by kernel (rows distributed), tail levels (gathered, one persistent
+        kernel), rows of the first tail level, CTAs of the tail kernel"""
+        o = np.zeros(4, dtype=np.int32)
+        self.L.tpp_amg_layout(self.h, o.ctypes.data_as(abi.c_int_p))
+        return dict(zip(("kernel_levels", "tail_levels", "tail_rows", "tail_ctas"), (int(x) for x in o)))
 
     def use_stream(self, cuda_stream):
         self.L.tpp_use_stream(self.h, C.c_void_p(cuda_stream))
