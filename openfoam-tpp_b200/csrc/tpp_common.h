@@ -141,6 +141,9 @@ inline void* dev_alloc(size_t bytes) {
     void* p = nullptr;
     CUDA_CHECK(cudaMalloc(&p, bytes ? bytes : 8));
     CUDA_CHECK(cudaMemset(p, 0, bytes ? bytes : 8));
+    // the memset runs on the legacy default stream, which does not order against a caller's
+    // non-blocking stream (tpp_use_stream with a torch stream): finish it before the buffer is used
+    CUDA_CHECK(cudaDeviceSynchronize());
     return p;
 }
 inline void dev_free(void* p) { if (p) cudaFree(p); }

@@ -295,6 +295,89 @@ __global__ void __launch_bounds__(256) k_init_residual(LV L, const double* x, co
 }
 __global__ void k_scal_copy(double* scal, int dst, int src) { scal[dst] = scal[src]; }
 
+
+// ---- halo exchange over peer memory (NVLink / NVSwitch), one kernel per exchange ---------------
+// Every rank owns a window (cudaMalloc, exported with cudaIpc): per processor patch two data
+// slots (sequence parity) and a flag.  The kernel
+//   1. packs the owned values behind its processor faces straight into the NEIGHBOURS' windows
+//      (peer stores), system fence, the last CTA then publishes the exchange's sequence number in
+//      the neighbours' flags;
+//   2. waits (bounded) until its own flags show that the neighbours' data of this exchange have
+//      arrived, and copies them into the ghost rows.
+// Step 1 never waits, so two ranks can never block each other; the parity slots are safe because
+// a rank can only be one exchange ahead of its neighbour (it needs the neighbour's flag of
+// exchange k to leave exchange k).  Replaces pack kernel + grouped ncclSend/ncclRecv (~16 us)
+// by one ~4 us kernel; the sequence counter lives on the device so the kernel is graph-replayable.
+constexpr int P2P_MAXPATCH = 8;
+struct P2PArgs {
+    int nG, nc, nPatch;
+    int off[P2P_MAXPATCH];                     // ghost offset of every patch (ascending)
+    char* peerData[P2P_MAXPATCH];              // my slot pair inside the neighbour's window
+    unsigned long long* peerFlag[P2P_MAXPATCH];
+    const char* myData[P2P_MAXPATCH];          // the neighbour's slot pair inside my window
+    unsigned long long* myFlag[P2P_MAXPATCH];
+    size_t slot[P2P_MAXPATCH];                 // bytes of one slot
+    const int* owner;                          // owned row behind every processor face
+    const void* src;
+    void* ghost;
+    unsigned long long* seq;                   // exchanges completed so far (device counter)
+    unsigned* putDone;
+    int* err;
+};
+DEV unsigned long long ld_acquire_sys(const unsigned long long* p) {
+    unsigned long long v;
+    asm volatile("ld.acquire.sys.global.u64 %0, [%1];" : "=l"(v) : "l"(p) : "memory");
+    return v;
+}
+DEV void st_release_sys(unsigned long long* p, unsigned long long v) {
+    asm volatile("st.release.sys.global.u64 [%0], %1;" ::"l"(p), "l"(v) : "memory");
+}
+DEV unsigned long long global_ns() {
+    unsigned long long t;
+    asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t));
+    return t;
+}
+template <class T>
+__global__ void __launch_bounds__(256) k_halo_p2p(const P2PArgs a) {
+    __shared__ int s_last;
+    const unsigned long long seq = *(volatile unsigned long long*)a.seq + 1;
+    const size_t par = (size_t)(seq & 1);
+    const long total = (long)a.nG * a.nc;
+    const T* src = (const T*)a.src;
+    for (long e = blockIdx.x * 256L + threadIdx.x; e < total; e += gridDim.x * 256L) {
+        int j = (int)(e / a.nc), k = (int)(e % a.nc), p = 0;
+        while (p + 1 < a.nPatch && j >= a.off[p + 1]) p++;
+        ((T*)(a.peerData[p] + par * a.slot[p]))[(size_t)(j - a.off[p]) * a.nc + k] = src[(size_t)a.owner[j] * a.nc + k];
+    }
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        __threadfence_system();
+        s_last = atomicAdd(a.putDone, 1u) == gridDim.x - 1;
+    }
+    __syncthreads();
+    if (s_last) {  // every CTA has finished its stores (and has read *seq)
+        if (threadIdx.x < a.nPatch) {
+            __threadfence_system();
+            st_release_sys(a.peerFlag[threadIdx.x], seq);
+        }
+        if (threadIdx.x == 0) { *a.putDone = 0; *(volatile unsigned long long*)a.seq = seq; }
+    }
+    if (threadIdx.x < a.nPatch) {
+        const unsigned long long t0 = global_ns();
+        long spins = 0;
+        while (ld_acquire_sys(a.myFlag[threadIdx.x]) < seq) {
+            if ((++spins & 255) == 0 && (*(volatile int*)a.err != 0 || global_ns() - t0 > 30000000000ull)) { *(volatile int*)a.err = 2; break; }
+        }
+        __threadfence_system();
+    }
+    __syncthreads();
+    T* ghost = (T*)a.ghost;
+    for (long e = blockIdx.x * 256L + threadIdx.x; e < total; e += gridDim.x * 256L) {
+        int j = (int)(e / a.nc), k = (int)(e % a.nc), p = 0;
+        while (p + 1 < a.nPatch && j >= a.off[p + 1]) p++;
+        ghost[e] = __ldcg(&((const T*)(a.myData[p] + par * a.slot[p]))[(size_t)(j - a.off[p]) * a.nc + k]);
+    }
+}
 #endif
 
 struct Reducer {

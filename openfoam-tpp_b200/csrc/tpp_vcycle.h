@@ -131,7 +131,8 @@ struct TailArgs {
     R omega, scaleJ;
     int nPre, nPost, cgIter;
     double cgTol;
-    R *cgR, *cgP, *cgAp;  // coarsest-level CG scratch
+    R *cgR, *cgP, *cgAp;  // coarsest-level CG scratch (global memory; unused when the level is staged in shared memory)
+    int cgSmem;           // the coarsest level fits the CTA's shared memory
 };
 // the buffer (x or y) that holds a level's iterate after `swaps` Jacobi sweeps when the final
 // iterate has to land in x
@@ -161,58 +162,127 @@ DEV void gsync(GridBar& g) {
     }
     __syncthreads();
 }
-// sum_k ev[k] * x[col(k)] over a row walked by `coop` lanes; col = cn[k] or, through the
-// aggregate map, map[cn[k]] (a prolonged coarse vector, never stored)
-template <class R>
-DEV R tail_row(const TLv<R>& L, int row, const R* x, const int* map, int lane, int coop) {
-    R s = 0;
-    const int e = L.rs[row + 1];
-    for (int k = L.rs[row] + lane; k < e; k += coop) {
-        int o = L.cn[k];
-        s += L.ev[k] * x[map ? map[o] : o];
+// Row sweep of a tail level.  These levels sit in L2 and every phase is a chain of dependent
+// loads (row start -> column/coefficient -> x[column]); with one CTA per SM the only way to hide
+// that latency is memory-level parallelism, so every thread keeps TAIL_U rows in flight: `coop`
+// lanes walk one row, rows base + u*rpp (u < TAIL_U) are handled together.  f(row, offdiag sum)
+// runs on lane 0 of the row.  col = cn[k] or, through the aggregate map, map[cn[k]] (a
+// prolonged coarse vector that is never stored).
+constexpr int TAIL_U = 4;
+template <class R, class F>
+DEV void tail_rows(const TLv<R>& L, const R* x, const int* map, int tid, int nth, F f) {
+    const int coop = L.coop, lane = tid % coop, sub = tid / coop, rpp = nth / coop, n = L.n;
+    for (int base = 0; base < n; base += TAIL_U * rpp) {
+        int row[TAIL_U], k[TAIL_U], e[TAIL_U];
+        R s[TAIL_U];
+#pragma unroll
+        for (int u = 0; u < TAIL_U; u++) {
+            int r = base + u * rpp + sub;
+            row[u] = r < n ? r : -1;
+            int q = r < n ? r : n - 1;
+            k[u] = L.rs[q] + lane;
+            e[u] = r < n ? L.rs[q + 1] : 0;
+            s[u] = 0;
+        }
+        bool any = true;
+        while (any) {
+            int o[TAIL_U];
+            R v[TAIL_U], xv[TAIL_U];
+#pragma unroll
+            for (int u = 0; u < TAIL_U; u++) {
+                bool in = k[u] < e[u];
+                o[u] = in ? L.cn[k[u]] : -1;
+                v[u] = in ? L.ev[k[u]] : R(0);
+            }
+            if (map) {
+#pragma unroll
+                for (int u = 0; u < TAIL_U; u++) o[u] = o[u] >= 0 ? map[o[u]] : -1;
+            }
+#pragma unroll
+            for (int u = 0; u < TAIL_U; u++) xv[u] = o[u] >= 0 ? x[o[u]] : R(0);
+            any = false;
+#pragma unroll
+            for (int u = 0; u < TAIL_U; u++) {
+                s[u] += v[u] * xv[u];
+                k[u] += coop;
+                any = any || k[u] < e[u];
+            }
+            any = __any_sync(0xffffffffu, any);  // warp-uniform trip count (shuffles below)
+        }
+#pragma unroll
+        for (int u = 0; u < TAIL_U; u++) {
+            R t = s[u];
+            for (int off = coop >> 1; off > 0; off >>= 1) t += __shfl_xor_sync(0xffffffffu, t, off);
+            if (row[u] >= 0 && lane == 0) f(row[u], t);
+        }
     }
-    for (int off = coop >> 1; off > 0; off >>= 1) s += __shfl_xor_sync(0xffffffffu, s, off);
-    return s;
 }
-DEV double tail_block_sum(double v, double* sh) {  // blockDim = TAIL_THREADS; result in every thread
+// result in every thread of the CTA; sh holds one double per warp
+DEV double tail_block_sum(double v, double* sh) {
     for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
     __syncthreads();
     if ((threadIdx.x & 31) == 0) sh[threadIdx.x >> 5] = v;
     __syncthreads();
-    double s = 0;
-    for (int k = 0; k < TAIL_THREADS / 32; k++) s += sh[k];  // the same 32 values in the same order everywhere
+    double s = (threadIdx.x & 31) < (blockDim.x >> 5) ? sh[threadIdx.x & 31] : 0.0;
+    for (int o = 16; o > 0; o >>= 1) s += __shfl_xor_sync(0xffffffffu, s, o);  // same tree in every warp
     return s;
 }
-// Jacobi-preconditioned CG on the coarsest tail level by ONE CTA (zero initial guess)
+// Jacobi-preconditioned CG on the coarsest tail level by ONE CTA (zero initial guess).  The
+// whole level - CSR with 16-bit columns, coefficients, diagonal, the CG vectors - is staged in
+// shared memory when it fits (`useSmem`, decided on the host), so an iteration costs a few
+// hundred cycles instead of a chain of L2 round trips.
 template <class R>
-DEV void tail_coarse_cg(const TLv<R>& L, R* r, R* p, R* Ap, int maxIter, double relTol, double* sh) {
+DEV void tail_coarse_cg(const TLv<R>& L, R* gr, R* gp, R* gAp, int maxIter, double relTol, double* sh, unsigned char* smem, int useSmem) {
     const int n = L.n, t = threadIdx.x, T = blockDim.x;
-    R* x = L.x;
+    const int nnz = L.rs[n];
+    const int* rs = L.rs;
+    const R *ev = L.ev, *dg = L.diag;
+    const int* cn32 = L.cn;
+    const unsigned short* cn16 = nullptr;
+    R *x = L.x, *r = gr, *p = gp, *Ap = gAp;
+    if (useSmem) {
+        // layout: ev[nnz] diag[n] x[n] r[n] p[n] Ap[n] (R) | rs[n+1] (int) | cn[nnz] (u16)
+        R* sev = (R*)smem;
+        R* sdg = sev + nnz;
+        R* sx = sdg + n; R* sr = sx + n; R* sp = sr + n; R* sAp = sp + n;
+        int* srs = (int*)(sAp + n);
+        unsigned short* scn = (unsigned short*)(srs + n + 1);
+        for (int k = t; k < nnz; k += T) { sev[k] = L.ev[k]; scn[k] = (unsigned short)L.cn[k]; }
+        for (int i = t; i < n; i += T) { sdg[i] = L.diag[i]; srs[i] = L.rs[i]; }
+        if (t == 0) srs[n] = nnz;
+        ev = sev; dg = sdg; rs = srs; cn16 = scn; x = sx; r = sr; p = sp; Ap = sAp;
+        __syncthreads();
+    }
     const R* b = L.b;
     double loc = 0;
-    for (int i = t; i < n; i += T) { x[i] = 0; r[i] = b[i]; R z = b[i] / L.diag[i]; p[i] = z; loc += (double)b[i] * (double)z; }
+    for (int i = t; i < n; i += T) { x[i] = 0; R bi = b[i]; r[i] = bi; R z = bi / dg[i]; p[i] = z; loc += (double)bi * (double)z; }
     double rz = tail_block_sum(loc, sh);
     const double rz0 = rz;
-    if (!(rz > 0)) return;
-    for (int it = 0; it < maxIter; it++) {
-        loc = 0;
-        __syncthreads();
-        for (int i = t; i < n; i += T) {
-            R s = 0;
-            for (int k = L.rs[i]; k < L.rs[i + 1]; k++) s += L.ev[k] * p[L.cn[k]];
-            R y = L.diag[i] * p[i] - s;
-            Ap[i] = y;
-            loc += (double)y * (double)p[i];
+    if (rz > 0)
+        for (int it = 0; it < maxIter; it++) {
+            loc = 0;
+            __syncthreads();
+            for (int i = t; i < n; i += T) {
+                R s = 0;
+                if (cn16) for (int k = rs[i]; k < rs[i + 1]; k++) s += ev[k] * p[cn16[k]];
+                else for (int k = rs[i]; k < rs[i + 1]; k++) s += ev[k] * p[cn32[k]];
+                R y = dg[i] * p[i] - s;
+                Ap[i] = y;
+                loc += (double)y * (double)p[i];
+            }
+            double pAp = tail_block_sum(loc, sh);
+            R alpha = (R)(rz / pAp);
+            loc = 0;
+            for (int i = t; i < n; i += T) { x[i] += alpha * p[i]; R rr = r[i] - alpha * Ap[i]; r[i] = rr; loc += (double)rr * (double)rr / (double)dg[i]; }
+            double rzn = tail_block_sum(loc, sh);
+            if (rzn <= relTol * relTol * rz0) break;
+            R beta = (R)(rzn / rz);
+            rz = rzn;
+            for (int i = t; i < n; i += T) p[i] = r[i] / dg[i] + beta * p[i];
         }
-        double pAp = tail_block_sum(loc, sh);
-        R alpha = (R)(rz / pAp);
-        loc = 0;
-        for (int i = t; i < n; i += T) { x[i] += alpha * p[i]; R rr = r[i] - alpha * Ap[i]; r[i] = rr; loc += (double)rr * (double)rr / (double)L.diag[i]; }
-        double rzn = tail_block_sum(loc, sh);
-        if (rzn <= relTol * relTol * rz0) break;
-        R beta = (R)(rzn / rz);
-        rz = rzn;
-        for (int i = t; i < n; i += T) p[i] = r[i] / L.diag[i] + beta * p[i];
+    if (useSmem) {
+        __syncthreads();
+        for (int i = t; i < n; i += T) L.x[i] = x[i];
     }
 }
 // The V-cycle over the tail levels lv[0..T-1]: lv[0].b -> lv[0].x.  Same cycle as the
@@ -220,35 +290,30 @@ DEV void tail_coarse_cg(const TLv<R>& L, R* r, R* p, R* Ap, int maxIter, double 
 // prolongation with GAMG's energy-minimising correction scaling, post-smoothing).
 template <class R>
 __global__ void __launch_bounds__(TAIL_THREADS, 1) vk_tail(const TailArgs<R> A) {
+    extern __shared__ __align__(16) unsigned char smem[];
     __shared__ double sh[TAIL_THREADS / 32];
     __shared__ double s_sf[2];
     GridBar gb{A.bar, gridDim.x, 0u, A.err};
     const int tid = blockIdx.x * blockDim.x + threadIdx.x, nth = gridDim.x * blockDim.x;
-    const int swaps = (A.nPre > 1 ? A.nPre - 1 : 0) + (A.nPost > 1 ? A.nPost : 1);
+    const int nPost = A.nPost > 1 ? A.nPost : 1, nPreSw = A.nPre > 1 ? A.nPre - 1 : 0;
+    const int swaps = nPreSw + nPost;
+    const R omega = A.omega;
     for (int t = 0; t < A.T - 1; t++) {
         const TLv<R>& L = A.lv[t];
-        const int coop = L.coop, lane = tid % coop, rpp = nth / coop;
         R* cur = tail_start(L, swaps);
         R* oth = cur == L.x ? L.y : L.x;
-        for (int i = tid; i < L.n; i += nth) cur[i] = A.omega * L.b[i] / L.diag[i];
+        for (int i = tid; i < L.n; i += nth) cur[i] = omega * L.b[i] / L.diag[i];
         gsync(gb);
-        for (int s = 1; s < A.nPre; s++) {
-            for (int base = 0; base < L.n; base += rpp) {
-                int row = base + tid / coop;
-                bool live = row < L.n;
-                int rr = live ? row : L.n - 1;
-                R off = tail_row(L, rr, cur, (const int*)nullptr, lane, coop);
-                if (live && lane == 0) oth[rr] = cur[rr] + A.omega * (L.b[rr] - (L.diag[rr] * cur[rr] - off)) / L.diag[rr];
-            }
+        for (int s = 0; s < nPreSw; s++) {
+            const R* in = cur;
+            R* out = oth;
+            tail_rows(L, in, (const int*)nullptr, tid, nth, [&](int i, R off) { out[i] = in[i] + omega * (L.b[i] - (L.diag[i] * in[i] - off)) / L.diag[i]; });
             R* tmp = cur; cur = oth; oth = tmp;
             gsync(gb);
         }
-        for (int base = 0; base < L.n; base += rpp) {
-            int row = base + tid / coop;
-            bool live = row < L.n;
-            int rr = live ? row : L.n - 1;
-            R off = tail_row(L, rr, cur, (const int*)nullptr, lane, coop);
-            if (live && lane == 0) L.r[rr] = L.b[rr] - (L.diag[rr] * cur[rr] - off);
+        {
+            const R* in = cur;
+            tail_rows(L, in, (const int*)nullptr, tid, nth, [&](int i, R off) { L.r[i] = L.b[i] - (L.diag[i] * in[i] - off); });
         }
         gsync(gb);
         const TLv<R>& C = A.lv[t + 1];
@@ -259,29 +324,25 @@ __global__ void __launch_bounds__(TAIL_THREADS, 1) vk_tail(const TailArgs<R> A) 
         }
         gsync(gb);
     }
-    if (blockIdx.x == 0) tail_coarse_cg(A.lv[A.T - 1], A.cgR, A.cgP, A.cgAp, A.cgIter, A.cgTol, sh);
+    if (blockIdx.x == 0) tail_coarse_cg(A.lv[A.T - 1], A.cgR, A.cgP, A.cgAp, A.cgIter, A.cgTol, sh, smem, A.cgSmem);
     gsync(gb);
     for (int t = A.T - 2; t >= 0; t--) {
         const TLv<R>& L = A.lv[t];
         const R* xc = A.lv[t + 1].x;
-        const int coop = L.coop, lane = tid % coop, rpp = nth / coop;
         R* cur = tail_start(L, swaps);
         R* oth = cur == L.x ? L.y : L.x;
-        if ((A.nPre > 1 ? A.nPre - 1 : 0) & 1) { R* tmp = cur; cur = oth; oth = tmp; }
+        if (nPreSw & 1) { R* tmp = cur; cur = oth; oth = tmp; }
         // A c for the prolonged correction c = xc[agg], with the dots r.c and c.Ac
         double v = 0, w = 0;
-        for (int base = 0; base < L.n; base += rpp) {
-            int row = base + tid / coop;
-            bool live = row < L.n;
-            int rr = live ? row : L.n - 1;
-            R off = tail_row(L, rr, xc, L.agg, lane, coop);
-            if (live && lane == 0) {
-                R c = xc[L.agg[rr]];
-                R ac = L.diag[rr] * c - off;
-                oth[rr] = ac;
-                v += (double)L.r[rr] * (double)c;
+        {
+            R* out = oth;
+            tail_rows(L, xc, L.agg, tid, nth, [&](int i, R off) {
+                R c = xc[L.agg[i]];
+                R ac = L.diag[i] * c - off;
+                out[i] = ac;
+                v += (double)L.r[i] * (double)c;
                 w += (double)ac * (double)c;
-            }
+            });
         }
         v = tail_block_sum(v, sh);
         w = tail_block_sum(w, sh);
@@ -298,15 +359,10 @@ __global__ void __launch_bounds__(TAIL_THREADS, 1) vk_tail(const TailArgs<R> A) 
         const R sf = (R)(s_sf[0] / (fabs(den) < VSMALL ? (den >= 0 ? VSMALL : -VSMALL) : den));
         for (int i = tid; i < L.n; i += nth) cur[i] += sf * xc[L.agg[i]] + A.scaleJ * (L.r[i] - sf * oth[i]) / L.diag[i];
         gsync(gb);
-        const int nPost = A.nPost > 1 ? A.nPost : 1;
         for (int s = 0; s < nPost; s++) {
-            for (int base = 0; base < L.n; base += rpp) {
-                int row = base + tid / coop;
-                bool live = row < L.n;
-                int rr = live ? row : L.n - 1;
-                R off = tail_row(L, rr, cur, (const int*)nullptr, lane, coop);
-                if (live && lane == 0) oth[rr] = cur[rr] + A.omega * (L.b[rr] - (L.diag[rr] * cur[rr] - off)) / L.diag[rr];
-            }
+            const R* in = cur;
+            R* out = oth;
+            tail_rows(L, in, (const int*)nullptr, tid, nth, [&](int i, R off) { out[i] = in[i] + omega * (L.b[i] - (L.diag[i] * in[i] - off)) / L.diag[i]; });
             R* tmp = cur; cur = oth; oth = tmp;
             if (s + 1 < nPost || t > 0) gsync(gb);
         }

@@ -68,6 +68,16 @@ struct Comm {
     ncclResult_t (*pAllReduce)(const void*, void*, size_t, ncclDataType_t, ncclRedOp_t, ncclComm_t, cudaStream_t) = nullptr;
     ncclResult_t (*pGroupStart)() = nullptr;
     ncclResult_t (*pGroupEnd)() = nullptr;
+    // halo exchange over peer memory (k_halo_p2p): my window, the neighbours' windows
+    bool p2p = false;
+    char* window = nullptr;
+    std::vector<void*> opened;               // cudaIpcOpenMemHandle results (closed at destroy)
+    std::vector<char*> peerBase;             // per patch: base of the neighbour's window
+    std::vector<size_t> myOff, peerOff, slot;  // per patch: data offset in my / the neighbour's window, slot bytes
+    std::vector<int> peerFlagIdx;            // per patch: my flag index inside the neighbour's window
+    unsigned long long* seq = nullptr;
+    unsigned* putDone = nullptr;
+    int* p2pErr = nullptr;
 #endif
 };
 
@@ -96,6 +106,7 @@ struct tpp_solver {
     std::vector<Level> levels;  // distributed coarse levels (levels[0] = first coarse); the last one is gathered
     std::vector<Level> tail;    // tail[0] = levels[gatherLevel] over all ranks, then the replicated coarser levels
     int gatherLevel = -1, tailRowOff = 0, tailFaceOff = 0, tailGrid = 1;
+    size_t tailSmem = 0;  // dynamic shared memory of vk_tail (coarsest level staged on chip), 0: not staged
     std::vector<std::array<int, 3>> tailCopy;  // processor-face coefficient ranges (src face, count, dst face) of the gather
     unsigned* tailBar = nullptr;
     int* tailErr = nullptr;
@@ -454,6 +465,9 @@ struct tpp_solver {
     // ---- halo exchange: owner-side values of my processor faces -> the neighbour's ghost cells
     void X(double* field, int nc) {
         if (!comm.active || nG == 0) return;
+#ifndef TPP_EMU
+        if (comm.p2p) { p2pExchange<double>(dProcOwner, procOff, nG, field, field + (size_t)nC * nc, nc); return; }
+#endif
         d.xsrc = field; d.xbuf = sendbuf; d.xnc = nc;
         LAUNCH(ctx, pack_halo, d, nG);
         double* ghost = field + (size_t)nC * nc;
@@ -476,6 +490,83 @@ struct tpp_solver {
         comm.xcb(comm.user, comm.hsend.data(), comm.hrecv.data(), nc);
         h2d(ctx, ghost, comm.hrecv.data(), (size_t)nG * nc * sizeof(double));
     }
+#ifndef TPP_EMU
+    // one halo exchange over peer memory; `off` = the level's patch offsets in ghost order
+    template <class T> void p2pExchange(const int* owner, const std::vector<int>& off, int ng, const T* src, T* ghost, int nc) {
+        P2PArgs a;
+        memset(&a, 0, sizeof(a));
+        a.nG = ng; a.nc = nc; a.nPatch = (int)off.size();
+        for (int p = 0; p < a.nPatch; p++) {
+            a.off[p] = off[p];
+            a.peerData[p] = comm.peerBase[p] + comm.peerOff[p];
+            a.peerFlag[p] = (unsigned long long*)(comm.peerBase[p] + 128 * (size_t)comm.peerFlagIdx[p]);
+            a.myData[p] = comm.window + comm.myOff[p];
+            a.myFlag[p] = (unsigned long long*)(comm.window + 128 * (size_t)p);
+            a.slot[p] = comm.slot[p];
+        }
+        a.owner = owner; a.src = src; a.ghost = ghost; a.seq = comm.seq; a.putDone = comm.putDone; a.err = comm.p2pErr;
+        const long total = (long)ng * nc;
+        const int grid = (int)std::max(1L, std::min(296L, (total + 1023) / 1024));
+        prof_begin(ctx, "halo_p2p");
+        k_halo_p2p<T><<<grid, 256, 0, ctx.stream>>>(a);
+        prof_end(ctx);
+        ctx.launches++;
+    }
+    // windows, IPC handles (gathered through the NCCL communicator), the neighbours' layout
+    void setupP2P() {
+        if (!comm.active || !comm.nccl || !knob("TPP_P2P", 1)) return;
+        const int np = (int)procCnt.size();
+        double fail = np > P2P_MAXPATCH ? 1.0 : 0.0;
+        size_t total = 4096;  // flags: 128 B apart
+        comm.myOff.assign(np, 0); comm.slot.assign(np, 0);
+        for (int p = 0; p < np; p++) {
+            comm.slot[p] = ((size_t)procCnt[p] * 9 * sizeof(double) + 255) / 256 * 256;  // up to 9 components (grad U)
+            comm.myOff[p] = total;
+            total += 2 * comm.slot[p];
+        }
+        comm.window = (char*)dev_alloc(total);
+        comm.seq = (unsigned long long*)dev_alloc(64); comm.putDone = (unsigned*)dev_alloc(64); comm.p2pErr = (int*)dev_alloc(64);
+        cudaIpcMemHandle_t mine;
+        if (cudaIpcGetMemHandle(&mine, comm.window) != cudaSuccess) { cudaGetLastError(); fail = 1.0; }
+        static_assert(sizeof(cudaIpcMemHandle_t) == 64, "cudaIpcMemHandle_t is 64 bytes");
+        std::vector<double> hv(64 * (size_t)comm.size, 0.0);  // one double per byte: summing with zeros is exact
+        for (int k = 0; k < 64; k++) hv[64 * (size_t)comm.rank + k] = (double)((unsigned char*)&mine)[k];
+        hostAllreduce(hv, 0);
+        std::map<int, char*> base;
+        for (int p = 0; p < np && fail == 0.0; p++) {
+            int q = procPeer[p];
+            if (base.count(q)) continue;
+            cudaIpcMemHandle_t h;
+            for (int k = 0; k < 64; k++) ((unsigned char*)&h)[k] = (unsigned char)(hv[64 * (size_t)q + k] + 0.5);
+            void* ptr = nullptr;
+            if (cudaIpcOpenMemHandle(&ptr, h, cudaIpcMemLazyEnablePeerAccess) != cudaSuccess) { cudaGetLastError(); fail = 1.0; break; }
+            comm.opened.push_back(ptr);
+            base[q] = (char*)ptr;
+        }
+        // what the neighbour calls the patch facing me: its data offset and flag index
+        std::vector<double> so((size_t)nG), sf((size_t)nG), ro, rf;
+        for (int p = 0; p < np; p++) for (int k = 0; k < procCnt[p]; k++) { so[procOff[p] + k] = (double)comm.myOff[p]; sf[procOff[p] + k] = (double)p; }
+        hostExchange(procOff, procCnt, procPeer, so, ro);
+        hostExchange(procOff, procCnt, procPeer, sf, rf);
+        std::vector<double> fv(1, fail);
+        hostAllreduce(fv, 1);
+        if (fv[0] != 0.0) {
+            if (comm.rank == 0) fprintf(stderr, "tppvof: peer-memory halo exchange unavailable (cudaIpc / peer access), using ncclSend/ncclRecv\n");
+            return;
+        }
+        comm.peerBase.assign(np, nullptr); comm.peerOff.assign(np, 0); comm.peerFlagIdx.assign(np, 0);
+        for (int p = 0; p < np; p++) {
+            comm.peerBase[p] = base[procPeer[p]];
+            comm.peerOff[p] = (size_t)(ro[procOff[p]] + 0.5);
+            comm.peerFlagIdx[p] = (int)(rf[procOff[p]] + 0.5);
+        }
+        // nobody may store into a window before everybody has opened and zeroed theirs
+        std::vector<double> bar(1, 0.0);
+        dev_sync(ctx);
+        hostAllreduce(bar, 0);
+        comm.p2p = true;
+    }
+#endif
     // all-reduce of n device scalars scal[idx..idx+n): op 0 sum, 1 max
     void allreduce(int idx, int n, int op) {
         if (!comm.active) return;
@@ -1036,7 +1127,7 @@ struct tpp_solver {
     void buildAMG() {
         amgBuilt = true;
         const int coarsestTarget = knob("TPP_COARSEST", 1500), maxLevels = 24;
-        const int tailRows = std::max(knob("TPP_TAIL_ROWS", 300000), coarsestTarget);
+        const int tailRows = std::max(knob("TPP_TAIL_ROWS", 60000), coarsestTarget);
         if (nGlobal <= coarsestTarget) return;
         // faceAreaPair weights |Sf/sqrt(|Sf|) * (1, 1.01, 1.02)|
         HostGraph g;
@@ -1083,13 +1174,24 @@ struct tpp_solver {
             int dev = 0, sms = 0, perSm = 0;
             cudaGetDevice(&dev);
             cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
-            if (knob("TPP_FP32", 1)) cudaOccupancyMaxActiveBlocksPerMultiprocessor(&perSm, vk_tail<float>, TAIL_THREADS, 0);
-            else cudaOccupancyMaxActiveBlocksPerMultiprocessor(&perSm, vk_tail<double>, TAIL_THREADS, 0);
+            // the coarsest level staged in the CTA's shared memory: CSR values + 5 vectors in R,
+            // row starts, 16-bit columns
+            const size_t rb = knob("TPP_FP32", 1) ? 4 : 8, cn_ = (size_t)tail.back().n, cz = (size_t)tail.back().nnz;
+            const size_t need_ = (cz + 5 * cn_) * rb + (cn_ + 1) * 4 + cz * 2 + 16;
+            tailSmem = (cn_ < 65536 && need_ <= 200 * 1024 && knob("TPP_CG_SMEM", 1)) ? need_ : 0;
+            if (knob("TPP_FP32", 1)) {
+                if (tailSmem) CUDA_CHECK(cudaFuncSetAttribute(vk_tail<float>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)tailSmem));
+                cudaOccupancyMaxActiveBlocksPerMultiprocessor(&perSm, vk_tail<float>, TAIL_THREADS, tailSmem);
+            } else {
+                if (tailSmem) CUDA_CHECK(cudaFuncSetAttribute(vk_tail<double>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)tailSmem));
+                cudaOccupancyMaxActiveBlocksPerMultiprocessor(&perSm, vk_tail<double>, TAIL_THREADS, tailSmem);
+            }
             tailGrid = std::min(sms * std::max(perSm, 1), 1024);
             if (perSm < 1) { fprintf(stderr, "tppvof: vk_tail does not fit an SM\n"); abort(); }
             // small tails do not need every SM: fewer CTAs make the grid barrier cheaper
             int need = (tail[0].n * 4 + TAIL_THREADS - 1) / TAIL_THREADS;
             tailGrid = std::max(1, std::min(tailGrid, need));
+            if (knob("TPP_TAIL_CTAS", 0) > 0) tailGrid = std::min(tailGrid, knob("TPP_TAIL_CTAS", 0));
         }
 #endif
     }
@@ -1204,6 +1306,9 @@ struct tpp_solver {
         const std::vector<int>& off = lv == 0 ? procOff : levels[lv - 1].poff;
         const std::vector<int>& cnt = lv == 0 ? procCnt : levels[lv - 1].pcnt;
         const std::vector<int>& peer = lv == 0 ? procPeer : levels[lv - 1].ppeer;
+#ifndef TPP_EMU
+        if (comm.p2p) { p2pExchange<R>(lv == 0 ? dProcOwner : levels[lv - 1].dOwner, off, ng, vec, vec + vRows(lv), 1); return; }
+#endif
         PackArgs<R> a;
         a.owner = lv == 0 ? dProcOwner : levels[lv - 1].dOwner; a.src = vec; a.dst = v.send[lv];
         VLAUNCH(ctx, pack, a, ng);
@@ -1229,6 +1334,18 @@ struct tpp_solver {
         hostExchange(off, cnt, peer, s, r);
         for (int j = 0; j < ng; j++) hr[j] = (R)r[j];
         h2d(ctx, ghost, hr.data(), ng * sizeof(R));
+    }
+    // ghost rows for a smoothing sweep that is not the first of its group.  Exact (default): a halo
+    // exchange.  TPP_LAG bit 0: the second pre-sweep from a zero guess sees zero ghosts; bit 1: a
+    // later post-sweep reuses the ghost values of the sweep before it (`prev`) - the smoother
+    // becomes block-Jacobi-like across rank interfaces for those sweeps only; residuals, the
+    // correction's A c and the first post-sweep always see exchanged values.
+    template <class R> void XLsmooth(int lv, R* vec, int kind, const R* prev = nullptr) {
+        const int ng = vGhosts(lv), lag = knob("TPP_LAG", 3);
+        if (!comm.active || ng == 0 || levels.empty()) return;
+        if (kind == 1 && (lag & 1)) { dev_zero(ctx, vec + vRows(lv), ng * sizeof(R)); ctx.launches++; return; }
+        if (kind == 2 && (lag & 2) && prev) { d2d(ctx, vec + vRows(lv), prev + vRows(lv), ng * sizeof(R)); ctx.launches++; return; }
+        XL<R>(lv, vec);
     }
     template <class R> void vRowOp(VL<R>& L, int mode) {  // 0 Jacobi sweep, 1 residual
 #ifndef TPP_EMU
@@ -1305,7 +1422,7 @@ struct tpp_solver {
             TLv<R>& L = A.lv[t];
             L.n = c.n;
             double deg = (double)c.nnz / std::max(c.n, 1);
-            L.coop = deg <= 6 ? 4 : deg <= 14 ? 8 : 16;
+            L.coop = deg <= 5 ? 4 : deg <= 10 ? 8 : 16;
             L.rs = c.rs; L.cn = c.cn; L.ev = v.tev[t]; L.diag = v.tdiag[t];
             if (t + 1 < A.T) L.agg = tail[t + 1].agg;
             if (t > 0) { L.aggStart = c.aggStart; L.aggRows = c.aggRows; }
@@ -1314,15 +1431,15 @@ struct tpp_solver {
         A.bar = tailBar; A.err = tailErr; A.partial = tailPartial;
         A.omega = (R)knobd("TPP_OMEGA", 0.8); A.scaleJ = (R)knobd("TPP_SCALEJ", 1.0);
         A.nPre = nPre; A.nPost = nPost; A.cgIter = knob("TPP_CITER", 16); A.cgTol = knobd("TPP_CTOL", 0.05);
-        A.cgR = v.cgR; A.cgP = v.cgP; A.cgAp = v.cgAp;
+        A.cgR = v.cgR; A.cgP = v.cgP; A.cgAp = v.cgAp; A.cgSmem = tailSmem > 0;
         prof_begin(ctx, "v_tail");
 #ifdef TPP_EMU
         tail_host(A);
 #else
         CUDA_CHECK(cudaMemsetAsync(tailBar, 0, sizeof(unsigned), ctx.stream));
         void* args[] = {&A};
-        if (knob("TPP_TAIL_COOP", 1)) CUDA_CHECK(cudaLaunchCooperativeKernel((void*)vk_tail<R>, dim3(tailGrid), dim3(TAIL_THREADS), args, 0, ctx.stream));
-        else vk_tail<R><<<tailGrid, TAIL_THREADS, 0, ctx.stream>>>(A);
+        if (knob("TPP_TAIL_COOP", 1)) CUDA_CHECK(cudaLaunchCooperativeKernel((void*)vk_tail<R>, dim3(tailGrid), dim3(TAIL_THREADS), args, tailSmem, ctx.stream));
+        else vk_tail<R><<<tailGrid, TAIL_THREADS, tailSmem, ctx.stream>>>(A);
 #endif
         prof_end(ctx);
         ctx.launches += 2;
@@ -1341,7 +1458,7 @@ struct tpp_solver {
         R *cur = x, *oth = v.t0[lv];
         for (int s = 0; s < std::max(nPre, 1); s++) {
             if (s == 0 && zeroGuess) { L.out = cur; VLAUNCH(ctx, jacobi0, L, L.n); }
-            else { XL<R>(lv, cur); L.in = cur; L.out = oth; vRowOp(L, 0); std::swap(cur, oth); }
+            else { XLsmooth<R>(lv, cur, s == 1 && zeroGuess ? 1 : 0); L.in = cur; L.out = oth; vRowOp(L, 0); std::swap(cur, oth); }
         }
         XL<R>(lv, cur);
         L.in = cur; L.out = v.r[lv];
@@ -1369,7 +1486,8 @@ struct tpp_solver {
         VLAUNCH(ctx, scale_apply, L, L.n);
         L.omega = omega;
         for (int s = 0; s < std::max(nPost, 1); s++) {
-            XL<R>(lv, cur);
+            if (s == 0) XL<R>(lv, cur);
+            else XLsmooth<R>(lv, cur, 2, oth);
             L.in = cur; L.out = oth;
             vRowOp(L, 0);
             std::swap(cur, oth);
@@ -1431,6 +1549,13 @@ struct tpp_solver {
             st.r = hscal[S_RES] / nf;
             if (!(fabs(hscal[S_WAPA]) / nf >= VSMALL)) break;
         } while (++st.iters < ctl.max_iter && !conv(st.r));
+#ifndef TPP_EMU
+        if (comm.p2p) {
+            int e = 0;
+            d2h(ctx, &e, comm.p2pErr, sizeof(int));
+            if (e) { ctx.err = "k_halo_p2p: a neighbour's halo did not arrive within 30 s"; fprintf(stderr, "tppvof: %s\n", ctx.err.c_str()); }
+        }
+#endif
         if (!tail.empty()) {  // a grid barrier of the tail kernel that timed out is a hard error
             int e = 0;
             d2h(ctx, &e, tailErr, sizeof(int));
@@ -1570,6 +1695,8 @@ struct tpp_solver {
         free(hscal);
 #else
         for (auto& g : graphs) cudaGraphExecDestroy(g.second.exec);
+        for (void* p : comm.opened) cudaIpcCloseMemHandle(p);
+        dev_free(comm.window); dev_free(comm.seq); dev_free(comm.putDone); dev_free(comm.p2pErr);
         if (hscal) cudaFreeHost(hscal);
         if (ctx.stream && ctx.ownStream) cudaStreamDestroy(ctx.stream);
 #endif
@@ -1884,6 +2011,7 @@ int tpp_comm_init(tpp_handle s, int rank, int n_ranks, const char* id128, const 
     CUDA_CHECK(cudaSetDevice(s->device));
     if (s->comm.pCommInitRank(&s->comm.nccl, n_ranks, id, rank) != ncclSuccess) { g_err = "ncclCommInitRank failed"; return -2; }
     s->comm.rank = rank; s->comm.size = n_ranks; s->comm.active = n_ranks > 1;
+    s->setupP2P();
     if (!s->finalizeParallel()) return -3;
     dev_sync(s->ctx);
     return 0;

@@ -36,7 +36,7 @@ if world > 1:
     mesh = mg.cylinder_mesh(C["H"], C["D"], nr, nl, "flat", "tet", k0=k0, k1=k1, proc=(rank, rank - 1 if rank > 0 else None, rank + 1 if rank < world - 1 else None))
 else:
     mesh = mg.cylinder_mesh(C["H"], C["D"], nr, nl, "flat", "tet")
-g = sv.Solver(mesh, bench.make_config(mesh), device=0, lib_path=args.lib)
+g = sv.Solver(mesh, bench.make_config(mesh), device=0, lib_path=None if args.lib == "gpu" else args.lib)
 if world > 1:
     g.comm_init_callbacks()
 g.set("alpha", bench.initial_alpha(mesh))
