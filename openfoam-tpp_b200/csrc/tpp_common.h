@@ -135,6 +135,12 @@ inline void dev_sync(Ctx&) {}
 #define DEF_KERNEL(name, VIEW) \
     inline void k_##name(const VIEW& d, int n) { for (int i = 0; i < n; i++) b_##name(d, i); }
 #define LAUNCH(ctx, name, view, n) do { if ((n) > 0) { prof_begin(ctx, #name); k_##name(view, n); prof_end(ctx); (ctx).launches++; } } while (0)
+// cell kernels templated on the ELL width WT (see FOR_CELL_FACES)
+#define DEF_KERNEL_W(name) \
+    template <int WT> inline void k_##name(const DV& d, int n) { for (int i = 0; i < n; i++) b_##name<WT>(d, i); }
+#define LAUNCH_W(ctx, name, view, n) do { if ((n) > 0) { prof_begin(ctx, #name); \
+    switch ((view).W) { case 4: k_##name<4>(view, n); break; case 5: k_##name<5>(view, n); break; case 6: k_##name<6>(view, n); break; default: k_##name<0>(view, n); } \
+    prof_end(ctx); (ctx).launches++; } } while (0)
 #else
 #define CUDA_CHECK(x) do { cudaError_t e_ = (x); if (e_ != cudaSuccess) { fprintf(stderr, "CUDA error %s at %s:%d\n", cudaGetErrorString(e_), __FILE__, __LINE__); abort(); } } while (0)
 inline void* dev_alloc(size_t bytes) {
@@ -158,6 +164,16 @@ inline void dev_sync(Ctx& c) { CUDA_CHECK(cudaStreamSynchronize(c.stream)); }
         if (i < n) b_##name(d, i);                                         \
     }
 #define LAUNCH(ctx, name, view, n) do { if ((n) > 0) { prof_begin(ctx, #name); k_##name<<<((n) + 255) / 256, 256, 0, (ctx).stream>>>(view, n); prof_end(ctx); (ctx).launches++; } } while (0)
+// cell kernels templated on the ELL width WT (see FOR_CELL_FACES)
+#define DEF_KERNEL_W(name)                                                              \
+    template <int WT> __global__ void __launch_bounds__(256) k_##name(const DV d, int n) { \
+        int i = blockIdx.x * blockDim.x + threadIdx.x;                                  \
+        if (i < n) b_##name<WT>(d, i);                                                  \
+    }
+#define LAUNCH_W(ctx, name, view, n) do { if ((n) > 0) { prof_begin(ctx, #name); const int g_ = ((n) + 255) / 256; \
+    switch ((view).W) { case 4: k_##name<4><<<g_, 256, 0, (ctx).stream>>>(view, n); break; case 5: k_##name<5><<<g_, 256, 0, (ctx).stream>>>(view, n); break; \
+                        case 6: k_##name<6><<<g_, 256, 0, (ctx).stream>>>(view, n); break; default: k_##name<0><<<g_, 256, 0, (ctx).stream>>>(view, n); } \
+    prof_end(ctx); (ctx).launches++; } } while (0)
 #endif
 
 template <class T>

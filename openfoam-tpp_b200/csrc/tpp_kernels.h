@@ -17,18 +17,32 @@
 
 namespace tpp {
 
+// WT = compile-time ELL width (tets 4, prisms 5, hexes 6; 0 = run-time width): the slot loop is
+// fully unrolled and has no early exit, so the index loads of all slots are issued together and
+// the gathers of the slots overlap - these kernels are latency-bound otherwise.  Padded slots
+// (e < 0) only ever follow the real ones, so skipping them keeps the summation order.
 #define FOR_CELL_FACES(d, c)                                  \
-    for (int s_ = 0; s_ < (d).W; s_++) {                      \
+    _Pragma("unroll")                                         \
+    for (int s_ = 0; s_ < (WT > 0 ? WT : (d).W); s_++) {      \
         const int e_ = (d).cf[(size_t)s_ * (d).nCp + (c)];    \
-        if (e_ < 0) break;                                    \
+        if (e_ < 0) { if (WT > 0) continue; else break; }     \
         const int f = e_ >> 1;                                \
         const int isN = e_ & 1;                               \
         const int o = (d).cn[(size_t)s_ * (d).nCp + (c)];     \
         (void)o; (void)isN;
 #define END_CELL_FACES }
+// Load-first form of the hottest cell kernels (WT > 0): the (face, neighbour) indices of all
+// slots, then every gathered operand of all slots, are loaded before the first dependent use,
+// so one thread keeps 4-6 x (operands per slot) loads in flight; the arithmetic that follows is
+// the run-time-width loop's, slot by slot in the same order (bit-identical sums).  A padded slot
+// reads face 0 / the cell itself (valid addresses) and is skipped in the arithmetic.
+template <int WT> HD void load_slots(const DV& d, int c, int* e, int* o) {
+#pragma unroll
+    for (int k = 0; k < WT; k++) { e[k] = d.cf[(size_t)k * d.nCp + c]; o[k] = d.cn[(size_t)k * d.nCp + c]; }
+}
 
 // ---- S0 Courant numbers ------------------------------------------------------------------
-HD void b_courant(const DV& d, int c) {
+template <int WT> HD void b_courant(const DV& d, int c) {
     double s = 0;
     FOR_CELL_FACES(d, c) s += fabs(d.phi[f]); END_CELL_FACES
     double v = s / d.V[c];
@@ -90,19 +104,49 @@ HD void b_p_evaluate(const DV& d, int b) {
 }
 
 // ---- Gauss linear gradient of a scalar (gs, gsb -> gout) -----------------------------------
-HD void b_grad_scalar(const DV& d, int c) {
+template <int WT> HD void b_grad_scalar(const DV& d, int c) {
     double g[3] = {0, 0, 0};
-    FOR_CELL_FACES(d, c)
-        if (f < d.nI) {
-            int P = isN ? o : c, N = isN ? c : o;
-            double sf = d.w[f] * d.gs[P] + (1.0 - d.w[f]) * d.gs[N];
-            for (int k = 0; k < 3; k++) {
-                double v = d.Sf[3 * f + k] * sf;
-                if (isN) g[k] -= v; else g[k] += v;
-            }
-        } else
-            for (int k = 0; k < 3; k++) g[k] += d.Sf[3 * f + k] * d.gsb[f - d.nI];
-    END_CELL_FACES
+    if constexpr (WT > 0) {
+        int e[WT], o[WT];
+        load_slots<WT>(d, c, e, o);
+        const double own = d.gs[c];
+        double wv[WT], S[WT][3], ov[WT];
+#pragma unroll
+        for (int k = 0; k < WT; k++) {
+            const bool live = e[k] >= 0;
+            const int f = live ? e[k] >> 1 : 0;
+            wv[k] = d.w[f];
+            S[k][0] = d.Sf[3 * f]; S[k][1] = d.Sf[3 * f + 1]; S[k][2] = d.Sf[3 * f + 2];
+            const double* q = f >= d.nI ? &d.gsb[f - d.nI] : &d.gs[live ? o[k] : c];
+            ov[k] = *q;
+        }
+#pragma unroll
+        for (int k = 0; k < WT; k++) {
+            if (e[k] < 0) continue;
+            const int f = e[k] >> 1, isN = e[k] & 1;
+            if (f < d.nI) {
+                double gP = isN ? ov[k] : own, gN = isN ? own : ov[k];
+                double sf = wv[k] * gP + (1.0 - wv[k]) * gN;
+                for (int j = 0; j < 3; j++) {
+                    double v = S[k][j] * sf;
+                    if (isN) g[j] -= v; else g[j] += v;
+                }
+            } else
+                for (int j = 0; j < 3; j++) g[j] += S[k][j] * ov[k];
+        }
+    } else {
+        FOR_CELL_FACES(d, c)
+            if (f < d.nI) {
+                int P = isN ? o : c, N = isN ? c : o;
+                double sf = d.w[f] * d.gs[P] + (1.0 - d.w[f]) * d.gs[N];
+                for (int k = 0; k < 3; k++) {
+                    double v = d.Sf[3 * f + k] * sf;
+                    if (isN) g[k] -= v; else g[k] += v;
+                }
+            } else
+                for (int k = 0; k < 3; k++) g[k] += d.Sf[3 * f + k] * d.gsb[f - d.nI];
+        END_CELL_FACES
+    }
     for (int k = 0; k < 3; k++) d.gout[3 * c + k] = g[k] / d.V[c];
 }
 
@@ -141,26 +185,62 @@ HD void b_alpha_flux(const DV& d, int f) {
     }
 }
 
-HD void b_mules_setup(const DV& d, int c) {
+template <int WT> HD void b_mules_setup(const DV& d, int c) {
     double mx = 0.0, mn = 1.0, sBD = 0, sP = 0, mM = 0;  // psiMin = 0, psiMax = 1
-    FOR_CELL_FACES(d, c)
-        if (f < d.nI) {
-            double a = d.alpha[o];
-            mx = dmax(mx, a);
-            mn = dmin(mn, a);
-            double bd = d.phiBD[f], pc = d.phiCorr[f];
-            if (isN) {
-                sBD -= bd;
-                if (pc > 0) mM += pc; else sP -= pc;
-            } else {
-                sBD += bd;
-                if (pc > 0) sP += pc; else mM -= pc;
-            }
-        } else {
-            sBD += d.phiBD[f];
-            mM -= 0.0;  // boundary phiCorr is identically 0 (non-coupled patches)
+    if constexpr (WT > 0) {
+        int e[WT], o[WT];
+        load_slots<WT>(d, c, e, o);
+        double av[WT], bdv[WT], pcv[WT];
+#pragma unroll
+        for (int k = 0; k < WT; k++) {
+            const bool live = e[k] >= 0;
+            const int f = live ? e[k] >> 1 : 0;
+            const bool in = f < d.nI;
+            av[k] = d.alpha[(live && in) ? o[k] : c];
+            bdv[k] = d.phiBD[f];
+            pcv[k] = d.phiCorr[in ? f : 0];
         }
-    END_CELL_FACES
+#pragma unroll
+        for (int k = 0; k < WT; k++) {
+            if (e[k] < 0) continue;
+            const int f = e[k] >> 1, isN = e[k] & 1;
+            if (f < d.nI) {
+                double a = av[k];
+                mx = dmax(mx, a);
+                mn = dmin(mn, a);
+                double bd = bdv[k], pc = pcv[k];
+                if (isN) {
+                    sBD -= bd;
+                    if (pc > 0) mM += pc; else sP -= pc;
+                } else {
+                    sBD += bd;
+                    if (pc > 0) sP += pc; else mM -= pc;
+                }
+            } else {
+                sBD += bdv[k];
+                mM -= 0.0;
+            }
+        }
+    } else {
+        FOR_CELL_FACES(d, c)
+            if (f < d.nI) {
+                double a = d.alpha[o];
+                mx = dmax(mx, a);
+                mn = dmin(mn, a);
+                double bd = d.phiBD[f], pc = d.phiCorr[f];
+                if (isN) {
+                    sBD -= bd;
+                    if (pc > 0) mM += pc; else sP -= pc;
+                } else {
+                    sBD += bd;
+                    if (pc > 0) sP += pc; else mM -= pc;
+                }
+            } else {
+                sBD += d.phiBD[f];
+                mM -= 0.0;  // boundary phiCorr is identically 0 (non-coupled patches)
+            }
+        END_CELL_FACES
+    }
     mx = dmin(mx, 1.0);
     mn = dmax(mn, 0.0);
     double V = d.V[c], a0 = d.alpha0[c];
@@ -170,19 +250,46 @@ HD void b_mules_setup(const DV& d, int c) {
     d.mSumPhim[c] = mM;
 }
 
-HD void b_mules_cell(const DV& d, int c) {
+template <int WT> HD void b_mules_cell(const DV& d, int c) {
     double sl = 0, ml = 0;
-    FOR_CELL_FACES(d, c)
-        if (f < d.nI) {
-            double lp = d.lambda[f] * d.phiCorr[f];
-            if (isN) {
-                if (lp > 0) ml += lp; else sl -= lp;
-            } else {
-                if (lp > 0) sl += lp; else ml -= lp;
-            }
-        } else
-            ml -= 0.0;
-    END_CELL_FACES
+    if constexpr (WT > 0) {
+        int e[WT], o[WT];
+        load_slots<WT>(d, c, e, o);
+        double lv[WT], pcv[WT];
+#pragma unroll
+        for (int k = 0; k < WT; k++) {
+            const int f = e[k] >= 0 ? e[k] >> 1 : 0;
+            const int fi = f < d.nI ? f : 0;
+            lv[k] = d.lambda[fi];
+            pcv[k] = d.phiCorr[fi];
+        }
+#pragma unroll
+        for (int k = 0; k < WT; k++) {
+            if (e[k] < 0) continue;
+            const int f = e[k] >> 1, isN = e[k] & 1;
+            if (f < d.nI) {
+                double lp = lv[k] * pcv[k];
+                if (isN) {
+                    if (lp > 0) ml += lp; else sl -= lp;
+                } else {
+                    if (lp > 0) sl += lp; else ml -= lp;
+                }
+            } else
+                ml -= 0.0;
+        }
+    } else {
+        FOR_CELL_FACES(d, c)
+            if (f < d.nI) {
+                double lp = d.lambda[f] * d.phiCorr[f];
+                if (isN) {
+                    if (lp > 0) ml += lp; else sl -= lp;
+                } else {
+                    if (lp > 0) sl += lp; else ml -= lp;
+                }
+            } else
+                ml -= 0.0;
+        END_CELL_FACES
+    }
     d.lambdam[c] = dmax(dmin((sl + d.psiMaxn[c]) / (d.mSumPhim[c] + ROOTVSMALL), 1.0), 0.0);
     d.lambdap[c] = dmax(dmin((ml + d.psiMinn[c]) / (d.sumPhip[c] + ROOTVSMALL), 1.0), 0.0);
 }
@@ -201,11 +308,24 @@ HD void b_mules_phipsi(const DV& d, int f) {
 
 HD void b_alphaphi_acc(const DV& d, int f) { d.alphaPhi[f] += d.subW * d.alphaPhiUn[f]; }
 
-HD void b_mules_update(const DV& d, int c) {
+template <int WT> HD void b_mules_update(const DV& d, int c) {
     double div = 0;
-    FOR_CELL_FACES(d, c)
-        if (isN) div -= d.alphaPhiUn[f]; else div += d.alphaPhiUn[f];
-    END_CELL_FACES
+    if constexpr (WT > 0) {
+        int e[WT], o[WT];
+        load_slots<WT>(d, c, e, o);
+        double pv[WT];
+#pragma unroll
+        for (int k = 0; k < WT; k++) pv[k] = d.alphaPhiUn[e[k] >= 0 ? e[k] >> 1 : 0];
+#pragma unroll
+        for (int k = 0; k < WT; k++) {
+            if (e[k] < 0) continue;
+            if (e[k] & 1) div -= pv[k]; else div += pv[k];
+        }
+    } else {
+        FOR_CELL_FACES(d, c)
+            if (isN) div -= d.alphaPhiUn[f]; else div += d.alphaPhiUn[f];
+        END_CELL_FACES
+    }
     double V = d.V[c];
     double psiIf = div / V;
     d.alpha[c] = (V * d.alpha0[c] * d.rDeltaT / V - psiIf) / d.rDeltaT;
@@ -223,7 +343,7 @@ HD double mu_of(const DV& d, double a, double r) {
 }
 
 // ---- S4 momentum matrix ---------------------------------------------------------------------
-HD void b_grad_U(const DV& d, int c) {
+template <int WT> HD void b_grad_U(const DV& d, int c) {
     double g[9] = {0, 0, 0, 0, 0, 0, 0, 0, 0};
     FOR_CELL_FACES(d, c)
         if (f < d.nI) {
@@ -340,7 +460,7 @@ HD void b_mom_bnd(const DV& d, int b) {
 // reference's relaxation factor 1 (fvSolution:89-95): D = max(|D + sum_b max|iC||, sum|offdiag|)
 // - sum_b min(iC), the difference goes to the source with the current U [OF13-MEM].  This is
 // what keeps A = D/V positive when a water-laden mass flux crosses an air cell.
-HD void b_mom_cell(const DV& d, int c) {
+template <int WT> HD void b_mom_cell(const DV& d, int c) {
     double ds = 0, so = 0, bmax = 0, bmin = 0, src[3] = {0, 0, 0};
     FOR_CELL_FACES(d, c)
         if (f < d.nI) {
@@ -370,7 +490,7 @@ HD void b_mom_cell(const DV& d, int c) {
 }
 
 // ---- S5 pressure corrector ---------------------------------------------------------------------
-HD void b_HbyA(const DV& d, int c) {
+template <int WT> HD void b_HbyA(const DV& d, int c) {
     double D = d.mDiag[c];
     double hb[3] = {0, 0, 0}, ldu[3] = {0, 0, 0}, bbc[3] = {0, 0, 0};
     const double* Uc = &d.U[3 * c];
@@ -457,7 +577,7 @@ HD void b_p_face(const DV& d, int f) {
     d.pCorrFlux[f] = c * dot3(&d.corrVec[3 * f], g);
 }
 
-HD void b_p_cell(const DV& d, int c) {
+template <int WT> HD void b_p_cell(const DV& d, int c) {
     double dg = 0, divPhi = 0, divCorr = 0, bDiag = 0, bSrc = 0;
     FOR_CELL_FACES(d, c)
         if (f < d.nI) {
@@ -503,17 +623,41 @@ HD void b_flux(const DV& d, int f) {
     d.rec[f] = (d.phig[f] - fl) / d.rAUf[f];
 }
 
-HD void b_U_recon(const DV& d, int c) {
+template <int WT> HD void b_U_recon(const DV& d, int c) {
     double T[9] = {0, 0, 0, 0, 0, 0, 0, 0, 0}, rv[3] = {0, 0, 0};
-    FOR_CELL_FACES(d, c)
-        double m = d.magSf[f];
-        double sh[3] = {d.Sf[3 * f] / m, d.Sf[3 * f + 1] / m, d.Sf[3 * f + 2] / m};
-        double ssf = d.rec[f];
-        for (int i = 0; i < 3; i++) {
-            for (int j = 0; j < 3; j++) T[3 * i + j] += sh[i] * d.Sf[3 * f + j];
-            rv[i] += sh[i] * ssf;
+    if constexpr (WT > 0) {
+        int e[WT], o[WT];
+        load_slots<WT>(d, c, e, o);
+        double mv[WT], S[WT][3], rc[WT];
+#pragma unroll
+        for (int k = 0; k < WT; k++) {
+            const int f = e[k] >= 0 ? e[k] >> 1 : 0;
+            mv[k] = d.magSf[f];
+            S[k][0] = d.Sf[3 * f]; S[k][1] = d.Sf[3 * f + 1]; S[k][2] = d.Sf[3 * f + 2];
+            rc[k] = d.rec[f];
         }
-    END_CELL_FACES
+#pragma unroll
+        for (int k = 0; k < WT; k++) {
+            if (e[k] < 0) continue;
+            double m = mv[k];
+            double sh[3] = {S[k][0] / m, S[k][1] / m, S[k][2] / m};
+            double ssf = rc[k];
+            for (int i = 0; i < 3; i++) {
+                for (int j = 0; j < 3; j++) T[3 * i + j] += sh[i] * S[k][j];
+                rv[i] += sh[i] * ssf;
+            }
+        }
+    } else {
+        FOR_CELL_FACES(d, c)
+            double m = d.magSf[f];
+            double sh[3] = {d.Sf[3 * f] / m, d.Sf[3 * f + 1] / m, d.Sf[3 * f + 2] / m};
+            double ssf = d.rec[f];
+            for (int i = 0; i < 3; i++) {
+                for (int j = 0; j < 3; j++) T[3 * i + j] += sh[i] * d.Sf[3 * f + j];
+                rv[i] += sh[i] * ssf;
+            }
+        END_CELL_FACES
+    }
     double xx = T[0], xy = T[1], xz = T[2], yx = T[3], yy = T[4], yz = T[5], zx = T[6], zy = T[7], zz = T[8];
     double det = xx * (yy * zz - yz * zy) - xy * (yx * zz - yz * zx) + xz * (yx * zy - yy * zx);
     double inv[9] = {yy * zz - zy * yz, xz * zy - xy * zz, xy * yz - xz * yy,
@@ -653,33 +797,33 @@ HD void b_file_to_face(const DV& d, int fd) {
 DEF_KERNEL(pack_halo, DV)
 DEF_KERNEL(face_to_file, DV)
 DEF_KERNEL(file_to_face, DV)
-DEF_KERNEL(courant, DV)
+DEF_KERNEL_W(courant)
 DEF_KERNEL(alpha_bc, DV)
 DEF_KERNEL(U_bc, DV)
 DEF_KERNEL(p_total, DV)
 DEF_KERNEL(p_evaluate, DV)
-DEF_KERNEL(grad_scalar, DV)
+DEF_KERNEL_W(grad_scalar)
 DEF_KERNEL(alpha_flux, DV)
-DEF_KERNEL(mules_setup, DV)
-DEF_KERNEL(mules_cell, DV)
+DEF_KERNEL_W(mules_setup)
+DEF_KERNEL_W(mules_cell)
 DEF_KERNEL(mules_face, DV)
 DEF_KERNEL(mules_phipsi, DV)
 DEF_KERNEL(alphaphi_acc, DV)
-DEF_KERNEL(mules_update, DV)
+DEF_KERNEL_W(mules_update)
 DEF_KERNEL(mixture_cell, DV)
 DEF_KERNEL(mixture_bnd, DV)
 DEF_KERNEL(rhophi, DV)
-DEF_KERNEL(grad_U, DV)
+DEF_KERNEL_W(grad_U)
 DEF_KERNEL(mom_face, DV)
 DEF_KERNEL(mom_bnd, DV)
-DEF_KERNEL(mom_cell, DV)
-DEF_KERNEL(HbyA, DV)
+DEF_KERNEL_W(mom_cell)
+DEF_KERNEL_W(HbyA)
 DEF_KERNEL(HbyA_bnd, DV)
 DEF_KERNEL(phiHbyA, DV)
 DEF_KERNEL(p_face, DV)
-DEF_KERNEL(p_cell, DV)
+DEF_KERNEL_W(p_cell)
 DEF_KERNEL(flux, DV)
-DEF_KERNEL(U_recon, DV)
+DEF_KERNEL_W(U_recon)
 DEF_KERNEL(Uf, DV)
 DEF_KERNEL(p, DV)
 DEF_KERNEL(p_shift, DV)

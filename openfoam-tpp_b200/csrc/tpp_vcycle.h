@@ -23,6 +23,12 @@ struct VL {
     int n, nf, nCp, W, ell, nOwn;
     const int *cn, *rs;  // adjacency: other row (ELL slot-major / CSR), CSR row starts
     const R *diag, *ev;  // matrix values (ev: off-diagonal magnitude per adjacency entry)
+    // coarse levels on the device: ELL part (the first ellW entries of every row, slot-major with
+    // stride nPad: coalesced, no row-start indirection, all gathers of a row in flight at once)
+    // plus the overflow entries of the few longer rows in CSR form
+    int ellW, nPad;
+    const int *ecn, *ors, *ocn;
+    const R *eev, *oev;
     // transfer (set on the level being restricted to / prolonged from)
     const int *agg, *aggStart, *aggRows;
     // kernel arguments
@@ -437,6 +443,53 @@ __global__ void __launch_bounds__(256) vk_csr_spmv_dot2(const VL<R> L, double* p
     __syncthreads();
     w = block_sum(w);
     if (threadIdx.x == 0) { partialNum[blockIdx.x] = v; partialDen[blockIdx.x] = w; }
+}
+// ---- coarse levels in ELL + overflow form: one thread per row ------------------------------------
+template <class R, int W>
+DEV R vl_ellc_off(const VL<R>& L, int c, const R* x) {
+    int o[W];
+    R v[W], xv[W];
+#pragma unroll
+    for (int k = 0; k < W; k++) { o[k] = L.ecn[(size_t)k * L.nPad + c]; v[k] = L.eev[(size_t)k * L.nPad + c]; }
+#pragma unroll
+    for (int k = 0; k < W; k++) xv[k] = o[k] >= 0 ? x[o[k]] : R(0);
+    R s = 0;
+#pragma unroll
+    for (int k = 0; k < W; k++) s += v[k] * xv[k];
+    for (int k = L.ors[c]; k < L.ors[c + 1]; k++) s += L.oev[k] * x[L.ocn[k]];
+    return s;
+}
+// mode 0: Jacobi sweep ; 1: residual
+template <class R, int W>
+__global__ void __launch_bounds__(256) vk_ellc_row_op(const VL<R> L, int mode) {
+    int c = blockIdx.x * blockDim.x + threadIdx.x;
+    if (c >= L.n) return;
+    R xc = L.in[c];
+    R ax = L.diag[c] * xc - vl_ellc_off<R, W>(L, c, L.in);
+    if (mode == 0) L.out[c] = xc + L.omega * (L.b[c] - ax) / L.diag[c];
+    else L.out[c] = L.b[c] - ax;
+}
+template <class R, int W>
+__global__ void __launch_bounds__(256) vk_ellc_spmv_dot2(const VL<R> L, double* partialNum, double* partialDen) {
+    double v = 0, w = 0;
+    for (int c = blockIdx.x * blockDim.x + threadIdx.x; c < L.n; c += gridDim.x * blockDim.x) {
+        R x = L.in[c];
+        R y = L.diag[c] * x - vl_ellc_off<R, W>(L, c, L.in);
+        L.out[c] = y;
+        v += (double)L.r[c] * (double)x;
+        w += (double)y * (double)x;
+    }
+    v = block_sum(v);
+    __syncthreads();
+    w = block_sum(w);
+    if (threadIdx.x == 0) { partialNum[blockIdx.x] = v; partialDen[blockIdx.x] = w; }
+}
+// ELL values from the CSR ones: dst[i] = src[idx[i]] (0 for padding)
+template <class R> struct GatherArgs { const double* src; const int* idx; R* dst; };
+template <class R>
+__global__ void __launch_bounds__(256) vk_cast_gather(const GatherArgs<R> a, int n) {
+    int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i < n) { int k = a.idx[i]; a.dst[i] = k >= 0 ? (R)a.src[k] : R(0); }
 }
 // Jacobi-preconditioned CG on a whole (tiny) mesh without any coarse level, one CTA; vectors
 // in R, reductions in double.  out = x, b = rhs

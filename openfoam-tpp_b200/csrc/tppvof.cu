@@ -32,7 +32,11 @@ struct Level {
     int *cf = nullptr, *cn = nullptr, *rs = nullptr, *own = nullptr, *nei = nullptr, *dOwner = nullptr;
     int *agg = nullptr, *aggStart = nullptr, *aggRows = nullptr, *segStart = nullptr, *segFaces = nullptr;
     double *ev = nullptr, *diag = nullptr, *upper = nullptr, *rsum = nullptr;
+    // ELL + overflow form of the CSR rows (distributed levels smoothed kernel by kernel)
+    int ellW = 0, nPad = 0, nOv = 0;
+    int *ecn = nullptr, *esrc = nullptr, *ors = nullptr, *ocn = nullptr, *osrc = nullptr;
     void free() {
+        for (void* p : {(void*)ecn, (void*)esrc, (void*)ors, (void*)ocn, (void*)osrc}) dev_free(p);
         for (void* p : {(void*)cf, (void*)cn, (void*)rs, (void*)own, (void*)nei, (void*)dOwner, (void*)agg, (void*)aggStart, (void*)aggRows, (void*)segStart, (void*)segFaces,
                         (void*)ev, (void*)diag, (void*)upper, (void*)rsum})
             dev_free(p);
@@ -634,7 +638,7 @@ struct tpp_solver {
     void readScal() { d2h(ctx, hscal, scal, S_COUNT * sizeof(double)); }
 
     void courant() {
-        LAUNCH(ctx, courant, d, nC);
+        LAUNCH_W(ctx, courant, d, nC);
         red.reduce(ctx, d.cellTmp, nullptr, nC, 3, scal + S_MAX0);
         red.reduce(ctx, d.cellTmp + nC, nullptr, nC, 3, scal + S_MAX1);
         allreduce(S_MAX0, 2, 1);
@@ -684,7 +688,7 @@ struct tpp_solver {
     void mixture() { LAUNCH(ctx, mixture_cell, d, nC); LAUNCH(ctx, mixture_bnd, d, nB); }
     void gradScalar(const double* s, const double* sb, double* out) {
         d.gs = s; d.gsb = sb; d.gout = out;
-        LAUNCH(ctx, grad_scalar, d, nC);
+        LAUNCH_W(ctx, grad_scalar, d, nC);
     }
     void alphaSubCycle(double dts) {
         d.rDeltaT = 1.0 / dts;
@@ -694,15 +698,15 @@ struct tpp_solver {
         gradScalar(d.alpha, d.alpha_b, d.grad);
         X(d.grad, 3);
         LAUNCH(ctx, alpha_flux, d, nF);
-        LAUNCH(ctx, mules_setup, d, nC);
+        LAUNCH_W(ctx, mules_setup, d, nC);
         for (int j = 0; j < cfg.n_limiter_iter; j++) {
-            LAUNCH(ctx, mules_cell, d, nC);
+            LAUNCH_W(ctx, mules_cell, d, nC);
             X(d.lambdap, 1);
             X(d.lambdam, 1);
             LAUNCH(ctx, mules_face, d, nI);
         }
         LAUNCH(ctx, mules_phipsi, d, nF);
-        LAUNCH(ctx, mules_update, d, nC);
+        LAUNCH_W(ctx, mules_update, d, nC);
         alphaBCs();
     }
     void alphaPredictor() {
@@ -728,14 +732,14 @@ struct tpp_solver {
         UBCs();
         X(d.U, 3);
         d.rDeltaT = 1.0 / dt;
-        LAUNCH(ctx, grad_U, d, nC);
+        LAUNCH_W(ctx, grad_U, d, nC);
         X(d.gradU, 9);
         LAUNCH(ctx, mom_face, d, nI);
         LAUNCH(ctx, mom_bnd, d, nB);
-        LAUNCH(ctx, mom_cell, d, nC);
+        LAUNCH_W(ctx, mom_cell, d, nC);
     }
     void computeHbyA() {
-        LAUNCH(ctx, HbyA, d, nC);
+        LAUNCH_W(ctx, HbyA, d, nC);
         LAUNCH(ctx, HbyA_bnd, d, nB);
         X(d.rAU, 1);
         X(d.HbyA, 3);
@@ -753,12 +757,12 @@ struct tpp_solver {
         gradScalar(d.p_rgh, d.p_rgh_b, d.grad);
         X(d.grad, 3);
         LAUNCH(ctx, p_face, d, nI);
-        LAUNCH(ctx, p_cell, d, nC);
+        LAUNCH_W(ctx, p_cell, d, nC);
     }
     void pcFinish() {
         X(d.p_rgh, 1);
         LAUNCH(ctx, flux, d, nF);
-        LAUNCH(ctx, U_recon, d, nC);
+        LAUNCH_W(ctx, U_recon, d, nC);
         UBCs();
         X(d.U, 3);
     }
@@ -1008,6 +1012,30 @@ struct tpp_solver {
         if (!h.empty()) h2d(ctx, p, h.data(), h.size() * sizeof(T));
         return p;
     }
+    // ELL + overflow form of a level's CSR rows: the width is the smallest of 6/8/12/16 that leaves
+    // at most 4 % of the entries in the overflow lists
+    void buildEllc(Level& v, const std::vector<int>& rs, const std::vector<int>& cn) {
+        const int n = v.n;
+        if (n == 0) return;
+        int Wl = 16;
+        for (int w : {6, 8, 12, 16}) {
+            long ov = 0;
+            for (int i = 0; i < n; i++) ov += std::max(0, rs[i + 1] - rs[i] - w);
+            if (ov * 25 <= (long)rs[n]) { Wl = w; break; }
+        }
+        const int nPad = (n + 31) / 32 * 32;
+        std::vector<int> ecn((size_t)Wl * nPad, -1), esrc((size_t)Wl * nPad, -1), ors(n + 1, 0), ocn, osrc;
+        for (int i = 0; i < n; i++) {
+            for (int k = rs[i]; k < rs[i + 1]; k++) {
+                int s = k - rs[i];
+                if (s < Wl) { ecn[(size_t)s * nPad + i] = cn[k]; esrc[(size_t)s * nPad + i] = k; }
+                else { ocn.push_back(cn[k]); osrc.push_back(k); }
+            }
+            ors[i + 1] = (int)ocn.size();
+        }
+        v.ellW = Wl; v.nPad = nPad; v.nOv = (int)ocn.size();
+        v.ecn = upNew(ctx, ecn); v.esrc = upNew(ctx, esrc); v.ors = upNew(ctx, ors); v.ocn = upNew(ctx, ocn); v.osrc = upNew(ctx, osrc);
+    }
     // one hierarchy level below `g`: `passes` matching passes merged (mergeLevels); g becomes the
     // coarse graph.  dist: rows are distributed (halo patches, global decisions).  Returns false
     // when the coarsening has stalled.
@@ -1073,6 +1101,7 @@ struct tpp_solver {
         csrOf(cur, rs, cf, cn);
         v.nnz = rs[cur.n];
         v.rs = upNew(ctx, rs); v.cf = upNew(ctx, cf); v.cn = upNew(ctx, cn); v.own = upNew(ctx, cur.own); v.nei = upNew(ctx, cur.nei);
+        if (dist && knob("TPP_ELLC", 1)) buildEllc(v, rs, cn);
         v.agg = upNew(ctx, aggTot); v.segStart = upNew(ctx, segS); v.segFaces = upNew(ctx, segF);
         std::vector<int> howner(cur.own.begin() + cur.nfLoc, cur.own.end());
         v.dOwner = upNew(ctx, howner);
@@ -1236,6 +1265,7 @@ struct tpp_solver {
     // ---- V-cycle in precision R (tpp_vcycle.h): per-level storage, conversion, cycle, preconditioner
     template <class R> struct VStore {
         std::vector<R*> diag, ev, x, b, t0, r, Ac, send;  // index 0 = fine level, 1.. = distributed coarse levels
+        std::vector<R*> eev, oev;                         // ELL + overflow values of the coarse levels
         std::vector<R*> tdiag, tev, tx, ty, tb, tr;       // tail levels
         R *cgR = nullptr, *cgP = nullptr, *cgAp = nullptr;
         bool ready = false;
@@ -1255,7 +1285,11 @@ struct tpp_solver {
             v.diag.push_back(dalloc<R>(n)); v.ev.push_back(dalloc<R>(vEntries(lv)));
             v.x.push_back(dalloc<R>(n)); v.b.push_back(dalloc<R>(n)); v.t0.push_back(dalloc<R>(n)); v.r.push_back(dalloc<R>(n)); v.Ac.push_back(dalloc<R>(n));
             v.send.push_back(dalloc<R>(std::max(vGhosts(lv), 1)));
+            const bool ellc = lv > 0 && levels[lv - 1].ellW > 0;
+            v.eev.push_back(dalloc<R>(ellc ? (size_t)levels[lv - 1].ellW * levels[lv - 1].nPad : 1));
+            v.oev.push_back(dalloc<R>(ellc ? (size_t)std::max(levels[lv - 1].nOv, 1) : 1));
         }
+        for (auto* vec : {&v.eev, &v.oev}) for (R* p : *vec) allocs.push_back(p);
         for (auto* vec : {&v.diag, &v.ev, &v.x, &v.b, &v.t0, &v.r, &v.Ac, &v.send}) for (R* p : *vec) allocs.push_back(p);
         for (size_t t = 0; t < tail.size(); t++) {
             size_t n = (size_t)tail[t].n;
@@ -1277,6 +1311,10 @@ struct tpp_solver {
         if (lv == 0) { L.n = nC; L.nf = nI; L.nCp = nCp; L.W = W; L.ell = 1; L.cn = d.cn; L.nOwn = levels.empty() ? nC : nC + nG; }
         else { Level& c = levels[lv - 1]; L.n = c.n; L.nf = c.nf; L.ell = 0; L.cn = c.cn; L.rs = c.rs; L.nOwn = c.n + c.nG; L.agg = c.agg; L.aggStart = c.aggStart; L.aggRows = c.aggRows; }
         if (lv < vLevels()) { L.diag = v.diag[lv]; L.ev = v.ev[lv]; }
+        if (lv > 0 && lv < vLevels() && levels[lv - 1].ellW > 0) {
+            Level& c = levels[lv - 1];
+            L.ellW = c.ellW; L.nPad = c.nPad; L.ecn = c.ecn; L.ors = c.ors; L.ocn = c.ocn; L.eev = v.eev[lv]; L.oev = v.oev[lv];
+        }
         return L;
     }
     // matrix values of every level in precision R (after galerkin(), once per solve)
@@ -1289,6 +1327,16 @@ struct tpp_solver {
             VLAUNCH(ctx, cast_in, a, vRows(lv));
             a.src = lv == 0 ? F0.ev : levels[lv - 1].ev; a.dst = v.ev[lv];
             VLAUNCH(ctx, cast_in, a, (int)vEntries(lv));
+#ifndef TPP_EMU
+            if (lv > 0 && levels[lv - 1].ellW > 0) {
+                Level& c = levels[lv - 1];
+                GatherArgs<R> ga{c.ev, c.esrc, v.eev[lv]};
+                const int ne = c.ellW * c.nPad;
+                vk_cast_gather<R><<<(ne + 255) / 256, 256, 0, ctx.stream>>>(ga, ne);
+                if (c.nOv > 0) { GatherArgs<R> go{c.ev, c.osrc, v.oev[lv]}; vk_cast_gather<R><<<(c.nOv + 255) / 256, 256, 0, ctx.stream>>>(go, c.nOv); }
+                ctx.launches += 2;
+            }
+#endif
         }
         for (size_t t = 0; t < tail.size(); t++) {
             a.src = tail[t].diag; a.dst = v.tdiag[t];
@@ -1349,6 +1397,19 @@ struct tpp_solver {
     }
     template <class R> void vRowOp(VL<R>& L, int mode) {  // 0 Jacobi sweep, 1 residual
 #ifndef TPP_EMU
+        if (!L.ell && L.ellW > 0) {
+            prof_begin(ctx, mode == 0 ? "v_jacobi_csr" : "v_residual_csr");
+            const int g_ = (L.n + 255) / 256;
+            switch (L.ellW) {
+                case 6: vk_ellc_row_op<R, 6><<<g_, 256, 0, ctx.stream>>>(L, mode); break;
+                case 8: vk_ellc_row_op<R, 8><<<g_, 256, 0, ctx.stream>>>(L, mode); break;
+                case 12: vk_ellc_row_op<R, 12><<<g_, 256, 0, ctx.stream>>>(L, mode); break;
+                default: vk_ellc_row_op<R, 16><<<g_, 256, 0, ctx.stream>>>(L, mode); break;
+            }
+            prof_end(ctx);
+            ctx.launches++;
+            return;
+        }
         if (!L.ell) {
             prof_begin(ctx, mode == 0 ? "v_jacobi_csr" : "v_residual_csr");
             if (2 * (long)L.nf <= 10 * (long)L.n) vk_csr_row_op<R, 4><<<(L.n * 4 + 255) / 256, 256, 0, ctx.stream>>>(L, mode);
@@ -1371,7 +1432,15 @@ struct tpp_solver {
         prof_begin(ctx, L.ell ? "v_spmv_dot2" : "v_spmv_dot2_csr");
         int nb = RED_BLOCKS;
         if (L.ell) vk_spmv_dot2<R><<<nb, BLOCK, 0, ctx.stream>>>(L, red.partial, red.partial2);
-        else {
+        else if (L.ellW > 0) {
+            nb = std::min(RED_BLOCKS, (L.n + 255) / 256);
+            switch (L.ellW) {
+                case 6: vk_ellc_spmv_dot2<R, 6><<<nb, BLOCK, 0, ctx.stream>>>(L, red.partial, red.partial2); break;
+                case 8: vk_ellc_spmv_dot2<R, 8><<<nb, BLOCK, 0, ctx.stream>>>(L, red.partial, red.partial2); break;
+                case 12: vk_ellc_spmv_dot2<R, 12><<<nb, BLOCK, 0, ctx.stream>>>(L, red.partial, red.partial2); break;
+                default: vk_ellc_spmv_dot2<R, 16><<<nb, BLOCK, 0, ctx.stream>>>(L, red.partial, red.partial2); break;
+            }
+        } else {
             const bool shortRows = 2 * (long)L.nf <= 10 * (long)L.n;
             nb = std::min(RED_BLOCKS, (L.n * (shortRows ? 4 : 8) + 255) / 256);
             if (shortRows) vk_csr_spmv_dot2<R, 4><<<nb, BLOCK, 0, ctx.stream>>>(L, red.partial, red.partial2);
