@@ -33,7 +33,7 @@ namespace tpp {
 
 constexpr double SMALL = 1e-15, VSMALL = 1e-300, ROOTVSMALL = 1e-150;
 constexpr int BLOCK = 256;
-constexpr int RED_BLOCKS = 148 * 4;  // one partial per CTA, fixed -> deterministic sums
+constexpr int RED_BLOCKS = 148 * 8;  // fixed grid of the reducing kernels (2048 threads per SM), one partial per CTA -> deterministic sums
 
 // Device view: raw pointers + per-launch scalars, passed by value to every kernel.
 struct DV {
@@ -136,6 +136,7 @@ inline void dev_sync(Ctx&) {}
     inline void k_##name(const VIEW& d, int n) { for (int i = 0; i < n; i++) b_##name(d, i); }
 #define LAUNCH(ctx, name, view, n) do { if ((n) > 0) { prof_begin(ctx, #name); k_##name(view, n); prof_end(ctx); (ctx).launches++; } } while (0)
 // cell kernels templated on the ELL width WT (see FOR_CELL_FACES)
+#define DEF_KERNEL_WB(name, minb) DEF_KERNEL_W(name)
 #define DEF_KERNEL_W(name) \
     template <int WT> inline void k_##name(const DV& d, int n) { for (int i = 0; i < n; i++) b_##name<WT>(d, i); }
 #define LAUNCH_W(ctx, name, view, n) do { if ((n) > 0) { prof_begin(ctx, #name); \
@@ -165,8 +166,9 @@ inline void dev_sync(Ctx& c) { CUDA_CHECK(cudaStreamSynchronize(c.stream)); }
     }
 #define LAUNCH(ctx, name, view, n) do { if ((n) > 0) { prof_begin(ctx, #name); k_##name<<<((n) + 255) / 256, 256, 0, (ctx).stream>>>(view, n); prof_end(ctx); (ctx).launches++; } } while (0)
 // cell kernels templated on the ELL width WT (see FOR_CELL_FACES)
-#define DEF_KERNEL_W(name)                                                              \
-    template <int WT> __global__ void __launch_bounds__(256) k_##name(const DV d, int n) { \
+#define DEF_KERNEL_W(name) DEF_KERNEL_WB(name, 4)
+#define DEF_KERNEL_WB(name, minb)                                                       \
+    template <int WT> __global__ void __launch_bounds__(256, minb) k_##name(const DV d, int n) { \
         int i = blockIdx.x * blockDim.x + threadIdx.x;                                  \
         if (i < n) b_##name<WT>(d, i);                                                  \
     }

@@ -106,6 +106,7 @@ HD void b_p_evaluate(const DV& d, int b) {
 // ---- Gauss linear gradient of a scalar (gs, gsb -> gout) -----------------------------------
 template <int WT> HD void b_grad_scalar(const DV& d, int c) {
     double g[3] = {0, 0, 0};
+    const double Vc = d.V[c];  // independent of the gathers: issued with the first batch of loads
     if constexpr (WT > 0) {
         int e[WT], o[WT];
         load_slots<WT>(d, c, e, o);
@@ -147,7 +148,7 @@ template <int WT> HD void b_grad_scalar(const DV& d, int c) {
                 for (int k = 0; k < 3; k++) g[k] += d.Sf[3 * f + k] * d.gsb[f - d.nI];
         END_CELL_FACES
     }
-    for (int k = 0; k < 3; k++) d.gout[3 * c + k] = g[k] / d.V[c];
+    for (int k = 0; k < 3; k++) d.gout[3 * c + k] = g[k] / Vc;
 }
 
 // ---- S3 alpha: interfaceCompression(vanLeer) flux, upwind flux, MULES -------------------------
@@ -187,6 +188,7 @@ HD void b_alpha_flux(const DV& d, int f) {
 
 template <int WT> HD void b_mules_setup(const DV& d, int c) {
     double mx = 0.0, mn = 1.0, sBD = 0, sP = 0, mM = 0;  // psiMin = 0, psiMax = 1
+    const double V = d.V[c], a0 = d.alpha0[c];
     if constexpr (WT > 0) {
         int e[WT], o[WT];
         load_slots<WT>(d, c, e, o);
@@ -243,7 +245,6 @@ template <int WT> HD void b_mules_setup(const DV& d, int c) {
     }
     mx = dmin(mx, 1.0);
     mn = dmax(mn, 0.0);
-    double V = d.V[c], a0 = d.alpha0[c];
     d.psiMaxn[c] = V * (d.rDeltaT * mx) - (V * d.rDeltaT) * a0 + sBD;
     d.psiMinn[c] = V * (0.0 - d.rDeltaT * mn) + (V * d.rDeltaT) * a0 - sBD;
     d.sumPhip[c] = sP;
@@ -252,6 +253,7 @@ template <int WT> HD void b_mules_setup(const DV& d, int c) {
 
 template <int WT> HD void b_mules_cell(const DV& d, int c) {
     double sl = 0, ml = 0;
+    const double pMax = d.psiMaxn[c], pMin = d.psiMinn[c], mSm = d.mSumPhim[c], sPp = d.sumPhip[c];
     if constexpr (WT > 0) {
         int e[WT], o[WT];
         load_slots<WT>(d, c, e, o);
@@ -290,8 +292,8 @@ template <int WT> HD void b_mules_cell(const DV& d, int c) {
                 ml -= 0.0;
         END_CELL_FACES
     }
-    d.lambdam[c] = dmax(dmin((sl + d.psiMaxn[c]) / (d.mSumPhim[c] + ROOTVSMALL), 1.0), 0.0);
-    d.lambdap[c] = dmax(dmin((ml + d.psiMinn[c]) / (d.sumPhip[c] + ROOTVSMALL), 1.0), 0.0);
+    d.lambdam[c] = dmax(dmin((sl + pMax) / (mSm + ROOTVSMALL), 1.0), 0.0);
+    d.lambdap[c] = dmax(dmin((ml + pMin) / (sPp + ROOTVSMALL), 1.0), 0.0);
 }
 
 HD void b_mules_face(const DV& d, int f) {
@@ -310,6 +312,7 @@ HD void b_alphaphi_acc(const DV& d, int f) { d.alphaPhi[f] += d.subW * d.alphaPh
 
 template <int WT> HD void b_mules_update(const DV& d, int c) {
     double div = 0;
+    const double V = d.V[c], a0 = d.alpha0[c];
     if constexpr (WT > 0) {
         int e[WT], o[WT];
         load_slots<WT>(d, c, e, o);
@@ -326,9 +329,8 @@ template <int WT> HD void b_mules_update(const DV& d, int c) {
             if (isN) div -= d.alphaPhiUn[f]; else div += d.alphaPhiUn[f];
         END_CELL_FACES
     }
-    double V = d.V[c];
     double psiIf = div / V;
-    d.alpha[c] = (V * d.alpha0[c] * d.rDeltaT / V - psiIf) / d.rDeltaT;
+    d.alpha[c] = (V * a0 * d.rDeltaT / V - psiIf) / d.rDeltaT;
 }
 
 HD void b_mixture_cell(const DV& d, int c) { d.rho[c] = d.alpha[c] * d.rho1 + (1.0 - d.alpha[c]) * d.rho2; }
@@ -823,7 +825,7 @@ DEF_KERNEL(phiHbyA, DV)
 DEF_KERNEL(p_face, DV)
 DEF_KERNEL_W(p_cell)
 DEF_KERNEL(flux, DV)
-DEF_KERNEL_W(U_recon)
+DEF_KERNEL_WB(U_recon, 2)  // 9 + 3 accumulators and 4 x 5 operands in flight: needs > 64 registers
 DEF_KERNEL(Uf, DV)
 DEF_KERNEL(p, DV)
 DEF_KERNEL(p_shift, DV)

@@ -246,12 +246,55 @@ __global__ void __launch_bounds__(256) k_reduce_final2(const double* p0, const d
     if (threadIdx.x == 0) *(blockIdx.x == 0 ? out0 : out1) = v;
 }
 // wA = A pA fused with partial sums of wA.pA
+// (grid-stride over a fixed grid of RED_BLOCKS CTAs = every warp the SMs can hold; a partial per
+// row-CTA instead was measured slower: the single-CTA final sum over 24 k partials costs more
+// than the main kernel gains)
 __global__ void __launch_bounds__(256) k_spmv_dot(LV L, double* partial) {
     double v = 0;
     for (int c = blockIdx.x * blockDim.x + threadIdx.x; c < L.n; c += gridDim.x * blockDim.x) {
         double y = row_Ax(L, c, L.in);
         L.out[c] = y;
         v += y * L.in[c];
+    }
+    v = block_sum(v);
+    if (threadIdx.x == 0) partial[blockIdx.x] = v;
+}
+// the same with two adjacent rows per thread on the ELL mesh level (16-byte loads of the slot-major
+// arrays: twice the bytes in flight per thread; every row's sum keeps its slot order)
+template <int W>
+DEV void ell2_Ax64(const LV& L, int c, const double* x, double& a0, double& a1) {
+    int2 o[W];
+    double2 v[W];
+    const double2 dg = *reinterpret_cast<const double2*>(L.diag + c), xi = *reinterpret_cast<const double2*>(x + c);
+#pragma unroll
+    for (int k = 0; k < W; k++) o[k] = *reinterpret_cast<const int2*>(L.cn + (size_t)k * L.nCp + c);
+#pragma unroll
+    for (int k = 0; k < W; k++) v[k] = *reinterpret_cast<const double2*>(L.ev + (size_t)k * L.nCp + c);
+    double xa[W], xb[W];
+#pragma unroll
+    for (int k = 0; k < W; k++) { xa[k] = o[k].x >= 0 ? x[o[k].x] : 0.0; xb[k] = o[k].y >= 0 ? x[o[k].y] : 0.0; }
+    double s0 = 0, s1 = 0;
+#pragma unroll
+    for (int k = 0; k < W; k++) { if (o[k].x >= 0) s0 += v[k].x * xa[k]; if (o[k].y >= 0) s1 += v[k].y * xb[k]; }
+    a0 = dg.x * xi.x - s0;
+    a1 = dg.y * xi.y - s1;
+}
+template <int W>
+__global__ void __launch_bounds__(256) k_spmv_dot_ell2(LV L, double* partial) {
+    double v = 0;
+    for (int c = 2 * (blockIdx.x * blockDim.x + threadIdx.x); c < L.n; c += 2 * gridDim.x * blockDim.x) {
+        if (c + 1 < L.n) {
+            double a0, a1;
+            ell2_Ax64<W>(L, c, L.in, a0, a1);
+            double2 y; y.x = a0; y.y = a1;
+            *reinterpret_cast<double2*>(L.out + c) = y;
+            v += a0 * L.in[c];
+            v += a1 * L.in[c + 1];
+        } else {
+            double y = row_Ax(L, c, L.in);
+            L.out[c] = y;
+            v += y * L.in[c];
+        }
     }
     v = block_sum(v);
     if (threadIdx.x == 0) partial[blockIdx.x] = v;
@@ -382,7 +425,8 @@ __global__ void __launch_bounds__(256) k_halo_p2p(const P2PArgs a) {
 
 struct Reducer {
     double *partial = nullptr, *partial2 = nullptr;
-    void init() { partial = dalloc<double>(RED_BLOCKS); partial2 = dalloc<double>(RED_BLOCKS); }
+    int cap = RED_BLOCKS;  // partials: at least one per 256 rows of the mesh (full-grid kernels)
+    void init(int rows = 0) { cap = std::max(RED_BLOCKS, (rows + BLOCK - 1) / BLOCK); partial = dalloc<double>(cap); partial2 = dalloc<double>(cap); }
     void free() { dev_free(partial); dev_free(partial2); }
     // mode as k_reduce
     void reduce(Ctx& ctx, const double* a, const double* b, int n, int mode, double* out) {

@@ -117,12 +117,15 @@ DEF_VKERNEL(pack, PackArgs)
 
 // ---- the tail: all small levels in one persistent kernel ---------------------------------------
 constexpr int TAIL_MAXLV = 12;
-constexpr int TAIL_THREADS = 1024;
+constexpr int TAIL_THREADS = 512;  // one CTA per SM: 128 registers per thread for the 16-wide ELL rows
 template <class R>
 struct TLv {
     int n, coop;                    // rows; lanes that walk one row together (4, 8 or 16)
     const int *rs, *cn;             // CSR (global numbering: the tail has no ghost rows)
     const R *ev, *diag;
+    int ellW, nPad;                 // ELL + overflow form of the same rows (0: CSR only)
+    const int *ecn, *ors, *ocn;
+    const R *eev, *oev;
     const int* agg;                 // [n] row of the next (coarser) tail level; unused on the last
     const int *aggStart, *aggRows;  // members (rows of the previous tail level) of each row; unused on level 0
     R *x, *y, *b, *r;               // work vectors [n]; level 0: b = input, x = output
@@ -153,18 +156,16 @@ struct GridBar {
 // all CTAs of the (cooperatively launched, hence co-resident) grid; bounded spin
 DEV void gsync(GridBar& g) {
     __syncthreads();
-    if (threadIdx.x == 0) {
+    if (threadIdx.x == 0) {  // release on arrival, acquire on departure; bar.sync extends both to the CTA
         g.gen += g.nb;
-        __threadfence();
-        atomicAdd(g.ctr, 1u);
+        asm volatile("red.release.gpu.global.add.u32 [%0], 1;" ::"l"(g.ctr) : "memory");
         unsigned v;
         long spins = 0;
         do {
-            asm volatile("ld.acquire.gpu.u32 %0, [%1];" : "=r"(v) : "l"(g.ctr) : "memory");
+            asm volatile("ld.acquire.gpu.global.u32 %0, [%1];" : "=r"(v) : "l"(g.ctr) : "memory");
             if (v >= g.gen) break;
             if ((++spins & 1023) == 0 && (*(volatile int*)g.err != 0 || spins > (1L << 24))) { *(volatile int*)g.err = 1; break; }
         } while (true);
-        __threadfence();
     }
     __syncthreads();
 }
@@ -177,6 +178,34 @@ DEV void gsync(GridBar& g) {
 constexpr int TAIL_U = 4;
 template <class R, class F>
 DEV void tail_rows(const TLv<R>& L, const R* x, const int* map, int tid, int nth, F f) {
+    if (L.ellW > 0) {
+        // ELL + overflow: one thread per row, no row-start indirection; the (up to 16) column
+        // indices and coefficients of the row are loaded together, then all x values
+        const int W = L.ellW;
+        for (int row = tid; row < L.n; row += nth) {
+            int o[16];
+            R v[16], xv[16];
+#pragma unroll
+            for (int k = 0; k < 16; k++) {
+                const bool in = k < W;
+                o[k] = in ? L.ecn[(size_t)k * L.nPad + row] : -1;
+                v[k] = in ? L.eev[(size_t)k * L.nPad + row] : R(0);
+            }
+            const int ob = L.ors[row], oe = L.ors[row + 1];
+            if (map) {
+#pragma unroll
+                for (int k = 0; k < 16; k++) o[k] = o[k] >= 0 ? map[o[k]] : -1;
+            }
+#pragma unroll
+            for (int k = 0; k < 16; k++) xv[k] = o[k] >= 0 ? x[o[k]] : R(0);
+            R s = 0;
+#pragma unroll
+            for (int k = 0; k < 16; k++) s += v[k] * xv[k];
+            for (int k = ob; k < oe; k++) { int oo = L.ocn[k]; s += L.oev[k] * x[map ? map[oo] : oo]; }
+            f(row, s);
+        }
+        return;
+    }
     const int coop = L.coop, lane = tid % coop, sub = tid / coop, rpp = nth / coop, n = L.n;
     for (int base = 0; base < n; base += TAIL_U * rpp) {
         int row[TAIL_U], k[TAIL_U], e[TAIL_U];
@@ -444,6 +473,87 @@ __global__ void __launch_bounds__(256) vk_csr_spmv_dot2(const VL<R> L, double* p
     w = block_sum(w);
     if (threadIdx.x == 0) { partialNum[blockIdx.x] = v; partialDen[blockIdx.x] = w; }
 }
+// ---- mesh level (ELL), two adjacent rows per thread ------------------------------------------------
+// The slot-major ELL arrays make rows c, c+1 adjacent in memory: one 8-byte (FP32) load serves
+// both, so a thread has twice the bytes in flight with half the load instructions - the kernels
+// are bound by how much the SM keeps outstanding, not by arithmetic.  Sums stay in slot order.
+template <class R> struct Vec2;
+template <> struct Vec2<float> { typedef float2 type; };
+template <> struct Vec2<double> { typedef double2 type; };
+template <class R, int W>
+DEV void vl_ell2_Ax(const VL<R>& L, int c, const R* x, R& ax0, R& ax1) {
+    typedef typename Vec2<R>::type R2;
+    int2 o[W];
+    R2 v[W];
+    const R2 dg = *reinterpret_cast<const R2*>(L.diag + c), xi = *reinterpret_cast<const R2*>(x + c);
+#pragma unroll
+    for (int k = 0; k < W; k++) o[k] = *reinterpret_cast<const int2*>(L.cn + (size_t)k * L.nCp + c);
+#pragma unroll
+    for (int k = 0; k < W; k++) v[k] = *reinterpret_cast<const R2*>(L.ev + (size_t)k * L.nCp + c);
+    R xa[W], xb[W];
+#pragma unroll
+    for (int k = 0; k < W; k++) {
+        xa[k] = (o[k].x >= 0 && o[k].x < L.nOwn) ? x[o[k].x] : R(0);
+        xb[k] = (o[k].y >= 0 && o[k].y < L.nOwn) ? x[o[k].y] : R(0);
+    }
+    R s0 = 0, s1 = 0;
+#pragma unroll
+    for (int k = 0; k < W; k++) { s0 += v[k].x * xa[k]; s1 += v[k].y * xb[k]; }
+    ax0 = dg.x * xi.x - s0;
+    ax1 = dg.y * xi.y - s1;
+}
+// mode 0: Jacobi sweep ; 1: residual
+template <class R, int W>
+__global__ void __launch_bounds__(256) vk_ell2_row_op(const VL<R> L, int mode) {
+    typedef typename Vec2<R>::type R2;
+    const int c = 2 * (blockIdx.x * blockDim.x + threadIdx.x);
+    if (c >= L.n) return;
+    if (c + 1 < L.n) {
+        R ax0, ax1;
+        const R2 bb = *reinterpret_cast<const R2*>(L.b + c);
+        vl_ell2_Ax<R, W>(L, c, L.in, ax0, ax1);
+        R2 res;
+        if (mode == 0) {
+            const R2 dg = *reinterpret_cast<const R2*>(L.diag + c), xi = *reinterpret_cast<const R2*>(L.in + c);
+            res.x = xi.x + L.omega * (bb.x - ax0) / dg.x;
+            res.y = xi.y + L.omega * (bb.y - ax1) / dg.y;
+        } else { res.x = bb.x - ax0; res.y = bb.y - ax1; }
+        *reinterpret_cast<R2*>(L.out + c) = res;
+    } else {  // odd row count: the last row alone
+        R ax = vl_Ax(L, c, L.in);
+        if (mode == 0) L.out[c] = L.in[c] + L.omega * (L.b[c] - ax) / L.diag[c];
+        else L.out[c] = L.b[c] - ax;
+    }
+}
+template <class R, int W>
+__global__ void __launch_bounds__(256) vk_ell2_spmv_dot2(const VL<R> L, double* partialNum, double* partialDen) {
+    typedef typename Vec2<R>::type R2;
+    double v = 0, w = 0;
+    for (int c = 2 * (blockIdx.x * blockDim.x + threadIdx.x); c < L.n; c += 2 * gridDim.x * blockDim.x) {
+        if (c + 1 < L.n) {
+            R ax0, ax1;
+            const R2 xi = *reinterpret_cast<const R2*>(L.in + c), rr = *reinterpret_cast<const R2*>(L.r + c);
+            vl_ell2_Ax<R, W>(L, c, L.in, ax0, ax1);
+            R2 y; y.x = ax0; y.y = ax1;
+            *reinterpret_cast<R2*>(L.out + c) = y;
+            v += (double)rr.x * (double)xi.x;
+            v += (double)rr.y * (double)xi.y;
+            w += (double)ax0 * (double)xi.x;
+            w += (double)ax1 * (double)xi.y;
+        } else {
+            R x = L.in[c];
+            R y = vl_Ax(L, c, L.in);
+            L.out[c] = y;
+            v += (double)L.r[c] * (double)x;
+            w += (double)y * (double)x;
+        }
+    }
+    v = block_sum(v);
+    __syncthreads();
+    w = block_sum(w);
+    if (threadIdx.x == 0) { partialNum[blockIdx.x] = v; partialDen[blockIdx.x] = w; }
+}
+
 // ---- coarse levels in ELL + overflow form: one thread per row ------------------------------------
 template <class R, int W>
 DEV R vl_ellc_off(const VL<R>& L, int c, const R* x) {

@@ -405,7 +405,7 @@ struct tpp_solver {
 #else
         CUDA_CHECK(cudaMallocHost(&hscal, S_COUNT * sizeof(double)));
 #endif
-        red.init();
+        red.init(nC);
         d.cAlpha = cfg.c_alpha; d.rho1 = cfg.rho1; d.rho2 = cfg.rho2; d.nu1 = cfg.nu1; d.nu2 = cfg.nu2;
         for (int k = 0; k < 3; k++) { d.g[k] = cfg.g[k]; d.cofg[k] = cfg.cofg[k]; }
         d.moving = cfg.n_motion > 0; d.rotating = hasRotation;
@@ -1014,14 +1014,14 @@ struct tpp_solver {
     }
     // ELL + overflow form of a level's CSR rows: the width is the smallest of 6/8/12/16 that leaves
     // at most 4 % of the entries in the overflow lists
-    void buildEllc(Level& v, const std::vector<int>& rs, const std::vector<int>& cn) {
+    void buildEllc(Level& v, const std::vector<int>& rs, const std::vector<int>& cn, int ovInv = 25) {
         const int n = v.n;
         if (n == 0) return;
         int Wl = 16;
         for (int w : {6, 8, 12, 16}) {
             long ov = 0;
             for (int i = 0; i < n; i++) ov += std::max(0, rs[i + 1] - rs[i] - w);
-            if (ov * 25 <= (long)rs[n]) { Wl = w; break; }
+            if (ov * ovInv <= (long)rs[n]) { Wl = w; break; }
         }
         const int nPad = (n + 31) / 32 * 32;
         std::vector<int> ecn((size_t)Wl * nPad, -1), esrc((size_t)Wl * nPad, -1), ors(n + 1, 0), ocn, osrc;
@@ -1101,7 +1101,7 @@ struct tpp_solver {
         csrOf(cur, rs, cf, cn);
         v.nnz = rs[cur.n];
         v.rs = upNew(ctx, rs); v.cf = upNew(ctx, cf); v.cn = upNew(ctx, cn); v.own = upNew(ctx, cur.own); v.nei = upNew(ctx, cur.nei);
-        if (dist && knob("TPP_ELLC", 1)) buildEllc(v, rs, cn);
+        if (knob("TPP_ELLC", 1)) buildEllc(v, rs, cn, dist ? 25 : 12);
         v.agg = upNew(ctx, aggTot); v.segStart = upNew(ctx, segS); v.segFaces = upNew(ctx, segF);
         std::vector<int> howner(cur.own.begin() + cur.nfLoc, cur.own.end());
         v.dOwner = upNew(ctx, howner);
@@ -1188,6 +1188,7 @@ struct tpp_solver {
             t.rs = upNew(ctx, rs); t.cf = upNew(ctx, cf); t.cn = upNew(ctx, cn); t.own = upNew(ctx, G.own); t.nei = upNew(ctx, G.nei);
             t.ev = dalloc<double>(std::max(t.nnz, 1));
             t.diag = dalloc<double>(t.n); t.upper = dalloc<double>(std::max(t.nf, 1)); t.rsum = dalloc<double>(t.n);
+            if (knob("TPP_ELLC", 1)) buildEllc(t, rs, cn, 12);
             tail.push_back(t);
         }
         while ((int)tail.size() < TAIL_MAXLV && G.n > coarsestTarget) {
@@ -1215,10 +1216,10 @@ struct tpp_solver {
                 if (tailSmem) CUDA_CHECK(cudaFuncSetAttribute(vk_tail<double>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)tailSmem));
                 cudaOccupancyMaxActiveBlocksPerMultiprocessor(&perSm, vk_tail<double>, TAIL_THREADS, tailSmem);
             }
-            tailGrid = std::min(sms * std::max(perSm, 1), 1024);
+            tailGrid = sms;  // one CTA per SM
             if (perSm < 1) { fprintf(stderr, "tppvof: vk_tail does not fit an SM\n"); abort(); }
             // small tails do not need every SM: fewer CTAs make the grid barrier cheaper
-            int need = (tail[0].n * 4 + TAIL_THREADS - 1) / TAIL_THREADS;
+            int need = (tail[0].n * (tail[0].ellW > 0 ? 1 : 4) + TAIL_THREADS - 1) / TAIL_THREADS;
             tailGrid = std::max(1, std::min(tailGrid, need));
             if (knob("TPP_TAIL_CTAS", 0) > 0) tailGrid = std::min(tailGrid, knob("TPP_TAIL_CTAS", 0));
         }
@@ -1266,7 +1267,7 @@ struct tpp_solver {
     template <class R> struct VStore {
         std::vector<R*> diag, ev, x, b, t0, r, Ac, send;  // index 0 = fine level, 1.. = distributed coarse levels
         std::vector<R*> eev, oev;                         // ELL + overflow values of the coarse levels
-        std::vector<R*> tdiag, tev, tx, ty, tb, tr;       // tail levels
+        std::vector<R*> tdiag, tev, tx, ty, tb, tr, teev, toev;  // tail levels
         R *cgR = nullptr, *cgP = nullptr, *cgAp = nullptr;
         bool ready = false;
     };
@@ -1295,8 +1296,10 @@ struct tpp_solver {
             size_t n = (size_t)tail[t].n;
             v.tdiag.push_back(dalloc<R>(n)); v.tev.push_back(dalloc<R>(std::max(tail[t].nnz, 1)));
             v.tx.push_back(dalloc<R>(n)); v.ty.push_back(dalloc<R>(n)); v.tb.push_back(dalloc<R>(n)); v.tr.push_back(dalloc<R>(n));
+            v.teev.push_back(dalloc<R>(tail[t].ellW > 0 ? (size_t)tail[t].ellW * tail[t].nPad : 1));
+            v.toev.push_back(dalloc<R>(std::max(tail[t].nOv, 1)));
         }
-        for (auto* vec : {&v.tdiag, &v.tev, &v.tx, &v.ty, &v.tb, &v.tr}) for (R* p : *vec) allocs.push_back(p);
+        for (auto* vec : {&v.tdiag, &v.tev, &v.tx, &v.ty, &v.tb, &v.tr, &v.teev, &v.toev}) for (R* p : *vec) allocs.push_back(p);
         if (!tail.empty()) {
             size_t n = (size_t)tail.back().n;
             v.cgR = dalloc<R>(n); v.cgP = dalloc<R>(n); v.cgAp = dalloc<R>(n);
@@ -1343,6 +1346,16 @@ struct tpp_solver {
             VLAUNCH(ctx, cast_in, a, tail[t].n);
             a.src = tail[t].ev; a.dst = v.tev[t];
             VLAUNCH(ctx, cast_in, a, std::max(tail[t].nnz, 1));
+#ifndef TPP_EMU
+            if (tail[t].ellW > 0) {
+                Level& c = tail[t];
+                GatherArgs<R> ga{c.ev, c.esrc, v.teev[t]};
+                const int ne = c.ellW * c.nPad;
+                vk_cast_gather<R><<<(ne + 255) / 256, 256, 0, ctx.stream>>>(ga, ne);
+                if (c.nOv > 0) { GatherArgs<R> go{c.ev, c.osrc, v.toev[t]}; vk_cast_gather<R><<<(c.nOv + 255) / 256, 256, 0, ctx.stream>>>(go, c.nOv); }
+                ctx.launches += 2;
+            }
+#endif
         }
     }
     // halo exchange of a V-cycle vector on level lv (0 = mesh): owned rows behind my processor
@@ -1397,6 +1410,15 @@ struct tpp_solver {
     }
     template <class R> void vRowOp(VL<R>& L, int mode) {  // 0 Jacobi sweep, 1 residual
 #ifndef TPP_EMU
+        if (L.ell && (L.W == 4 || L.W == 6) && knob("TPP_ELL2", 1)) {
+            prof_begin(ctx, mode == 0 ? "v_jacobi" : "v_residual");
+            const int g_ = ((L.n + 1) / 2 + 255) / 256;
+            if (L.W == 4) vk_ell2_row_op<R, 4><<<g_, 256, 0, ctx.stream>>>(L, mode);
+            else vk_ell2_row_op<R, 6><<<g_, 256, 0, ctx.stream>>>(L, mode);
+            prof_end(ctx);
+            ctx.launches++;
+            return;
+        }
         if (!L.ell && L.ellW > 0) {
             prof_begin(ctx, mode == 0 ? "v_jacobi_csr" : "v_residual_csr");
             const int g_ = (L.n + 255) / 256;
@@ -1430,10 +1452,13 @@ struct tpp_solver {
         scal[S_TMP0] = v; scal[S_TMP1] = w;
 #else
         prof_begin(ctx, L.ell ? "v_spmv_dot2" : "v_spmv_dot2_csr");
-        int nb = RED_BLOCKS;
-        if (L.ell) vk_spmv_dot2<R><<<nb, BLOCK, 0, ctx.stream>>>(L, red.partial, red.partial2);
+        int nb = std::min(RED_BLOCKS, (L.n + BLOCK - 1) / BLOCK);
+        if (L.ell && (L.W == 4 || L.W == 6) && knob("TPP_ELL2", 1)) {
+            nb = std::min(RED_BLOCKS, ((L.n + 1) / 2 + BLOCK - 1) / BLOCK);
+            if (L.W == 4) vk_ell2_spmv_dot2<R, 4><<<nb, BLOCK, 0, ctx.stream>>>(L, red.partial, red.partial2);
+            else vk_ell2_spmv_dot2<R, 6><<<nb, BLOCK, 0, ctx.stream>>>(L, red.partial, red.partial2);
+        } else if (L.ell) vk_spmv_dot2<R><<<nb, BLOCK, 0, ctx.stream>>>(L, red.partial, red.partial2);
         else if (L.ellW > 0) {
-            nb = std::min(RED_BLOCKS, (L.n + 255) / 256);
             switch (L.ellW) {
                 case 6: vk_ellc_spmv_dot2<R, 6><<<nb, BLOCK, 0, ctx.stream>>>(L, red.partial, red.partial2); break;
                 case 8: vk_ellc_spmv_dot2<R, 8><<<nb, BLOCK, 0, ctx.stream>>>(L, red.partial, red.partial2); break;
@@ -1493,6 +1518,7 @@ struct tpp_solver {
             double deg = (double)c.nnz / std::max(c.n, 1);
             L.coop = deg <= 5 ? 4 : deg <= 10 ? 8 : 16;
             L.rs = c.rs; L.cn = c.cn; L.ev = v.tev[t]; L.diag = v.tdiag[t];
+            if (c.ellW > 0 && t + 1 < A.T && knob("TPP_TAIL_ELL", 1)) { L.ellW = c.ellW; L.nPad = c.nPad; L.ecn = c.ecn; L.ors = c.ors; L.ocn = c.ocn; L.eev = v.teev[t]; L.oev = v.toev[t]; }
             if (t + 1 < A.T) L.agg = tail[t + 1].agg;
             if (t > 0) { L.aggStart = c.aggStart; L.aggRows = c.aggRows; }
             L.x = v.tx[t]; L.y = v.ty[t]; L.b = v.tb[t]; L.r = v.tr[t];
@@ -1705,11 +1731,11 @@ struct tpp_solver {
         ctx.launches += 3;
 #else
         prof_begin(ctx, "init_residual");
-        k_init_residual<<<RED_BLOCKS, BLOCK, 0, ctx.stream>>>(F0, x, b, kr, scal, red.partial, red.partial2);
-        k_reduce_final<<<1, BLOCK, 0, ctx.stream>>>(red.partial, RED_BLOCKS, 2, scal + S_RES);
-        k_reduce_final<<<1, BLOCK, 0, ctx.stream>>>(red.partial2, RED_BLOCKS, 2, scal + S_NORM);
+        const int nb = std::min(RED_BLOCKS, (nC + BLOCK - 1) / BLOCK);
+        k_init_residual<<<nb, BLOCK, 0, ctx.stream>>>(F0, x, b, kr, scal, red.partial, red.partial2);
+        k_reduce_final2<<<2, BLOCK, 0, ctx.stream>>>(red.partial, red.partial2, nb, scal + S_RES, scal + S_NORM);
         prof_end(ctx);
-        ctx.launches += 3;
+        ctx.launches += 2;
 #endif
     }
     void updateP() {
@@ -1733,8 +1759,11 @@ struct tpp_solver {
         LV L = F0;
         L.in = kp; L.out = kw;
         prof_begin(ctx, "spmv_dot");
-        k_spmv_dot<<<RED_BLOCKS, BLOCK, 0, ctx.stream>>>(L, red.partial);
-        k_reduce_final<<<1, BLOCK, 0, ctx.stream>>>(red.partial, RED_BLOCKS, 2, scal + S_WAPA);
+        const int nb = std::min(RED_BLOCKS, (nC + BLOCK - 1) / BLOCK);
+        if (L.ell && L.W == 4 && knob("TPP_ELL2", 1)) k_spmv_dot_ell2<4><<<nb, BLOCK, 0, ctx.stream>>>(L, red.partial);
+        else if (L.ell && L.W == 6 && knob("TPP_ELL2", 1)) k_spmv_dot_ell2<6><<<nb, BLOCK, 0, ctx.stream>>>(L, red.partial);
+        else k_spmv_dot<<<nb, BLOCK, 0, ctx.stream>>>(L, red.partial);
+        k_reduce_final<<<1, BLOCK, 0, ctx.stream>>>(red.partial, nb, 2, scal + S_WAPA);
         prof_end(ctx);
 #endif
         ctx.launches += 2;
@@ -1746,8 +1775,9 @@ struct tpp_solver {
         scal[S_RES] = v;
 #else
         prof_begin(ctx, "update_xr");
-        k_update_xr<<<RED_BLOCKS, BLOCK, 0, ctx.stream>>>(nC, x, kr, kp, kw, scal, red.partial);
-        k_reduce_final<<<1, BLOCK, 0, ctx.stream>>>(red.partial, RED_BLOCKS, 2, scal + S_RES);
+        const int nb = std::min(RED_BLOCKS, (nC + BLOCK - 1) / BLOCK);
+        k_update_xr<<<nb, BLOCK, 0, ctx.stream>>>(nC, x, kr, kp, kw, scal, red.partial);
+        k_reduce_final<<<1, BLOCK, 0, ctx.stream>>>(red.partial, nb, 2, scal + S_RES);
         prof_end(ctx);
 #endif
         ctx.launches += 2;
