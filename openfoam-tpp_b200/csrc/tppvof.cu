@@ -1478,7 +1478,7 @@ struct tpp_solver {
         allreduce(S_TMP0, 2, 0);
     }
     template <class R> void vCoarseSolve(VL<R>& L, R* r, R* p, R* Ap) {  // L.b -> L.out (a mesh without coarse levels)
-        const int maxIt = knob("TPP_CITER", 16);
+        const int maxIt = knob("TPP_CITER", 8);
         const double tol = knobd("TPP_CTOL", 0.05);
 #ifdef TPP_EMU
         int n = L.n;
@@ -1525,7 +1525,10 @@ struct tpp_solver {
         }
         A.bar = tailBar; A.err = tailErr; A.partial = tailPartial;
         A.omega = (R)knobd("TPP_OMEGA", 0.8); A.scaleJ = (R)knobd("TPP_SCALEJ", 1.0);
-        A.nPre = nPre; A.nPost = nPost; A.cgIter = knob("TPP_CITER", 16); A.cgTol = knobd("TPP_CTOL", 0.05);
+        // 8 CG iterations on the coarsest level give the same PCG counts as 16; fewer sweeps on the
+        // small levels cost 1-2 PCG iterations at 6 M cells (tools/knob_sweep.py), so they keep nPre/nPost
+        A.nPre = knob("TPP_TAIL_NPRE", nPre); A.nPost = knob("TPP_TAIL_NPOST", nPost);
+        A.cgIter = knob("TPP_CITER", 8); A.cgTol = knobd("TPP_CTOL", 0.05);
         A.cgR = v.cgR; A.cgP = v.cgP; A.cgAp = v.cgAp; A.cgSmem = tailSmem > 0;
         prof_begin(ctx, "v_tail");
 #ifdef TPP_EMU
