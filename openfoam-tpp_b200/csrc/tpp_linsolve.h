@@ -421,6 +421,63 @@ __global__ void __launch_bounds__(256) k_halo_p2p(const P2PArgs a) {
         ghost[e] = __ldcg(&((const T*)(a.myData[p] + par * a.slot[p]))[(size_t)(j - a.off[p]) * a.nc + k]);
     }
 }
+
+// ---- the same exchange with data and flag in one word ("LL" protocol) -----------------------------
+// Every 32 data bits travel in an 8-byte store together with the exchange's sequence number, and an
+// aligned 8-byte store is single-copy atomic: the receiver simply polls each word until the flag
+// matches, so there is no system fence, no "last CTA publishes a flag" round and no ordering
+// between words at all - the cost of an exchange is one kernel launch plus one NVLink traversal.
+// (Twice the bytes on the wire; the messages are a few hundred KB, latency is what matters.)
+DEV void st_ll(uint2* p, unsigned data, unsigned flag) {
+    asm volatile("st.volatile.global.v2.u32 [%0], {%1, %2};" ::"l"(p), "r"(data), "r"(flag) : "memory");
+}
+DEV uint2 ld_ll(const uint2* p) {
+    uint2 v;
+    asm volatile("ld.volatile.global.v2.u32 {%0, %1}, [%2];" : "=r"(v.x), "=r"(v.y) : "l"(p) : "memory");
+    return v;
+}
+template <class T>
+__global__ void __launch_bounds__(256) k_halo_ll(const P2PArgs a) {
+    constexpr int WPV = sizeof(T) / 4;  // 32-bit words per value
+    __shared__ int s_last;
+    const unsigned long long seq = *(volatile unsigned long long*)a.seq + 1;
+    const unsigned flag = (unsigned)seq;
+    const size_t par = (size_t)(seq & 1);
+    const long total = (long)a.nG * a.nc;
+    const T* src = (const T*)a.src;
+    for (long e = blockIdx.x * 256L + threadIdx.x; e < total; e += gridDim.x * 256L) {
+        int j = (int)(e / a.nc), k = (int)(e % a.nc), p = 0;
+        while (p + 1 < a.nPatch && j >= a.off[p + 1]) p++;
+        union { T v; unsigned w[WPV]; } u;
+        u.v = src[(size_t)a.owner[j] * a.nc + k];
+        uint2* dst = reinterpret_cast<uint2*>(a.peerData[p] + par * a.slot[p]) + ((size_t)(j - a.off[p]) * a.nc + k) * WPV;
+#pragma unroll
+        for (int q = 0; q < WPV; q++) st_ll(dst + q, u.w[q], flag);
+    }
+    T* ghost = (T*)a.ghost;
+    const unsigned long long t0 = global_ns();
+    for (long e = blockIdx.x * 256L + threadIdx.x; e < total; e += gridDim.x * 256L) {
+        int j = (int)(e / a.nc), k = (int)(e % a.nc), p = 0;
+        while (p + 1 < a.nPatch && j >= a.off[p + 1]) p++;
+        const uint2* from = reinterpret_cast<const uint2*>(a.myData[p] + par * a.slot[p]) + ((size_t)(j - a.off[p]) * a.nc + k) * WPV;
+        union { T v; unsigned w[WPV]; } u;
+#pragma unroll
+        for (int q = 0; q < WPV; q++) {
+            uint2 r = ld_ll(from + q);
+            long spins = 0;
+            while (r.y != flag) {
+                if ((++spins & 1023) == 0 && (*(volatile int*)a.err != 0 || global_ns() - t0 > 30000000000ull)) { *(volatile int*)a.err = 2; break; }
+                r = ld_ll(from + q);
+            }
+            u.w[q] = r.x;
+        }
+        ghost[e] = u.v;
+    }
+    __syncthreads();
+    if (threadIdx.x == 0) s_last = atomicAdd(a.putDone, 1u) == gridDim.x - 1;
+    __syncthreads();
+    if (s_last && threadIdx.x == 0) { *a.putDone = 0; *(volatile unsigned long long*)a.seq = seq; }
+}
 #endif
 
 struct Reducer {

@@ -73,7 +73,7 @@ struct Comm {
     ncclResult_t (*pGroupStart)() = nullptr;
     ncclResult_t (*pGroupEnd)() = nullptr;
     // halo exchange over peer memory (k_halo_p2p): my window, the neighbours' windows
-    bool p2p = false;
+    bool p2p = false, ll = false;  // ll: data + flag in one 8-byte word (k_halo_ll) instead of slots + flags (k_halo_p2p)
     char* window = nullptr;
     std::vector<void*> opened;               // cudaIpcOpenMemHandle results (closed at destroy)
     std::vector<char*> peerBase;             // per patch: base of the neighbour's window
@@ -512,19 +512,20 @@ struct tpp_solver {
         const long total = (long)ng * nc;
         const int grid = (int)std::max(1L, std::min(296L, (total + 1023) / 1024));
         prof_begin(ctx, "halo_p2p");
-        k_halo_p2p<T><<<grid, 256, 0, ctx.stream>>>(a);
+        if (comm.ll) k_halo_ll<T><<<grid, 256, 0, ctx.stream>>>(a);
+        else k_halo_p2p<T><<<grid, 256, 0, ctx.stream>>>(a);
         prof_end(ctx);
         ctx.launches++;
     }
     // windows, IPC handles (gathered through the NCCL communicator), the neighbours' layout
     void setupP2P() {
-        if (!comm.active || !comm.nccl || !knob("TPP_P2P", 1)) return;
+        if (!comm.active || !comm.nccl || !knob("TPP_P2P", 2)) return;
         const int np = (int)procCnt.size();
         double fail = np > P2P_MAXPATCH ? 1.0 : 0.0;
         size_t total = 4096;  // flags: 128 B apart
         comm.myOff.assign(np, 0); comm.slot.assign(np, 0);
         for (int p = 0; p < np; p++) {
-            comm.slot[p] = ((size_t)procCnt[p] * 9 * sizeof(double) + 255) / 256 * 256;  // up to 9 components (grad U)
+            comm.slot[p] = ((size_t)procCnt[p] * 9 * 2 * sizeof(double) + 255) / 256 * 256;  // up to 9 components (grad U); LL words carry 4 data bytes in 8
             comm.myOff[p] = total;
             total += 2 * comm.slot[p];
         }
@@ -569,6 +570,7 @@ struct tpp_solver {
         dev_sync(ctx);
         hostAllreduce(bar, 0);
         comm.p2p = true;
+        comm.ll = knob("TPP_P2P", 2) >= 2;
     }
 #endif
     // all-reduce of n device scalars scal[idx..idx+n): op 0 sum, 1 max
