@@ -304,8 +304,15 @@ def main():
     if args.kernel_table and rank == 0:
         full = [[k, v[0], round(v[1], 4), (round(alg_bytes(k, v[0]) / (v[1] * 1e-3) / 1e9, 1) if alg_bytes(k, v[0]) else None)] for k, v in top]
         json.dump({"profiled_steps": 2, "cells": nC, "internal_faces": nI, "total_ms": tot_ms, "kernels_launches_ms_GBps": full}, open(args.kernel_table, "w"), indent=1)
+    # measured DRAM traffic of the dominant kernel (committed ncu --set full capture), scaled per cell
+    traffic = None
+    tp = os.path.join(ROOT, "profiles", "ncu_traffic_r1.json")
+    if os.path.exists(tp):
+        tr = json.load(open(tp))
+        if dom in tr["kernels"]:
+            traffic = tr["kernels"][dom]["dram_bytes"] * nC / tr["cells"]
     roofline = {"bound": "hbm", "kernel": f"k_{dom}", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak if achieved else None,
-                "traffic": None, "peak_source": "measured (MEASURED_PEAKS.json)" if peaks else "fallback",
+                "traffic": traffic, "algorithmic_bytes": ab / dom_n if ab else None, "peak_source": "measured (MEASURED_PEAKS.json)" if peaks else "fallback",
                 "share_of_step": dom_ms / tot_ms, "amg_levels_rows_faces": levels, "amg_layout": layout,
                 "top_kernels_launches_ms_GBps": table}
 

@@ -483,7 +483,7 @@ __global__ void __launch_bounds__(256) k_halo_ll(const P2PArgs a) {
 struct Reducer {
     double *partial = nullptr, *partial2 = nullptr;
     int cap = RED_BLOCKS;  // partials: at least one per 256 rows of the mesh (full-grid kernels)
-    void init(int rows = 0) { cap = std::max(RED_BLOCKS, (rows + BLOCK - 1) / BLOCK); partial = dalloc<double>(cap); partial2 = dalloc<double>(cap); }
+    void init(int rows = 0) { cap = std::max(4 * RED_BLOCKS, (rows + BLOCK - 1) / BLOCK); partial = dalloc<double>(cap); partial2 = dalloc<double>(cap); }
     void free() { dev_free(partial); dev_free(partial2); }
     // mode as k_reduce
     void reduce(Ctx& ctx, const double* a, const double* b, int n, int mode, double* out) {

@@ -1456,7 +1456,7 @@ struct tpp_solver {
         prof_begin(ctx, L.ell ? "v_spmv_dot2" : "v_spmv_dot2_csr");
         int nb = std::min(RED_BLOCKS, (L.n + BLOCK - 1) / BLOCK);
         if (L.ell && (L.W == 4 || L.W == 6) && knob("TPP_ELL2", 1)) {
-            nb = std::min(RED_BLOCKS, ((L.n + 1) / 2 + BLOCK - 1) / BLOCK);
+            nb = std::min(4 * RED_BLOCKS, ((L.n + 1) / 2 + BLOCK - 1) / BLOCK);  // row pairs: more CTAs than the streaming kernels need
             if (L.W == 4) vk_ell2_spmv_dot2<R, 4><<<nb, BLOCK, 0, ctx.stream>>>(L, red.partial, red.partial2);
             else vk_ell2_spmv_dot2<R, 6><<<nb, BLOCK, 0, ctx.stream>>>(L, red.partial, red.partial2);
         } else if (L.ell) vk_spmv_dot2<R><<<nb, BLOCK, 0, ctx.stream>>>(L, red.partial, red.partial2);
@@ -1764,7 +1764,8 @@ struct tpp_solver {
         LV L = F0;
         L.in = kp; L.out = kw;
         prof_begin(ctx, "spmv_dot");
-        const int nb = std::min(RED_BLOCKS, (nC + BLOCK - 1) / BLOCK);
+        int nb = std::min(RED_BLOCKS, (nC + BLOCK - 1) / BLOCK);
+        if (L.ell && (L.W == 4 || L.W == 6) && knob("TPP_ELL2", 1)) nb = std::min(4 * RED_BLOCKS, ((nC + 1) / 2 + BLOCK - 1) / BLOCK);
         if (L.ell && L.W == 4 && knob("TPP_ELL2", 1)) k_spmv_dot_ell2<4><<<nb, BLOCK, 0, ctx.stream>>>(L, red.partial);
         else if (L.ell && L.W == 6 && knob("TPP_ELL2", 1)) k_spmv_dot_ell2<6><<<nb, BLOCK, 0, ctx.stream>>>(L, red.partial);
         else k_spmv_dot<<<nb, BLOCK, 0, ctx.stream>>>(L, red.partial);
