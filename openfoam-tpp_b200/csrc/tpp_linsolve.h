@@ -478,6 +478,55 @@ __global__ void __launch_bounds__(256) k_halo_ll(const P2PArgs a) {
     __syncthreads();
     if (s_last && threadIdx.x == 0) { *a.putDone = 0; *(volatile unsigned long long*)a.seq = seq; }
 }
+
+// ---- all-reduce of a few device scalars over the same peer windows (LL words, all-to-all) ---------
+// The Krylov scalars and the multigrid scaling dots are 1-2 doubles, ~300 times per step: pure
+// latency.  Every rank stores its values (LL words) into every rank's window and then sums what
+// arrived in rank order - one small kernel, no fence, and bit-identical results on all ranks (the
+// ranks must agree on every convergence decision).  Slots: [parity][source rank][value][word].
+constexpr int AR_MAXR = 8, AR_MAXV = 4;
+struct ARArgs {
+    int rank, size, n, op;            // op 0: sum, 1: max
+    uint2* win[AR_MAXR];              // the all-reduce region of every rank's window (win[rank] = mine)
+    double* vals;                     // in/out: n device scalars
+    unsigned long long* seq;
+    int* err;
+};
+__global__ void __launch_bounds__(64) k_allreduce_ll(const ARArgs a) {
+    __shared__ unsigned sw[AR_MAXR][AR_MAXV][2];
+    const unsigned long long seq = *(volatile unsigned long long*)a.seq + 1;
+    const unsigned flag = (unsigned)seq;
+    const int par = (int)(seq & 1);
+    const int t = threadIdx.x, r = t / (AR_MAXV * 2), i = (t / 2) % AR_MAXV, q = t % 2;
+    const bool live = r < a.size && i < a.n;
+    if (live) {
+        union { double v; unsigned w[2]; } u;
+        u.v = a.vals[i];
+        st_ll(a.win[r] + ((par * AR_MAXR + a.rank) * AR_MAXV + i) * 2 + q, u.w[q], flag);
+    }
+    if (live) {
+        const uint2* from = a.win[a.rank] + ((par * AR_MAXR + r) * AR_MAXV + i) * 2 + q;
+        const unsigned long long t0 = global_ns();
+        uint2 v = ld_ll(from);
+        long spins = 0;
+        while (v.y != flag) {
+            if ((++spins & 1023) == 0 && (*(volatile int*)a.err != 0 || global_ns() - t0 > 30000000000ull)) { *(volatile int*)a.err = 3; break; }
+            v = ld_ll(from);
+        }
+        sw[r][i][q] = v.x;
+    }
+    __syncthreads();
+    if (t < a.n) {
+        double acc = 0;
+        for (int rr = 0; rr < a.size; rr++) {
+            union { double v; unsigned w[2]; } u;
+            u.w[0] = sw[rr][t][0]; u.w[1] = sw[rr][t][1];
+            acc = rr == 0 ? u.v : (a.op == 0 ? acc + u.v : fmax(acc, u.v));
+        }
+        a.vals[t] = acc;
+    }
+    if (t == 0) *(volatile unsigned long long*)a.seq = seq;
+}
 #endif
 
 struct Reducer {

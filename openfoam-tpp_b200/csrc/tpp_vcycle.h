@@ -85,6 +85,8 @@ template <class R> HD void vb_scale_apply(const VL<R>& L, int i) {
     R sf = (R)(L.sf[0] / (fabs(den) < VSMALL ? (den >= 0 ? VSMALL : -VSMALL) : den));
     L.out[i] += sf * L.c[i] + L.omega * (L.r[i] - sf * L.Ac[i]) / L.diag[i];
 }
+// unscaled correction: out[i] += xc[agg[i]]
+template <class R> HD void vb_prolong_add(const VL<R>& L, int i) { L.out[i] += L.xc[L.agg[i]]; }
 template <class R> struct CastArgs { const double* src; R* dst; const R* rsrc; double* ddst; };
 template <class R> HD void vb_cast_in(const CastArgs<R>& a, int i) { a.dst[i] = (R)a.src[i]; }
 template <class R> HD void vb_cast_out(const CastArgs<R>& a, int i) { a.ddst[i] = (double)a.rsrc[i]; }
@@ -111,6 +113,7 @@ DEF_VKERNEL(residual, VL)
 DEF_VKERNEL(restrict, VL)
 DEF_VKERNEL(prolong, VL)
 DEF_VKERNEL(scale_apply, VL)
+DEF_VKERNEL(prolong_add, VL)
 DEF_VKERNEL(cast_in, CastArgs)
 DEF_VKERNEL(cast_out, CastArgs)
 DEF_VKERNEL(pack, PackArgs)

@@ -80,6 +80,8 @@ struct Comm {
     std::vector<size_t> myOff, peerOff, slot;  // per patch: data offset in my / the neighbour's window, slot bytes
     std::vector<int> peerFlagIdx;            // per patch: my flag index inside the neighbour's window
     unsigned long long* seq = nullptr;
+    unsigned long long* arSeq = nullptr;     // all-reduce sequence counter
+    std::vector<char*> allBase;              // every rank's window (all-reduce over peer memory), empty: NCCL
     unsigned* putDone = nullptr;
     int* p2pErr = nullptr;
 #endif
@@ -530,7 +532,7 @@ struct tpp_solver {
             total += 2 * comm.slot[p];
         }
         comm.window = (char*)dev_alloc(total);
-        comm.seq = (unsigned long long*)dev_alloc(64); comm.putDone = (unsigned*)dev_alloc(64); comm.p2pErr = (int*)dev_alloc(64);
+        comm.seq = (unsigned long long*)dev_alloc(64); comm.arSeq = (unsigned long long*)dev_alloc(64); comm.putDone = (unsigned*)dev_alloc(64); comm.p2pErr = (int*)dev_alloc(64);
         cudaIpcMemHandle_t mine;
         if (cudaIpcGetMemHandle(&mine, comm.window) != cudaSuccess) { cudaGetLastError(); fail = 1.0; }
         static_assert(sizeof(cudaIpcMemHandle_t) == 64, "cudaIpcMemHandle_t is 64 bytes");
@@ -538,8 +540,13 @@ struct tpp_solver {
         for (int k = 0; k < 64; k++) hv[64 * (size_t)comm.rank + k] = (double)((unsigned char*)&mine)[k];
         hostAllreduce(hv, 0);
         std::map<int, char*> base;
-        for (int p = 0; p < np && fail == 0.0; p++) {
-            int q = procPeer[p];
+        // every rank's window for the all-reduce (<= 8 ranks), the neighbours' for the halos
+        std::vector<int> toOpen;
+        const bool llar = comm.size <= AR_MAXR && knob("TPP_LLAR", 1);
+        if (llar) { for (int q = 0; q < comm.size; q++) if (q != comm.rank) toOpen.push_back(q); }
+        else for (int p = 0; p < np; p++) toOpen.push_back(procPeer[p]);
+        for (size_t p = 0; p < toOpen.size() && fail == 0.0; p++) {
+            int q = toOpen[p];
             if (base.count(q)) continue;
             cudaIpcMemHandle_t h;
             for (int k = 0; k < 64; k++) ((unsigned char*)&h)[k] = (unsigned char)(hv[64 * (size_t)q + k] + 0.5);
@@ -571,14 +578,32 @@ struct tpp_solver {
         hostAllreduce(bar, 0);
         comm.p2p = true;
         comm.ll = knob("TPP_P2P", 2) >= 2;
+        if (llar) {
+            comm.allBase.assign(comm.size, nullptr);
+            for (int q = 0; q < comm.size; q++) comm.allBase[q] = q == comm.rank ? comm.window : base[q];
+        }
     }
 #endif
     // all-reduce of n device scalars scal[idx..idx+n): op 0 sum, 1 max
     void allreduce(int idx, int n, int op) {
         if (!comm.active) return;
 #ifndef TPP_EMU
+        if (!comm.allBase.empty() && n <= AR_MAXV) {
+            ARArgs a;
+            memset(&a, 0, sizeof(a));
+            a.rank = comm.rank; a.size = comm.size; a.n = n; a.op = op;
+            for (int r = 0; r < comm.size; r++) a.win[r] = reinterpret_cast<uint2*>(comm.allBase[r] + 2048);
+            a.vals = scal + idx; a.seq = comm.arSeq; a.err = comm.p2pErr;
+            prof_begin(ctx, "allreduce_ll");
+            k_allreduce_ll<<<1, 64, 0, ctx.stream>>>(a);
+            prof_end(ctx);
+            ctx.launches++;
+            return;
+        }
         if (comm.nccl) {
+            prof_begin(ctx, "allreduce_nccl");
             comm.pAllReduce(scal + idx, scal + idx, n, ncclDouble, op == 0 ? ncclSum : ncclMax, comm.nccl, ctx.stream);
+            prof_end(ctx);
             ctx.launches++;
             return;
         }
@@ -1577,14 +1602,20 @@ struct tpp_solver {
         } else vcycleT<R>(lv + 1, v.b[lv + 1], v.x[lv + 1], true, nPre, nPost);
         // prolonged correction c = P x_c in `oth`, A c, scaling, x += ...
         VL<R> Pn = vview<R>(lv + 1);
-        Pn.xc = toTail ? v.tx[0] + tailRowOff : v.x[lv + 1]; Pn.out = oth;
-        VLAUNCH(ctx, prolong, Pn, L.n);
-        XL<R>(lv, oth);
-        L.in = oth; L.out = v.Ac[lv]; L.r = v.r[lv];
-        vSpmvDot2(L);
-        L.c = oth; L.Ac = v.Ac[lv]; L.r = v.r[lv]; L.out = cur; L.sf = scal + S_TMP0; L.omega = (R)knobd("TPP_SCALEJ", 1.0);
-        VLAUNCH(ctx, scale_apply, L, L.n);
-        L.omega = omega;
+        Pn.xc = toTail ? v.tx[0] + tailRowOff : v.x[lv + 1];
+        if (lv >= knob("TPP_NOSCALE_FROM", 99)) {  // experiment: plain correction on the deeper levels
+            Pn.out = cur;
+            VLAUNCH(ctx, prolong_add, Pn, L.n);
+        } else {
+            Pn.out = oth;
+            VLAUNCH(ctx, prolong, Pn, L.n);
+            XL<R>(lv, oth);
+            L.in = oth; L.out = v.Ac[lv]; L.r = v.r[lv];
+            vSpmvDot2(L);
+            L.c = oth; L.Ac = v.Ac[lv]; L.r = v.r[lv]; L.out = cur; L.sf = scal + S_TMP0; L.omega = (R)knobd("TPP_SCALEJ", 1.0);
+            VLAUNCH(ctx, scale_apply, L, L.n);
+            L.omega = omega;
+        }
         for (int s = 0; s < std::max(nPost, 1); s++) {
             if (s == 0) XL<R>(lv, cur);
             else XLsmooth<R>(lv, cur, 2, oth);
@@ -1801,7 +1832,7 @@ struct tpp_solver {
 #else
         for (auto& g : graphs) cudaGraphExecDestroy(g.second.exec);
         for (void* p : comm.opened) cudaIpcCloseMemHandle(p);
-        dev_free(comm.window); dev_free(comm.seq); dev_free(comm.putDone); dev_free(comm.p2pErr);
+        dev_free(comm.window); dev_free(comm.seq); dev_free(comm.arSeq); dev_free(comm.putDone); dev_free(comm.p2pErr);
         if (hscal) cudaFreeHost(hscal);
         if (ctx.stream && ctx.ownStream) cudaStreamDestroy(ctx.stream);
 #endif
