@@ -305,10 +305,19 @@ def latest_time(case_dir, need="alpha.water"):
 class Case:
     """A case directory loaded into memory: mesh, config, start fields."""
 
-    def __init__(self, case_dir):
+    def __init__(self, case_dir, processor=None):
+        """processor = k: the rank's share of a decomposed case - mesh and fields from
+        `processor<k>/` (as `foamRun -parallel` reads them), dictionaries from the case root;
+        time directories are then written under `processor<k>/` too."""
+        self.root = case_dir
+        self.processor = processor
+        if processor is not None:
+            case_dir = os.path.join(case_dir, f"processor{processor}")
+            if not os.path.isdir(case_dir):
+                raise FoamError(f"{case_dir}: not found (run decomposePar first)")
         self.dir = case_dir
         self.mesh = ff.read_polymesh(case_dir)
-        self.cfg = read_config(case_dir, self.mesh)
+        self.cfg = read_config(self.root, self.mesh)
         if self.cfg.start_from == "latestTime":
             self.start_value, self.start_name = latest_time(case_dir)
         else:

@@ -50,9 +50,22 @@ def write_time(case, solver, name, binary=True, precision=6):
     nI = mesh.n_internal
     tdir = os.path.join(case.dir, name)
 
+    nBphys = sum(q["nFaces"] for q in mesh.patches if q["type"] != "processor")  # the solver's boundary arrays hold these
+
     def patch_slices(arr, ncomp):
+        """per-patch views of an array over ALL boundary faces of the file (surface fields)"""
         a = arr.reshape(-1, ncomp) if ncomp > 1 else arr
         return {p["name"]: a[p["startFace"] - nI : p["startFace"] - nI + p["nFaces"]] for p in mesh.patches}
+
+    def vol_patches(cells, bnd, ncomp):
+        """vol field: physical patches from the solver's boundary array, processor patches (not
+        needed by a restart or by reconstructPar) from the adjacent cells"""
+        b = bnd.reshape(-1, ncomp) if ncomp > 1 else bnd
+        out = {}
+        for p in mesh.patches:
+            sl = slice(p["startFace"], p["startFace"] + p["nFaces"])
+            out[p["name"]] = cells[mesh.owner[sl]] if p["type"] == "processor" else b[p["startFace"] - nI : p["startFace"] - nI + p["nFaces"]]
+        return out
 
     alpha, alpha_b = solver.get("alpha"), solver.get("alpha_b")
     U, U_b = solver.get("U").reshape(-1, 3), solver.get("U_b")
@@ -62,15 +75,14 @@ def write_time(case, solver, name, binary=True, precision=6):
     phi = solver.get("phi")
     Uf = solver.get("Uf").reshape(-1, 3)
     W = lambda fld: ff.write_field(os.path.join(tdir, fld.name), fld, binary=binary, precision=precision, location=name)
-    W(ff.Field("volScalarField", "alpha.water", "[0 0 0 0 0 0 0]", alpha, _boundary_dict(case, "alpha.water", patch_slices(alpha_b, 1))))
-    W(ff.Field("volVectorField", "U", "[0 1 -1 0 0 0 0]", U, _boundary_dict(case, "U", patch_slices(U_b, 3))))
-    W(ff.Field("volScalarField", "p_rgh", "[1 -1 -2 0 0 0 0]", p_rgh, _boundary_dict(case, "p_rgh", patch_slices(p_rgh_b, 1))))
-    calc = {q["name"]: {"type": "calculated"} for q in mesh.patches}
-    own_b = mesh.owner[nI:]
-    pb = p_rgh_b + rho_b * solver.get("ghf")[nI:]
-    bd = {k: dict(v, value=patch_slices(pb, 1)[k]) for k, v in calc.items()}
+    W(ff.Field("volScalarField", "alpha.water", "[0 0 0 0 0 0 0]", alpha, _boundary_dict(case, "alpha.water", vol_patches(alpha, alpha_b, 1))))
+    W(ff.Field("volVectorField", "U", "[0 1 -1 0 0 0 0]", U, _boundary_dict(case, "U", vol_patches(U, U_b, 3))))
+    W(ff.Field("volScalarField", "p_rgh", "[1 -1 -2 0 0 0 0]", p_rgh, _boundary_dict(case, "p_rgh", vol_patches(p_rgh, p_rgh_b, 1))))
+    calc = {q["name"]: {"type": "processor" if q["type"] == "processor" else "calculated"} for q in mesh.patches}
+    pb = p_rgh_b + rho_b * solver.get("ghf")[nI : nI + nBphys]
+    bd = {k: dict(v, value=vol_patches(p, pb, 1)[k]) for k, v in calc.items()}
     W(ff.Field("volScalarField", "p", "[1 -1 -2 0 0 0 0]", p, bd))
-    bd = {k: dict(v, value=patch_slices(rho_b, 1)[k]) for k, v in calc.items()}
+    bd = {k: dict(v, value=vol_patches(rho, rho_b, 1)[k]) for k, v in calc.items()}
     W(ff.Field("volScalarField", "rho", "[1 -3 0 0 0 0 0]", rho, bd))
     bd = {k: dict(v, value=patch_slices(phi[nI:], 1)[k]) for k, v in calc.items()}
     W(ff.Field("surfaceScalarField", "phi", "[0 3 -1 0 0 0 0]", phi[:nI], bd))
@@ -108,11 +120,38 @@ class ProbesWriter:
         self.f.close()
 
 
-def run_case(case_dir, device=0, lib_path=None, max_steps=None, log=sys.stdout, write=True):
-    """Advance a case from its latest time to endTime.  Returns a summary dict."""
-    case = Case(case_dir)
+def run_case(case_dir, device=0, lib_path=None, max_steps=None, log=sys.stdout, write=True, parallel=False):
+    """Advance a case from its latest time to endTime.  Returns a summary dict.
+
+    parallel: `foamRun -parallel` - this process is one rank of a torch.distributed job
+    (torchrun / mpirun-style RANK, WORLD_SIZE); it runs the `processor<rank>` share written by
+    decomposePar (the reference's Makefile:77-78, or decompose.decompose_par here) and writes its
+    time directories there, for reconstructPar."""
+    rank, world = 0, 1
+    if parallel:
+        import torch.distributed as dist
+
+        if not dist.is_initialized():
+            import torch
+
+            nccl = torch.cuda.is_available() and lib_path is None
+            if nccl:
+                device = int(os.environ.get("LOCAL_RANK", "0"))
+                torch.cuda.set_device(device)
+                dist.init_process_group("nccl", device_id=torch.device("cuda", device))
+            else:
+                dist.init_process_group("gloo")
+        rank, world = dist.get_rank(), dist.get_world_size()
+        if rank != 0:
+            log = None
+    case = Case(case_dir, processor=rank if parallel else None)
     cfg = case.cfg
     s = Solver(case.mesh, cfg, device=device, lib_path=lib_path)
+    if parallel and world > 1:
+        if lib_path is None:
+            s.comm_init_nccl()
+        else:
+            s.comm_init_callbacks()
     s.load_case_fields(case)
     nF = case.mesh.n_faces
     if "phi" in case.fields and "Uf" in case.fields and case.start_value > 0:
@@ -131,7 +170,7 @@ def run_case(case_dir, device=0, lib_path=None, max_steps=None, log=sys.stdout, 
         s.set("Uf", full(case.fields["Uf"], 3))
         s.set_time(case.start_value, case.restart_delta_t or cfg.delta_t)
     probes = None
-    if cfg.probes is not None and len(cfg.probes):
+    if cfg.probes is not None and len(cfg.probes) and not (parallel and world > 1):
         cells = [s.find_cell(x) for x in cfg.probes]
         s.set_probes(cells)
         probes = ProbesWriter(case, case.start_name, cfg.probe_fields[0] if cfg.probe_fields else "p")
@@ -164,7 +203,12 @@ def run_case(case_dir, device=0, lib_path=None, max_steps=None, log=sys.stdout, 
     nsteps = int(info["step"] - steps0)
     if probes is not None:
         probes.close()
-    out = {"steps": nsteps, "seconds": el, "t": info["t"], "writes": n_writes, "cells": case.mesh.n_cells, "mcell_steps_per_s": case.mesh.n_cells * nsteps / max(el, 1e-30) / 1e6}
+    ncells = case.mesh.n_cells
+    if parallel and world > 1:
+        from . import ensemble
+
+        ncells = int(ensemble.sum_over_ranks([float(ncells)])[0])
+    out = {"steps": nsteps, "seconds": el, "t": info["t"], "writes": n_writes, "cells": ncells, "mcell_steps_per_s": ncells * nsteps / max(el, 1e-30) / 1e6}
     s.close()
     return out
 
@@ -180,11 +224,16 @@ def run_case_local(case_dir, n_cpus=1, device=0):
 def main(argv=None):
     argv = list(sys.argv[1:] if argv is None else argv)
     case_dir = os.getcwd()
+    parallel = False
     while argv:
         a = argv.pop(0)
         if a == "-case":
             case_dir = argv.pop(0)
-        elif a in ("-parallel", "-noFunctionObjects"):
+        elif a == "-parallel":
+            # one rank of `torchrun --nproc-per-node N -m openfoam_tpp_b200.foamrun -parallel`; without
+            # a launcher (WORLD_SIZE unset) the whole case runs on one GPU, as before
+            parallel = int(os.environ.get("WORLD_SIZE", "1")) > 1
+        elif a == "-noFunctionObjects":
             pass
         elif a == "-solver":
             if argv.pop(0) != "incompressibleVoF":
@@ -192,7 +241,7 @@ def main(argv=None):
         else:
             raise SystemExit(f"foamRun (tppvof): unknown option {a}")
     try:
-        out = run_case(case_dir)
+        out = run_case(case_dir, parallel=parallel)
     except Exception as e:  # non-zero exit status, as `check=True` expects (main.py:345,348)
         print(f"--> FOAM FATAL ERROR: {e}", file=sys.stderr)
         return 1

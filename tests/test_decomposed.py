@@ -64,11 +64,11 @@ dist.destroy_process_group()
 """
 
 
-def _run(tmp_path, lib, nr, nl, steps, port, nproc=2):
+def _run(tmp_path, lib, nr, nl, steps, port, nproc=2, env=None):
     script = tmp_path / "worker.py"
     script.write_text(textwrap.dedent(WORKER.format(root=ROOT, lib=lib, nr=nr, nl=nl, steps=steps)))
     r = subprocess.run([sys.executable, "-m", "torch.distributed.run", "--nnodes=1", f"--nproc-per-node={nproc}", "--master-addr", "127.0.0.1", "--master-port", str(port), str(script)],
-                       capture_output=True, text=True, timeout=900)
+                       capture_output=True, text=True, timeout=900, env=dict(os.environ, **(env or {})))
     out = r.stdout + r.stderr
     assert r.returncode == 0, out[-4000:]
     for k in range(nproc):
@@ -82,6 +82,12 @@ def test_two_rank_decomposition_matches_single_rank_gloo(tmp_path, emu_lib):
 def test_three_rank_decomposition_gloo(tmp_path, emu_lib):
     """a middle slab has two processor patches (two neighbours)"""
     _run(tmp_path, emu_lib, nr=4, nl=9, steps=3, port=29632, nproc=3)
+
+
+def test_distributed_coarse_levels_gloo(tmp_path, emu_lib):
+    """tiny TPP_TAIL_ROWS: several multigrid levels stay distributed, so the agglomerated processor
+    interfaces and the per-level halo exchanges are exercised, then the gathered tail"""
+    _run(tmp_path, emu_lib, nr=6, nl=12, steps=3, port=29634, nproc=3, env={"TPP_TAIL_ROWS": "300", "TPP_COARSEST": "100"})
 
 
 @pytest.mark.gpu
