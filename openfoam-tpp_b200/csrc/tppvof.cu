@@ -1715,7 +1715,7 @@ struct tpp_solver {
     void iteration(LV& F0, LV& FG, const tpp_solver_t& ctl, double* x) {
 #ifndef TPP_EMU
         // (the legacy default stream cannot be captured)
-        if (!ctx.prof && ctx.stream != nullptr && ctx.stream != cudaStreamLegacy && knob("TPP_GRAPH", 1) && (useFp32() || (ctl.type == 0 && ctl.precond == 0)) && (!comm.active || (comm.nccl && knob("TPP_GRAPH_PAR", 1)))) {
+        if (!ctx.prof && ctx.stream != nullptr && ctx.stream != cudaStreamLegacy && knob("TPP_GRAPH", 1) && (useFp32() || (ctl.type == 0 && ctl.precond == 0) || knob("TPP_GRAPH_FP64", 0)) && (!comm.active || (comm.nccl && knob("TPP_GRAPH_PAR", 1)))) {
             GraphKey key{x, F0.diag, ctl.type, ctl.precond, ctl.n_vcycles};
             auto it = graphs.find(key);
             if (it == graphs.end()) {
