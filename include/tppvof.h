@@ -154,10 +154,15 @@ long tpp_profile_report(tpp_handle, char* buf, long cap);
  * tpp_create is the rank's processorN mesh; its `processor` patches (BC codes -1, listed after
  * the physical patches, faces in the neighbour's matching order as decomposePar writes them)
  * become halo interfaces.  tpp_comm_init joins the ranks over NCCL (the library the host
- * process already loaded: pass its path, e.g. torch's nvidia/nccl/lib/libnccl.so.2) and
- * finishes the processor-face geometry; every stencil kernel is then preceded by a halo
- * exchange (pack kernel + ncclSend/ncclRecv on the solver's stream) and every Krylov dot,
- * residual norm and Courant maximum is all-reduced. */
+ * process already loaded: pass its path, e.g. torch's nvidia/nccl/lib/libnccl.so.2), exchanges
+ * cudaIpc handles of one peer-memory window per rank through that communicator and finishes the
+ * processor-face geometry.  Every stencil kernel is then preceded by a halo exchange - one
+ * kernel that stores the owner-side values straight into the neighbours' windows over NVLink
+ * and unpacks what arrived (falls back to ncclSend/ncclRecv without peer access) - and every
+ * Krylov dot, residual norm and Courant maximum is all-reduced over the same windows (<= 8
+ * ranks) or by ncclAllReduce; the multigrid keeps its inter-rank couplings on every level and
+ * gathers its smallest levels onto every rank.  The replacement, on one node, of
+ * `mpirun -np N foamRun -parallel` (/root/reference/circularSloshingTank/Makefile:78,91). */
 int tpp_nccl_unique_id(const char* nccl_path, char* out128);
 int tpp_comm_init(tpp_handle, int rank, int n_ranks, const char* id128, const char* nccl_path);
 /* the same over two host callbacks (CPU tests with gloo): exchange(user, send[nGhost*ncomp],

@@ -1708,14 +1708,15 @@ struct tpp_solver {
         updateXR(x);
         allreduce(S_RES, 1, 0);
     }
-    // OPEN ITEM: the FP64 V-cycle (TPP_FP32=0, a diagnostic option) produced NaNs under graph
-    // replay at >= 2 M cells on B200 while it is correct ungraphed; it therefore runs ungraphed.
+    // (The FP64 V-cycle, TPP_FP32=0, once produced NaNs under graph replay; that was the
+    // allocation-time memset racing a non-blocking caller stream, fixed in dev_alloc - it is
+    // graphed like the FP32 one now and gives the same PCG counts.)
     // The iteration is ~110 small launches with fixed arguments: captured once per
     // (solver entry, solution vector) into a CUDA graph and replayed (launch-bound otherwise).
     void iteration(LV& F0, LV& FG, const tpp_solver_t& ctl, double* x) {
 #ifndef TPP_EMU
         // (the legacy default stream cannot be captured)
-        if (!ctx.prof && ctx.stream != nullptr && ctx.stream != cudaStreamLegacy && knob("TPP_GRAPH", 1) && (useFp32() || (ctl.type == 0 && ctl.precond == 0) || knob("TPP_GRAPH_FP64", 0)) && (!comm.active || (comm.nccl && knob("TPP_GRAPH_PAR", 1)))) {
+        if (!ctx.prof && ctx.stream != nullptr && ctx.stream != cudaStreamLegacy && knob("TPP_GRAPH", 1) &&  (!comm.active || (comm.nccl && knob("TPP_GRAPH_PAR", 1)))) {
             GraphKey key{x, F0.diag, ctl.type, ctl.precond, ctl.n_vcycles};
             auto it = graphs.find(key);
             if (it == graphs.end()) {

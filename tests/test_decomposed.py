@@ -1,6 +1,7 @@
 """One case decomposed over ranks: z-slabs with `processor` patches, halo
 exchange before every stencil kernel, all-reduced Courant numbers / Krylov dots / residuals,
-rank-local (block-Jacobi) multigrid inside a global PCG.
+a global multigrid (processor interfaces agglomerated level by level, smallest levels gathered
+onto every rank) inside a global PCG.
 
 world_size 2, gloo, host emulation of the kernels (CPU CI of the N > 1 logic): the decomposed run
 must reproduce the whole-mesh single-rank run - identical time-step sequence, fields to the
