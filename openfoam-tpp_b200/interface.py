@@ -81,3 +81,101 @@ def mesh_layout(mesh, C=None):
     if per * n_tri * n_layers != mesh.n_cells:
         raise ValueError("unexpected cell layout")
     return n_layers, n_tri, per
+
+
+# ---- the reference's own metric, without VTK -------------------------------------------------------
+def cell_to_point(mesh, cell_values):
+    """vtkCellDataToPointData: a point takes the plain average of the cells that use it."""
+    off, lab = mesh.face_offsets.astype(np.int64), mesh.face_labels.astype(np.int64)
+    cnt = np.diff(off)
+    nI = mesh.n_internal
+    fc_own = np.repeat(mesh.owner.astype(np.int64), cnt)
+    pairs = [fc_own * mesh.n_points + lab]
+    if nI:
+        sel = np.repeat(np.arange(mesh.n_faces) < nI, cnt)
+        fc_nei = np.repeat(np.concatenate([mesh.neighbour.astype(np.int64), np.zeros(mesh.n_faces - nI, dtype=np.int64)]), cnt)
+        pairs.append(fc_nei[sel] * mesh.n_points + lab[sel])
+    key = np.unique(np.concatenate(pairs))  # distinct (cell, point) incidences
+    cell, point = key // mesh.n_points, key % mesh.n_points
+    s = np.zeros(mesh.n_points)
+    n = np.zeros(mesh.n_points)
+    np.add.at(s, point, np.asarray(cell_values, dtype=np.float64)[cell])
+    np.add.at(n, point, 1.0)
+    return s / np.maximum(n, 1.0)
+
+
+def mesh_edges(mesh):
+    """distinct point pairs joined by a face edge (= every cell edge of tets, prisms and hexes)"""
+    off, lab = mesh.face_offsets.astype(np.int64), mesh.face_labels.astype(np.int64)
+    cnt = np.diff(off)
+    pos = np.arange(lab.size) - np.repeat(off[:-1], cnt)
+    nxt = np.where(pos + 1 < np.repeat(cnt, cnt), np.arange(lab.size) + 1, np.repeat(off[:-1], cnt))
+    a, b = lab, lab[nxt]
+    key = np.unique(np.minimum(a, b) * mesh.n_points + np.maximum(a, b))
+    return key // mesh.n_points, key % mesh.n_points
+
+
+def iso_points(mesh, points, point_values, iso=0.5, edges=None):
+    """The points of the iso-surface a contour filter produces on linear cells: one per mesh edge
+    whose end values straddle `iso`, linearly interpolated along the edge."""
+    a, b = edges if edges is not None else mesh_edges(mesh)
+    va, vb = point_values[a], point_values[b]
+    cut = (va >= iso) != (vb >= iso)
+    a, b, va, vb = a[cut], b[cut], va[cut], vb[cut]
+    t = (iso - va) / (vb - va)
+    return points[a] + t[:, None] * (points[b] - points[a])
+
+
+def extract_interface(case_dir, r_target=None, write=True):
+    """VTK-free restatement of the reference's `extract_interface` (main.py:727-818): for every
+    time directory the alpha.water = 0.5 iso-surface of the point-averaged field on the mesh at
+    that time (`<time>/polyMesh/points`: lab frame), reduced to
+    postProcessing/interface/interface_summary.csv (time,max_z,min_z,mean_z,num_points) and
+    wall_elevation.csv (time,theta,zeta_wall; points with r > 0.98 R in 64 theta bins).
+    (The per-frame .vtp files are not written.)  Returns the summary rows."""
+    import os
+    import re
+
+    from . import foamfile as ff
+
+    mesh = ff.read_polymesh(case_dir)
+    edges = mesh_edges(mesh)
+    if r_target is None:
+        m = re.search(r"_D([\d.]+)_", os.path.basename(os.path.normpath(case_dir)))
+        r_target = float(m.group(1)) / 2.0 if m else 0.1
+    summary, wall = ["time,max_z,min_z,mean_z,num_points"], ["time,theta,zeta_wall"]
+    rows = []
+    bins = np.linspace(-np.pi, np.pi, 65)
+    for t, name in ff.time_dirs(case_dir):
+        fp = os.path.join(case_dir, name, "alpha.water")
+        if not os.path.exists(fp):
+            continue
+        alpha = ff.read_field(fp).internal_array(mesh.n_cells)
+        pp = os.path.join(case_dir, name, "polyMesh", "points")
+        pts_mesh = ff.read_points(pp) if os.path.exists(pp) else mesh.points
+        pts = iso_points(mesh, pts_mesh, cell_to_point(mesh, alpha), 0.5, edges)
+        if len(pts) == 0:
+            summary.append(f"{t},0,0,0,0")
+            rows.append((t, 0.0, 0.0, 0.0, 0))
+            continue
+        z = pts[:, 2]
+        summary.append(f"{t},{z.max()},{z.min()},{z.mean()},{len(pts)}")
+        rows.append((t, float(z.max()), float(z.min()), float(z.mean()), len(pts)))
+        r = np.hypot(pts[:, 0], pts[:, 1])
+        wm = r > r_target * 0.98
+        if wm.any():
+            wp = pts[wm]
+            th = np.arctan2(wp[:, 1], wp[:, 0])
+            which = np.digitize(th, bins) - 1
+            for b in range(64):
+                sel = which == b
+                if sel.any():
+                    wall.append(f"{t},{(bins[b] + bins[b + 1]) / 2.0},{wp[sel, 2].mean()}")
+    if write:
+        out = os.path.join(case_dir, "postProcessing", "interface")
+        os.makedirs(out, exist_ok=True)
+        with open(os.path.join(out, "interface_summary.csv"), "w") as f:
+            f.write("\n".join(summary))
+        with open(os.path.join(out, "wall_elevation.csv"), "w") as f:
+            f.write("\n".join(wall))
+    return rows

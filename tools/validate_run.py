@@ -63,16 +63,20 @@ def main():
         s.stage("mixture")
     cols = interface.ColumnSampler(mesh)
     V = cols.V
+    edges = interface.mesh_edges(mesh)  # the reference's own metric: points of the alpha = 0.5 iso-surface (main.py:751-780)
     t0 = time.perf_counter()
     with open(a.out, "w") as f:
-        f.write("time,max_z,min_z,mean_z,A_m1,phase_m1,alpha_volume,step,it_final,res_final,wall_s\n")
+        f.write("time,max_z,min_z,mean_z,A_m1,phase_m1,alpha_volume,step,it_final,res_final,wall_s,iso_max_z,iso_min_z,iso_mean_z,iso_points\n")
 
         def rec():
             al = s.get("alpha")
             mx, mn, me = cols.summary(al)
             A, ph, _ = cols.wall_mode1(al)
             i = s.info()
-            f.write(f"{i['t']:.9g},{mx:.9g},{mn:.9g},{me:.9g},{A:.9g},{ph:.9g},{float((al * V).sum()):.15g},{int(i['step'])},{int(i['it1'])},{i['r1']:.3e},{time.perf_counter() - t0:.2f}\n")
+            pts = s.get("points").reshape(-1, 3) if a.impl == "gpu" else mesh.points
+            iso = interface.iso_points(mesh, pts, interface.cell_to_point(mesh, al), 0.5, edges)
+            z = iso[:, 2] if len(iso) else np.zeros(1)
+            f.write(f"{i['t']:.9g},{mx:.9g},{mn:.9g},{me:.9g},{A:.9g},{ph:.9g},{float((al * V).sum()):.15g},{int(i['step'])},{int(i['it1'])},{i['r1']:.3e},{time.perf_counter() - t0:.2f},{z.max():.9g},{z.min():.9g},{z.mean():.9g},{len(iso)}\n")
             f.flush()
 
         rec()
