@@ -455,7 +455,7 @@ struct tpp_solver {
             double s = dot3(dd, &Sf0[3 * f]);
             double tol = 1e-12 * magSf[f] * sqrt(magSf[f]);
             if (s > tol) nbad[own[f]]++;
-            if (f < nI && s < -tol) nbad[nei[f]]++;
+            if (f < nI && nei[f] < nC && s < -tol) nbad[nei[f]]++;  // (a processor face's neighbour is a ghost row)
         }
         int best = -1;
         double bd = 1e300;

@@ -378,6 +378,14 @@ def reconstruct_par(case_dir, times=None, binary=True, log=None):
                             dst[k] = v
             _ = oriented
             ff.write_field(os.path.join(case_dir, tn, nm), ff.Field(f0.cls, f0.name, f0.dimensions, glob, bvals), binary, location=tn)
+        # moved points of a dynamic mesh (<time>/polyMesh/points) through pointProcAddressing
+        if os.path.exists(os.path.join(pdirs[0], tn, "polyMesh", "points")):
+            pts = np.zeros_like(mesh.points)
+            for pd in pdirs:
+                pa = _read_labels(os.path.join(pd, "constant", "polyMesh", "pointProcAddressing"))
+                pts[pa] = ff.read_points(os.path.join(pd, tn, "polyMesh", "points"))
+            os.makedirs(os.path.join(case_dir, tn, "polyMesh"), exist_ok=True)
+            ff.write_points(os.path.join(case_dir, tn, "polyMesh", "points"), pts, binary, f"{tn}/polyMesh")
         up = os.path.join(pdirs[0], tn, "uniform", "time")
         if os.path.exists(up):
             os.makedirs(os.path.join(case_dir, tn, "uniform"), exist_ok=True)

@@ -170,13 +170,34 @@ def run_case(case_dir, device=0, lib_path=None, max_steps=None, log=sys.stdout, 
         s.set("Uf", full(case.fields["Uf"], 3))
         s.set_time(case.start_value, case.restart_delta_t or cfg.delta_t)
     probes = None
-    if cfg.probes is not None and len(cfg.probes) and not (parallel and world > 1):
+    multi = parallel and world > 1
+    vg = -1.79769e307
+
+    def merge_rows(rows):
+        """probe rows of a decomposed run: every probe lives on one rank (-1.79769e307 elsewhere,
+        OpenFOAM's own 'not found' value), so the element-wise maximum over the ranks is the row"""
+        a = np.ascontiguousarray(np.asarray(rows, dtype=np.float64).reshape(-1, 1 + len(cfg.probes)))
+        if multi:
+            import torch
+            import torch.distributed as dist
+
+            t = torch.from_numpy(a.copy())
+            if dist.get_backend() == "nccl":
+                t = t.cuda()
+            dist.all_reduce(t, op=dist.ReduceOp.MAX)
+            a = t.cpu().numpy()
+        return a
+
+    if cfg.probes is not None and len(cfg.probes):
         cells = [s.find_cell(x) for x in cfg.probes]
         s.set_probes(cells)
-        probes = ProbesWriter(case, case.start_name, cfg.probe_fields[0] if cfg.probe_fields else "p")
-        vg = -1.79769e307
+        if rank == 0:  # the master writes postProcessing/ at the case root, as OpenFOAM does
+            root_case = case if not multi else type("RootDir", (), {"dir": case.root, "cfg": cfg})()
+            probes = ProbesWriter(root_case, case.start_name, cfg.probe_fields[0] if cfg.probe_fields else "p")
         pnow = s.get("p")
-        probes.rows([[case.start_value] + [pnow[c] if c >= 0 else vg for c in cells]])
+        row0 = merge_rows([[case.start_value] + [pnow[c] if c >= 0 else vg for c in cells]])
+        if probes is not None:
+            probes.rows(row0)
     t0 = _time.perf_counter()
     steps0 = s.info()["step"]
     n_writes = 0
@@ -186,8 +207,10 @@ def run_case(case_dir, device=0, lib_path=None, max_steps=None, log=sys.stdout, 
             break
         rc = s.run_to_write(budget)
         info = s.info()
-        if probes is not None:
-            probes.rows(s.probe_log())
+        if cfg.probes is not None and len(cfg.probes):
+            rows = merge_rows(s.probe_log())
+            if probes is not None:
+                probes.rows(rows)
         if rc == 1:
             name = ff.time_name(info["t"], cfg.time_precision)
             if write:

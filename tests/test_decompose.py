@@ -193,4 +193,15 @@ def test_foamrun_parallel_matches_serial(tmp_path, emu_lib):
             n = mesh.n_internal if b[nm].cls.startswith("surface") else mesh.n_cells
             x, y = a[nm].internal_array(n), b[nm].internal_array(n)
             assert np.abs(x - y).max() <= tol * max(np.abs(y).max(), 1e-300), (tn, nm, np.abs(x - y).max())
+        # the moved mesh of that time, merged through pointProcAddressing
+        pa, pb = ff.read_points(os.path.join(par, tn, "polyMesh", "points")), ff.read_points(os.path.join(serial, tn, "polyMesh", "points"))
+        assert np.abs(pa - pb).max() <= 1e-15
     assert out["steps"] == steps
+    # probes: written once, by the master, at the case root; same rows as the serial run
+    pr_s = open(os.path.join(serial, "postProcessing", "probes", "0", "p")).read().splitlines()
+    pr_p = open(os.path.join(par, "postProcessing", "probes", "0", "p")).read().splitlines()
+    assert len(pr_p) == len(pr_s) and pr_p[:3] == pr_s[:3]
+    for a, b in zip(pr_p[3:], pr_s[3:]):
+        va, vb = [float(x) for x in a.split()], [float(x) for x in b.split()]
+        assert va[0] == vb[0]
+        assert all(abs(x - y) <= 1e-5 * max(abs(y), 1.0) for x, y in zip(va[1:], vb[1:])), (a, b)
