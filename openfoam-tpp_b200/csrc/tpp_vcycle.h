@@ -646,8 +646,29 @@ __global__ void __launch_bounds__(1024) vk_coarse_cg(const VL<R> L, R* r, R* p, 
 }
 #else
 // ---- host emulation of the tail (tests of the launch logic only) --------------------------------
+template <class R> inline void tail_host_once(const TailArgs<R>& A);
+// experiment knob (host emulation only): TPP_TAIL_CYCLES > 1 iterates the tail cycle on the
+// residual of its first level, i.e. a nearly exact solve of that level
 template <class R>
 inline void tail_host(const TailArgs<R>& A) {
+    const char* e = getenv("TPP_TAIL_CYCLES");
+    const int nc = e ? atoi(e) : 1;
+    if (nc <= 1 || A.T < 2) { tail_host_once(A); return; }
+    const TLv<R>& L = A.lv[0];
+    std::vector<R> b0(L.b, L.b + L.n), xs(L.n, R(0));
+    for (int c = 0; c < nc; c++) {
+        tail_host_once(A);
+        for (int i = 0; i < L.n; i++) xs[i] += L.x[i];
+        for (int i = 0; i < L.n; i++) {
+            R s = 0;
+            for (int k = L.rs[i]; k < L.rs[i + 1]; k++) s += L.ev[k] * xs[L.cn[k]];
+            L.b[i] = b0[i] - (L.diag[i] * xs[i] - s);
+        }
+    }
+    for (int i = 0; i < L.n; i++) { L.x[i] = xs[i]; L.b[i] = b0[i]; }
+}
+template <class R>
+inline void tail_host_once(const TailArgs<R>& A) {
     const int swaps = (A.nPre > 1 ? A.nPre - 1 : 0) + (A.nPost > 1 ? A.nPost : 1);
     auto off = [](const TLv<R>& L, int row, const R* x, const int* map) {
         R s = 0;
