@@ -494,3 +494,32 @@ def setup_tutorial_case(case_dir, nx=10, ny=20, nz=15, end_time=40.0, overwrite=
     ff.write_polymesh(case_dir, meshgen.sloshing_tank3d_mesh(nx, ny, nz), binary=True)
     set_fields(case_dir)
     return case_dir
+
+
+def main(argv=None):
+    """`setFields [-case DIR]` (circularSloshingTank/Makefile:74) for the box dictionary
+    update_setFields.py writes."""
+    import sys
+
+    argv = list(sys.argv[1:] if argv is None else argv)
+    if argv and argv[0] == "setFields":
+        argv.pop(0)
+    case_dir = os.getcwd()
+    while argv:
+        a = argv.pop(0)
+        if a == "-case":
+            case_dir = argv.pop(0)
+        else:
+            raise SystemExit(f"setFields (tppvof): unknown option {a}")
+    try:
+        set_fields(case_dir)
+    except Exception as e:
+        print(f"--> FOAM FATAL ERROR: {e}", file=sys.stderr)
+        return 1
+    return 0
+
+
+if __name__ == "__main__":
+    import sys
+
+    sys.exit(main())

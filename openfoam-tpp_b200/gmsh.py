@@ -148,3 +148,42 @@ def write_msh(path, mesh: PolyMesh, volume_name="internalMesh"):
             f.write(f"{e} 4 2 {vtag} 1 {v[0] + 1} {v[1] + 1} {v[2] + 1} {v[3] + 1}\n")
             e += 1
         f.write("$EndElements\n")
+
+
+def main(argv=None):
+    """`gmshToFoam <file.msh> [-case DIR]` (circularSloshingTank/Makefile:73): writes
+    constant/polyMesh of the case from a Gmsh 2.2 ASCII mesh."""
+    import os
+    import sys
+
+    from . import foamfile as ff
+
+    argv = list(sys.argv[1:] if argv is None else argv)
+    if argv and argv[0] == "gmshToFoam":
+        argv.pop(0)
+    case_dir, msh = os.getcwd(), None
+    while argv:
+        a = argv.pop(0)
+        if a == "-case":
+            case_dir = argv.pop(0)
+        elif a.startswith("-"):
+            raise SystemExit(f"gmshToFoam (tppvof): unknown option {a}")
+        else:
+            msh = a
+    if msh is None:
+        raise SystemExit("usage: gmshToFoam <file.msh> [-case DIR]")
+    try:
+        mesh = msh_to_polymesh(msh if os.path.isabs(msh) else os.path.join(case_dir, msh))
+        mesh.check()
+        ff.write_polymesh(case_dir, mesh, binary=True)
+    except Exception as e:
+        print(f"--> FOAM FATAL ERROR: {e}", file=sys.stderr)
+        return 1
+    print(f"gmshToFoam (tppvof): {mesh.n_cells} cells, {mesh.n_faces} faces, patches " + ", ".join(f"{p['name']}({p['nFaces']})" for p in mesh.patches))
+    return 0
+
+
+if __name__ == "__main__":
+    import sys
+
+    sys.exit(main())
