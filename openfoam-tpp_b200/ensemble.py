@@ -82,3 +82,37 @@ def sum_over_ranks(values, group=None):
     t = torch.tensor(values, dtype=torch.float64, device=dev)
     dist.all_reduce(t, op=dist.ReduceOp.SUM, group=group)
     return t.tolist()
+
+
+def run_sweep(root_dir, base, sweeps, lc_to_mesh=None, max_steps=None, lib_path=None, log=None):
+    """The sweep loop of main.py:599-608 on the GPUs of one box: every rank of the
+    torch.distributed job (one process per GPU; a plain process is rank 0 of 1) sets up and runs
+    its share of the cases, one after another, each through the ordinary case-directory path
+    (case.setup_case -> foamrun.run_case).  Nothing is exchanged between ranks.
+
+    base / sweeps as in build_param_sets (keys H, D, geo, R, freq, duration, mesh = gmsh lc);
+    lc_to_mesh(p) -> (n_rings, n_layers) replaces gmsh where it is absent (default: cells of
+    about lc).  Returns [(case name, summary dict)] of this rank."""
+    import os
+
+    from . import case as cs
+    from . import foamrun
+
+    try:
+        import torch.distributed as dist
+
+        rank, world = (dist.get_rank(), dist.get_world_size()) if dist.is_initialized() else (0, 1)
+    except ImportError:
+        rank, world = 0, 1
+    device = int(os.environ.get("LOCAL_RANK", "0"))
+    lc_to_mesh = lc_to_mesh or (lambda p: (max(3, round(p["D"] / 2 / p["mesh"])), max(3, round(p["H"] / p["mesh"]))))
+    done = []
+    for p in shard(build_param_sets(base, sweeps), world, rank):
+        name = case_name(p)
+        d = os.path.join(root_dir, name)
+        if not os.path.isdir(os.path.join(d, "constant", "polyMesh")):
+            nr, nl = lc_to_mesh(p)
+            cs.setup_case(d, H=p["H"], D=p["D"], geo=p["geo"], R=p["R"], freq=p["freq"], duration=p["duration"], n_rings=nr, n_layers=nl)
+        out = foamrun.run_case(d, device=device, lib_path=lib_path, max_steps=max_steps, log=log)  # resumes from the latest time
+        done.append((name, out))
+    return done

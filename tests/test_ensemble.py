@@ -69,3 +69,16 @@ def test_two_rank_ensemble_gloo(tmp_path, emu_lib):
     n0 = 18 * 16 * 3
     n1 = 18 * 25 * 3
     assert f"total={n0 + n1}" in out
+
+
+def test_run_sweep_sets_up_and_runs_every_case(tmp_path, emu_lib):
+    """the sweep loop (main.py:599-608) on one rank: 2 x 2 cases, a few steps each, named as the
+    reference names them, each leaving a restartable case directory"""
+    base = {"H": 0.004, "D": 0.0221, "geo": "flat", "R": 0.005, "freq": 2.0, "duration": 0.02, "mesh": 0.003}
+    done = en.run_sweep(str(tmp_path), base, {"R": [0.004, 0.005], "freq": [1.5, 2.0, 2.5][:2] + [3.0]}, max_steps=3, lib_path=emu_lib)
+    names = [n for n, _ in done]
+    assert len(done) == 6 and len(set(names)) == 6 and all(o["steps"] == 3 for _, o in done)
+    assert "case_H0.004_D0.0221_flat_R0.004_f1.5_d0.02_m0.003" in names
+    for n in names:
+        assert os.path.isfile(os.path.join(str(tmp_path), n, "constant", "polyMesh", "owner"))
+        assert os.path.isfile(os.path.join(str(tmp_path), n, "constant", "6DoF.dat"))
