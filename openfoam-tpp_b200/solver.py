@@ -281,5 +281,23 @@ class Solver:
         self.set("U", case.fields["U"].internal_array(nC))
         self.set("p_rgh", case.fields["p_rgh"].internal_array(nC))
         self.init_fields()
+        # boundary values the next step reads before it re-evaluates them (the old-time wall /
+        # atmosphere velocity in ddtCorr, p_rgh on the fixedFluxPressure walls in the non-orthogonal
+        # correction): a restart takes them from the time directory, as OpenFOAM does
+        for fname, arr, nc in (("U", "U_b", 3), ("p_rgh", "p_rgh_b", 1)):
+            cur = self.get(arr).reshape(-1, nc) if nc > 1 else self.get(arr)
+            nI, changed = self.mesh.n_internal, False
+            for p in self.mesh.patches:
+                if p["type"] == "processor" or p["nFaces"] == 0:
+                    continue
+                v = case.fields[fname].boundary.get(p["name"], {}).get("value")
+                if v is None:
+                    continue
+                v = np.asarray(v, dtype=np.float64)
+                sl = slice(p["startFace"] - nI, p["startFace"] - nI + p["nFaces"])
+                cur[sl] = v if v.ndim == (1 if nc == 1 else 2) else np.broadcast_to(v, cur[sl].shape)
+                changed = True
+            if changed:
+                self.set(arr, np.ascontiguousarray(cur).reshape(-1))
         if case.restart_delta_t is not None:
             self.set_delta_t(case.restart_delta_t)
