@@ -135,7 +135,11 @@ def _declared_symbols():
 
 def test_product_library_exports_every_declared_symbol():
     """libtppvof.so (the sm_100a build) loads without a GPU and exports the whole C-ABI."""
-    assert os.path.exists(sv.LIB_PATH), "libtppvof.so missing: run __graft_entry__.build()"
+    if not os.path.exists(sv.LIB_PATH):  # a fresh checkout: the library is a build product (nvcc cross-compiles without a GPU)
+        import __graft_entry__
+
+        __graft_entry__.build()
+    assert os.path.exists(sv.LIB_PATH), "libtppvof.so missing after __graft_entry__.build()"
     lib = ctypes.CDLL(sv.LIB_PATH)
     names = _declared_symbols()
     assert len(names) >= 20
