@@ -55,3 +55,26 @@ def test_free_sloshing_period_matches_potential_flow_emu(emu_lib):
     # the tank is open at the top (inletOutlet): on 6 layers a trace of smeared alpha reaches the
     # lid and leaves with the displaced air; the walls are tight (phi_b = 0 exactly)
     assert 0 <= vol0 - vol1 < 5e-3 * vol0
+
+
+def test_hydrostatic_rest_state_stays_at_rest_emu(emu_lib):
+    """A flat free surface on a cell-layer boundary of an orthogonal (hex) tank at rest is a discrete
+    equilibrium of the p_rgh formulation: it must stay at rest - no spurious currents from the
+    1000:1 density jump beyond what the pressure tolerance (2e-9) admits, alpha unchanged.  (On the
+    tet meshes the start from p_rgh = 0 is violent in OpenFOAM too: golden G2 pins that start-up
+    deltaT collapse in tests/test_golden.py.)"""
+    mesh = mg.box_mesh(4, 4, 6, lo=(0, 0, 0), hi=(0.1, 0.1, 0.2), cell="hex", top_patch="atmosphere")
+    cfg = bench.make_config(mesh)
+    cfg.n_motion, cfg.motion = 0, None
+    cfg.max_delta_t = cfg.delta_t = 0.002
+    C, V = mg.cell_geometry(mesh)
+    alpha = (C[:, 2] < 0.1).astype(float)
+    g = sv.Solver(mesh, cfg, lib_path=emu_lib)
+    g.set("alpha", alpha)
+    g.init_fields()
+    g.step(20)
+    U, a, i = g.get("U"), g.get("alpha"), g.info()
+    g.close()
+    assert i["t"] > 0.03
+    assert np.abs(U).max() < 1e-5, np.abs(U).max()       # m/s; the gravity-wave speed here is ~1 m/s
+    assert np.abs(a - alpha).max() < 1e-6
