@@ -150,7 +150,7 @@ class ProcMesh:
 def decompose_mesh(mesh: PolyMesh, cell_proc, nproc=None):
     cell_proc = np.asarray(cell_proc, dtype=np.int64)
     nproc = int(cell_proc.max()) + 1 if nproc is None else nproc
-    nI, nF = mesh.n_internal, mesh.n_faces
+    nI = mesh.n_internal
     own, nei = mesh.owner.astype(np.int64), mesh.neighbour.astype(np.int64)
     po = cell_proc[own]                 # processor of every face's owner
     pn = cell_proc[nei]                 # ... of every internal face's neighbour
@@ -348,7 +348,6 @@ def reconstruct_par(case_dir, times=None, binary=True, log=None):
             shape = (mesh.n_internal if surface else mesh.n_cells,) + (() if scalar else (ncomp,))
             glob = np.zeros(shape)
             bvals = {p["name"]: {} for p in mesh.patches}
-            oriented = f0.cls == "surfaceScalarField"
             for (pm, ca, fa, ba), fld in zip(addr, parts):
                 gfa = np.abs(fa.astype(np.int64)) - 1
                 if surface:
@@ -376,7 +375,6 @@ def reconstruct_par(case_dir, times=None, binary=True, log=None):
                                 dst[k][gfa[sl] - gp["startFace"]] = v
                         elif k not in dst:
                             dst[k] = v
-            _ = oriented
             ff.write_field(os.path.join(case_dir, tn, nm), ff.Field(f0.cls, f0.name, f0.dimensions, glob, bvals), binary, location=tn)
         # moved points of a dynamic mesh (<time>/polyMesh/points) through pointProcAddressing
         if os.path.exists(os.path.join(pdirs[0], tn, "polyMesh", "points")):
