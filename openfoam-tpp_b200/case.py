@@ -254,9 +254,10 @@ def read_config(case_dir, mesh=None):
                 raise FoamError(f"{p}:{name}: function object type '{typ}' is not supported (probes)")
             cfg.probes = np.array([[float(c) for c in v] for v in lookup(fo, "probeLocations", p)])
             cfg.probe_fields = list(lookup(fo, "fields", p))
-            for f in cfg.probe_fields:
-                if f not in ("p", "p_rgh", "alpha.water"):
-                    raise FoamError(f"{p}:{name}: probing field '{f}' is not supported")
+            # the solver samples p (system/functions:28-31 of the reference); any other selection
+            # would be written under the wrong name, so it is an error, not a silent default
+            if cfg.probe_fields != ["p"]:
+                raise FoamError(f"{p}:{name}: probes 'fields ({' '.join(map(str, cfg.probe_fields))})' is not supported: exactly 'fields (p)'")
     p = os.path.join(case_dir, "system", "decomposeParDict")
     if os.path.exists(p):
         dp = ff.read_dict(p)
@@ -293,10 +294,18 @@ def _bc_tables(cfg, mesh, fields, tdir):
 
 
 def latest_time(case_dir, need="alpha.water"):
+    """Newest COMPLETE time directory.  A directory the solver wrote is complete once
+    `uniform/time` exists (write_time writes it last; a run killed mid-write leaves a directory
+    without it, which `make resume` must not pick).  A hand-made initial directory (0/ after
+    setFields: no `phi`) has no uniform/ and counts as soon as it holds `need`."""
     best = None
     for v, nm in ff.time_dirs(case_dir):
-        if os.path.exists(os.path.join(case_dir, nm, need)):
-            best = (v, nm)
+        d = os.path.join(case_dir, nm)
+        if not os.path.exists(os.path.join(d, need)):
+            continue
+        if v > 0 and os.path.exists(os.path.join(d, "phi")) and not os.path.exists(os.path.join(d, "uniform", "time")):
+            continue  # partially written
+        best = (v, nm)
     if best is None:
         raise FoamError(f"{case_dir}: no time directory holds {need}")
     return best

@@ -124,6 +124,9 @@ inline void prof_end(Ctx& c) {
 #endif
 }
 
+struct CudaFailure {  // thrown by CUDA_CHECK / LAUNCH_CHECK, caught at the C-ABI (API_CATCH)
+    std::string what;
+};
 #ifdef TPP_EMU
 inline void* dev_alloc(size_t bytes) { return calloc(1, bytes ? bytes : 1); }
 inline void dev_free(void* p) { free(p); }
@@ -143,7 +146,18 @@ inline void dev_sync(Ctx&) {}
     switch ((view).W) { case 4: k_##name<4>(view, n); break; case 5: k_##name<5>(view, n); break; case 6: k_##name<6>(view, n); break; default: k_##name<0>(view, n); } \
     prof_end(ctx); (ctx).launches++; } } while (0)
 #else
-#define CUDA_CHECK(x) do { cudaError_t e_ = (x); if (e_ != cudaSuccess) { fprintf(stderr, "CUDA error %s at %s:%d\n", cudaGetErrorString(e_), __FILE__, __LINE__); abort(); } } while (0)
+// A failed CUDA call becomes a C++ exception that every C-ABI entry point catches (API_GUARD in
+// tppvof.cu) and turns into a negative return code + tpp_last_error(): no abort(), no exception
+// across the ABI (include/tppvof.h).
+[[noreturn]] inline void cuda_fail(cudaError_t e, const char* expr, const char* file, int line) {
+    char buf[512];
+    snprintf(buf, sizeof buf, "CUDA error '%s' in %s at %s:%d", cudaGetErrorString(e), expr, file, line);
+    throw CudaFailure{buf};
+}
+#define CUDA_CHECK(x) do { cudaError_t e_ = (x); if (e_ != cudaSuccess) ::tpp::cuda_fail(e_, #x, __FILE__, __LINE__); } while (0)
+// after a kernel launch: configuration errors (too many resources, bad grid) surface here and not
+// at an unrelated later call.  Not a synchronisation.
+#define LAUNCH_CHECK(name) do { cudaError_t e_ = cudaPeekAtLastError(); if (e_ != cudaSuccess) ::tpp::cuda_fail(e_, "launch of " name, __FILE__, __LINE__); } while (0)
 inline void* dev_alloc(size_t bytes) {
     void* p = nullptr;
     CUDA_CHECK(cudaMalloc(&p, bytes ? bytes : 8));
@@ -164,7 +178,7 @@ inline void dev_sync(Ctx& c) { CUDA_CHECK(cudaStreamSynchronize(c.stream)); }
         int i = blockIdx.x * blockDim.x + threadIdx.x;                     \
         if (i < n) b_##name(d, i);                                         \
     }
-#define LAUNCH(ctx, name, view, n) do { if ((n) > 0) { prof_begin(ctx, #name); k_##name<<<((n) + 255) / 256, 256, 0, (ctx).stream>>>(view, n); prof_end(ctx); (ctx).launches++; } } while (0)
+#define LAUNCH(ctx, name, view, n) do { if ((n) > 0) { prof_begin(ctx, #name); k_##name<<<((n) + 255) / 256, 256, 0, (ctx).stream>>>(view, n); LAUNCH_CHECK(#name); prof_end(ctx); (ctx).launches++; } } while (0)
 // cell kernels templated on the ELL width WT (see FOR_CELL_FACES)
 #define DEF_KERNEL_W(name) DEF_KERNEL_WB(name, 4)
 #define DEF_KERNEL_WB(name, minb)                                                       \
@@ -175,7 +189,7 @@ inline void dev_sync(Ctx& c) { CUDA_CHECK(cudaStreamSynchronize(c.stream)); }
 #define LAUNCH_W(ctx, name, view, n) do { if ((n) > 0) { prof_begin(ctx, #name); const int g_ = ((n) + 255) / 256; \
     switch ((view).W) { case 4: k_##name<4><<<g_, 256, 0, (ctx).stream>>>(view, n); break; case 5: k_##name<5><<<g_, 256, 0, (ctx).stream>>>(view, n); break; \
                         case 6: k_##name<6><<<g_, 256, 0, (ctx).stream>>>(view, n); break; default: k_##name<0><<<g_, 256, 0, (ctx).stream>>>(view, n); } \
-    prof_end(ctx); (ctx).launches++; } } while (0)
+    LAUNCH_CHECK(#name); prof_end(ctx); (ctx).launches++; } } while (0)
 #endif
 
 template <class T>

@@ -85,8 +85,8 @@ template <class R> HD void vb_scale_apply(const VL<R>& L, int i) {
     R sf = (R)(L.sf[0] / (fabs(den) < VSMALL ? (den >= 0 ? VSMALL : -VSMALL) : den));
     L.out[i] += sf * L.c[i] + L.omega * (L.r[i] - sf * L.Ac[i]) / L.diag[i];
 }
-// unscaled correction: out[i] += xc[agg[i]]
-template <class R> HD void vb_prolong_add(const VL<R>& L, int i) { L.out[i] += L.xc[L.agg[i]]; }
+// correction with a fixed over-correction factor: out[i] += omega xc[agg[i]]
+template <class R> HD void vb_prolong_add(const VL<R>& L, int i) { L.out[i] += L.omega * L.xc[L.agg[i]]; }
 template <class R> struct CastArgs { const double* src; R* dst; const R* rsrc; double* ddst; };
 template <class R> HD void vb_cast_in(const CastArgs<R>& a, int i) { a.dst[i] = (R)a.src[i]; }
 template <class R> HD void vb_cast_out(const CastArgs<R>& a, int i) { a.ddst[i] = (double)a.rsrc[i]; }
@@ -104,7 +104,7 @@ template <class R> HD void vb_pack(const PackArgs<R>& a, int j) { a.dst[j] = a.s
         int i = blockIdx.x * blockDim.x + threadIdx.x;                                   \
         if (i < n) vb_##name(L, i);                                                      \
     }
-#define VLAUNCH(ctx, name, view, n) do { if ((n) > 0) { prof_begin(ctx, "v_" #name); vk_##name<<<((n) + 255) / 256, 256, 0, (ctx).stream>>>(view, n); prof_end(ctx); (ctx).launches++; } } while (0)
+#define VLAUNCH(ctx, name, view, n) do { if ((n) > 0) { prof_begin(ctx, "v_" #name); vk_##name<<<((n) + 255) / 256, 256, 0, (ctx).stream>>>(view, n); LAUNCH_CHECK("v_" #name); prof_end(ctx); (ctx).launches++; } } while (0)
 #endif
 
 DEF_VKERNEL(jacobi0, VL)
@@ -120,6 +120,7 @@ DEF_VKERNEL(pack, PackArgs)
 
 // ---- the tail: all small levels in one persistent kernel ---------------------------------------
 constexpr int TAIL_MAXLV = 12;
+constexpr int TAIL_MAXSW = 8;  // most sweeps per smoothing group in the tail
 constexpr int TAIL_THREADS = 512;  // one CTA per SM: 128 registers per thread for the 16-wide ELL rows
 template <class R>
 struct TLv {
@@ -139,17 +140,13 @@ struct TailArgs {
     TLv<R> lv[TAIL_MAXLV];
     unsigned* bar;    // grid-barrier counter, zeroed before every launch
     int* err;         // set if a barrier timed out (never in a healthy launch)
-    double* partial;  // [2 * gridDim.x] block partials of the scaling dots
-    R omega, scaleJ;
+    R overcorr;                               // fixed over-correction factor of the prolonged correction
+    R omPre[TAIL_MAXSW], omPost[TAIL_MAXSW];  // relaxation factor of every sweep (smootherOmega)
     int nPre, nPost, cgIter;
     double cgTol;
     R *cgR, *cgP, *cgAp;  // coarsest-level CG scratch (global memory; unused when the level is staged in shared memory)
     int cgSmem;           // the coarsest level fits the CTA's shared memory
 };
-// the buffer (x or y) that holds a level's iterate after `swaps` Jacobi sweeps when the final
-// iterate has to land in x
-template <class R> HD R* tail_start(const TLv<R>& L, int swaps) { return (swaps & 1) ? L.y : L.x; }
-
 #ifndef TPP_EMU
 struct GridBar {
     unsigned* ctr;
@@ -179,8 +176,12 @@ DEV void gsync(GridBar& g) {
 // runs on lane 0 of the row.  col = cn[k] or, through the aggregate map, map[cn[k]] (a
 // prolonged coarse vector that is never stored).
 constexpr int TAIL_U = 4;
-template <class R, class F>
-DEV void tail_rows(const TLv<R>& L, const R* x, const int* map, int tid, int nth, F f) {
+template <class R, class G, class F>
+DEV void tail_rows(const TLv<R>& L, G colval, int tid, int nth, F f) {
+    // colval(j): the value of column j of the vector the operator is applied to - a stored vector,
+    // or one that is never stored (the first Jacobi iterate omega0 b/diag; the iterate plus the
+    // prolonged coarse correction): fusing those into the sweep that consumes them saves a phase
+    // (a grid barrier) each
     if (L.ellW > 0) {
         // ELL + overflow: one thread per row, no row-start indirection; the (up to 16) column
         // indices and coefficients of the row are loaded together, then all x values
@@ -195,16 +196,12 @@ DEV void tail_rows(const TLv<R>& L, const R* x, const int* map, int tid, int nth
                 v[k] = in ? L.eev[(size_t)k * L.nPad + row] : R(0);
             }
             const int ob = L.ors[row], oe = L.ors[row + 1];
-            if (map) {
 #pragma unroll
-                for (int k = 0; k < 16; k++) o[k] = o[k] >= 0 ? map[o[k]] : -1;
-            }
-#pragma unroll
-            for (int k = 0; k < 16; k++) xv[k] = o[k] >= 0 ? x[o[k]] : R(0);
+            for (int k = 0; k < 16; k++) xv[k] = o[k] >= 0 ? colval(o[k]) : R(0);
             R s = 0;
 #pragma unroll
             for (int k = 0; k < 16; k++) s += v[k] * xv[k];
-            for (int k = ob; k < oe; k++) { int oo = L.ocn[k]; s += L.oev[k] * x[map ? map[oo] : oo]; }
+            for (int k = ob; k < oe; k++) s += L.oev[k] * colval(L.ocn[k]);
             f(row, s);
         }
         return;
@@ -232,12 +229,8 @@ DEV void tail_rows(const TLv<R>& L, const R* x, const int* map, int tid, int nth
                 o[u] = in ? L.cn[k[u]] : -1;
                 v[u] = in ? L.ev[k[u]] : R(0);
             }
-            if (map) {
 #pragma unroll
-                for (int u = 0; u < TAIL_U; u++) o[u] = o[u] >= 0 ? map[o[u]] : -1;
-            }
-#pragma unroll
-            for (int u = 0; u < TAIL_U; u++) xv[u] = o[u] >= 0 ? x[o[u]] : R(0);
+            for (int u = 0; u < TAIL_U; u++) xv[u] = o[u] >= 0 ? colval(o[u]) : R(0);
             any = false;
 #pragma unroll
             for (int u = 0; u < TAIL_U; u++) {
@@ -323,35 +316,43 @@ DEV void tail_coarse_cg(const TLv<R>& L, R* gr, R* gp, R* gAp, int maxIter, doub
         for (int i = t; i < n; i += T) L.x[i] = x[i];
     }
 }
-// The V-cycle over the tail levels lv[0..T-1]: lv[0].b -> lv[0].x.  Same cycle as the
-// per-kernel levels (damped Jacobi from a zero guess, residual, restriction; coarsest CG;
-// prolongation with GAMG's energy-minimising correction scaling, post-smoothing).
+// The V-cycle over the tail levels lv[0..T-1]: lv[0].b -> lv[0].x.  Same cycle as the per-kernel
+// levels: nPre Chebyshev-Jacobi sweeps from a zero guess, residual, restriction; CG on the coarsest
+// level; prolongation with the fixed over-correction factor, nPost sweeps.  A phase costs a grid
+// barrier (the levels sit in L2: a phase is a few dependent L2 round trips plus the barrier), so the
+// first iterate omega0 b/diag is never stored (the second sweep, or the residual, recomputes it per
+// column) and the corrected iterate x + oc P xc is formed inside the first post-sweep: 3 + nPost
+// phases per level for nPre <= 2.
 template <class R>
 __global__ void __launch_bounds__(TAIL_THREADS, 1) vk_tail(const TailArgs<R> A) {
     extern __shared__ __align__(16) unsigned char smem[];
     __shared__ double sh[TAIL_THREADS / 32];
-    __shared__ double s_sf[2];
     GridBar gb{A.bar, gridDim.x, 0u, A.err};
     const int tid = blockIdx.x * blockDim.x + threadIdx.x, nth = gridDim.x * blockDim.x;
-    const int nPost = A.nPost > 1 ? A.nPost : 1, nPreSw = A.nPre > 1 ? A.nPre - 1 : 0;
-    const int swaps = nPreSw + nPost;
-    const R omega = A.omega;
+    const int nPre = A.nPre > 1 ? A.nPre : 1, nPost = A.nPost > 1 ? A.nPost : 1;
     for (int t = 0; t < A.T - 1; t++) {
         const TLv<R>& L = A.lv[t];
-        R* cur = tail_start(L, swaps);
-        R* oth = cur == L.x ? L.y : L.x;
-        for (int i = tid; i < L.n; i += nth) cur[i] = omega * L.b[i] / L.diag[i];
-        gsync(gb);
-        for (int s = 0; s < nPreSw; s++) {
-            const R* in = cur;
-            R* out = oth;
-            tail_rows(L, in, (const int*)nullptr, tid, nth, [&](int i, R off) { out[i] = in[i] + omega * (L.b[i] - (L.diag[i] * in[i] - off)) / L.diag[i]; });
-            R* tmp = cur; cur = oth; oth = tmp;
+        // iterate after the pre-sweeps ends in L.x: sweeps 1..nPre-1 alternate buffers, the last writes x
+        const R om0 = A.omPre[0];
+        auto first = [&](int j) { return om0 * L.b[j] / L.diag[j]; };  // sweep 0, never stored
+        const R* cur = nullptr;  // nullptr: the iterate is `first`
+        for (int s = 1; s < nPre; s++) {
+            R* out = ((nPre - 1 - s) & 1) ? L.y : L.x;
+            const R om = A.omPre[s];
+            if (cur == nullptr)
+                tail_rows(L, first, tid, nth, [&](int i, R off) { R xi = first(i); out[i] = xi + om * (L.b[i] - (L.diag[i] * xi - off)) / L.diag[i]; });
+            else {
+                const R* in = cur;
+                tail_rows(L, [&](int j) { return in[j]; }, tid, nth, [&](int i, R off) { out[i] = in[i] + om * (L.b[i] - (L.diag[i] * in[i] - off)) / L.diag[i]; });
+            }
+            cur = out;
             gsync(gb);
         }
-        {
+        if (cur == nullptr) {  // nPre == 1: x = first, residual from the on-the-fly iterate
+            tail_rows(L, first, tid, nth, [&](int i, R off) { R xi = first(i); L.x[i] = xi; L.r[i] = L.b[i] - (L.diag[i] * xi - off); });
+        } else {
             const R* in = cur;
-            tail_rows(L, in, (const int*)nullptr, tid, nth, [&](int i, R off) { L.r[i] = L.b[i] - (L.diag[i] * in[i] - off); });
+            tail_rows(L, [&](int j) { return in[j]; }, tid, nth, [&](int i, R off) { L.r[i] = L.b[i] - (L.diag[i] * in[i] - off); });
         }
         gsync(gb);
         const TLv<R>& C = A.lv[t + 1];
@@ -367,41 +368,28 @@ __global__ void __launch_bounds__(TAIL_THREADS, 1) vk_tail(const TailArgs<R> A) 
     for (int t = A.T - 2; t >= 0; t--) {
         const TLv<R>& L = A.lv[t];
         const R* xc = A.lv[t + 1].x;
-        R* cur = tail_start(L, swaps);
-        R* oth = cur == L.x ? L.y : L.x;
-        if (nPreSw & 1) { R* tmp = cur; cur = oth; oth = tmp; }
-        // A c for the prolonged correction c = xc[agg], with the dots r.c and c.Ac
-        double v = 0, w = 0;
-        {
-            R* out = oth;
-            tail_rows(L, xc, L.agg, tid, nth, [&](int i, R off) {
-                R c = xc[L.agg[i]];
-                R ac = L.diag[i] * c - off;
-                out[i] = ac;
-                v += (double)L.r[i] * (double)c;
-                w += (double)ac * (double)c;
-            });
-        }
-        v = tail_block_sum(v, sh);
-        w = tail_block_sum(w, sh);
-        if (threadIdx.x == 0) { A.partial[blockIdx.x] = v; A.partial[gridDim.x + blockIdx.x] = w; }
-        gsync(gb);
-        if (threadIdx.x < 32) {  // every CTA sums the partials in the same order
-            double a = 0, b = 0;
-            for (int k = threadIdx.x; k < (int)gridDim.x; k += 32) { a += A.partial[k]; b += A.partial[gridDim.x + k]; }
-            for (int o = 16; o > 0; o >>= 1) { a += __shfl_xor_sync(0xffffffffu, a, o); b += __shfl_xor_sync(0xffffffffu, b, o); }
-            if (threadIdx.x == 0) { s_sf[0] = a; s_sf[1] = b; }
-        }
-        __syncthreads();
-        const double den = s_sf[1];
-        const R sf = (R)(s_sf[0] / (fabs(den) < VSMALL ? (den >= 0 ? VSMALL : -VSMALL) : den));
-        for (int i = tid; i < L.n; i += nth) cur[i] += sf * xc[L.agg[i]] + A.scaleJ * (L.r[i] - sf * oth[i]) / L.diag[i];
-        gsync(gb);
+        const R oc = A.overcorr;
+        // first post-sweep on the corrected iterate x + oc xc[agg] (formed per column), then the
+        // remaining sweeps; the last one writes x
+        const R* in = L.x;
+        auto corrected = [&](int j) { return in[j] + oc * xc[L.agg[j]]; };
         for (int s = 0; s < nPost; s++) {
-            const R* in = cur;
-            R* out = oth;
-            tail_rows(L, in, (const int*)nullptr, tid, nth, [&](int i, R off) { out[i] = in[i] + omega * (L.b[i] - (L.diag[i] * in[i] - off)) / L.diag[i]; });
-            R* tmp = cur; cur = oth; oth = tmp;
+            R* out = ((nPost - 1 - s) & 1) ? L.y : L.x;
+            const R om = A.omPost[s];
+            if (s == 0) {
+                // (in == L.x; out may alias it only when nPost is odd: then write through y and fix up below)
+                R* o2 = out == L.x ? L.y : out;
+                tail_rows(L, corrected, tid, nth, [&](int i, R off) { R xi = corrected(i); o2[i] = xi + om * (L.b[i] - (L.diag[i] * xi - off)) / L.diag[i]; });
+                if (out == L.x) {  // nPost odd: copy back after the phase
+                    gsync(gb);
+                    for (int i = tid; i < L.n; i += nth) L.x[i] = L.y[i];
+                }
+                in = out;
+            } else {
+                const R* ii = in;
+                tail_rows(L, [&](int j) { return ii[j]; }, tid, nth, [&](int i, R off) { out[i] = ii[i] + om * (L.b[i] - (L.diag[i] * ii[i] - off)) / L.diag[i]; });
+                in = out;
+            }
             if (s + 1 < nPost || t > 0) gsync(gb);
         }
     }
@@ -669,22 +657,22 @@ inline void tail_host(const TailArgs<R>& A) {
 }
 template <class R>
 inline void tail_host_once(const TailArgs<R>& A) {
-    const int swaps = (A.nPre > 1 ? A.nPre - 1 : 0) + (A.nPost > 1 ? A.nPost : 1);
-    auto off = [](const TLv<R>& L, int row, const R* x, const int* map) {
+    // the same cycle as vk_tail, phase by phase, with the vectors it never stores materialised
+    auto off = [](const TLv<R>& L, int row, const std::vector<R>& x) {
         R s = 0;
-        for (int k = L.rs[row]; k < L.rs[row + 1]; k++) { int o = L.cn[k]; s += L.ev[k] * x[map ? map[o] : o]; }
+        for (int k = L.rs[row]; k < L.rs[row + 1]; k++) s += L.ev[k] * x[L.cn[k]];
         return s;
     };
+    const int nPre = A.nPre > 1 ? A.nPre : 1, nPost = A.nPost > 1 ? A.nPost : 1;
     for (int t = 0; t < A.T - 1; t++) {
         const TLv<R>& L = A.lv[t];
-        R* cur = tail_start(L, swaps);
-        R* oth = cur == L.x ? L.y : L.x;
-        for (int i = 0; i < L.n; i++) cur[i] = A.omega * L.b[i] / L.diag[i];
-        for (int s = 1; s < A.nPre; s++) {
-            for (int i = 0; i < L.n; i++) oth[i] = cur[i] + A.omega * (L.b[i] - (L.diag[i] * cur[i] - off(L, i, cur, nullptr))) / L.diag[i];
-            std::swap(cur, oth);
+        std::vector<R> cur(L.n), nxt(L.n);
+        for (int i = 0; i < L.n; i++) cur[i] = A.omPre[0] * L.b[i] / L.diag[i];
+        for (int s = 1; s < nPre; s++) {
+            for (int i = 0; i < L.n; i++) nxt[i] = cur[i] + A.omPre[s] * (L.b[i] - (L.diag[i] * cur[i] - off(L, i, cur))) / L.diag[i];
+            cur.swap(nxt);
         }
-        for (int i = 0; i < L.n; i++) L.r[i] = L.b[i] - (L.diag[i] * cur[i] - off(L, i, cur, nullptr));
+        for (int i = 0; i < L.n; i++) { L.x[i] = cur[i]; L.r[i] = L.b[i] - (L.diag[i] * cur[i] - off(L, i, cur)); }
         const TLv<R>& C = A.lv[t + 1];
         for (int I = 0; I < C.n; I++) {
             R s = 0;
@@ -696,13 +684,15 @@ inline void tail_host_once(const TailArgs<R>& A) {
         const TLv<R>& L = A.lv[A.T - 1];
         const int n = L.n;
         R *x = L.x, *r = A.cgR, *p = A.cgP, *Ap = A.cgAp;
+        std::vector<R> pv(n);
         double rz = 0;
         for (int i = 0; i < n; i++) { x[i] = 0; r[i] = L.b[i]; p[i] = L.b[i] / L.diag[i]; rz += (double)L.b[i] * (double)p[i]; }
         const double rz0 = rz;
         if (rz > 0)
             for (int it = 0; it < A.cgIter; it++) {
                 double pAp = 0;
-                for (int i = 0; i < n; i++) { Ap[i] = L.diag[i] * p[i] - off(L, i, p, nullptr); pAp += (double)Ap[i] * (double)p[i]; }
+                pv.assign(p, p + n);
+                for (int i = 0; i < n; i++) { Ap[i] = L.diag[i] * p[i] - off(L, i, pv); pAp += (double)Ap[i] * (double)p[i]; }
                 R alpha = (R)(rz / pAp);
                 double rzn = 0;
                 for (int i = 0; i < n; i++) { x[i] += alpha * p[i]; r[i] -= alpha * Ap[i]; rzn += (double)r[i] * (double)r[i] / (double)L.diag[i]; }
@@ -715,24 +705,13 @@ inline void tail_host_once(const TailArgs<R>& A) {
     for (int t = A.T - 2; t >= 0; t--) {
         const TLv<R>& L = A.lv[t];
         const R* xc = A.lv[t + 1].x;
-        R* cur = tail_start(L, swaps);
-        R* oth = cur == L.x ? L.y : L.x;
-        if ((A.nPre > 1 ? A.nPre - 1 : 0) & 1) std::swap(cur, oth);
-        double v = 0, w = 0;
-        for (int i = 0; i < L.n; i++) {
-            R c = xc[L.agg[i]];
-            R ac = L.diag[i] * c - off(L, i, xc, L.agg);
-            oth[i] = ac;
-            v += (double)L.r[i] * (double)c;
-            w += (double)ac * (double)c;
-        }
-        const R sf = (R)(v / (std::fabs(w) < VSMALL ? (w >= 0 ? VSMALL : -VSMALL) : w));
-        for (int i = 0; i < L.n; i++) cur[i] += sf * xc[L.agg[i]] + A.scaleJ * (L.r[i] - sf * oth[i]) / L.diag[i];
-        const int nPost = A.nPost > 1 ? A.nPost : 1;
+        std::vector<R> cur(L.n), nxt(L.n);
+        for (int i = 0; i < L.n; i++) cur[i] = L.x[i] + A.overcorr * xc[L.agg[i]];
         for (int s = 0; s < nPost; s++) {
-            for (int i = 0; i < L.n; i++) oth[i] = cur[i] + A.omega * (L.b[i] - (L.diag[i] * cur[i] - off(L, i, cur, nullptr))) / L.diag[i];
-            std::swap(cur, oth);
+            for (int i = 0; i < L.n; i++) nxt[i] = cur[i] + A.omPost[s] * (L.b[i] - (L.diag[i] * cur[i] - off(L, i, cur))) / L.diag[i];
+            cur.swap(nxt);
         }
+        for (int i = 0; i < L.n; i++) L.x[i] = cur[i];
     }
 }
 #endif

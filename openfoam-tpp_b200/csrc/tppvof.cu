@@ -21,7 +21,14 @@ using namespace tpp;
 
 namespace {
 
-std::string g_err;
+// last error of the calling thread (handles may be driven from different host threads)
+thread_local std::string g_err;
+// every C-ABI entry point is a function-try-block ending in API_CATCH: nothing escapes as an
+// exception or an abort(); the message is kept for tpp_last_error()
+#define API_CATCH(code)                                                                         \
+    catch (const tpp::CudaFailure& e) { g_err = e.what; fprintf(stderr, "tppvof: %s\n", g_err.c_str()); return (code); } \
+    catch (const std::exception& e) { g_err = std::string("internal error: ") + e.what(); return (code); }               \
+    catch (...) { g_err = "internal error"; return (code); }
 
 struct Level {
     int n = 0, nf = 0, nfLoc = 0, nG = 0, nnz = 0;  // rows, faces (local + processor), ghost rows, CSR entries
@@ -48,6 +55,18 @@ struct SolveStats { int iters = 0; double r0 = 0, r = 0; };
 // tuning knobs (environment overrides of the multigrid defaults; used by the tuning scripts)
 inline int knob(const char* name, int dflt) { const char* v = getenv(name); return v ? atoi(v) : dflt; }
 inline double knobd(const char* name, double dflt) { const char* v = getenv(name); return v ? atof(v) : dflt; }
+// Relaxation factor of sweep k of a group of m Jacobi sweeps.  TPP_CHEB=1 (default): the m sweeps
+// together apply the degree-m Chebyshev polynomial of D^-1 A on [lmax/ratio, lmax] (Richardson
+// form: omega_k = 1/root_k, no extra vector; fine for the m <= 4 used here).  lmax = 2 is the
+// Gershgorin bound of these diagonally dominant M-matrices (every level: piecewise-constant
+// Galerkin sums keep the sign pattern).  TPP_CHEB=0: plain damped Jacobi, TPP_OMEGA.
+inline double smootherOmega(int k, int m) {
+    static const int cheb = knob("TPP_CHEB", 1);
+    static const double om = knobd("TPP_OMEGA", 0.8), lmax = knobd("TPP_CHEB_MAX", 2.0), ratio = knobd("TPP_CHEB_RATIO", 4.0);
+    if (!cheb || m < 1) return om;
+    const double a = lmax / ratio, theta = 0.5 * (lmax + a), delta = 0.5 * (lmax - a);
+    return 1.0 / (theta - delta * cos(M_PI * (2.0 * k + 1.0) / (2.0 * m)));
+}
 
 // Inter-rank transport.  Product: NCCL send/recv + all-reduce on the solver's stream, resolved
 // from the NCCL library the host process (torch) already loaded.  Tests / host emulation: two
@@ -817,15 +836,37 @@ struct tpp_solver {
         }
         pcEnd();
     }
+    void fail(const std::string& msg) {
+        if (ctx.err.empty()) { ctx.err = msg; fprintf(stderr, "tppvof: %s\n", msg.c_str()); }
+    }
+    // device-side error flags (bounded waits that gave up), read once per step: a run that lost a
+    // halo or a grid barrier must stop with an error, not carry on with stale data
+    void checkDeviceFlags() {
+#ifndef TPP_EMU
+        if (comm.p2p) {
+            int e = 0;
+            d2h(ctx, &e, comm.p2pErr, sizeof(int));
+            if (e) fail("peer-memory halo exchange / all-reduce: a neighbour's data did not arrive within 30 s");
+        }
+#endif
+        if (!tail.empty()) {
+            int e = 0;
+            d2h(ctx, &e, tailErr, sizeof(int));
+            if (e) fail("vk_tail: grid barrier timed out (the cooperative grid was not co-resident?)");
+        }
+    }
     bool oneStep() {
         courant();
+        if (!std::isfinite(Co) || !std::isfinite(alphaCo)) fail("Courant number is not finite (the solution diverged)");
         adjustDeltaT();
+        if (!std::isfinite(dt) || !(dt > 0)) fail("deltaT is not finite / positive");
         bool wr = advanceTime();
         moveMesh();
         alphaPredictor();
         momentum();
         for (int corr = 0; corr < cfg.n_correctors; corr++) pressureCorrector(corr == cfg.n_correctors - 1);
         if (!probeCells.empty()) sampleProbes();
+        checkDeviceFlags();
         return wr;
     }
     void sampleProbes() {
@@ -1244,7 +1285,7 @@ struct tpp_solver {
                 cudaOccupancyMaxActiveBlocksPerMultiprocessor(&perSm, vk_tail<double>, TAIL_THREADS, tailSmem);
             }
             tailGrid = sms;  // one CTA per SM
-            if (perSm < 1) { fprintf(stderr, "tppvof: vk_tail does not fit an SM\n"); abort(); }
+            if (perSm < 1) throw tpp::CudaFailure{"vk_tail does not fit an SM"};
             // small tails do not need every SM: fewer CTAs make the grid barrier cheaper
             int need = (tail[0].n * (tail[0].ellW > 0 ? 1 : 4) + TAIL_THREADS - 1) / TAIL_THREADS;
             tailGrid = std::max(1, std::min(tailGrid, need));
@@ -1550,11 +1591,12 @@ struct tpp_solver {
             if (t > 0) { L.aggStart = c.aggStart; L.aggRows = c.aggRows; }
             L.x = v.tx[t]; L.y = v.ty[t]; L.b = v.tb[t]; L.r = v.tr[t];
         }
-        A.bar = tailBar; A.err = tailErr; A.partial = tailPartial;
-        A.omega = (R)knobd("TPP_OMEGA", 0.8); A.scaleJ = (R)knobd("TPP_SCALEJ", 1.0);
+        A.bar = tailBar; A.err = tailErr;
+        A.overcorr = (R)knobd("TPP_OVERCORR", 1.8);
         // 8 CG iterations on the coarsest level give the same PCG counts as 16; fewer sweeps on the
         // small levels cost 1-2 PCG iterations at 6 M cells (tools/knob_sweep.py), so they keep nPre/nPost
-        A.nPre = knob("TPP_TAIL_NPRE", nPre); A.nPost = knob("TPP_TAIL_NPOST", nPost);
+        A.nPre = std::min(knob("TPP_TAIL_NPRE", nPre), TAIL_MAXSW); A.nPost = std::min(knob("TPP_TAIL_NPOST", nPost), TAIL_MAXSW);
+        for (int k = 0; k < TAIL_MAXSW; k++) { A.omPre[k] = (R)smootherOmega(k, std::max(A.nPre, 1)); A.omPost[k] = (R)smootherOmega(k, std::max(A.nPost, 1)); }
         A.cgIter = knob("TPP_CITER", 8); A.cgTol = knobd("TPP_CTOL", 0.05);
         A.cgR = v.cgR; A.cgP = v.cgP; A.cgAp = v.cgAp; A.cgSmem = tailSmem > 0;
         prof_begin(ctx, "v_tail");
@@ -1582,6 +1624,7 @@ struct tpp_solver {
         L.omega = omega; L.b = b;
         R *cur = x, *oth = v.t0[lv];
         for (int s = 0; s < std::max(nPre, 1); s++) {
+            L.omega = (R)smootherOmega(s, std::max(nPre, 1));
             if (s == 0 && zeroGuess) { L.out = cur; VLAUNCH(ctx, jacobi0, L, L.n); }
             else { XLsmooth<R>(lv, cur, s == 1 && zeroGuess ? 1 : 0); L.in = cur; L.out = oth; vRowOp(L, 0); std::swap(cur, oth); }
         }
@@ -1603,8 +1646,14 @@ struct tpp_solver {
         // prolonged correction c = P x_c in `oth`, A c, scaling, x += ...
         VL<R> Pn = vview<R>(lv + 1);
         Pn.xc = toTail ? v.tx[0] + tailRowOff : v.x[lv + 1];
-        if (lv >= knob("TPP_NOSCALE_FROM", 99)) {  // experiment: plain correction on the deeper levels
-            Pn.out = cur;
+        // Coarse correction with a FIXED over-correction factor (Braess' remedy for the constant
+        // interpolation of plain aggregation): as many PCG iterations as the energy-minimising
+        // scaling of GAMG's scaleCorrection (measured at 0.4 M and 6.2 M cells: 11 vs 12 and 13-14 vs
+        // 14 iterations of p_rghFinal), without its A c product, its two dot products and - on several
+        // GPUs - their halo exchange and all-reduce on every level of every cycle.  The factor must
+        // stay below 2 (2.2 diverges).  TPP_NOSCALE_FROM=99 restores the scaled correction.
+        if (lv >= knob("TPP_NOSCALE_FROM", 0)) {
+            Pn.out = cur; Pn.omega = (R)knobd("TPP_OVERCORR", 1.8);
             VLAUNCH(ctx, prolong_add, Pn, L.n);
         } else {
             Pn.out = oth;
@@ -1619,6 +1668,7 @@ struct tpp_solver {
         for (int s = 0; s < std::max(nPost, 1); s++) {
             if (s == 0) XL<R>(lv, cur);
             else XLsmooth<R>(lv, cur, 2, oth);
+            L.omega = (R)smootherOmega(s, std::max(nPost, 1));
             L.in = cur; L.out = oth;
             vRowOp(L, 0);
             std::swap(cur, oth);
@@ -1680,18 +1730,7 @@ struct tpp_solver {
             st.r = hscal[S_RES] / nf;
             if (!(fabs(hscal[S_WAPA]) / nf >= VSMALL)) break;
         } while (++st.iters < ctl.max_iter && !conv(st.r));
-#ifndef TPP_EMU
-        if (comm.p2p) {
-            int e = 0;
-            d2h(ctx, &e, comm.p2pErr, sizeof(int));
-            if (e) { ctx.err = "k_halo_p2p: a neighbour's halo did not arrive within 30 s"; fprintf(stderr, "tppvof: %s\n", ctx.err.c_str()); }
-        }
-#endif
-        if (!tail.empty()) {  // a grid barrier of the tail kernel that timed out is a hard error
-            int e = 0;
-            d2h(ctx, &e, tailErr, sizeof(int));
-            if (e) { ctx.err = "vk_tail: grid barrier timed out (the cooperative grid was not co-resident?)"; fprintf(stderr, "tppvof: %s\n", ctx.err.c_str()); }
-        }
+        if (!std::isfinite(st.r)) fail("the p_rgh solver residual is not finite (diverged)");
         return st;
     }
 
@@ -1857,7 +1896,7 @@ const char* tpp_version(void) {
 #endif
 }
 
-int tpp_create(const tpp_mesh_t* mesh, const tpp_config_t* cfg, int device, tpp_handle* out) {
+int tpp_create(const tpp_mesh_t* mesh, const tpp_config_t* cfg, int device, tpp_handle* out) try {
     *out = nullptr;
 #ifndef TPP_EMU
     int ndev = 0;
@@ -1879,9 +1918,9 @@ int tpp_create(const tpp_mesh_t* mesh, const tpp_config_t* cfg, int device, tpp_
     dev_sync(s->ctx);
     *out = s;
     return 0;
-}
+} API_CATCH(-100)
 
-int tpp_destroy(tpp_handle s) {
+int tpp_destroy(tpp_handle s) try {
     if (!s) return 0;
 #ifndef TPP_EMU
     cudaSetDevice(s->device);
@@ -1890,7 +1929,7 @@ int tpp_destroy(tpp_handle s) {
     s->destroy();
     delete s;
     return 0;
-}
+} API_CATCH(-100)
 
 static void pointsNow(tpp_solver* s, std::vector<double>& out) {
     out.resize(3 * (size_t)s->nP);
@@ -1900,11 +1939,11 @@ static void pointsNow(tpp_solver* s, std::vector<double>& out) {
     }
 }
 
-long tpp_size(tpp_handle s, const char* name) {
+long tpp_size(tpp_handle s, const char* name) try {
     if (!strcmp(name, "points")) return 3L * s->nP;
     auto it = s->reg.find(name);
     return it == s->reg.end() ? -1 : it->second.second;
-}
+} API_CATCH(-100)
 // face-sized arrays are kept in device face order (processor faces right after the internal
 // ones); callers see OpenFOAM's file order
 static int faceComp(tpp_solver* s, const char* name) {
@@ -1915,7 +1954,7 @@ static int faceComp(tpp_solver* s, const char* name) {
     for (auto n : f3) if (!strcmp(n, name)) return 3;
     return 0;
 }
-long tpp_get(tpp_handle s, const char* name, double* out, long cap) {
+long tpp_get(tpp_handle s, const char* name, double* out, long cap) try {
     if (!strcmp(name, "points")) {
         std::vector<double> p;
         pointsNow(s, p);
@@ -1935,8 +1974,8 @@ long tpp_get(tpp_handle s, const char* name, double* out, long cap) {
     }
     d2h(s->ctx, out, it->second.first, n * sizeof(double));
     return it->second.second;
-}
-long tpp_set(tpp_handle s, const char* name, const double* in, long n) {
+} API_CATCH(-100)
+long tpp_set(tpp_handle s, const char* name, const double* in, long n) try {
     auto it = s->reg.find(name);
     if (it == s->reg.end()) { g_err = std::string("unknown array ") + name; return -1; }
     if (n != it->second.second) { g_err = std::string("size mismatch for ") + name; return -2; }
@@ -1951,24 +1990,24 @@ long tpp_set(tpp_handle s, const char* name, const double* in, long n) {
     }
     h2d(s->ctx, it->second.first, in, n * sizeof(double));
     return n;
-}
-int tpp_device_ptr(tpp_handle s, const char* name, void** ptr, long* n) {
+} API_CATCH(-100)
+int tpp_device_ptr(tpp_handle s, const char* name, void** ptr, long* n) try {
     auto it = s->reg.find(name);
     if (it == s->reg.end()) { g_err = std::string("unknown array ") + name; return -1; }
     *ptr = it->second.first;
     *n = it->second.second;
     return 0;
-}
-int tpp_init_fields(tpp_handle s) {
+} API_CATCH(-100)
+int tpp_init_fields(tpp_handle s) try {
     s->alphaBCs();
     s->mixture();
     s->X(s->d.alpha, 1); s->X(s->d.rho, 1); s->X(s->d.U, 3); s->X(s->d.p_rgh, 1);
     d2d(s->ctx, s->d.rho0, s->d.rho, (size_t)(s->nC + s->nG) * sizeof(double));
     dev_sync(s->ctx);
     return 0;
-}
+} API_CATCH(-100)
 int tpp_set_delta_t(tpp_handle s, double dt) { s->dt = s->dt0 = dt; return 0; }
-int tpp_set_time(tpp_handle s, double t, double dt) {
+int tpp_set_time(tpp_handle s, double t, double dt) try {
     s->t = t; s->dt = s->dt0 = dt;
     s->motionAt(t, s->Rn, s->Tn);
     memcpy(s->Ro, s->Rn, sizeof(s->Rn)); memcpy(s->To, s->Tn, sizeof(s->Tn));
@@ -1976,23 +2015,25 @@ int tpp_set_time(tpp_handle s, double t, double dt) {
     s->orientGeometry();
     dev_sync(s->ctx);
     return 0;
-}
+} API_CATCH(-100)
 
-int tpp_step(tpp_handle s, int n) {
-    for (int i = 0; i < n; i++) s->oneStep();
+int tpp_step(tpp_handle s, int n) try {
+    for (int i = 0; i < n && s->ctx.err.empty(); i++) s->oneStep();
     dev_sync(s->ctx);
     if (!s->ctx.err.empty()) { g_err = s->ctx.err; return -1; }
     return 0;
-}
-int tpp_run_to_write(tpp_handle s, long max_steps) {
+} API_CATCH(-100)
+int tpp_run_to_write(tpp_handle s, long max_steps) try {
     for (long i = 0; i < max_steps; i++) {
         if (!(s->t < s->cfg.end_time - 0.5 * s->dt)) { dev_sync(s->ctx); return 0; }
-        if (s->oneStep()) { dev_sync(s->ctx); return 1; }
+        const bool wr = s->oneStep();
+        if (!s->ctx.err.empty()) { dev_sync(s->ctx); g_err = s->ctx.err; return -1; }
+        if (wr) { dev_sync(s->ctx); return 1; }
     }
     dev_sync(s->ctx);
     return 2;
-}
-int tpp_stage(tpp_handle s, const char* name) {
+} API_CATCH(-100)
+int tpp_stage(tpp_handle s, const char* name) try {
     std::string n(name);
     s->d.dt = s->dt;
     if (n == "courant") s->courant();
@@ -2015,16 +2056,16 @@ int tpp_stage(tpp_handle s, const char* name) {
     else { g_err = "unknown stage " + n; return -1; }
     dev_sync(s->ctx);
     return 0;
-}
-int tpp_info(tpp_handle s, double* o) {
+} API_CATCH(-100)
+int tpp_info(tpp_handle s, double* o) try {
     o[0] = s->t; o[1] = s->dt; o[2] = (double)s->step; o[3] = s->Co; o[4] = s->alphaCo;
     o[5] = s->lastSolve[0].iters; o[6] = s->lastSolve[0].r0; o[7] = s->lastSolve[0].r;
     o[8] = s->lastSolve[1].iters; o[9] = s->lastSolve[1].r0; o[10] = s->lastSolve[1].r;
     o[11] = s->d.needRef ? s->d.refCell : -1; o[12] = s->d.deltaN; o[13] = s->writeTimeIndex;
     o[14] = (double)s->levels.size(); o[15] = (double)s->ctx.launches;
     return 0;
-}
-int tpp_solve(tpp_handle s, const tpp_solver_t* ctl, const double* diag, const double* upper, const double* b, double* x, double* r0, double* r) {
+} API_CATCH(-100)
+int tpp_solve(tpp_handle s, const tpp_solver_t* ctl, const double* diag, const double* upper, const double* b, double* x, double* r0, double* r) try {
     h2d(s->ctx, s->d.pDiag, diag, s->nC * sizeof(double));
     h2d(s->ctx, s->d.pUpper, upper, s->nI * sizeof(double));
     h2d(s->ctx, s->d.pSource, b, s->nC * sizeof(double));
@@ -2034,18 +2075,18 @@ int tpp_solve(tpp_handle s, const tpp_solver_t* ctl, const double* diag, const d
     d2h(s->ctx, x, xd, s->nC * sizeof(double));
     *r0 = st.r0; *r = st.r;
     return st.iters;
-}
+} API_CATCH(-100)
 int tpp_set_probes(tpp_handle s, int n, const int* cells) { s->probeCells.assign(cells, cells + n); return 0; }
-long tpp_probe_log(tpp_handle s, double* out, long cap_rows) {
+long tpp_probe_log(tpp_handle s, double* out, long cap_rows) try {
     long w = 1 + (long)s->probeCells.size();
     long rows = (long)s->probeLog.size() / w;
     long n = std::min(rows, cap_rows);
     memcpy(out, s->probeLog.data(), n * w * sizeof(double));
     s->probeLog.erase(s->probeLog.begin(), s->probeLog.begin() + n * w);
     return n;
-}
+} API_CATCH(-100)
 int tpp_find_cell(tpp_handle s, const double* xyz) { return s->findCell(xyz); }
-int tpp_use_stream(tpp_handle s, void* stream) {
+int tpp_use_stream(tpp_handle s, void* stream) try {
 #ifndef TPP_EMU
     cudaStreamSynchronize(s->ctx.stream);
     if (s->ctx.ownStream) cudaStreamDestroy(s->ctx.stream);
@@ -2055,12 +2096,12 @@ int tpp_use_stream(tpp_handle s, void* stream) {
     (void)s; (void)stream;
 #endif
     return 0;
-}
-int tpp_profile(tpp_handle s, int on) {
+} API_CATCH(-100)
+int tpp_profile(tpp_handle s, int on) try {
     s->ctx.prof = on != 0;
     return 0;
-}
-long tpp_profile_report(tpp_handle s, char* buf, long cap) {
+} API_CATCH(-100)
+long tpp_profile_report(tpp_handle s, char* buf, long cap) try {
     dev_sync(s->ctx);
     std::map<std::string, std::pair<long, double>> agg;
     for (auto& r : s->ctx.recs) {
@@ -2084,35 +2125,35 @@ long tpp_profile_report(tpp_handle s, char* buf, long cap) {
     if ((long)out.size() + 1 > cap) return -(long)out.size() - 1;
     memcpy(buf, out.c_str(), out.size() + 1);
     return (long)out.size();
-}
-int tpp_amg_levels(tpp_handle s, int* n_rows, int* n_faces, int cap) {
+} API_CATCH(-100)
+int tpp_amg_levels(tpp_handle s, int* n_rows, int* n_faces, int cap) try {
     int k = 0;
     if (k < cap) { n_rows[k] = s->nC; n_faces[k] = s->nIloc; }
     k++;
     for (auto& l : s->levels) { if (k < cap) { n_rows[k] = l.n; n_faces[k] = l.nfLoc; } k++; }
     for (size_t t = 1; t < s->tail.size(); t++) { if (k < cap) { n_rows[k] = s->tail[t].n; n_faces[k] = s->tail[t].nf; } k++; }
     return k;
-}
-int tpp_amg_layout(tpp_handle s, int* out4) {
+} API_CATCH(-100)
+int tpp_amg_layout(tpp_handle s, int* out4) try {
     out4[0] = s->levels.empty() ? 0 : s->vLevels();
     out4[1] = (int)s->tail.size();
     out4[2] = s->tail.empty() ? 0 : s->tail[0].n;
     out4[3] = s->tailGrid;
     return 0;
-}
-int tpp_ghost_layout(tpp_handle s, int* n_ghost, int* n_patches, int* off, int* cnt, int* peer, int cap) {
+} API_CATCH(-100)
+int tpp_ghost_layout(tpp_handle s, int* n_ghost, int* n_patches, int* off, int* cnt, int* peer, int cap) try {
     *n_ghost = s->nG;
     *n_patches = (int)s->procCnt.size();
     for (int i = 0; i < (int)s->procCnt.size() && i < cap; i++) { off[i] = s->procOff[i]; cnt[i] = s->procCnt[i]; peer[i] = s->procPeer[i]; }
     return 0;
-}
-int tpp_comm_callbacks(tpp_handle s, int rank, int n_ranks, exchange_cb_t xcb, allreduce_cb_t rcb, void* user) {
+} API_CATCH(-100)
+int tpp_comm_callbacks(tpp_handle s, int rank, int n_ranks, exchange_cb_t xcb, allreduce_cb_t rcb, void* user) try {
     s->comm.rank = rank; s->comm.size = n_ranks; s->comm.xcb = xcb; s->comm.rcb = rcb; s->comm.user = user;
     s->comm.active = n_ranks > 1;
     if (!s->finalizeParallel()) return -1;
     dev_sync(s->ctx);
     return 0;
-}
+} API_CATCH(-100)
 #ifndef TPP_EMU
 static bool loadNccl(Comm& c, const char* path) {
     if (c.lib) return true;
@@ -2125,7 +2166,7 @@ static bool loadNccl(Comm& c, const char* path) {
     return true;
 }
 #endif
-int tpp_nccl_unique_id(const char* nccl_path, char* out128) {
+int tpp_nccl_unique_id(const char* nccl_path, char* out128) try {
 #ifndef TPP_EMU
     Comm c;
     if (!loadNccl(c, nccl_path)) return -1;
@@ -2139,8 +2180,8 @@ int tpp_nccl_unique_id(const char* nccl_path, char* out128) {
     g_err = "host emulation has no NCCL transport (use tpp_comm_callbacks)";
     return -1;
 #endif
-}
-int tpp_comm_init(tpp_handle s, int rank, int n_ranks, const char* id128, const char* nccl_path) {
+} API_CATCH(-100)
+int tpp_comm_init(tpp_handle s, int rank, int n_ranks, const char* id128, const char* nccl_path) try {
 #ifndef TPP_EMU
     if (!loadNccl(s->comm, nccl_path)) return -1;
     ncclUniqueId id;
@@ -2157,5 +2198,5 @@ int tpp_comm_init(tpp_handle s, int rank, int n_ranks, const char* id128, const 
     g_err = "host emulation has no NCCL transport (use tpp_comm_callbacks)";
     return -1;
 #endif
-}
+} API_CATCH(-100)
 }

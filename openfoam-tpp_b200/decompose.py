@@ -287,11 +287,8 @@ def decompose_par(case_dir, time_name=None, binary=True, log=None):
     fields = []
     for nm in sorted(os.listdir(tdir)):
         fp = os.path.join(tdir, nm)
-        if os.path.isfile(fp):
-            try:
-                fields.append(ff.read_field(fp))
-            except Exception:
-                pass
+        if os.path.isfile(fp) and _is_field_file(fp):
+            fields.append(ff.read_field(fp))  # a corrupt field is an error, not a silently dropped file
     for k, part in enumerate(parts):
         pd = os.path.join(case_dir, f"processor{k}")
         ff.write_polymesh(pd, part.mesh, binary)
@@ -314,6 +311,20 @@ def decompose_par(case_dir, time_name=None, binary=True, log=None):
     return parts
 
 
+_FIELD_CLASSES = ("volScalarField", "volVectorField", "volTensorField", "volSymmTensorField", "surfaceScalarField", "surfaceVectorField")
+
+
+def _is_field_file(path):
+    """True when the FoamFile header names a geometric field class; other files of a time directory
+    (dictionaries, logs) are left alone by decomposePar / reconstructPar."""
+    try:
+        with open(path, "rb") as f:
+            hdr = ff.parse_header(f.read(4096), path)[0]
+    except Exception:
+        return False
+    return hdr.get("class") in _FIELD_CLASSES
+
+
 def processor_dirs(case_dir):
     k = 0
     out = []
@@ -323,9 +334,12 @@ def processor_dirs(case_dir):
     return out
 
 
-def reconstruct_par(case_dir, times=None, binary=True, log=None):
+def reconstruct_par(case_dir, times=None, binary=True, log=None, with_zero=False, new_times=False):
     """reconstructPar: merge processorN/<time>/<field> into <time>/<field> through the
-    *ProcAddressing files.  vol fields and surface fields of the solver's output set."""
+    *ProcAddressing files.  vol fields and surface fields of the solver's output set.
+    Like OpenFOAM's utility, time 0 is skipped unless `with_zero` (-withZero) or named in
+    `times` (so the user's 0/ files are not overwritten by flattened copies), and `new_times`
+    (-newTimes) skips the times that already exist at the case root."""
     mesh = ff.read_polymesh(case_dir)
     pdirs = processor_dirs(case_dir)
     if not pdirs:
@@ -334,10 +348,16 @@ def reconstruct_par(case_dir, times=None, binary=True, log=None):
     for pd in pdirs:
         md = os.path.join(pd, "constant", "polyMesh")
         addr.append((ff.read_polymesh(pd), _read_labels(os.path.join(md, "cellProcAddressing")), _read_labels(os.path.join(md, "faceProcAddressing")), _read_labels(os.path.join(md, "boundaryProcAddressing"))))
-    tnames = times or [nm for _, nm in ff.time_dirs(pdirs[0])]
+    if times:
+        tnames = list(times)
+    else:
+        tnames = [nm for v, nm in ff.time_dirs(pdirs[0]) if with_zero or v != 0]
+        if new_times:
+            have = {nm for _, nm in ff.time_dirs(case_dir)}
+            tnames = [nm for nm in tnames if nm not in have]
     done = []
     for tn in tnames:
-        names = [nm for nm in sorted(os.listdir(os.path.join(pdirs[0], tn))) if os.path.isfile(os.path.join(pdirs[0], tn, nm))]
+        names = [nm for nm in sorted(os.listdir(os.path.join(pdirs[0], tn))) if os.path.isfile(os.path.join(pdirs[0], tn, nm)) and _is_field_file(os.path.join(pdirs[0], tn, nm))]
         os.makedirs(os.path.join(case_dir, tn), exist_ok=True)
         for nm in names:
             parts = [ff.read_field(os.path.join(pd, tn, nm)) for pd in pdirs]
@@ -403,14 +423,18 @@ def main(argv=None):
     argv = list(sys.argv[1:] if argv is None else argv)
     if not argv or argv[0] not in ("decomposePar", "reconstructPar"):
         raise SystemExit("usage: decompose decomposePar|reconstructPar [-case DIR] [-force] [-latestTime]")
-    tool, case_dir, latest = argv.pop(0), os.getcwd(), False
+    tool, case_dir, latest, with_zero, new_times = argv.pop(0), os.getcwd(), False, False, False
     while argv:
         a = argv.pop(0)
         if a == "-case":
             case_dir = argv.pop(0)
         elif a == "-latestTime":
             latest = True
-        elif a in ("-force", "-newTimes"):
+        elif a == "-withZero":
+            with_zero = True
+        elif a == "-newTimes":
+            new_times = True
+        elif a == "-force":
             pass
         else:
             raise SystemExit(f"{tool} (tppvof): unknown option {a}")
@@ -421,7 +445,7 @@ def main(argv=None):
             times = None
             if latest:
                 times = [ff.time_dirs(processor_dirs(case_dir)[0])[-1][1]]
-            reconstruct_par(case_dir, times, log=sys.stdout)
+            reconstruct_par(case_dir, times, log=sys.stdout, with_zero=with_zero, new_times=new_times)
     except Exception as e:
         print(f"--> FOAM FATAL ERROR: {e}", file=sys.stderr)
         return 1

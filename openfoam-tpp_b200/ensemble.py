@@ -11,31 +11,40 @@ from __future__ import annotations
 import itertools
 
 
-def parse_range(s):
-    """`start:step:end`, `start:end` (step 1) or a comma list -> floats.  Inclusive end with a
-    1e-9 slack and values rounded to 6 decimals, exactly as main.py:118-142."""
-    s = s.strip()
-    if ":" in s:
-        parts = s.split(":")
-        if len(parts) == 2:
-            start, end = float(parts[0]), float(parts[1])
-            step = 1.0
-        elif len(parts) == 3:
-            start, step, end = float(parts[0]), float(parts[1]), float(parts[2])
-        else:
-            raise ValueError(f"Invalid range format: {s}")
-        vals = []
-        v = start
-        while v <= end + 1e-9:
-            vals.append(round(v, 6))
-            v += step
-        return vals
-    return [float(x.strip()) for x in s.split(",")]
+_SLACK = 1e-9  # inclusive-end tolerance of the reference's range syntax
 
 
-def case_name(p):
-    """main.py:163-165."""
-    return f"case_H{p['H']}_D{p['D']}_{p['geo']}_R{p['R']}_f{p['freq']}_d{p['duration']}_m{p['mesh']}"
+def parse_range(text):
+    """Sweep values from the reference's MATLAB-style syntax (main.py:118-142): `a:b` (step 1),
+    `a:step:b`, or a comma list.  Same values as the reference produces: the k-th value is `a`
+    plus k sequential additions of `step` (not a + k*step), the end is inclusive with a 1e-9
+    slack, and range values are rounded to 6 decimals; list entries are taken as written."""
+    import numpy as np
+
+    fields = [f.strip() for f in text.strip().split(":")]
+    if len(fields) == 1:
+        return [float(tok) for tok in fields[0].split(",")]
+    if len(fields) > 3:
+        raise ValueError(f"Invalid range format: {text.strip()}")
+    lo, hi = float(fields[0]), float(fields[-1])
+    inc = float(fields[1]) if len(fields) == 3 else 1.0
+    if not inc > 0:
+        raise ValueError(f"Invalid range format: {text.strip()} (the step must be positive)")
+    if lo > hi + _SLACK:
+        return []
+    room = int((hi - lo) / inc) + 3  # an upper bound on the count; the slack test below trims it
+    running = np.cumsum(np.concatenate(([lo], np.full(room, inc))))  # sequential float64 additions
+    keep = running <= hi + _SLACK
+    return [round(float(v), 6) for v in running[: int(np.argmin(keep)) if not keep.all() else running.size]]
+
+
+_NAME_FIELDS = (("H", "H"), ("D", "D"), ("", "geo"), ("R", "R"), ("f", "freq"), ("d", "duration"), ("m", "mesh"))
+
+
+def case_name(params):
+    """Directory name of a sweep member, the reference's naming contract (main.py:163-165):
+    case_H<H>_D<D>_<geo>_R<R>_f<freq>_d<duration>_m<mesh>, values printed with str()."""
+    return "_".join(["case"] + [tag + str(params[key]) for tag, key in _NAME_FIELDS])
 
 
 def build_param_sets(base, sweeps):

@@ -474,7 +474,10 @@ class PolyMesh:
 
     @property
     def n_cells(self):
-        return int(self.owner.max()) + 1 if self.owner.size else 0
+        if not self.owner.size:
+            return 0
+        # the last cell may own no face at all (all four faces shared with lower-numbered cells)
+        return max(int(self.owner.max()), int(self.neighbour.max()) if self.neighbour.size else -1) + 1
 
     def patch(self, name):
         for p in self.patches:
@@ -509,10 +512,6 @@ def _hdr(cls, obj, location, fmt="ascii", note=None):
         s += f'    location    "{location}";\n'
     s += f"    object      {obj};\n}}\n" + SEP + "\n"
     return s
-
-
-def _fmt_g(x, prec):
-    return np.format_float_positional if False else None  # placeholder to keep linters quiet
 
 
 def write_polymesh(case_dir, mesh: PolyMesh, binary=True, region_dir="constant/polyMesh"):

@@ -21,6 +21,7 @@ import numpy as np
 
 from . import foamfile as ff
 from .case import Case
+from .foamfile import FoamError
 from .solver import Solver
 
 
@@ -146,6 +147,13 @@ def run_case(case_dir, device=0, lib_path=None, max_steps=None, log=sys.stdout, 
             log = None
     case = Case(case_dir, processor=rank if parallel else None)
     cfg = case.cfg
+    if parallel and world > 1:
+        # every rank resolved `latestTime` in its own processorN/: they must agree
+        from . import ensemble
+
+        hi = ensemble.max_over_ranks([case.start_value, -case.start_value])
+        if hi[0] != case.start_value or -hi[1] != case.start_value:
+            raise FoamError(f"{case.dir}: start time {case.start_name} differs between the processor directories (latest complete times {-hi[1]:g} .. {hi[0]:g}); remove the partial time directories")
     s = Solver(case.mesh, cfg, device=device, lib_path=lib_path)
     if parallel and world > 1:
         if lib_path is None:

@@ -1,12 +1,13 @@
 """VTK-free interface diagnostics (the parity metric of SURVEY.md §4 / §8f-3).
 
-The reference extracts the alpha = 0.5 iso-surface with PyVista and reduces it to
-`interface_summary.csv` (time,max_z,min_z,mean_z,num_points; main.py:751-780) and to a wall
-elevation series (main.py:784-798).  PyVista/VTK are not available here, and the quantity that
-matters for parity is the free-surface elevation, so this module measures it directly from the
-cell data: the water column height h(x, y) = (1/A_col) * sum_col alpha V over each vertical
-column of the extruded tank mesh, in the tank frame.  For a single-valued interface this is the
-iso-surface elevation up to the O(cell) smearing of the VOF front.
+The reference extracts the alpha = 0.5 iso-surface with PyVista (cell data averaged to the points,
+then a contour filter) and reduces it to `interface_summary.csv` (time,max_z,min_z,mean_z,
+num_points; main.py:751-780) and to a wall elevation series (main.py:784-798).  PyVista/VTK are
+not available here; `cell_to_point` + `iso_points` restate those two filters on the mesh edges
+(any cell type), `extract_interface` writes the same two CSV files, `iso_wall_mode1` / `beat_fit`
+reduce the iso-surface to the first azimuthal sloshing mode the way the golden series G4 was
+reduced.  `ColumnSampler` is an independent second measure for extruded meshes only: the water
+column height h(x, y) = (1/A_col) sum_col alpha V in the tank frame.
 """
 from __future__ import annotations
 
@@ -124,6 +125,55 @@ def iso_points(mesh, points, point_values, iso=0.5, edges=None):
     a, b, va, vb = a[cut], b[cut], va[cut], vb[cut]
     t = (iso - va) / (vb - va)
     return points[a] + t[:, None] * (points[b] - points[a])
+
+
+def iso_wall_mode1(pts, centre_xy=(0.0, 0.0), R=0.1, r_frac=0.9):
+    """First azimuthal mode of the interface at the wall, from iso-surface points: least-squares
+    fit z = z0 + C cos(theta) + S sin(theta) over the points with tank-frame radius > r_frac R
+    (theta about the tank centre `centre_xy`).  This is the fit SURVEY.md §4 applies to the
+    reference's committed iso-surfaces (golden G4, tests/golden/g4_m1_series.csv), so a run and the
+    golden are reduced by the same arithmetic.  -> (amplitude, phase, z0, n_points)"""
+    x, y = pts[:, 0] - centre_xy[0], pts[:, 1] - centre_xy[1]
+    m = np.hypot(x, y) > r_frac * R
+    if m.sum() < 3:
+        return 0.0, 0.0, 0.0, int(m.sum())
+    th = np.arctan2(y[m], x[m])
+    A = np.stack([np.ones(m.sum()), np.cos(th), np.sin(th)], axis=1)
+    z0, c, s = np.linalg.lstsq(A, pts[m, 2], rcond=None)[0]
+    return float(np.hypot(c, s)), float(np.arctan2(s, c)), float(z0), int(m.sum())
+
+
+def beat_fit(t, amp, phase, f_forcing, t0=2.0, t1=None):
+    """Reduces an m = 1 series (amplitude, phase in the tank frame, as `iso_wall_mode1` gives them)
+    to the four numbers that describe a forced, lightly damped sloshing mode after the ramp:
+    q(t) = a_f exp(i w t) + a_n exp((i w0 - gamma) t).  Linear least squares in (a_f, a_n) inside a
+    scan over (w0, gamma).  -> dict(f0 [Hz], gamma [1/s], A_forced [m], A_free [m] at t0, rms [m])"""
+    t = np.asarray(t, dtype=float)
+    q = np.asarray(amp) * np.exp(1j * np.asarray(phase))
+    m = t >= t0
+    if t1 is not None:
+        m &= t <= t1
+    t, q = t[m], q[m]
+    w = 2 * np.pi * f_forcing
+
+    def solve(f0, g):
+        B = np.stack([np.exp(1j * w * t), np.exp((1j * 2 * np.pi * f0 - g) * (t - t0))], axis=1)
+        c, *_ = np.linalg.lstsq(B, q, rcond=None)
+        return c, float(np.sqrt(np.mean(np.abs(B @ c - q) ** 2)))
+
+    best = None
+    f_grid, g_grid = np.linspace(f_forcing + 0.05, f_forcing + 0.6, 111), np.linspace(0.0, 0.6, 31)
+    for _ in range(3):
+        for f0 in f_grid:
+            for g in g_grid:
+                c, r = solve(f0, g)
+                if best is None or r < best[0]:
+                    best = (r, f0, g, c)
+        df, dg = f_grid[1] - f_grid[0], g_grid[1] - g_grid[0]
+        f_grid = np.linspace(best[1] - df, best[1] + df, 21)
+        g_grid = np.linspace(max(best[2] - dg, 0.0), best[2] + dg, 21)
+    r, f0, g, c = best
+    return {"f0": float(f0), "gamma": float(g), "A_forced": float(abs(c[0])), "A_free": float(abs(c[1])), "rms": r}
 
 
 def extract_interface(case_dir, r_target=None, write=True):

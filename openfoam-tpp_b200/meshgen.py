@@ -437,3 +437,119 @@ def cell_geometry(mesh: PolyMesh, Cf=None, Sf=None):
     C /= V[:, None]
     V /= 3.0
     return C, V
+
+
+# ----------------------------------------------------------------------------------------
+# unstructured tets (stand-in for `gmsh -3 cylinder.geo`, generate_mesh.py:17-51: Delaunay tets of
+# uniform size lc, in no particular cell order)
+# ----------------------------------------------------------------------------------------
+def _tet_quality(p, t):
+    """(volume, radius-ratio-like quality in [0,1]: 1 for the regular tet)."""
+    a = p[t]
+    v = np.einsum("ij,ij->i", np.cross(a[:, 1] - a[:, 0], a[:, 2] - a[:, 0]), a[:, 3] - a[:, 0]) / 6.0
+    e2 = np.zeros(t.shape[0])
+    for i in range(4):
+        for j in range(i + 1, 4):
+            e2 += ((a[:, i] - a[:, j]) ** 2).sum(axis=1)
+    return v, 6.0 * np.sqrt(2.0) * np.abs(v) / np.maximum((e2 / 6.0) ** 1.5, 1e-300)
+
+
+def unstructured_cylinder_tets(H, D, lc, seed=0, iters=60, q_min=0.12):
+    """Points and tetrahedra of an unstructured Delaunay mesh of the flat-bottom cylinder
+    (0 <= z <= H, r <= D/2) with target edge length lc: boundary nodes fixed on rings, interior
+    nodes relaxed with Persson-Strang spring forces between Delaunay retriangulations, then
+    slivers removed by local perturbation.  Needs scipy."""
+    from scipy.spatial import Delaunay
+
+    rng = np.random.default_rng(seed)
+    R = 0.5 * D
+    h = lc * 1.21  # node spacing for which the cell count matches gmsh's at this lc (41 895 tets at 9 mm, G1)
+    # fixed boundary nodes: wall rings, and concentric rings on both end discs
+    nz = max(int(round(H / h)), 1)
+    nth = max(int(round(2 * np.pi * R / h)), 8)
+    bnd = []
+    for k in range(nz + 1):
+        th = 2 * np.pi * (np.arange(nth) + 0.5 * (k % 2)) / nth
+        bnd.append(np.c_[R * np.cos(th), R * np.sin(th), np.full(nth, H * k / nz)])
+    nr = max(int(round(R / h)), 1)
+    for z in (0.0, H):
+        for i in range(nr):
+            r = R * i / nr
+            n = max(int(round(2 * np.pi * r / h)), 1)
+            th = 2 * np.pi * (np.arange(n) + 0.37 * i) / n
+            bnd.append(np.c_[r * np.cos(th), r * np.sin(th), np.full(n, z)])
+    bnd = np.concatenate(bnd)
+    nb = bnd.shape[0]
+    # interior nodes: jittered body-centred lattice clipped half a spacing inside
+    a = h * 2.0 / np.sqrt(3.0) * 0.97
+    g = np.arange(-R, R + a, a)
+    gz = np.arange(0.0, H + a, a)
+    X, Y, Z = np.meshgrid(g, g, gz, indexing="ij")
+    lat = np.c_[X.ravel(), Y.ravel(), Z.ravel()]
+    lat = np.concatenate([lat, lat + 0.5 * a])
+    lat += rng.uniform(-0.3 * a, 0.3 * a, lat.shape)  # destroys the lattice: the relaxed mesh is irregular
+    m = (np.hypot(lat[:, 0], lat[:, 1]) < R - 0.55 * h) & (lat[:, 2] > 0.55 * h) & (lat[:, 2] < H - 0.55 * h)
+    p = np.concatenate([bnd, lat[m]])
+
+    def inside(q, s):
+        r = np.hypot(q[:, 0], q[:, 1])
+        sc = np.minimum((R - s) / np.maximum(r, 1e-300), 1.0)
+        q[:, 0] *= sc
+        q[:, 1] *= sc
+        q[:, 2] = np.clip(q[:, 2], s, H - s)
+
+    def triangulate(p):
+        t = Delaunay(p).simplices.astype(np.int64)
+        v, q = _tet_quality(p, t)
+        # hull slivers: four boundary nodes, (almost) no volume
+        flat = (t < nb).all(axis=1) & (q < 0.05)
+        return t[~flat], q[~flat]
+
+    t, q = triangulate(p)
+    for it in range(iters):
+        e = np.concatenate([t[:, [i, j]] for i in range(4) for j in range(i + 1, 4)])
+        e = np.unique(np.sort(e, axis=1), axis=0)
+        d = p[e[:, 0]] - p[e[:, 1]]
+        L = np.linalg.norm(d, axis=1)
+        L0 = 1.15 * np.sqrt((L**2).mean())
+        F = np.maximum(L0 - L, 0.0)
+        fv = (F / np.maximum(L, 1e-300))[:, None] * d
+        tot = np.zeros_like(p)
+        np.add.at(tot, e[:, 0], fv)
+        np.add.at(tot, e[:, 1], -fv)
+        tot[:nb] = 0.0
+        p = p + 0.15 * tot
+        inside(p[nb:], 0.35 * h)
+        if it % 4 == 3 or it == iters - 1:
+            t, q = triangulate(p)
+    # slivers: jiggle one interior node of each bad tet and retriangulate
+    for _ in range(40):
+        bad = np.nonzero(q < q_min)[0]
+        if bad.size == 0:
+            break
+        nodes = np.unique(t[bad].ravel())
+        nodes = nodes[nodes >= nb]
+        if nodes.size == 0:
+            break
+        p[nodes] += rng.normal(0.0, 0.12 * h, (nodes.size, 3))
+        inside(p[nb:], 0.35 * h)
+        t, q = triangulate(p)
+    used = np.unique(t.ravel())
+    lut = np.full(p.shape[0], -1, dtype=np.int64)
+    lut[used] = np.arange(used.size)
+    return p[used], lut[t]
+
+
+def unstructured_cylinder_mesh(H, D, lc, seed=0, iters=60):
+    """polyMesh of `unstructured_cylinder_tets` with the reference's naming (patches `walls`,
+    `atmosphere`, zone `internalMesh`); cells in the triangulator's order, like a gmshToFoam mesh."""
+    pts, tets = unstructured_cylinder_tets(H, D, lc, seed, iters)
+    tets = _orient_tets(pts, tets)
+    faces4, fcell = _tet_faces(tets)
+    eps = 1e-9 * max(H, D)
+
+    def classify(fc, fn, bf):
+        z = pts[bf[:, :3]][:, :, 2]
+        return (np.abs(z - H).max(axis=1) < eps).astype(np.int64)
+
+    return build_polymesh(pts, faces4, fcell, classify, ["walls", "atmosphere"], ["patch", "patch"])

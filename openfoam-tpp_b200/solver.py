@@ -157,7 +157,13 @@ class Solver:
             self._err("tpp_step")
 
     def run_to_write(self, max_steps=10**9):
-        return self.L.tpp_run_to_write(self.h, max_steps)
+        """1: stopped at a write time, 0: endTime reached, 2: max_steps used up.  A failed run (lost
+        halo, grid-barrier timeout, non-finite Courant number / residual, CUDA error) raises: foamRun
+        exits non-zero, as OpenFOAM does and `check=True` expects (main.py:345)."""
+        rc = self.L.tpp_run_to_write(self.h, max_steps)
+        if rc < 0:
+            self._err("tpp_run_to_write")
+        return rc
 
     def info(self):
         o = np.zeros(16)

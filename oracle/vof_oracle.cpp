@@ -12,6 +12,7 @@
 #include <algorithm>
 #include <cmath>
 #include <cstdio>
+#include <cstdlib>
 #include <cstring>
 #include <map>
 #include <string>
@@ -467,6 +468,13 @@ struct orc_state {
     dvec Cf, Sf, magSf, C, V, V0, w, dc, corrVec, CfOld;
     dvec meshPhi;
     double deltaN = 0;
+    // experiment switches for the [OF13-MEM] choices that cannot be checked against upstream source
+    // (tools/of13_toggles.py; all default to the restatement documented in DESIGN.md §2)
+    int xClip = 0;       // ORC_X_CLIP=1: clip the compressed face value to [0,1]
+    int xOwn = 0;        // ORC_X_OWN=1: MULES local extrema include the cell's own value
+    int xBndExt = 0;     // ORC_X_BND=1: boundary face values enter the MULES extrema
+    double xDdt = -1;    // ORC_X_DDT=c: fixed ddtCorr coupling coefficient c instead of 1 - min(|corr|/|phi|, 1)
+    int xNoRelax = 0;    // ORC_X_NORELAX=1: skip the diagonal-dominance step of UEqn.relax(1)
     // fields
     dvec alpha, alpha_b, U, U_b, p_rgh, p_rgh_b, p, rho, rho_b, phi, Uf;
     dvec U0, U0_b, rho0, Uf0;
@@ -858,6 +866,7 @@ struct orc_state {
             double mg = mag3(gf) + deltaN;
             double nHatf = (gf[0] / mg) * Sf[3 * f] + (gf[1] / mg) * Sf[3 * f + 1] + (gf[2] / mg) * Sf[3 * f + 2];
             vf += cfg.c_alpha * sign(phi[f]) * vf * (1.0 - vf) * nHatf / magSf[f];
+            if (xClip) vf = std::min(std::max(vf, 0.0), 1.0);
             alphaPhiUn[f] = phi[f] * vf;
             phiBD[f] = phi[f] * (phi[f] >= 0 ? alpha[P] : alpha[N]);
             phiCorr[f] = alphaPhiUn[f] - phiBD[f];
@@ -882,9 +891,18 @@ struct orc_state {
             if (pc > 0) { sumPhip[P] += pc; mSumPhim[N] += pc; }
             else { mSumPhim[P] -= pc; sumPhip[N] -= pc; }
         }
+        if (xOwn)
+            for (int c = 0; c < nC; c++) {
+                psiMaxn[c] = std::max(psiMaxn[c], alpha[c]);
+                psiMinn[c] = std::min(psiMinn[c], alpha[c]);
+            }
         for (int f = nI; f < nF; f++) {
             // neither zeroGradient nor inletOutlet fixesValue(): no boundary extrema are added
             int P = own[f];
+            if (xBndExt) {
+                psiMaxn[P] = std::max(psiMaxn[P], alpha_b[f - nI]);
+                psiMinn[P] = std::min(psiMinn[P], alpha_b[f - nI]);
+            }
             sumPhiBD[P] += phiBD[f];
             double pc = phiCorr[f];
             if (pc > 0) sumPhip[P] += pc; else mSumPhim[P] -= pc;
@@ -1114,6 +1132,7 @@ struct orc_state {
             double D = D0 + bMax[c];
             D = std::max(std::fabs(D), sumOff[c]);
             D = D - bMin[c];
+            if (xNoRelax) D = D0;
             mDiag[c] = D;
             for (int k = 0; k < 3; k++)
                 mSource[3 * c + k] = (rDeltaT * rho0[c] * U0[3 * c + k] * V0[c] + src[3 * c + k]) + (D - D0) * U[3 * c + k];
@@ -1180,6 +1199,7 @@ struct orc_state {
                 double phiUf0 = dot3(S, &Uf0[3 * f]);
                 double pc = phiUf0 - dot3(S, u0f);
                 double coeff = 1.0 - std::min(std::fabs(pc) / (std::fabs(phiUf0) + SMALL), 1.0);
+                if (xDdt >= 0) coeff = xDdt;
                 ddtCorr = coeff * rDeltaT * pc;
                 rhorAUf = wf * (rho[P] * rAU[P]) + (1.0 - wf) * (rho[N] * rAU[N]);
                 snGradRho = dc[f] * (rho[N] - rho[P]) + dot3(&corrVec[3 * f], gr);
@@ -1433,6 +1453,11 @@ orc_state* orc_create(const orc_mesh_t* m, const orc_config_t* c) {
     double vs = 0;
     for (double v : s->V) vs += v;
     s->deltaN = 1e-8 / std::cbrt(vs / s->nC);  // interfaceProperties deltaN [OF13-MEM]
+    if (const char* e = getenv("ORC_X_CLIP")) s->xClip = atoi(e);
+    if (const char* e = getenv("ORC_X_OWN")) s->xOwn = atoi(e);
+    if (const char* e = getenv("ORC_X_BND")) s->xBndExt = atoi(e);
+    if (const char* e = getenv("ORC_X_DDT")) s->xDdt = atof(e);
+    if (const char* e = getenv("ORC_X_NORELAX")) s->xNoRelax = atoi(e);
     int nC = s->nC, nF = s->nF, nB = s->nB;
     s->meshPhi.assign(nF, 0); s->alpha.assign(nC, 0); s->alpha_b.assign(nB, 0); s->U.assign(3 * nC, 0);
     s->U_b.assign(3 * nB, 0); s->p_rgh.assign(nC, 0); s->p_rgh_b.assign(nB, 0); s->p.assign(nC, 0);

@@ -28,9 +28,15 @@ def main():
     ap.add_argument("--every", type=float, default=0.05)
     ap.add_argument("--out", default="series.csv")
     ap.add_argument("--tight", action="store_true", help="solve p_rgh to 1e-12 instead of the reference's tolerances")
+    ap.add_argument("--mesh", default="structured", choices=("structured", "unstructured"), help="unstructured: Delaunay tets of size --lc (the gmsh stand-in), cells in triangulator order")
+    ap.add_argument("--lc", type=float, default=0.009, help="generate_mesh.py's MeshSize (main.py:113; the golden case m0.009)")
+    ap.add_argument("--seed", type=int, default=0)
     a = ap.parse_args()
     C = bench.CASE
-    mesh = meshgen.cylinder_mesh(C["H"], C["D"], a.rings, a.layers, "flat", "tet")
+    if a.mesh == "unstructured":
+        mesh = meshgen.unstructured_cylinder_mesh(C["H"], C["D"], a.lc, seed=a.seed, iters=40)
+    else:
+        mesh = meshgen.cylinder_mesh(C["H"], C["D"], a.rings, a.layers, "flat", "tet")
     import tempfile
 
     from openfoam_tpp_b200 import case as cs
@@ -61,22 +67,27 @@ def main():
         s.set("alpha", bench.initial_alpha(mesh))
         s.stage("alphaBCs")
         s.stage("mixture")
-    cols = interface.ColumnSampler(mesh)
-    V = cols.V
+    cols = interface.ColumnSampler(mesh) if a.mesh == "structured" else None
+    V = meshgen.cell_geometry(mesh)[1]
     edges = interface.mesh_edges(mesh)  # the reference's own metric: points of the alpha = 0.5 iso-surface (main.py:751-780)
     t0 = time.perf_counter()
     with open(a.out, "w") as f:
-        f.write("time,max_z,min_z,mean_z,A_m1,phase_m1,alpha_volume,step,it_final,res_final,wall_s,iso_max_z,iso_min_z,iso_mean_z,iso_points\n")
+        f.write("time,max_z,min_z,mean_z,A_m1,phase_m1,alpha_volume,step,it_final,res_final,wall_s,iso_max_z,iso_min_z,iso_mean_z,iso_points,iso_A_m1,iso_phase_m1\n")
 
         def rec():
             al = s.get("alpha")
-            mx, mn, me = cols.summary(al)
-            A, ph, _ = cols.wall_mode1(al)
             i = s.info()
-            pts = s.get("points").reshape(-1, 3) if a.impl == "gpu" else mesh.points
-            iso = interface.iso_points(mesh, pts, interface.cell_to_point(mesh, al), 0.5, edges)
+            # tank frame: z statistics do not see the horizontal translation, and the m = 1 fit
+            # wants the tank-frame azimuth (the golden G4 series subtracts the orbit centre)
+            iso = interface.iso_points(mesh, mesh.points, interface.cell_to_point(mesh, al), 0.5, edges)
             z = iso[:, 2] if len(iso) else np.zeros(1)
-            f.write(f"{i['t']:.9g},{mx:.9g},{mn:.9g},{me:.9g},{A:.9g},{ph:.9g},{float((al * V).sum()):.15g},{int(i['step'])},{int(i['it1'])},{i['r1']:.3e},{time.perf_counter() - t0:.2f},{z.max():.9g},{z.min():.9g},{z.mean():.9g},{len(iso)}\n")
+            iA, iph, _, _ = interface.iso_wall_mode1(iso, (0.0, 0.0), 0.5 * C["D"])
+            if cols is not None:
+                mx, mn, me = cols.summary(al)
+                A, ph, _ = cols.wall_mode1(al)
+            else:
+                mx, mn, me, A, ph = z.max(), z.min(), z.mean(), iA, iph
+            f.write(f"{i['t']:.9g},{mx:.9g},{mn:.9g},{me:.9g},{A:.9g},{ph:.9g},{float((al * V).sum()):.15g},{int(i['step'])},{int(i['it1'])},{i['r1']:.3e},{time.perf_counter() - t0:.2f},{z.max():.9g},{z.min():.9g},{z.mean():.9g},{len(iso)},{iA:.9g},{iph:.9g}\n")
             f.flush()
 
         rec()
