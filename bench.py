@@ -202,6 +202,52 @@ def run_reference(args):
     print(json.dumps(line))
 
 
+def parity_nranks(rank, world, local, dist, steps=3):
+    """N > 1, before the timed loop (what `mpirun -np N foamRun -parallel` must guarantee,
+    circularSloshingTank/Makefile:75-82): a ~100 k-cell tank decomposed into `world` z-slabs steps
+    next to the same tank on one GPU (every rank runs its own copy), both solving p_rgh tightly.
+    The time-step sequence must be identical and the fields agree (alpha 1e-9, U / p_rgh 1e-7 of
+    scale).  Exercises the peer-memory halo / all-reduce kernels the timed run uses."""
+    from openfoam_tpp_b200 import ensemble, meshgen
+    from openfoam_tpp_b200 import solver as sv
+
+    nr, nl = 14, max(world, 32 // world * world)
+    whole = meshgen.cylinder_mesh(CASE["H"], CASE["D"], nr, nl, "flat", "tet")
+    k0, k1 = rank * nl // world, (rank + 1) * nl // world
+    part = meshgen.cylinder_mesh(CASE["H"], CASE["D"], nr, nl, "flat", "tet", k0=k0, k1=k1, proc=(rank, rank - 1 if rank > 0 else None, rank + 1 if rank < world - 1 else None))
+
+    def tight(cfg):
+        for sc in (cfg.p_rgh, cfg.p_rgh_final):
+            sc.tolerance, sc.rel_tol, sc.max_iter = 1e-13, 0.0, 800
+        return cfg
+
+    g = sv.Solver(part, tight(make_config(part)), device=local)
+    with stdout_to_stderr():
+        g.comm_init_nccl()
+    gw = sv.Solver(whole, tight(make_config(whole)), device=local)
+    for s_, m_ in ((g, part), (gw, whole)):
+        s_.set("alpha", initial_alpha(m_))
+        s_.init_fields()
+    cpl = whole.n_cells // nl
+    sl = slice(k0 * cpl, k1 * cpl)
+    errs = {"alpha": 0.0, "U": 0.0, "p_rgh": 0.0}
+    dt_equal = True
+    for _ in range(steps):
+        g.step(1)
+        gw.step(1)
+        gi, wi = g.info(), gw.info()
+        dt_equal = dt_equal and abs(gi["t"] - wi["t"]) <= 1e-12 * wi["t"]
+        for nm, nc in (("alpha", 1), ("U", 3), ("p_rgh", 1)):
+            a, b = g.get(nm), gw.get(nm).reshape(-1, nc)
+            errs[nm] = max(errs[nm], float(np.abs(a - b[sl].reshape(-1)).max() / max(np.abs(b).max(), 1e-300)))
+    worst = ensemble.max_over_ranks([errs["alpha"], errs["U"], errs["p_rgh"], 0.0 if dt_equal else 1.0])
+    g.close()
+    gw.close()
+    ok = worst[0] <= 1e-9 and worst[1] <= 1e-7 and worst[2] <= 1e-7 and worst[3] == 0.0
+    return {"ok": bool(ok), "cells": whole.n_cells, "ranks": world, "steps": steps, "time_step_sequence_equal": worst[3] == 0.0,
+            "max_rel_err": {"alpha": worst[0], "U": worst[1], "p_rgh": worst[2]}, "tolerance": {"alpha": 1e-9, "U": 1e-7, "p_rgh": 1e-7}}
+
+
 def main():
     global VB
     VB = 8 if os.environ.get("TPP_FP32", "1") == "0" else 4
@@ -216,6 +262,10 @@ def main():
     ap.add_argument("--no-cpu", action="store_true")
     ap.add_argument("--kernel-table", default=None, help="write the full per-kernel table (launches, ms, algorithmic GB/s) of the profiled steps to this JSON file")
     ap.add_argument("--mode", default="decomposed", choices=["decomposed", "ensemble"], help="N > 1: one tank over N GPUs (halo exchange) or N independent sweep cases")
+    ap.add_argument("--t0", type=float, default=2.0, help="start time of the run: 2.0 = the end of the shaker's ramp (full orbit amplitude, SURVEY.md 8d); 0 = from rest")
+    ap.add_argument("--spinup", type=int, default=45, help="untimed steps before the --warmup steps (start-up transient of the impulsively started tank)")
+    ap.add_argument("--order", default="structured", choices=["structured", "gmsh"], help="cell order of the mesh file: the generator's (layer by layer) or a random one, as a gmsh mesh has")
+    ap.add_argument("--no-parity", action="store_true", help="N > 1: skip the decomposed-vs-whole check before the timed loop")
     args = ap.parse_args()
     if args.impl == "reference":
         return run_reference(args)
@@ -262,9 +312,14 @@ def main():
     else:
         mesh, nr, nl = mesh_for(args.cells)
         cfg = make_config(mesh)
+    if args.order == "gmsh":
+        mesh = meshgen.shuffled(mesh, seed=1234 + rank)
     nC, nI, nF = mesh.n_cells, mesh.n_internal, mesh.n_faces
-    g = sv.Solver(mesh, cfg, device=local)
     decomposed = world > 1 and args.mode != "ensemble"
+    parity = None
+    if decomposed and not args.no_parity:
+        parity = parity_nranks(rank, world, local, dist)
+    g = sv.Solver(mesh, cfg, device=local)
     # a side stream shared with the solver: CUDA events recorded here bracket its kernels, and
     # (unlike the legacy default stream) it can be graph-captured
     stream = torch.cuda.Stream()
@@ -285,7 +340,11 @@ def main():
         torch.cuda.synchronize()
 
     # ---- resident-state throughput ---------------------------------------------------------
+    if args.t0 > 0:
+        g.set_time(args.t0, cfg.delta_t)  # the shaker at full orbit amplitude (end of its ramp), fluid still at rest
+    g.step(args.spinup)
     g.step(args.warmup)
+    g.stats(1)
     l0 = g.info()["launches"]
     sampler = ClockSampler(local)
     sampler.start()
@@ -297,8 +356,9 @@ def main():
     barrier()
     sec = e0.elapsed_time(e1) / 1e3
     sampler.stop_flag = True
-    launches = int(g.info()["launches"] - l0)
     info = g.info()
+    stats = g.stats(0)
+    launches = int(info["launches"] - l0) - 4 * args.steps  # (the statistics' own two small reductions per step are not counted)
 
     # ---- per-kernel CUDA-event timing (separate pass, same state) ---------------------------
     g.profile(True)
@@ -389,7 +449,11 @@ def main():
     barrier()
     sec_e2e = time.perf_counter() - t0
 
-    sec, sec_e2e = ensemble.max_over_ranks([sec, sec_e2e])
+    sec, sec_e2e, it0_mean, it1_mean, it1_max, cap_hits, bal = ensemble.max_over_ranks([sec, sec_e2e, stats["it0_mean"], stats["it1_mean"], stats["it1_max"], stats["cap_hits"], 0.0])
+    vols = ensemble.sum_over_ranks([stats["alpha_volume_start"], stats["alpha_volume"], stats["alpha_boundary_outflow"]])
+    bal = abs(vols[1] - vols[0] + vols[2]) / max(abs(vols[0]), 1e-300)
+    checks = {"alpha_volume_balance_rel": bal, "alpha_volume_balance_ok": bool(bal <= 1e-10), "p_rghFinal_max_iter": int(cfg.p_rgh_final.max_iter),
+              "p_rghFinal_iters_max": int(it1_max), "p_rghFinal_below_max_iter": bool(it1_max < cfg.p_rgh_final.max_iter), "steps_capped": int(cap_hits)}
     total_cells = int(ensemble.sum_over_ranks([float(nC)])[0])
     launches = int(ensemble.sum_over_ranks([float(launches)])[0])
     value = total_cells * args.steps / sec / 1e6
@@ -409,11 +473,15 @@ def main():
                        "cells_per_gpu": nC, "internal_faces_per_gpu": nI, "parallelism": "single GPU" if world == 1 else (f"one tank decomposed into {world} z-slabs (simple (1 1 {world})), NCCL halo exchange + all-reduced Krylov dots, {total_cells} cells in total" if decomposed else f"ensemble: {world} independent sweep cases (f = {freqs[0]}..{freqs[-1]} Hz), one per GPU, no collective"),
                        "l2": "working set (>1 kB/cell) far exceeds the 126 MB L2; no flush needed",
                        "vof_steps_per_s": args.steps / sec, "solver_iters_last_step": [int(info["it0"]), int(info["it1"])], "amg_levels": int(info["levels"]),
+                       "t_start": args.t0, "t_end": float(info["t"]), "spinup_steps": args.spinup, "iters_mean": [round(it0_mean, 2), round(it1_mean, 2)],
+                       "cell_order": args.order,
                        "precision": "FP64 fields, operators, Krylov iteration and residuals; multigrid preconditioner in " + ("FP64" if VB == 8 else "FP32")},
             "clocks": sampler.summary(), "gpu_launches": launches,
             "e2e": {"value": e2e, "unit": UNIT, "h2d_bytes_per_step": h2d_b, "d2h_bytes_per_step": d2h_b, "steps": e2e_steps},
-            "roofline": roofline, "cpu_baseline": cpu,
+            "roofline": roofline, "cpu_baseline": cpu, "checks": checks,
         }
+        if parity is not None:
+            line["parity_nranks"] = parity
         print(json.dumps(line))
     if world > 1:
         dist.destroy_process_group()

@@ -124,6 +124,14 @@ int tpp_stage(tpp_handle, const char* name);
  * p_rghFinal solves, reference cell, deltaN, write index, AMG levels, kernel launches */
 int tpp_info(tpp_handle, double* out16);
 
+/* Run statistics over the steps since the last reset (what an OpenFOAM log is grepped for:
+ * "No Iterations", and the alpha.water volume balance).  out9 (may be NULL): steps, sum and
+ * maximum of the p_rgh / p_rghFinal iteration counts [1..4], steps whose p_rghFinal solve stopped at
+ * maxIter [5], sum(alpha V) at the reset [6] and now [7], time integral of the alpha flux through
+ * the physical boundary [8] ([7] - [6] + [8] is the volume-conservation defect).  Then, reset > 0:
+ * start collecting (two small reductions per step); reset == 0: stop; reset < 0: leave as is. */
+int tpp_stats(tpp_handle, int reset, double* out9);
+
 /* solve A x = b on the mesh's LDU addressing with the positive Laplacian coefficients
  * `upper` (off-diagonals are -upper); returns iterations */
 int tpp_solve(tpp_handle, const tpp_solver_t* ctl, const double* diag, const double* upper,

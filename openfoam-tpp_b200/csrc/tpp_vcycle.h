@@ -36,41 +36,69 @@ struct VL {
     R* out;
     const double* sf;  // device scalars [num, den] of the correction scaling
     R omega;
+    // fused sweeps (vcol_*): first iterate om0 b/diag formed per column (mode 2); corrected iterate
+    // in + oc xc[aggF] formed per column (mode 3)
+    R om0, oc;
+    const int* aggF;  // [n] coarse row of every row of THIS level
+};
+
+// column functors: the value of column j of the vector a row operator is applied to
+template <class R> struct ColPlain {
+    const R* x; int nOwn;
+    HD R operator()(int j) const { return x[j]; }
+};
+template <class R> struct ColFirst {  // om0 b/diag, never stored; rows of other ranks (ghosts) count as zero
+    const R *b, *d; R om0; int n;
+    HD R operator()(int j) const { return j < n ? om0 * b[j] / d[j] : R(0); }
+};
+template <class R> struct ColCorr {  // in + oc xc[aggF] (levels without ghost rows only)
+    const R *x, *xc; const int* aggF; R oc;
+    HD R operator()(int j) const { return x[j] + oc * xc[aggF[j]]; }
 };
 
 // ---- row operators -------------------------------------------------------------------------
-template <class R, int W>
-HD R vl_ell_off(const VL<R>& L, int c, const R* x) {
+template <class R, int W, class G>
+HD R vl_ell_off_g(const VL<R>& L, int c, const G& g) {
     int o[W];
     R v[W], xv[W];
 #pragma unroll
     for (int k = 0; k < W; k++) { o[k] = L.cn[(size_t)k * L.nCp + c]; v[k] = L.ev[(size_t)k * L.nCp + c]; }
 #pragma unroll
-    for (int k = 0; k < W; k++) xv[k] = (o[k] >= 0 && o[k] < L.nOwn) ? x[o[k]] : R(0);
+    for (int k = 0; k < W; k++) xv[k] = (o[k] >= 0 && o[k] < L.nOwn) ? g(o[k]) : R(0);
     R s = 0;
 #pragma unroll
     for (int k = 0; k < W; k++) s += v[k] * xv[k];
     return s;
 }
-template <class R>
-HD R vl_off(const VL<R>& L, int c, const R* x) {
+template <class R, class G>
+HD R vl_off_g(const VL<R>& L, int c, const G& g) {
     if (L.ell) {
-        if (L.W == 4) return vl_ell_off<R, 4>(L, c, x);
-        if (L.W == 5) return vl_ell_off<R, 5>(L, c, x);
-        if (L.W == 6) return vl_ell_off<R, 6>(L, c, x);
+        if (L.W == 4) return vl_ell_off_g<R, 4>(L, c, g);
+        if (L.W == 5) return vl_ell_off_g<R, 5>(L, c, g);
+        if (L.W == 6) return vl_ell_off_g<R, 6>(L, c, g);
         R s = 0;
-        for (int k = 0; k < L.W; k++) { int o = L.cn[(size_t)k * L.nCp + c]; if (o >= 0 && o < L.nOwn) s += L.ev[(size_t)k * L.nCp + c] * x[o]; }
+        for (int k = 0; k < L.W; k++) { int o = L.cn[(size_t)k * L.nCp + c]; if (o >= 0 && o < L.nOwn) s += L.ev[(size_t)k * L.nCp + c] * g(o); }
         return s;
     }
     R s = 0;
-    for (int k = L.rs[c]; k < L.rs[c + 1]; k++) { int o = L.cn[k]; if (o >= 0 && o < L.nOwn) s += L.ev[k] * x[o]; }
+    for (int k = L.rs[c]; k < L.rs[c + 1]; k++) { int o = L.cn[k]; if (o >= 0 && o < L.nOwn) s += L.ev[k] * g(o); }
     return s;
 }
+template <class R> HD R vl_off(const VL<R>& L, int c, const R* x) { return vl_off_g(L, c, ColPlain<R>{x, L.nOwn}); }
 template <class R> HD R vl_Ax(const VL<R>& L, int c, const R* x) { return L.diag[c] * x[c] - vl_off(L, c, x); }
+// one Jacobi sweep on the vector g (value of row c: xc_), relaxation L.omega
+template <class R, class G> HD R vl_sweep_g(const VL<R>& L, int c, const G& g) {
+    const R xi = g(c);
+    return xi + L.omega * (L.b[c] - (L.diag[c] * xi - vl_off_g(L, c, g))) / L.diag[c];
+}
 
 template <class R> HD void vb_jacobi0(const VL<R>& L, int c) { L.out[c] = L.omega * L.b[c] / L.diag[c]; }
 template <class R> HD void vb_jacobi(const VL<R>& L, int c) { L.out[c] = L.in[c] + L.omega * (L.b[c] - vl_Ax(L, c, L.in)) / L.diag[c]; }
 template <class R> HD void vb_residual(const VL<R>& L, int c) { L.out[c] = L.b[c] - vl_Ax(L, c, L.in); }
+// the first two sweeps from a zero guess in one pass (the iterate om0 b/diag is never stored)
+template <class R> HD void vb_jacobi_first(const VL<R>& L, int c) { L.out[c] = vl_sweep_g(L, c, ColFirst<R>{L.b, L.diag, L.om0, L.n}); }
+// prolongation + over-correction + the first post-sweep in one pass
+template <class R> HD void vb_jacobi_corr(const VL<R>& L, int c) { L.out[c] = vl_sweep_g(L, c, ColCorr<R>{L.in, L.xc, L.aggF, L.oc}); }
 // restriction: out[I] = sum of the fine residual r over the members of coarse row I (fixed order)
 template <class R> HD void vb_restrict(const VL<R>& L, int I) {
     R s = 0;
@@ -110,6 +138,8 @@ template <class R> HD void vb_pack(const PackArgs<R>& a, int j) { a.dst[j] = a.s
 DEF_VKERNEL(jacobi0, VL)
 DEF_VKERNEL(jacobi, VL)
 DEF_VKERNEL(residual, VL)
+DEF_VKERNEL(jacobi_first, VL)
+DEF_VKERNEL(jacobi_corr, VL)
 DEF_VKERNEL(restrict, VL)
 DEF_VKERNEL(prolong, VL)
 DEF_VKERNEL(scale_apply, VL)
@@ -396,30 +426,34 @@ __global__ void __launch_bounds__(TAIL_THREADS, 1) vk_tail(const TailArgs<R> A) 
 }
 
 // ---- CSR levels: COOP lanes per row ---------------------------------------------------------
-template <class R, int COOP>
-DEV R vl_coop_off(const VL<R>& L, int c, const R* x, int lane) {
+template <class R, int COOP, class G>
+DEV R vl_coop_off_g(const VL<R>& L, int c, const G& g, int lane) {
     R s = 0;
     const int b = L.rs[c], e = L.rs[c + 1];
     for (int k = b + lane; k < e; k += COOP) {
         int o = L.cn[k];
-        if (o >= 0 && o < L.nOwn) s += L.ev[k] * x[o];
+        if (o >= 0 && o < L.nOwn) s += L.ev[k] * g(o);
     }
 #pragma unroll
     for (int off = COOP / 2; off > 0; off >>= 1) s += __shfl_xor_sync(0xffffffffu, s, off);
     return s;
 }
-// mode 0: Jacobi sweep ; 1: residual
+template <class R, int COOP> DEV R vl_coop_off(const VL<R>& L, int c, const R* x, int lane) { return vl_coop_off_g<R, COOP>(L, c, ColPlain<R>{x, L.nOwn}, lane); }
+// mode 0: Jacobi sweep ; 1: residual ; 2: first two sweeps fused ; 3: correction + sweep fused
 template <class R, int COOP>
 __global__ void __launch_bounds__(256) vk_csr_row_op(const VL<R> L, int mode) {
     int gid = blockIdx.x * blockDim.x + threadIdx.x;
     int c = gid / COOP, lane = gid % COOP;
     bool live = c < L.n;
     int cc = live ? c : L.n - 1;
-    R off = vl_coop_off<R, COOP>(L, cc, L.in, lane);
+    R off, xi;
+    if (mode == 2) { ColFirst<R> g{L.b, L.diag, L.om0, L.n}; off = vl_coop_off_g<R, COOP>(L, cc, g, lane); xi = g(cc); }
+    else if (mode == 3) { ColCorr<R> g{L.in, L.xc, L.aggF, L.oc}; off = vl_coop_off_g<R, COOP>(L, cc, g, lane); xi = g(cc); }
+    else { off = vl_coop_off<R, COOP>(L, cc, L.in, lane); xi = L.in[cc]; }
     if (live && lane == 0) {
-        R ax = L.diag[c] * L.in[c] - off;
-        if (mode == 0) L.out[c] = L.in[c] + L.omega * (L.b[c] - ax) / L.diag[c];
-        else L.out[c] = L.b[c] - ax;
+        R ax = L.diag[c] * xi - off;
+        if (mode == 1) L.out[c] = L.b[c] - ax;
+        else L.out[c] = xi + L.omega * (L.b[c] - ax) / L.diag[c];
     }
 }
 // out = A in fused with the partial sums of r.in and in.out (double accumulation)
@@ -471,12 +505,13 @@ __global__ void __launch_bounds__(256) vk_csr_spmv_dot2(const VL<R> L, double* p
 template <class R> struct Vec2;
 template <> struct Vec2<float> { typedef float2 type; };
 template <> struct Vec2<double> { typedef double2 type; };
-template <class R, int W>
-DEV void vl_ell2_Ax(const VL<R>& L, int c, const R* x, R& ax0, R& ax1) {
+template <class R, int W, class G>
+DEV void vl_ell2_Ax_g(const VL<R>& L, int c, const G& x, R xi0, R xi1, R& ax0, R& ax1) {
     typedef typename Vec2<R>::type R2;
     int2 o[W];
     R2 v[W];
-    const R2 dg = *reinterpret_cast<const R2*>(L.diag + c), xi = *reinterpret_cast<const R2*>(x + c);
+    const R2 dg = *reinterpret_cast<const R2*>(L.diag + c);
+    R2 xi; xi.x = xi0; xi.y = xi1;
 #pragma unroll
     for (int k = 0; k < W; k++) o[k] = *reinterpret_cast<const int2*>(L.cn + (size_t)k * L.nCp + c);
 #pragma unroll
@@ -484,8 +519,8 @@ DEV void vl_ell2_Ax(const VL<R>& L, int c, const R* x, R& ax0, R& ax1) {
     R xa[W], xb[W];
 #pragma unroll
     for (int k = 0; k < W; k++) {
-        xa[k] = (o[k].x >= 0 && o[k].x < L.nOwn) ? x[o[k].x] : R(0);
-        xb[k] = (o[k].y >= 0 && o[k].y < L.nOwn) ? x[o[k].y] : R(0);
+        xa[k] = (o[k].x >= 0 && o[k].x < L.nOwn) ? x(o[k].x) : R(0);
+        xb[k] = (o[k].y >= 0 && o[k].y < L.nOwn) ? x(o[k].y) : R(0);
     }
     R s0 = 0, s1 = 0;
 #pragma unroll
@@ -493,27 +528,48 @@ DEV void vl_ell2_Ax(const VL<R>& L, int c, const R* x, R& ax0, R& ax1) {
     ax0 = dg.x * xi.x - s0;
     ax1 = dg.y * xi.y - s1;
 }
-// mode 0: Jacobi sweep ; 1: residual
 template <class R, int W>
-__global__ void __launch_bounds__(256) vk_ell2_row_op(const VL<R> L, int mode) {
+DEV void vl_ell2_Ax(const VL<R>& L, int c, const R* x, R& ax0, R& ax1) {
+    typedef typename Vec2<R>::type R2;
+    const R2 xi = *reinterpret_cast<const R2*>(x + c);
+    vl_ell2_Ax_g<R, W>(L, c, ColPlain<R>{x, L.nOwn}, xi.x, xi.y, ax0, ax1);
+}
+// MODE 0: Jacobi sweep ; 1: residual ; 2: first two sweeps from a zero guess fused (the iterate
+// om0 b/diag is formed per column) ; 3: prolongation + over-correction + sweep fused
+template <class R, int W, int MODE>
+__global__ void __launch_bounds__(256) vk_ell2_row_op(const VL<R> L) {
     typedef typename Vec2<R>::type R2;
     const int c = 2 * (blockIdx.x * blockDim.x + threadIdx.x);
     if (c >= L.n) return;
     if (c + 1 < L.n) {
         R ax0, ax1;
         const R2 bb = *reinterpret_cast<const R2*>(L.b + c);
-        vl_ell2_Ax<R, W>(L, c, L.in, ax0, ax1);
+        const R2 dg = *reinterpret_cast<const R2*>(L.diag + c);
+        R2 xi;
+        if (MODE == 2) {
+            xi.x = L.om0 * bb.x / dg.x; xi.y = L.om0 * bb.y / dg.y;
+            vl_ell2_Ax_g<R, W>(L, c, ColFirst<R>{L.b, L.diag, L.om0, L.n}, xi.x, xi.y, ax0, ax1);
+        } else if (MODE == 3) {
+            const R2 xin = *reinterpret_cast<const R2*>(L.in + c);
+            const int2 ag = *reinterpret_cast<const int2*>(L.aggF + c);
+            xi.x = xin.x + L.oc * L.xc[ag.x]; xi.y = xin.y + L.oc * L.xc[ag.y];
+            vl_ell2_Ax_g<R, W>(L, c, ColCorr<R>{L.in, L.xc, L.aggF, L.oc}, xi.x, xi.y, ax0, ax1);
+        } else {
+            xi = *reinterpret_cast<const R2*>(L.in + c);
+            vl_ell2_Ax_g<R, W>(L, c, ColPlain<R>{L.in, L.nOwn}, xi.x, xi.y, ax0, ax1);
+        }
         R2 res;
-        if (mode == 0) {
-            const R2 dg = *reinterpret_cast<const R2*>(L.diag + c), xi = *reinterpret_cast<const R2*>(L.in + c);
+        if (MODE == 1) { res.x = bb.x - ax0; res.y = bb.y - ax1; }
+        else {
             res.x = xi.x + L.omega * (bb.x - ax0) / dg.x;
             res.y = xi.y + L.omega * (bb.y - ax1) / dg.y;
-        } else { res.x = bb.x - ax0; res.y = bb.y - ax1; }
+        }
         *reinterpret_cast<R2*>(L.out + c) = res;
     } else {  // odd row count: the last row alone
-        R ax = vl_Ax(L, c, L.in);
-        if (mode == 0) L.out[c] = L.in[c] + L.omega * (L.b[c] - ax) / L.diag[c];
-        else L.out[c] = L.b[c] - ax;
+        if (MODE == 1) L.out[c] = L.b[c] - vl_Ax(L, c, L.in);
+        else if (MODE == 2) vb_jacobi_first(L, c);
+        else if (MODE == 3) vb_jacobi_corr(L, c);
+        else vb_jacobi(L, c);
     }
 }
 template <class R, int W>
@@ -546,29 +602,33 @@ __global__ void __launch_bounds__(256) vk_ell2_spmv_dot2(const VL<R> L, double* 
 }
 
 // ---- coarse levels in ELL + overflow form: one thread per row ------------------------------------
-template <class R, int W>
-DEV R vl_ellc_off(const VL<R>& L, int c, const R* x) {
+template <class R, int W, class G>
+DEV R vl_ellc_off_g(const VL<R>& L, int c, const G& x) {
     int o[W];
     R v[W], xv[W];
 #pragma unroll
     for (int k = 0; k < W; k++) { o[k] = L.ecn[(size_t)k * L.nPad + c]; v[k] = L.eev[(size_t)k * L.nPad + c]; }
 #pragma unroll
-    for (int k = 0; k < W; k++) xv[k] = o[k] >= 0 ? x[o[k]] : R(0);
+    for (int k = 0; k < W; k++) xv[k] = o[k] >= 0 ? x(o[k]) : R(0);
     R s = 0;
 #pragma unroll
     for (int k = 0; k < W; k++) s += v[k] * xv[k];
-    for (int k = L.ors[c]; k < L.ors[c + 1]; k++) s += L.oev[k] * x[L.ocn[k]];
+    for (int k = L.ors[c]; k < L.ors[c + 1]; k++) s += L.oev[k] * x(L.ocn[k]);
     return s;
 }
-// mode 0: Jacobi sweep ; 1: residual
+template <class R, int W> DEV R vl_ellc_off(const VL<R>& L, int c, const R* x) { return vl_ellc_off_g<R, W>(L, c, ColPlain<R>{x, L.nOwn}); }
+// mode 0: Jacobi sweep ; 1: residual ; 2: first two sweeps fused ; 3: correction + sweep fused
 template <class R, int W>
 __global__ void __launch_bounds__(256) vk_ellc_row_op(const VL<R> L, int mode) {
     int c = blockIdx.x * blockDim.x + threadIdx.x;
     if (c >= L.n) return;
-    R xc = L.in[c];
-    R ax = L.diag[c] * xc - vl_ellc_off<R, W>(L, c, L.in);
-    if (mode == 0) L.out[c] = xc + L.omega * (L.b[c] - ax) / L.diag[c];
-    else L.out[c] = L.b[c] - ax;
+    R xi, off;
+    if (mode == 2) { ColFirst<R> g{L.b, L.diag, L.om0, L.n}; xi = g(c); off = vl_ellc_off_g<R, W>(L, c, g); }
+    else if (mode == 3) { ColCorr<R> g{L.in, L.xc, L.aggF, L.oc}; xi = g(c); off = vl_ellc_off_g<R, W>(L, c, g); }
+    else { xi = L.in[c]; off = vl_ellc_off<R, W>(L, c, L.in); }
+    R ax = L.diag[c] * xi - off;
+    if (mode == 1) L.out[c] = L.b[c] - ax;
+    else L.out[c] = xi + L.omega * (L.b[c] - ax) / L.diag[c];
 }
 template <class R, int W>
 __global__ void __launch_bounds__(256) vk_ellc_spmv_dot2(const VL<R> L, double* partialNum, double* partialDen) {

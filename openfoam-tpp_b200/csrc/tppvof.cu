@@ -836,6 +836,31 @@ struct tpp_solver {
         }
         pcEnd();
     }
+    // ---- run statistics (tpp_stats): iteration counts over the steps since the last reset and the
+    // alpha-volume balance sum(alpha V)(t) - sum(alpha V)(t_reset) + int dt sum_b alphaPhi_b = 0
+    bool statsOn = false;
+    double stSteps = 0, stIt[2] = {0, 0}, stItMax[2] = {0, 0}, stCap = 0, stVol0 = 0, stBndInt = 0;
+    double alphaVolume() {
+        red.reduce(ctx, d.alpha, d.V, nC, 0, scal + S_TMP0);
+        double v;
+        d2h(ctx, &v, scal + S_TMP0, sizeof(double));
+        return v;
+    }
+    void statsReset() {
+        stSteps = stIt[0] = stIt[1] = stItMax[0] = stItMax[1] = stCap = stBndInt = 0;
+        stVol0 = alphaVolume();
+    }
+    void statsStep() {
+        stSteps += 1;
+        for (int k = 0; k < 2; k++) { stIt[k] += lastSolve[k].iters; stItMax[k] = std::max(stItMax[k], (double)lastSolve[k].iters); }
+        if (lastSolve[1].iters >= cfg.p_rgh_final.max_iter) stCap += 1;
+        if (nB > 0) {
+            red.reduce(ctx, d.alphaPhi + nI, nullptr, nB, 2, scal + S_TMP0);  // nI counts the processor faces; nB the physical boundary
+            double v;
+            d2h(ctx, &v, scal + S_TMP0, sizeof(double));
+            stBndInt += dt * v;
+        }
+    }
     void fail(const std::string& msg) {
         if (ctx.err.empty()) { ctx.err = msg; fprintf(stderr, "tppvof: %s\n", msg.c_str()); }
     }
@@ -866,6 +891,7 @@ struct tpp_solver {
         momentum();
         for (int corr = 0; corr < cfg.n_correctors; corr++) pressureCorrector(corr == cfg.n_correctors - 1);
         if (!probeCells.empty()) sampleProbes();
+        if (statsOn) statsStep();
         checkDeviceFlags();
         return wr;
     }
@@ -1476,19 +1502,26 @@ struct tpp_solver {
         if (kind == 2 && (lag & 2) && prev) { d2d(ctx, vec + vRows(lv), prev + vRows(lv), ng * sizeof(R)); ctx.launches++; return; }
         XL<R>(lv, vec);
     }
-    template <class R> void vRowOp(VL<R>& L, int mode) {  // 0 Jacobi sweep, 1 residual
+    // 0 Jacobi sweep, 1 residual, 2 the first two sweeps from a zero guess in one pass, 3 prolongation
+    // + over-correction + first post-sweep in one pass
+    template <class R> void vRowOp(VL<R>& L, int mode) {
+        static const char* ellName[4] = {"v_jacobi", "v_residual", "v_jacobi_first", "v_jacobi_corr"};
+        static const char* csrName[4] = {"v_jacobi_csr", "v_residual_csr", "v_jacobi_first_csr", "v_jacobi_corr_csr"};
 #ifndef TPP_EMU
         if (L.ell && (L.W == 4 || L.W == 6) && knob("TPP_ELL2", 1)) {
-            prof_begin(ctx, mode == 0 ? "v_jacobi" : "v_residual");
+            prof_begin(ctx, ellName[mode]);
             const int g_ = ((L.n + 1) / 2 + 255) / 256;
-            if (L.W == 4) vk_ell2_row_op<R, 4><<<g_, 256, 0, ctx.stream>>>(L, mode);
-            else vk_ell2_row_op<R, 6><<<g_, 256, 0, ctx.stream>>>(L, mode);
+#define ELL2_CASE(WW) switch (mode) { case 0: vk_ell2_row_op<R, WW, 0><<<g_, 256, 0, ctx.stream>>>(L); break; case 1: vk_ell2_row_op<R, WW, 1><<<g_, 256, 0, ctx.stream>>>(L); break; \
+                                      case 2: vk_ell2_row_op<R, WW, 2><<<g_, 256, 0, ctx.stream>>>(L); break; default: vk_ell2_row_op<R, WW, 3><<<g_, 256, 0, ctx.stream>>>(L); }
+            if (L.W == 4) { ELL2_CASE(4) } else { ELL2_CASE(6) }
+#undef ELL2_CASE
+            LAUNCH_CHECK("vk_ell2_row_op");
             prof_end(ctx);
             ctx.launches++;
             return;
         }
         if (!L.ell && L.ellW > 0) {
-            prof_begin(ctx, mode == 0 ? "v_jacobi_csr" : "v_residual_csr");
+            prof_begin(ctx, csrName[mode]);
             const int g_ = (L.n + 255) / 256;
             switch (L.ellW) {
                 case 6: vk_ellc_row_op<R, 6><<<g_, 256, 0, ctx.stream>>>(L, mode); break;
@@ -1496,21 +1529,25 @@ struct tpp_solver {
                 case 12: vk_ellc_row_op<R, 12><<<g_, 256, 0, ctx.stream>>>(L, mode); break;
                 default: vk_ellc_row_op<R, 16><<<g_, 256, 0, ctx.stream>>>(L, mode); break;
             }
+            LAUNCH_CHECK("vk_ellc_row_op");
             prof_end(ctx);
             ctx.launches++;
             return;
         }
         if (!L.ell) {
-            prof_begin(ctx, mode == 0 ? "v_jacobi_csr" : "v_residual_csr");
+            prof_begin(ctx, csrName[mode]);
             if (2 * (long)L.nf <= 10 * (long)L.n) vk_csr_row_op<R, 4><<<(L.n * 4 + 255) / 256, 256, 0, ctx.stream>>>(L, mode);
             else vk_csr_row_op<R, 8><<<(L.n * 8 + 255) / 256, 256, 0, ctx.stream>>>(L, mode);
+            LAUNCH_CHECK("vk_csr_row_op");
             prof_end(ctx);
             ctx.launches++;
             return;
         }
 #endif
         if (mode == 0) VLAUNCH(ctx, jacobi, L, L.n);
-        else VLAUNCH(ctx, residual, L, L.n);
+        else if (mode == 1) VLAUNCH(ctx, residual, L, L.n);
+        else if (mode == 2) VLAUNCH(ctx, jacobi_first, L, L.n);
+        else VLAUNCH(ctx, jacobi_corr, L, L.n);
     }
     // out = A in ; scal[S_TMP0] = r.in ; scal[S_TMP1] = in.out  (summed over the ranks)
     template <class R> void vSpmvDot2(VL<R>& L) {
@@ -1518,6 +1555,7 @@ struct tpp_solver {
         double v = 0, w = 0;
         for (int c = 0; c < L.n; c++) { R y = vl_Ax(L, c, L.in); L.out[c] = y; v += (double)L.r[c] * (double)L.in[c]; w += (double)y * (double)L.in[c]; }
         scal[S_TMP0] = v; scal[S_TMP1] = w;
+        if (knob("TPP_VERBOSE", 0) >= 2) fprintf(stderr, "sf n=%d %.4f\n", L.n, v / w);
 #else
         prof_begin(ctx, L.ell ? "v_spmv_dot2" : "v_spmv_dot2_csr");
         int nb = std::min(RED_BLOCKS, (L.n + BLOCK - 1) / BLOCK);
@@ -1592,7 +1630,7 @@ struct tpp_solver {
             L.x = v.tx[t]; L.y = v.ty[t]; L.b = v.tb[t]; L.r = v.tr[t];
         }
         A.bar = tailBar; A.err = tailErr;
-        A.overcorr = (R)knobd("TPP_OVERCORR", 1.8);
+        A.overcorr = (R)knobd("TPP_TAIL_OVERCORR", knobd("TPP_OVERCORR", 1.8));
         // 8 CG iterations on the coarsest level give the same PCG counts as 16; fewer sweeps on the
         // small levels cost 1-2 PCG iterations at 6 M cells (tools/knob_sweep.py), so they keep nPre/nPost
         A.nPre = std::min(knob("TPP_TAIL_NPRE", nPre), TAIL_MAXSW); A.nPost = std::min(knob("TPP_TAIL_NPOST", nPost), TAIL_MAXSW);
@@ -1623,9 +1661,16 @@ struct tpp_solver {
         }
         L.omega = omega; L.b = b;
         R *cur = x, *oth = v.t0[lv];
+        const bool ghosts = comm.active && vGhosts(lv) > 0;
+        const int fuse = knob("TPP_FUSE", 3);
+        // the first iterate om0 b/diag is not stored when a second sweep follows: that sweep forms it per
+        // column (one pass and one launch less); rows of other ranks count as zero there, which is what
+        // TPP_LAG bit 0 does to the second sweep anyway
+        const bool fuseFirst = zeroGuess && nPre >= 2 && (fuse & 1) && (!ghosts || (knob("TPP_LAG", 3) & 1));
         for (int s = 0; s < std::max(nPre, 1); s++) {
             L.omega = (R)smootherOmega(s, std::max(nPre, 1));
-            if (s == 0 && zeroGuess) { L.out = cur; VLAUNCH(ctx, jacobi0, L, L.n); }
+            if (s == 0 && zeroGuess) { if (fuseFirst) continue; L.out = cur; VLAUNCH(ctx, jacobi0, L, L.n); }
+            else if (s == 1 && fuseFirst) { L.om0 = (R)smootherOmega(0, std::max(nPre, 1)); L.in = nullptr; L.out = cur; vRowOp(L, 2); }
             else { XLsmooth<R>(lv, cur, s == 1 && zeroGuess ? 1 : 0); L.in = cur; L.out = oth; vRowOp(L, 0); std::swap(cur, oth); }
         }
         XL<R>(lv, cur);
@@ -1652,8 +1697,12 @@ struct tpp_solver {
         // 14 iterations of p_rghFinal), without its A c product, its two dot products and - on several
         // GPUs - their halo exchange and all-reduce on every level of every cycle.  The factor must
         // stay below 2 (2.2 diverges).  TPP_NOSCALE_FROM=99 restores the scaled correction.
-        if (lv >= knob("TPP_NOSCALE_FROM", 0)) {
-            Pn.out = cur; Pn.omega = (R)knobd("TPP_OVERCORR", 1.8);
+        bool corrFused = false;
+        if (lv >= knob("TPP_NOSCALE_FROM", 0) && !ghosts && (fuse & 2)) {
+            // prolongation, over-correction and the first post-sweep in one pass over the matrix
+            corrFused = true;
+        } else if (lv >= knob("TPP_NOSCALE_FROM", 0)) {
+            Pn.out = cur; Pn.omega = (R)(lv == 0 ? knobd("TPP_OVERCORR0", knobd("TPP_OVERCORR", 1.8)) : lv == 1 ? knobd("TPP_OVERCORR1", knobd("TPP_OVERCORR", 1.8)) : knobd("TPP_OVERCORR", 1.8));
             VLAUNCH(ctx, prolong_add, Pn, L.n);
         } else {
             Pn.out = oth;
@@ -1666,11 +1715,17 @@ struct tpp_solver {
             L.omega = omega;
         }
         for (int s = 0; s < std::max(nPost, 1); s++) {
-            if (s == 0) XL<R>(lv, cur);
-            else XLsmooth<R>(lv, cur, 2, oth);
             L.omega = (R)smootherOmega(s, std::max(nPost, 1));
             L.in = cur; L.out = oth;
-            vRowOp(L, 0);
+            if (s == 0 && corrFused) {
+                L.xc = Pn.xc; L.aggF = Pn.agg;
+                L.oc = (R)(lv == 0 ? knobd("TPP_OVERCORR0", knobd("TPP_OVERCORR", 1.8)) : lv == 1 ? knobd("TPP_OVERCORR1", knobd("TPP_OVERCORR", 1.8)) : knobd("TPP_OVERCORR", 1.8));
+                vRowOp(L, 3);
+            } else {
+                if (s == 0) XL<R>(lv, cur);
+                else XLsmooth<R>(lv, cur, 2, oth);
+                vRowOp(L, 0);
+            }
             std::swap(cur, oth);
         }
         if (cur != x) d2d(ctx, x, cur, L.n * sizeof(R));
@@ -2063,6 +2118,15 @@ int tpp_info(tpp_handle s, double* o) try {
     o[8] = s->lastSolve[1].iters; o[9] = s->lastSolve[1].r0; o[10] = s->lastSolve[1].r;
     o[11] = s->d.needRef ? s->d.refCell : -1; o[12] = s->d.deltaN; o[13] = s->writeTimeIndex;
     o[14] = (double)s->levels.size(); o[15] = (double)s->ctx.launches;
+    return 0;
+} API_CATCH(-100)
+int tpp_stats(tpp_handle s, int reset, double* o) try {
+    if (o) {
+        o[0] = s->stSteps; o[1] = s->stIt[0]; o[2] = s->stIt[1]; o[3] = s->stItMax[0]; o[4] = s->stItMax[1]; o[5] = s->stCap;
+        o[6] = s->stVol0; o[7] = s->statsOn ? s->alphaVolume() : 0.0; o[8] = s->stBndInt;
+        dev_sync(s->ctx);
+    }
+    if (reset >= 0) { s->statsOn = reset != 0; if (s->statsOn) s->statsReset(); }
     return 0;
 } API_CATCH(-100)
 int tpp_solve(tpp_handle s, const tpp_solver_t* ctl, const double* diag, const double* upper, const double* b, double* x, double* r0, double* r) try {

@@ -553,3 +553,40 @@ def unstructured_cylinder_mesh(H, D, lc, seed=0, iters=60):
         return (np.abs(z - H).max(axis=1) < eps).astype(np.int64)
 
     return build_polymesh(pts, faces4, fcell, classify, ["walls", "atmosphere"], ["patch", "patch"])
+
+
+def renumbered(mesh: PolyMesh, new_of_old):
+    """The same mesh with cell `c` renamed `new_of_old[c]`, in valid OpenFOAM order again: faces
+    whose owner would exceed their neighbour are flipped (vertex order reversed), internal faces
+    re-sorted upper-triangular, boundary faces keep their patch and their order inside it."""
+    new_of_old = np.asarray(new_of_old, dtype=np.int64)
+    nI, nF = mesh.n_internal, mesh.n_faces
+    off, lab = mesh.face_offsets.astype(np.int64), mesh.face_labels.astype(np.int64)
+    o = new_of_old[mesh.owner.astype(np.int64)]
+    n = new_of_old[mesh.neighbour.astype(np.int64)]
+    flip = np.zeros(nF, dtype=bool)
+    flip[:nI] = o[:nI] > n
+    own_i, nei_i = np.minimum(o[:nI], n), np.maximum(o[:nI], n)
+    order = np.concatenate([np.lexsort((nei_i, own_i)), np.arange(nI, nF)])
+    cnt = np.diff(off)
+    # vertex lists in the new face order; a flipped face keeps its first vertex and reverses the rest
+    starts = off[:-1][order]
+    c2 = cnt[order]
+    new_off = np.zeros(nF + 1, dtype=np.int64)
+    new_off[1:] = np.cumsum(c2)
+    pos = np.arange(new_off[-1]) - np.repeat(new_off[:-1], c2)
+    fl = np.repeat(flip[order], c2)
+    cc = np.repeat(c2, c2)
+    src = np.repeat(starts, c2) + np.where(fl & (pos > 0), cc - pos, pos)
+    new_lab = lab[src]
+    owner = np.concatenate([own_i, o[nI:]])[order]
+    neighbour = nei_i[order[:nI]]
+    zones = {k: np.sort(new_of_old[np.asarray(v, dtype=np.int64)]).astype(np.int32) for k, v in (mesh.cell_zones or {}).items()}
+    return PolyMesh(mesh.points, new_off, new_lab, owner, neighbour, [dict(p) for p in mesh.patches], zones)
+
+
+def shuffled(mesh: PolyMesh, seed=0):
+    """Random cell order (what gmsh + gmshToFoam leave: no spatial coherence between neighbouring
+    cell labels) - the worst case for the gathers; the reference never calls renumberMesh
+    (circularSloshingTank/Makefile:71-86)."""
+    return renumbered(mesh, np.random.default_rng(seed).permutation(mesh.n_cells))

@@ -67,6 +67,7 @@ def load(lib_path=None):
     L.tpp_set_time.argtypes = [H, C.c_double, C.c_double]
     L.tpp_step.argtypes = [H, C.c_int]
     L.tpp_run_to_write.argtypes = [H, C.c_long]
+    L.tpp_stats.argtypes = [H, C.c_int, abi.c_double_p]
     L.tpp_stage.argtypes = [H, C.c_char_p]
     L.tpp_info.argtypes = [H, abi.c_double_p]
     L.tpp_solve.argtypes = [H, C.POINTER(abi.SolverStruct)] + [abi.c_double_p] * 6
@@ -169,6 +170,16 @@ class Solver:
         o = np.zeros(16)
         self.L.tpp_info(self.h, o.ctypes.data_as(abi.c_double_p))
         return dict(zip(INFO_KEYS, o))
+
+    def stats(self, reset=-1):
+        """tpp_stats: iteration statistics and alpha-volume balance since the last reset."""
+        o = np.zeros(9)
+        if self.L.tpp_stats(self.h, int(reset), o.ctypes.data_as(abi.c_double_p)) != 0:
+            self._err("tpp_stats")
+        n = max(o[0], 1.0)
+        return {"steps": int(o[0]), "it0_mean": o[1] / n, "it1_mean": o[2] / n, "it0_max": int(o[3]), "it1_max": int(o[4]), "cap_hits": int(o[5]),
+                "alpha_volume_start": o[6], "alpha_volume": o[7], "alpha_boundary_outflow": o[8],
+                "alpha_balance_rel": abs(o[7] - o[6] + o[8]) / max(abs(o[6]), 1e-300)}
 
     def solve(self, ctl, diag, upper, b, x0=None):
         x = np.zeros(self.mesh.n_cells) if x0 is None else np.array(x0, dtype=np.float64)
