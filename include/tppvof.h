@@ -122,6 +122,12 @@ int tpp_stage(tpp_handle, const char* name);
 
 /* out[16]: t, deltaT, step, Co, alphaCo, iters/initial/final residual of the last p_rgh and
  * p_rghFinal solves, reference cell, deltaN, write index, AMG levels, kernel launches */
+/* Integer addressing as the kernels use it (for the bit-exactness tests of SURVEY.md 8a row a1):
+ * "owner" [n_faces], "neighbour" [n_internal] (lduAddressing, device face order), the cell -> face
+ * ELL table "cf" / "cn" [W x nCp, slot-major: (face << 1) | isNeighbourSide, other cell or -1], and
+ * "layout" = {nC, nCp, W, nI, nB, nGhost}.  Returns the array length. */
+long tpp_get_int(tpp_handle, const char* name, int* out, long cap);
+
 int tpp_info(tpp_handle, double* out16);
 
 /* Run statistics over the steps since the last reset (what an OpenFOAM log is grepped for:

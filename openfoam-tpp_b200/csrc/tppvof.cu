@@ -1630,7 +1630,7 @@ struct tpp_solver {
             L.x = v.tx[t]; L.y = v.ty[t]; L.b = v.tb[t]; L.r = v.tr[t];
         }
         A.bar = tailBar; A.err = tailErr;
-        A.overcorr = (R)knobd("TPP_TAIL_OVERCORR", knobd("TPP_OVERCORR", 1.8));
+        A.overcorr = (R)knobd("TPP_TAIL_OVERCORR", 1.8);
         // 8 CG iterations on the coarsest level give the same PCG counts as 16; fewer sweeps on the
         // small levels cost 1-2 PCG iterations at 6 M cells (tools/knob_sweep.py), so they keep nPre/nPost
         A.nPre = std::min(knob("TPP_TAIL_NPRE", nPre), TAIL_MAXSW); A.nPost = std::min(knob("TPP_TAIL_NPOST", nPost), TAIL_MAXSW);
@@ -1692,17 +1692,21 @@ struct tpp_solver {
         VL<R> Pn = vview<R>(lv + 1);
         Pn.xc = toTail ? v.tx[0] + tailRowOff : v.x[lv + 1];
         // Coarse correction with a FIXED over-correction factor (Braess' remedy for the constant
-        // interpolation of plain aggregation): as many PCG iterations as the energy-minimising
-        // scaling of GAMG's scaleCorrection (measured at 0.4 M and 6.2 M cells: 11 vs 12 and 13-14 vs
-        // 14 iterations of p_rghFinal), without its A c product, its two dot products and - on several
-        // GPUs - their halo exchange and all-reduce on every level of every cycle.  The factor must
-        // stay below 2 (2.2 diverges).  TPP_NOSCALE_FROM=99 restores the scaled correction.
+        // interpolation of plain aggregation) instead of GAMG's energy-minimising scaleCorrection:
+        // no A c product, no dot products and - on several GPUs - no halo exchange / all-reduce for them
+        // on every level of every cycle.  Measured on the 6.2 M-cell tank (B200, 12 steps, p_rghFinal
+        // iterations at the end): scaled everywhere 11-12; 1.6 on the kernel levels + 1.8 in the tail
+        // 10-12 (also with five kernel levels, TPP_TAIL_ROWS=5000: 11-12 vs 12-14 scaled); 1.8 everywhere
+        // does not converge (nested over-corrections compound), nor does 2.2 on a single level.  A solve
+        // that nevertheless stops at maxIter switches the handle back to the scaled correction
+        // (`scaledFallback`).  TPP_NOSCALE_FROM=99 selects the scaled correction outright.
         bool corrFused = false;
-        if (lv >= knob("TPP_NOSCALE_FROM", 0) && !ghosts && (fuse & 2)) {
+        const int noScaleFrom = scaledFallback ? 99 : knob("TPP_NOSCALE_FROM", 0);
+        if (lv >= noScaleFrom && !ghosts && (fuse & 2)) {
             // prolongation, over-correction and the first post-sweep in one pass over the matrix
             corrFused = true;
-        } else if (lv >= knob("TPP_NOSCALE_FROM", 0)) {
-            Pn.out = cur; Pn.omega = (R)(lv == 0 ? knobd("TPP_OVERCORR0", knobd("TPP_OVERCORR", 1.8)) : lv == 1 ? knobd("TPP_OVERCORR1", knobd("TPP_OVERCORR", 1.8)) : knobd("TPP_OVERCORR", 1.8));
+        } else if (lv >= noScaleFrom) {
+            Pn.out = cur; Pn.omega = (R)(lv == 0 ? knobd("TPP_OVERCORR0", overcorrKernel()) : lv == 1 ? knobd("TPP_OVERCORR1", overcorrKernel()) : overcorrKernel());
             VLAUNCH(ctx, prolong_add, Pn, L.n);
         } else {
             Pn.out = oth;
@@ -1719,7 +1723,7 @@ struct tpp_solver {
             L.in = cur; L.out = oth;
             if (s == 0 && corrFused) {
                 L.xc = Pn.xc; L.aggF = Pn.agg;
-                L.oc = (R)(lv == 0 ? knobd("TPP_OVERCORR0", knobd("TPP_OVERCORR", 1.8)) : lv == 1 ? knobd("TPP_OVERCORR1", knobd("TPP_OVERCORR", 1.8)) : knobd("TPP_OVERCORR", 1.8));
+                L.oc = (R)(lv == 0 ? knobd("TPP_OVERCORR0", overcorrKernel()) : lv == 1 ? knobd("TPP_OVERCORR1", overcorrKernel()) : overcorrKernel());
                 vRowOp(L, 3);
             } else {
                 if (s == 0) XL<R>(lv, cur);
@@ -1743,6 +1747,8 @@ struct tpp_solver {
         VLAUNCH(ctx, cast_out, a, nC);
     }
     bool useFp32() const { return knob("TPP_FP32", 1) != 0; }
+    bool scaledFallback = false;  // set when a fixed-factor solve hit maxIter: scaled corrections from then on
+    static double overcorrKernel() { static const double v = knobd("TPP_OVERCORR", 1.6); return v; }
     void precondition(LV& F0, const tpp_solver_t& ctl, const double* r, double* z) {
         if (ctl.type == 0 && ctl.precond == 0) {  // PCG + DIC requested: diagonal preconditioning
             LV L = F0;
@@ -1786,6 +1792,15 @@ struct tpp_solver {
             if (!(fabs(hscal[S_WAPA]) / nf >= VSMALL)) break;
         } while (++st.iters < ctl.max_iter && !conv(st.r));
         if (!std::isfinite(st.r)) fail("the p_rgh solver residual is not finite (diverged)");
+        if (useAMG && !scaledFallback && knob("TPP_NOSCALE_FROM", 0) < 99 && st.iters >= ctl.max_iter && ctl.max_iter >= 20 && !conv(st.r) && st.r > 10 * ctl.tolerance) {
+            // the fixed over-correction factors did not suit this hierarchy: use the adaptive scaling
+            scaledFallback = true;
+#ifndef TPP_EMU
+            for (auto& g : graphs) cudaGraphExecDestroy(g.second.exec);
+            graphs.clear();
+#endif
+            fprintf(stderr, "tppvof: p_rgh solve stopped at maxIter %d (residual %.3g): switching the multigrid to the scaled coarse correction\n", ctl.max_iter, st.r);
+        }
         return st;
     }
 
@@ -2044,6 +2059,21 @@ long tpp_set(tpp_handle s, const char* name, const double* in, long n) try {
         return n;
     }
     h2d(s->ctx, it->second.first, in, n * sizeof(double));
+    return n;
+} API_CATCH(-100)
+long tpp_get_int(tpp_handle s, const char* name, int* out, long cap) try {
+    const int* src = nullptr;
+    long n = 0;
+    if (!strcmp(name, "cf")) { src = s->d.cf; n = (long)s->W * s->nCp; }
+    else if (!strcmp(name, "cn")) { src = s->d.cn; n = (long)s->W * s->nCp; }
+    else if (!strcmp(name, "owner")) { src = s->d.own; n = s->nF; }
+    else if (!strcmp(name, "neighbour")) { src = s->d.nei; n = s->nI; }
+    else if (!strcmp(name, "layout")) {
+        int v[6] = {s->nC, s->nCp, s->W, s->nI, s->nB, s->nG};
+        memcpy(out, v, std::min<long>(cap, 6) * sizeof(int));
+        return 6;
+    } else { g_err = std::string("unknown integer array ") + name; return -1; }
+    if (out) d2h(s->ctx, out, src, std::min(cap, n) * sizeof(int));
     return n;
 } API_CATCH(-100)
 int tpp_device_ptr(tpp_handle s, const char* name, void** ptr, long* n) try {

@@ -68,6 +68,8 @@ def load(lib_path=None):
     L.tpp_step.argtypes = [H, C.c_int]
     L.tpp_run_to_write.argtypes = [H, C.c_long]
     L.tpp_stats.argtypes = [H, C.c_int, abi.c_double_p]
+    L.tpp_get_int.restype = C.c_long
+    L.tpp_get_int.argtypes = [H, C.c_char_p, abi.c_int_p, C.c_long]
     L.tpp_stage.argtypes = [H, C.c_char_p]
     L.tpp_info.argtypes = [H, abi.c_double_p]
     L.tpp_solve.argtypes = [H, C.POINTER(abi.SolverStruct)] + [abi.c_double_p] * 6
@@ -170,6 +172,15 @@ class Solver:
         o = np.zeros(16)
         self.L.tpp_info(self.h, o.ctypes.data_as(abi.c_double_p))
         return dict(zip(INFO_KEYS, o))
+
+    def get_int(self, name):
+        n = self.L.tpp_get_int(self.h, name.encode(), None, 0)
+        if n < 0:
+            raise KeyError(name)
+        a = np.empty(n, dtype=np.int32)
+        if self.L.tpp_get_int(self.h, name.encode(), a.ctypes.data_as(abi.c_int_p), n) < 0:
+            self._err("tpp_get_int")
+        return a
 
     def stats(self, reset=-1):
         """tpp_stats: iteration statistics and alpha-volume balance since the last reset."""

@@ -25,8 +25,65 @@ def load(path, name):
     return m
 
 
+def read_vtp_arrays(path):
+    """The appended-data-free VTP files PyVista wrote for the reference (main.py:773-774): every
+    DataArray is base64( UInt32 header [nblocks, blocksize, lastsize, csize...] ) followed by
+    base64( zlib blocks ).  stdlib only."""
+    import base64
+    import re
+    import struct
+    import zlib
+
+    s = open(path, "rb").read().decode("latin1")
+    out = {}
+    for m in re.finditer(r"<DataArray ([^>]*)>\s*([^<]*)<", s):
+        attrs = dict(re.findall(r'(\w+)="([^"]*)"', m.group(1)))
+        if attrs.get("format") != "binary":
+            continue
+        b64 = m.group(2).strip()
+        nb, _, _ = struct.unpack("<3I", base64.b64decode(b64[:16])[:12])
+        hlen = (3 + nb) * 4
+        hb64 = ((hlen + 2) // 3) * 4
+        csizes = struct.unpack(f"<{nb}I", base64.b64decode(b64[:hb64])[12:hlen])
+        data = base64.b64decode(b64[hb64:])
+        raw, off = b"", 0
+        for c in csizes:
+            raw += zlib.decompress(data[off : off + c])
+            off += c
+        dt = {"Float32": "<f4", "Float64": "<f8", "Int64": "<i8", "Int32": "<i4", "UInt8": "u1"}[attrs["type"]]
+        a = np.frombuffer(raw, dt)
+        nc = int(attrs.get("NumberOfComponents", "1"))
+        out[attrs.get("Name", "?")] = a.reshape(-1, nc) if nc > 1 else a
+    return out
+
+
+def g4_series():
+    """G4: the reference's 401 committed iso-surfaces (case_..._m0.009/postProcessing/interface/
+    interface_t*.vtp, lab frame) reduced frame by frame with the repo's own `iso_wall_mode1` in the
+    tank frame (orbit centre from the reference's generate_motion.py law, ramp 2 s: main.py:111-112)."""
+    import glob
+    import re
+
+    from openfoam_tpp_b200 import interface
+
+    d = os.path.join(REF, "case_H0.208_D0.2_flat_R0.004_f1.88_d20.0_m0.009", "postProcessing", "interface")
+    tt = lambda p: float(re.search(r"t([\d.]+)\.vtp", p).group(1))
+    rows = []
+    for p in sorted(glob.glob(os.path.join(d, "interface_t*.vtp")), key=tt):
+        t = tt(p)
+        P = read_vtp_arrays(p)["Points"].astype(np.float64)
+        tau = min(t / 2.0, 1.0)
+        r = 0.004 * (tau * tau * tau * (tau * (tau * 6 - 15) + 10))
+        c = (r * np.cos(2 * np.pi * 1.88 * t), r * np.sin(2 * np.pi * 1.88 * t))
+        A, ph, z0, n = interface.iso_wall_mode1(P, c, 0.1)
+        rows.append((t, A, ph, z0, n, P[:, 2].max(), P[:, 2].min(), P[:, 2].mean(), len(P)))
+    return np.array(rows)
+
+
 def main():
     out = {}
+    g4 = g4_series()
+    np.savetxt(os.path.join(HERE, "g4_m1_series.csv"), g4, delimiter=",", fmt="%.9g", header="time,A_m1,phase_m1,z0,n_wall_points,max_z,min_z,mean_z,n_points", comments="")
     # G1: post-setFields alpha.water (binary volScalarField written by OpenFOAM 13)
     from openfoam_tpp_b200 import foamfile as ff
 

@@ -79,3 +79,63 @@ def test_make_run_stops_loudly_without_a_gpu(tmp_path):
         # only the solver step itself reports the failure)
         assert ncpu > 1 or r.returncode != 0, out[-2000:]
         assert "FOAM FATAL ERROR" in out and ("no CPU path" in out or "CUDA" in out or "no usable" in out), out[-2000:]
+
+
+def _tighten(case_dir):
+    """p_rgh solves to round-off so that two different (valid) linear solvers give the same fields"""
+    p = os.path.join(case_dir, "system", "fvSolution")
+    s = open(p).read()
+    import re
+
+    s = re.sub(r"tolerance\s+[0-9.e+-]+;", "tolerance       1e-13;", s)
+    s = re.sub(r"relTol\s+[0-9.e+-]+;", "relTol          0;", s)
+    s = re.sub(r"maxIter\s+\d+;", "maxIter         500;", s)
+    open(p, "w").write(s)
+
+
+import pytest  # noqa: E402
+
+
+@pytest.mark.gpu
+def test_make_run_on_the_gpu_matches_the_oracle(tmp_path, gpu_lib):
+    """SURVEY.md section 8a row a15 end to end on the device: `PATH=tools/shims:$PATH make run` (the
+    reference's recipe: gmshToFoam, setFields, foamRun) writes OpenFOAM time directories and
+    postProcessing/probes/0/p; the oracle steps the same case; every written time agrees."""
+    import oracle
+    from openfoam_tpp_b200 import case as cs2
+
+    d, mesh = _case(tmp_path)
+    _tighten(d)
+    # probes inside the tank (the reference's own locations lie outside every mesh, system/functions:25-26)
+    fp = os.path.join(d, "system", "functions")
+    s = open(fp).read().replace("(0 9.95 19.77)", "(0.002 0.001 0.001)").replace("(0 -9.95 19.77)", "(-0.003 0.002 0.003)")
+    open(fp, "w").write(s)
+    r = subprocess.run(["make", "run", "N_CPUS=1"], cwd=d, env=_env(), capture_output=True, text=True, timeout=900)
+    assert r.returncode == 0, (r.stdout + r.stderr)[-3000:]
+    assert "End" in r.stdout
+    times = [(v, nm) for v, nm in ff.time_dirs(d) if v > 0]
+    assert len(times) >= 1 and abs(times[-1][0] - 0.01) < 1e-12, times
+    c = cs2.Case(d)  # after gmshToFoam + setFields: the mesh and 0/ the solver saw ...
+    c.start_value, c.start_name = 0.0, "0"
+    c.fields = {nm: ff.read_field(os.path.join(d, "0", nm)) for nm in ("alpha.water", "U", "p_rgh")}
+    c.cfg.start_time = 0.0
+    o = oracle.Oracle(c.mesh, c.cfg)
+    o.load_case_fields(c)
+    cells = [o.find_cell(x) for x in c.cfg.probes]
+    assert all(k >= 0 for k in cells)
+    o.set_probes(cells)
+    nC = c.mesh.n_cells
+    for v, nm in times:
+        assert o.run_to_write() == 1
+        assert abs(o.info()["t"] - v) < 1e-12
+        for fld, key, tol in (("alpha.water", "alpha", 1e-9), ("U", "U", 1e-7), ("p_rgh", "p_rgh", 1e-7), ("p", "p", 1e-7), ("rho", "rho", 1e-9)):
+            a = ff.read_field(os.path.join(d, nm, fld)).internal_array(nC).reshape(-1)
+            b = o.get(key)
+            assert np.abs(a - b).max() <= tol * max(np.abs(b).max(), 1e-300), (nm, fld, np.abs(a - b).max())
+        assert os.path.exists(os.path.join(d, nm, "polyMesh", "points")) and os.path.exists(os.path.join(d, nm, "uniform", "time"))
+    # probes file: header + one row per step (plus the start row), values = the oracle's p at the probe cells
+    rows = np.loadtxt(os.path.join(d, "postProcessing", "probes", "0", "p"), comments="#")
+    log = np.asarray(o.probe_log()).reshape(-1, 1 + len(cells))
+    assert rows.shape[0] == log.shape[0] + 1 and rows.shape[1] == 1 + len(cells)
+    assert np.allclose(rows[1:, 0], log[:, 0], rtol=1e-5)       # times are printed with 6 significant digits
+    assert np.allclose(rows[1:, 1:], log[:, 1:], rtol=2e-5, atol=1e-4 * np.abs(log[:, 1:]).max())
