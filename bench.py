@@ -202,6 +202,96 @@ def run_reference(args):
     print(json.dumps(line))
 
 
+SMALL = {
+    # BASELINE.json configs 1-3 as concrete synthetic cases; meshes from the repo's
+    # generators, sized like the reference's own (cfg1: 7 766 gmsh tets -> 7 776 here)
+    "cfg1": dict(name="case_H0.004_D0.0221_flat_R0.005_f2.0", H=0.004, D=0.0221, geo="flat", R=0.005, freq=2.0, n_rings=12, n_layers=3),
+    "cfg3": dict(name="case_H0.004_D0.0221_cap_R0.005_f2.0", H=0.004, D=0.0221, geo="cap", R=0.005, freq=2.0, n_rings=12, n_layers=3),
+}
+
+
+def small_config(which):
+    """(mesh, config, initial alpha, workload text) of cfg1 / cfg2 / cfg3, through the ordinary case-directory
+    path (template + motion table + mesh + setFields, then the case reader)."""
+    import tempfile
+
+    from openfoam_tpp_b200 import case as cs
+
+    with tempfile.TemporaryDirectory() as tmp:
+        d = os.path.join(tmp, "case")
+        if which == "cfg2":
+            cs.setup_tutorial_case(d, nx=20, ny=40, nz=30)
+            text = "cfg2 sloshingTank3D6DoF: closed tutorial tank, 20 x 40 x 30 hexes, tabulated 6-DoF motion (gen6DoF restated), p reference cell"
+        else:
+            c = SMALL[which]
+            cs.setup_case(d, H=c["H"], D=c["D"], geo=c["geo"], R=c["R"], freq=c["freq"], duration=10.0, n_rings=c["n_rings"], n_layers=c["n_layers"])
+            text = f"{which} {c['name']}: tets, n_rings {c['n_rings']}, n_layers {c['n_layers']}, orbital shaking {c['freq']} Hz (ramp 1 s)"
+        case = cs.Case(d)
+        a0 = case.fields["alpha.water"].internal_array(case.mesh.n_cells).copy()
+    return case.mesh, case.cfg, a0, text + f", {case.mesh.n_cells} cells"
+
+
+def run_sweep_config(args):
+    """cfg5: the 64-case sweep of BASELINE.json (H x R x f grid in main.py's range syntax) sharded over the
+    ranks, --cases-per-gpu cases at a time on every GPU (one host thread + one CUDA stream each).  value =
+    all cell-steps of the sweep / the slowest rank's wall time; every case runs --steps steps."""
+    import tempfile
+    import time as _t
+
+    import torch
+
+    from openfoam_tpp_b200 import ensemble
+
+    rank = int(os.environ.get("RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    if not torch.cuda.is_available():
+        raise SystemExit("bench.py needs a CUDA device: the solver has no CPU path")
+    torch.cuda.set_device(local)
+    if world > 1:
+        import torch.distributed as dist
+
+        with stdout_to_stderr():
+            dist.init_process_group("nccl", device_id=torch.device("cuda", local))
+            dist.barrier()
+    base = {"H": 0.004, "D": 0.0221, "geo": "flat", "R": 0.005, "freq": 2.0, "duration": 10.0, "mesh": 0.0009}
+    sweeps = {"H": ensemble.parse_range("0.004,0.008"), "R": ensemble.parse_range("0.002:0.001:0.005"), "freq": ensemble.parse_range("1.6:0.2:3.0")}
+    lc_to_mesh = lambda p: (12, 3 if p["H"] < 0.006 else 6)  # 7 776 / 15 552 tets: the reference's small-case sizes
+    sampler = ClockSampler(local)
+    out = {}
+    with tempfile.TemporaryDirectory() as tmp, stdout_to_stderr():
+        # set-up (meshes, dictionaries, setFields) and a warm-up of --warmup steps are not timed
+        ensemble.run_sweep(tmp, base, sweeps, lc_to_mesh=lc_to_mesh, max_steps=args.warmup, log=None, cases_per_gpu=args.cases_per_gpu, write=False)
+        torch.cuda.synchronize()
+        if world > 1:
+            dist.barrier()
+        for mode, per in (("concurrent", args.cases_per_gpu), ("sequential", 1)):
+            if mode == "concurrent":
+                sampler.start()
+            t0 = _t.perf_counter()
+            done = ensemble.run_sweep(tmp, base, sweeps, lc_to_mesh=lc_to_mesh, max_steps=args.steps, log=None, cases_per_gpu=per, write=False)
+            torch.cuda.synchronize()
+            sec = _t.perf_counter() - t0
+            if mode == "concurrent":
+                sampler.stop_flag = True
+            sec = ensemble.max_over_ranks([sec])[0]
+            cs_ = ensemble.sum_over_ranks([float(sum(o["cells"] * o["steps"] for _, o in done)), float(sum(o["steps"] for _, o in done)), float(len(done))])
+            out[mode] = {"seconds": sec, "cell_steps": cs_[0], "steps": cs_[1], "cases": int(cs_[2])}
+    if rank == 0:
+        c = out["concurrent"]
+        line = {"metric": METRIC, "value": c["cell_steps"] / c["seconds"] / 1e6, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
+                "ms_per_step": c["seconds"] / max(args.steps, 1) * 1e3, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
+                "config": {"workload": f"cfg5: {c['cases']} sweep cases (H 0.004,0.008 x R 0.002:0.001:0.005 x f 1.6:0.2:3.0, D 0.0221 flat, 7 776 / 15 552 tets), {args.steps} steps each after {args.warmup} warm-up steps, through foamrun.run_case (case directories, no field writes)",
+                           "parallelism": f"ensemble: cases dealt round-robin to {world} GPU(s), {args.cases_per_gpu} concurrent cases (host threads / CUDA streams) per GPU, no collective",
+                           "vof_steps_per_s": c["steps"] / c["seconds"], "vof_steps_per_s_one_case_at_a_time": out["sequential"]["steps"] / out["sequential"]["seconds"],
+                           "concurrency_gain": out["sequential"]["seconds"] / c["seconds"], "l2": "every case lives in L2 (a few MB): latency-bound, no HBM roofline (BASELINE.md section 4)"},
+                "clocks": sampler.summary(), "gpu_launches": None, "e2e": {"value": c["cell_steps"] / c["seconds"] / 1e6, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0, "note": "the sweep is timed end to end on the host clock (case directory in, solver stepping through the C-ABI)"},
+                "roofline": None, "cpu_baseline": None}
+        print(json.dumps(line))
+    if world > 1:
+        dist.destroy_process_group()
+
+
 def parity_nranks(rank, world, local, dist, steps=3):
     """N > 1, before the timed loop (what `mpirun -np N foamRun -parallel` must guarantee,
     circularSloshingTank/Makefile:75-82): a ~100 k-cell tank decomposed into `world` z-slabs steps
@@ -262,7 +352,10 @@ def main():
     ap.add_argument("--no-cpu", action="store_true")
     ap.add_argument("--kernel-table", default=None, help="write the full per-kernel table (launches, ms, algorithmic GB/s) of the profiled steps to this JSON file")
     ap.add_argument("--mode", default="decomposed", choices=["decomposed", "ensemble"], help="N > 1: one tank over N GPUs (halo exchange) or N independent sweep cases")
-    ap.add_argument("--t0", type=float, default=2.0, help="start time of the run: 2.0 = the end of the shaker's ramp (full orbit amplitude, SURVEY.md 8d); 0 = from rest")
+    ap.add_argument("--config", default="cfg4", choices=["cfg1", "cfg2", "cfg3", "cfg4", "cfg5"],
+                    help="BASELINE.json configs: cfg4 (default) = the refined D 0.2 m tank, the configuration the metric is quoted on; cfg1 / cfg3 = the small flat / cap cylinders, cfg2 = the sloshingTank3D6DoF tutorial tank, cfg5 = the 64-case sweep (cases sharded over the GPUs, --cases-per-gpu at a time on each)")
+    ap.add_argument("--cases-per-gpu", type=int, default=8)
+    ap.add_argument("--t0", type=float, default=None, help="start time of the run: 2.0 = the end of the shaker's ramp (full orbit amplitude, SURVEY.md 8d); 0 = from rest")
     ap.add_argument("--spinup", type=int, default=45, help="untimed steps before the --warmup steps (start-up transient of the impulsively started tank)")
     ap.add_argument("--order", default="structured", choices=["structured", "gmsh"], help="cell order of the mesh file: the generator's (layer by layer) or a random one, as a gmsh mesh has")
     ap.add_argument("--no-parity", action="store_true", help="N > 1: skip the decomposed-vs-whole check before the timed loop")
@@ -271,6 +364,10 @@ def main():
         return run_reference(args)
     if args.warmup < 3:
         args.warmup = 3
+    if args.t0 is None:
+        args.t0 = 2.0 if args.config == "cfg4" else 0.0
+    if args.config == "cfg5":
+        return run_sweep_config(args)
 
     import torch
 
@@ -309,6 +406,9 @@ def main():
         mesh = meshgen.cylinder_mesh(CASE["H"], CASE["D"], nr, nl, "flat", "tet", k0=k0, k1=k1,
                                      proc=(rank, rank - 1 if rank > 0 else None, rank + 1 if rank < world - 1 else None))
         cfg = make_config(mesh)
+    elif args.config != "cfg4":
+        mesh, cfg, a0, workload = small_config(args.config)
+        nr = nl = 0
     else:
         mesh, nr, nl = mesh_for(args.cells)
         cfg = make_config(mesh)
@@ -329,7 +429,9 @@ def main():
         with stdout_to_stderr():
             g.comm_init_nccl()
             torch.cuda.synchronize()
-    a0 = initial_alpha(mesh)
+    if args.config == "cfg4":
+        a0 = initial_alpha(mesh)
+        workload = f"cfg4 case_H0.208_D0.2_flat_R0.004_f1.88 tet mesh refined to {nC} cells per GPU (n_rings {nr}, n_layers {nl})"
     g.set("alpha", a0)
     g.init_fields()
 
@@ -469,7 +571,7 @@ def main():
         line = {
             "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
             "ms_per_step": sec / args.steps * 1e3, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
-            "config": {"workload": f"cfg4 case_H0.208_D0.2_flat_R0.004_f1.88 tet mesh refined to {nC} cells per GPU (n_rings {nr}, n_layers {nl})",
+            "config": {"workload": workload, "launches_per_step": launches / max(args.steps, 1) / world,
                        "cells_per_gpu": nC, "internal_faces_per_gpu": nI, "parallelism": "single GPU" if world == 1 else (f"one tank decomposed into {world} z-slabs (simple (1 1 {world})), NCCL halo exchange + all-reduced Krylov dots, {total_cells} cells in total" if decomposed else f"ensemble: {world} independent sweep cases (f = {freqs[0]}..{freqs[-1]} Hz), one per GPU, no collective"),
                        "l2": "working set (>1 kB/cell) far exceeds the 126 MB L2; no flush needed",
                        "vof_steps_per_s": args.steps / sec, "solver_iters_last_step": [int(info["it0"]), int(info["it1"])], "amg_levels": int(info["levels"]),

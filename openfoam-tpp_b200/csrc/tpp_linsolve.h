@@ -190,7 +190,7 @@ DEF_KERNEL(match_root, LV)
 // reductions and fused Krylov kernels (fixed grid -> fixed summation order)
 // ---------------------------------------------------------------------------------------
 // scal[] layout on the device
-enum { S_WARA = 0, S_WARA_OLD, S_WAPA, S_RES, S_NORM, S_XSUM, S_TMP0, S_TMP1, S_MAX0, S_MAX1, S_COUNT = 16 };
+enum { S_WARA = 0, S_WARA_OLD, S_WAPA, S_RES, S_NORM, S_XSUM, S_TMP0, S_TMP1, S_MAX0, S_MAX1, S_DONE, S_ITERS, S_TOLA, S_TOLR, S_MAXIT, S_COUNT = 16 };
 
 #ifndef TPP_EMU
 DEV double block_sum(double v) {
@@ -301,6 +301,7 @@ __global__ void __launch_bounds__(256) k_spmv_dot_ell2(LV L, double* partial) {
 }
 // x += alpha pA ; r -= alpha wA ; partial sums of |r|   (alpha = scal[WARA]/scal[WAPA])
 __global__ void __launch_bounds__(256) k_update_xr(int n, double* x, double* r, const double* pA, const double* wA, const double* scal, double* partial) {
+    if (scal[S_DONE] != 0.0) return;  // converged earlier in this chunk of iterations: x, r and the partial sums stay
     double alpha = scal[S_WARA] / scal[S_WAPA];
     double v = 0;
     for (int c = blockIdx.x * blockDim.x + threadIdx.x; c < n; c += gridDim.x * blockDim.x) {
@@ -337,6 +338,20 @@ __global__ void __launch_bounds__(256) k_init_residual(LV L, const double* x, co
     if (threadIdx.x == 0) { partialRes[blockIdx.x] = v; partialNorm[blockIdx.x] = w; }
 }
 __global__ void k_scal_copy(double* scal, int dst, int src) { scal[dst] = scal[src]; }
+// End of a PCG iteration, on the device: count it and apply OpenFOAM's stopping rule (residual
+// below tolerance or relTol * initial, singular search direction, maxIter), so that a short solve
+// can run several iterations per host round trip and still stop at exactly the same iteration.
+// Thresholds are pre-multiplied by the normFactor: S_RES is the raw L1 norm.
+__global__ void k_pcg_check(double* scal) {
+    if (scal[S_DONE] != 0.0) return;
+    const double it = scal[S_ITERS] + 1.0, res = scal[S_RES];
+    scal[S_ITERS] = it;
+    if (res < scal[S_TOLA] || res < scal[S_TOLR] || !(fabs(scal[S_WAPA]) >= scal[S_NORM] * VSMALL) || it >= scal[S_MAXIT] || !(res == res)) scal[S_DONE] = 1.0;
+}
+__global__ void k_pcg_begin(double* scal, double tolA, double tolR, double maxIt) {
+    scal[S_DONE] = 0.0; scal[S_ITERS] = 0.0; scal[S_TOLA] = tolA; scal[S_TOLR] = tolR; scal[S_MAXIT] = maxIt;
+    scal[S_WARA] = 0.0;  // WARA_OLD == 0 marks the first iteration for k_update_p
+}
 
 
 // ---- halo exchange over peer memory (NVLink / NVSwitch), one kernel per exchange ---------------

@@ -25,6 +25,13 @@ namespace {
 thread_local std::string g_err;
 // every C-ABI entry point is a function-try-block ending in API_CATCH: nothing escapes as an
 // exception or an abort(); the message is kept for tpp_last_error()
+#ifdef TPP_EMU
+#define API_DEVICE(s) (void)0
+#else
+// a handle may be driven from any host thread (one thread per concurrent sweep case): make its
+// device current for the calling thread
+#define API_DEVICE(s) do { if ((s) != nullptr) cudaSetDevice((s)->device); } while (0)
+#endif
 #define API_CATCH(code)                                                                         \
     catch (const tpp::CudaFailure& e) { g_err = e.what; fprintf(stderr, "tppvof: %s\n", g_err.c_str()); return (code); } \
     catch (const std::exception& e) { g_err = std::string("internal error: ") + e.what(); return (code); }               \
@@ -1783,14 +1790,27 @@ struct tpp_solver {
         st.r0 = st.r = hscal[S_RES] / nf;
         auto conv = [&](double r) { return r < ctl.tolerance || (ctl.rel_tol > 0 && r < ctl.rel_tol * st.r0); };
         if (conv(st.r)) return st;
-        scalSet(S_WARA, 0.0);  // WARA_OLD == 0 marks the first iteration for k_update_p
+        // The stopping rule runs on the device (k_pcg_check after every iteration).  Large meshes read the
+        // scalars back after every iteration (an iteration is ~1 ms, the round trip nothing); small ones
+        // (the reference's own 8 k - 42 k-cell cases) launch as many iterations as the previous solve of
+        // this kind took, less one, before the first read-back: a converged solve ignores the rest of its
+        // chunk (k_update_xr returns at once), so the result is the same as with a check per iteration.
+        pcgBegin(ctl.tolerance * nf, ctl.rel_tol > 0 ? ctl.rel_tol * st.r0 * nf : -1.0, (double)ctl.max_iter);
         dev_zero(ctx, kp, nC * sizeof(double));
-        do {
-            iteration(F0, FG, ctl, x);
+        const int which = &ctl == &cfg.p_rgh_final ? 1 : 0;
+        const bool chunked = knob("TPP_CHUNK", nGlobal < 500000 ? 1 : 0) != 0 && !ctx.prof;
+        int chunk = chunked ? std::max(1, std::min(lastIters[which] - 1, ctl.max_iter)) : 1;
+        int launched = 0;
+        while (true) {
+            for (int k = 0; k < chunk; k++) iteration(F0, FG, ctl, x);
+            launched += chunk;
             readScal();
-            st.r = hscal[S_RES] / nf;
-            if (!(fabs(hscal[S_WAPA]) / nf >= VSMALL)) break;
-        } while (++st.iters < ctl.max_iter && !conv(st.r));
+            if (hscal[S_DONE] != 0.0 || launched >= ctl.max_iter) break;
+            chunk = 1;
+        }
+        st.iters = (int)(hscal[S_ITERS] + 0.5);
+        st.r = hscal[S_RES] / nf;
+        lastIters[which] = st.iters;
         if (!std::isfinite(st.r)) fail("the p_rgh solver residual is not finite (diverged)");
         if (useAMG && !scaledFallback && knob("TPP_NOSCALE_FROM", 0) < 99 && st.iters >= ctl.max_iter && ctl.max_iter >= 20 && !conv(st.r) && st.r > 10 * ctl.tolerance) {
             // the fixed over-correction factors did not suit this hierarchy: use the adaptive scaling
@@ -1816,6 +1836,7 @@ struct tpp_solver {
         allreduce(S_WAPA, 1, 0);
         updateXR(x);
         allreduce(S_RES, 1, 0);
+        pcgCheck();
     }
     // (The FP64 V-cycle, TPP_FP32=0, once produced NaNs under graph replay; that was the
     // allocation-time memset racing a non-blocking caller stream, fixed in dev_alloc - it is
@@ -1847,6 +1868,27 @@ struct tpp_solver {
         }
 #endif
         iterationBody(F0, FG, ctl, x);
+    }
+    int lastIters[2] = {1, 1};
+    void pcgCheck() {
+#ifdef TPP_EMU
+        if (scal[S_DONE] == 0.0) {
+            scal[S_ITERS] += 1.0;
+            const double res = scal[S_RES];
+            if (res < scal[S_TOLA] || res < scal[S_TOLR] || !(fabs(scal[S_WAPA]) >= scal[S_NORM] * VSMALL) || scal[S_ITERS] >= scal[S_MAXIT] || !(res == res)) scal[S_DONE] = 1.0;
+        }
+#else
+        k_pcg_check<<<1, 1, 0, ctx.stream>>>(scal);
+#endif
+        ctx.launches++;
+    }
+    void pcgBegin(double tolA, double tolR, double maxIt) {
+#ifdef TPP_EMU
+        scal[S_DONE] = 0.0; scal[S_ITERS] = 0.0; scal[S_TOLA] = tolA; scal[S_TOLR] = tolR; scal[S_MAXIT] = maxIt; scal[S_WARA] = 0.0;
+#else
+        k_pcg_begin<<<1, 1, 0, ctx.stream>>>(scal, tolA, tolR, maxIt);
+#endif
+        ctx.launches++;
     }
     void scalSet(int dst, double v) {
 #ifdef TPP_EMU
@@ -1917,9 +1959,11 @@ struct tpp_solver {
     }
     void updateXR(double* x) {
 #ifdef TPP_EMU
-        double alpha = scal[S_WARA] / scal[S_WAPA], v = 0;
-        for (int c = 0; c < nC; c++) { x[c] += alpha * kp[c]; kr[c] -= alpha * kw[c]; v += fabs(kr[c]); }
-        scal[S_RES] = v;
+        if (scal[S_DONE] == 0.0) {
+            double alpha = scal[S_WARA] / scal[S_WAPA], v = 0;
+            for (int c = 0; c < nC; c++) { x[c] += alpha * kp[c]; kr[c] -= alpha * kw[c]; v += fabs(kr[c]); }
+            scal[S_RES] = v;
+        }
 #else
         prof_begin(ctx, "update_xr");
         const int nb = std::min(RED_BLOCKS, (nC + BLOCK - 1) / BLOCK);
@@ -2010,6 +2054,7 @@ static void pointsNow(tpp_solver* s, std::vector<double>& out) {
 }
 
 long tpp_size(tpp_handle s, const char* name) try {
+    API_DEVICE(s);
     if (!strcmp(name, "points")) return 3L * s->nP;
     auto it = s->reg.find(name);
     return it == s->reg.end() ? -1 : it->second.second;
@@ -2025,6 +2070,7 @@ static int faceComp(tpp_solver* s, const char* name) {
     return 0;
 }
 long tpp_get(tpp_handle s, const char* name, double* out, long cap) try {
+    API_DEVICE(s);
     if (!strcmp(name, "points")) {
         std::vector<double> p;
         pointsNow(s, p);
@@ -2046,6 +2092,7 @@ long tpp_get(tpp_handle s, const char* name, double* out, long cap) try {
     return it->second.second;
 } API_CATCH(-100)
 long tpp_set(tpp_handle s, const char* name, const double* in, long n) try {
+    API_DEVICE(s);
     auto it = s->reg.find(name);
     if (it == s->reg.end()) { g_err = std::string("unknown array ") + name; return -1; }
     if (n != it->second.second) { g_err = std::string("size mismatch for ") + name; return -2; }
@@ -2062,6 +2109,7 @@ long tpp_set(tpp_handle s, const char* name, const double* in, long n) try {
     return n;
 } API_CATCH(-100)
 long tpp_get_int(tpp_handle s, const char* name, int* out, long cap) try {
+    API_DEVICE(s);
     const int* src = nullptr;
     long n = 0;
     if (!strcmp(name, "cf")) { src = s->d.cf; n = (long)s->W * s->nCp; }
@@ -2077,6 +2125,7 @@ long tpp_get_int(tpp_handle s, const char* name, int* out, long cap) try {
     return n;
 } API_CATCH(-100)
 int tpp_device_ptr(tpp_handle s, const char* name, void** ptr, long* n) try {
+    API_DEVICE(s);
     auto it = s->reg.find(name);
     if (it == s->reg.end()) { g_err = std::string("unknown array ") + name; return -1; }
     *ptr = it->second.first;
@@ -2084,6 +2133,7 @@ int tpp_device_ptr(tpp_handle s, const char* name, void** ptr, long* n) try {
     return 0;
 } API_CATCH(-100)
 int tpp_init_fields(tpp_handle s) try {
+    API_DEVICE(s);
     s->alphaBCs();
     s->mixture();
     s->X(s->d.alpha, 1); s->X(s->d.rho, 1); s->X(s->d.U, 3); s->X(s->d.p_rgh, 1);
@@ -2093,6 +2143,7 @@ int tpp_init_fields(tpp_handle s) try {
 } API_CATCH(-100)
 int tpp_set_delta_t(tpp_handle s, double dt) { s->dt = s->dt0 = dt; return 0; }
 int tpp_set_time(tpp_handle s, double t, double dt) try {
+    API_DEVICE(s);
     s->t = t; s->dt = s->dt0 = dt;
     s->motionAt(t, s->Rn, s->Tn);
     memcpy(s->Ro, s->Rn, sizeof(s->Rn)); memcpy(s->To, s->Tn, sizeof(s->Tn));
@@ -2103,12 +2154,14 @@ int tpp_set_time(tpp_handle s, double t, double dt) try {
 } API_CATCH(-100)
 
 int tpp_step(tpp_handle s, int n) try {
+    API_DEVICE(s);
     for (int i = 0; i < n && s->ctx.err.empty(); i++) s->oneStep();
     dev_sync(s->ctx);
     if (!s->ctx.err.empty()) { g_err = s->ctx.err; return -1; }
     return 0;
 } API_CATCH(-100)
 int tpp_run_to_write(tpp_handle s, long max_steps) try {
+    API_DEVICE(s);
     for (long i = 0; i < max_steps; i++) {
         if (!(s->t < s->cfg.end_time - 0.5 * s->dt)) { dev_sync(s->ctx); return 0; }
         const bool wr = s->oneStep();
@@ -2119,6 +2172,7 @@ int tpp_run_to_write(tpp_handle s, long max_steps) try {
     return 2;
 } API_CATCH(-100)
 int tpp_stage(tpp_handle s, const char* name) try {
+    API_DEVICE(s);
     std::string n(name);
     s->d.dt = s->dt;
     if (n == "courant") s->courant();
@@ -2143,6 +2197,7 @@ int tpp_stage(tpp_handle s, const char* name) try {
     return 0;
 } API_CATCH(-100)
 int tpp_info(tpp_handle s, double* o) try {
+    API_DEVICE(s);
     o[0] = s->t; o[1] = s->dt; o[2] = (double)s->step; o[3] = s->Co; o[4] = s->alphaCo;
     o[5] = s->lastSolve[0].iters; o[6] = s->lastSolve[0].r0; o[7] = s->lastSolve[0].r;
     o[8] = s->lastSolve[1].iters; o[9] = s->lastSolve[1].r0; o[10] = s->lastSolve[1].r;
@@ -2151,6 +2206,7 @@ int tpp_info(tpp_handle s, double* o) try {
     return 0;
 } API_CATCH(-100)
 int tpp_stats(tpp_handle s, int reset, double* o) try {
+    API_DEVICE(s);
     if (o) {
         o[0] = s->stSteps; o[1] = s->stIt[0]; o[2] = s->stIt[1]; o[3] = s->stItMax[0]; o[4] = s->stItMax[1]; o[5] = s->stCap;
         o[6] = s->stVol0; o[7] = s->statsOn ? s->alphaVolume() : 0.0; o[8] = s->stBndInt;
@@ -2160,6 +2216,7 @@ int tpp_stats(tpp_handle s, int reset, double* o) try {
     return 0;
 } API_CATCH(-100)
 int tpp_solve(tpp_handle s, const tpp_solver_t* ctl, const double* diag, const double* upper, const double* b, double* x, double* r0, double* r) try {
+    API_DEVICE(s);
     h2d(s->ctx, s->d.pDiag, diag, s->nC * sizeof(double));
     h2d(s->ctx, s->d.pUpper, upper, s->nI * sizeof(double));
     h2d(s->ctx, s->d.pSource, b, s->nC * sizeof(double));
@@ -2172,6 +2229,7 @@ int tpp_solve(tpp_handle s, const tpp_solver_t* ctl, const double* diag, const d
 } API_CATCH(-100)
 int tpp_set_probes(tpp_handle s, int n, const int* cells) { s->probeCells.assign(cells, cells + n); return 0; }
 long tpp_probe_log(tpp_handle s, double* out, long cap_rows) try {
+    API_DEVICE(s);
     long w = 1 + (long)s->probeCells.size();
     long rows = (long)s->probeLog.size() / w;
     long n = std::min(rows, cap_rows);
@@ -2181,6 +2239,7 @@ long tpp_probe_log(tpp_handle s, double* out, long cap_rows) try {
 } API_CATCH(-100)
 int tpp_find_cell(tpp_handle s, const double* xyz) { return s->findCell(xyz); }
 int tpp_use_stream(tpp_handle s, void* stream) try {
+    API_DEVICE(s);
 #ifndef TPP_EMU
     cudaStreamSynchronize(s->ctx.stream);
     if (s->ctx.ownStream) cudaStreamDestroy(s->ctx.stream);
@@ -2192,10 +2251,12 @@ int tpp_use_stream(tpp_handle s, void* stream) try {
     return 0;
 } API_CATCH(-100)
 int tpp_profile(tpp_handle s, int on) try {
+    API_DEVICE(s);
     s->ctx.prof = on != 0;
     return 0;
 } API_CATCH(-100)
 long tpp_profile_report(tpp_handle s, char* buf, long cap) try {
+    API_DEVICE(s);
     dev_sync(s->ctx);
     std::map<std::string, std::pair<long, double>> agg;
     for (auto& r : s->ctx.recs) {
@@ -2221,6 +2282,7 @@ long tpp_profile_report(tpp_handle s, char* buf, long cap) try {
     return (long)out.size();
 } API_CATCH(-100)
 int tpp_amg_levels(tpp_handle s, int* n_rows, int* n_faces, int cap) try {
+    API_DEVICE(s);
     int k = 0;
     if (k < cap) { n_rows[k] = s->nC; n_faces[k] = s->nIloc; }
     k++;
@@ -2229,6 +2291,7 @@ int tpp_amg_levels(tpp_handle s, int* n_rows, int* n_faces, int cap) try {
     return k;
 } API_CATCH(-100)
 int tpp_amg_layout(tpp_handle s, int* out4) try {
+    API_DEVICE(s);
     out4[0] = s->levels.empty() ? 0 : s->vLevels();
     out4[1] = (int)s->tail.size();
     out4[2] = s->tail.empty() ? 0 : s->tail[0].n;
@@ -2236,12 +2299,14 @@ int tpp_amg_layout(tpp_handle s, int* out4) try {
     return 0;
 } API_CATCH(-100)
 int tpp_ghost_layout(tpp_handle s, int* n_ghost, int* n_patches, int* off, int* cnt, int* peer, int cap) try {
+    API_DEVICE(s);
     *n_ghost = s->nG;
     *n_patches = (int)s->procCnt.size();
     for (int i = 0; i < (int)s->procCnt.size() && i < cap; i++) { off[i] = s->procOff[i]; cnt[i] = s->procCnt[i]; peer[i] = s->procPeer[i]; }
     return 0;
 } API_CATCH(-100)
 int tpp_comm_callbacks(tpp_handle s, int rank, int n_ranks, exchange_cb_t xcb, allreduce_cb_t rcb, void* user) try {
+    API_DEVICE(s);
     s->comm.rank = rank; s->comm.size = n_ranks; s->comm.xcb = xcb; s->comm.rcb = rcb; s->comm.user = user;
     s->comm.active = n_ranks > 1;
     if (!s->finalizeParallel()) return -1;
@@ -2276,6 +2341,7 @@ int tpp_nccl_unique_id(const char* nccl_path, char* out128) try {
 #endif
 } API_CATCH(-100)
 int tpp_comm_init(tpp_handle s, int rank, int n_ranks, const char* id128, const char* nccl_path) try {
+    API_DEVICE(s);
 #ifndef TPP_EMU
     if (!loadNccl(s->comm, nccl_path)) return -1;
     ncclUniqueId id;

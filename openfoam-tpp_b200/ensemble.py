@@ -93,15 +93,20 @@ def sum_over_ranks(values, group=None):
     return t.tolist()
 
 
-def run_sweep(root_dir, base, sweeps, lc_to_mesh=None, max_steps=None, lib_path=None, log=None):
+def run_sweep(root_dir, base, sweeps, lc_to_mesh=None, max_steps=None, lib_path=None, log=None, cases_per_gpu=1, write=True):
     """The sweep loop of main.py:599-608 on the GPUs of one box: every rank of the
     torch.distributed job (one process per GPU; a plain process is rank 0 of 1) sets up and runs
-    its share of the cases, one after another, each through the ordinary case-directory path
+    its share of the cases, each through the ordinary case-directory path
     (case.setup_case -> foamrun.run_case).  Nothing is exchanged between ranks.
+
+    cases_per_gpu > 1: that many cases of the rank's share advance at the same time, one host thread
+    and one solver handle (CUDA stream) each ("one case per stream, 8 per GPU").
+    The reference's cases are small (8 k - 42 k cells: a step is a chain of short kernels and a few
+    host round trips), so one case alone leaves most of a B200 idle; the streams fill it.
 
     base / sweeps as in build_param_sets (keys H, D, geo, R, freq, duration, mesh = gmsh lc);
     lc_to_mesh(p) -> (n_rings, n_layers) replaces gmsh where it is absent (default: cells of
-    about lc).  Returns [(case name, summary dict)] of this rank."""
+    about lc).  Returns [(case name, summary dict)] of this rank, in sweep order."""
     import os
 
     from . import case as cs
@@ -115,13 +120,20 @@ def run_sweep(root_dir, base, sweeps, lc_to_mesh=None, max_steps=None, lib_path=
         rank, world = 0, 1
     device = int(os.environ.get("LOCAL_RANK", "0"))
     lc_to_mesh = lc_to_mesh or (lambda p: (max(3, round(p["D"] / 2 / p["mesh"])), max(3, round(p["H"] / p["mesh"]))))
-    done = []
-    for p in shard(build_param_sets(base, sweeps), world, rank):
+    mine = shard(build_param_sets(base, sweeps), world, rank)
+
+    def one(p):
         name = case_name(p)
         d = os.path.join(root_dir, name)
         if not os.path.isdir(os.path.join(d, "constant", "polyMesh")):
             nr, nl = lc_to_mesh(p)
             cs.setup_case(d, H=p["H"], D=p["D"], geo=p["geo"], R=p["R"], freq=p["freq"], duration=p["duration"], n_rings=nr, n_layers=nl)
-        out = foamrun.run_case(d, device=device, lib_path=lib_path, max_steps=max_steps, log=log)  # resumes from the latest time
-        done.append((name, out))
-    return done
+        out = foamrun.run_case(d, device=device, lib_path=lib_path, max_steps=max_steps, log=log, write=write)  # resumes from the latest time
+        return name, out
+
+    if cases_per_gpu <= 1 or len(mine) <= 1:
+        return [one(p) for p in mine]
+    from concurrent.futures import ThreadPoolExecutor
+
+    with ThreadPoolExecutor(max_workers=cases_per_gpu) as pool:
+        return list(pool.map(one, mine))  # results in sweep order; an exception in any case propagates

@@ -82,3 +82,19 @@ def test_run_sweep_sets_up_and_runs_every_case(tmp_path, emu_lib):
     for n in names:
         assert os.path.isfile(os.path.join(str(tmp_path), n, "constant", "polyMesh", "owner"))
         assert os.path.isfile(os.path.join(str(tmp_path), n, "constant", "6DoF.dat"))
+
+
+def test_run_sweep_concurrent_cases_match_sequential(tmp_path, emu_lib):
+    """cases_per_gpu = 3: the same cases advanced by three host threads at once (one handle each) end
+    in the same state as when they run one after another."""
+    import numpy as np
+
+    from openfoam_tpp_b200 import foamfile as ff
+
+    base = {"H": 0.004, "D": 0.0221, "geo": "flat", "R": 0.005, "freq": 2.0, "duration": 0.002, "mesh": 0.003}
+    sw = {"freq": [1.5, 2.0, 2.5, 3.0]}
+    a = en.run_sweep(str(tmp_path / "seq"), base, sw, max_steps=4, lib_path=emu_lib)
+    b = en.run_sweep(str(tmp_path / "par"), base, sw, max_steps=4, lib_path=emu_lib, cases_per_gpu=3)
+    assert [n for n, _ in a] == [n for n, _ in b] and len(b) == 4
+    for (n, oa), (_, ob) in zip(a, b):
+        assert oa["steps"] == ob["steps"] == 4 and oa["t"] == ob["t"], (n, oa, ob)
