@@ -158,13 +158,20 @@ inline void dev_sync(Ctx&) {}
 // after a kernel launch: configuration errors (too many resources, bad grid) surface here and not
 // at an unrelated later call.  Not a synchronisation.
 #define LAUNCH_CHECK(name) do { cudaError_t e_ = cudaPeekAtLastError(); if (e_ != cudaSuccess) ::tpp::cuda_fail(e_, "launch of " name, __FILE__, __LINE__); } while (0)
+// Zero-filled device memory.  The fill runs on a per-thread non-blocking utility stream and is
+// waited for here: nothing touches the legacy default stream, which would order against every
+// blocking stream of the process - illegal while another host thread (another handle of a sweep)
+// is capturing a CUDA graph.
 inline void* dev_alloc(size_t bytes) {
     void* p = nullptr;
+    thread_local cudaStream_t util = nullptr;
+    thread_local int utilDev = -1;
+    int dev = 0;
+    CUDA_CHECK(cudaGetDevice(&dev));
+    if (util == nullptr || utilDev != dev) { CUDA_CHECK(cudaStreamCreateWithFlags(&util, cudaStreamNonBlocking)); utilDev = dev; }
     CUDA_CHECK(cudaMalloc(&p, bytes ? bytes : 8));
-    CUDA_CHECK(cudaMemset(p, 0, bytes ? bytes : 8));
-    // the memset runs on the legacy default stream, which does not order against a caller's
-    // non-blocking stream (tpp_use_stream with a torch stream): finish it before the buffer is used
-    CUDA_CHECK(cudaDeviceSynchronize());
+    CUDA_CHECK(cudaMemsetAsync(p, 0, bytes ? bytes : 8, util));
+    CUDA_CHECK(cudaStreamSynchronize(util));
     return p;
 }
 inline void dev_free(void* p) { if (p) cudaFree(p); }

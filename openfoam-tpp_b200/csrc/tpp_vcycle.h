@@ -174,6 +174,7 @@ struct TailArgs {
     R omPre[TAIL_MAXSW], omPost[TAIL_MAXSW];  // relaxation factor of every sweep (smootherOmega)
     int nPre, nPost, cgIter;
     double cgTol;
+    int cgDeflate;        // remove the constant mode before the CG (closed domains: see tail_coarse_cg)
     R *cgR, *cgP, *cgAp;  // coarsest-level CG scratch (global memory; unused when the level is staged in shared memory)
     int cgSmem;           // the coarsest level fits the CTA's shared memory
 };
@@ -293,7 +294,7 @@ DEV double tail_block_sum(double v, double* sh) {
 // shared memory when it fits (`useSmem`, decided on the host), so an iteration costs a few
 // hundred cycles instead of a chain of L2 round trips.
 template <class R>
-DEV void tail_coarse_cg(const TLv<R>& L, R* gr, R* gp, R* gAp, int maxIter, double relTol, double* sh, unsigned char* smem, int useSmem) {
+DEV void tail_coarse_cg(const TLv<R>& L, R* gr, R* gp, R* gAp, int maxIter, double relTol, double* sh, unsigned char* smem, int useSmem, int deflate) {
     const int n = L.n, t = threadIdx.x, T = blockDim.x;
     const int nnz = L.rs[n];
     const int* rs = L.rs;
@@ -315,8 +316,27 @@ DEV void tail_coarse_cg(const TLv<R>& L, R* gr, R* gp, R* gAp, int maxIter, doub
         __syncthreads();
     }
     const R* b = L.b;
+    // Constant-mode deflation.  A closed tank (pressure level fixed by a reference cell only,
+    // fvSolution:85-86) leaves the operator nearly singular: the constant vector has the energy of the
+    // one doubled diagonal entry, and a handful of Jacobi-CG iterations does not see it - the outer PCG
+    // then stalls (24 k-cell tutorial tank: 20 capped iterations at 1e-7 instead of 9-13).  The best
+    // constant c = (1.b)/(1.A 1) is taken out first; with a Dirichlet boundary (the open tanks) 1.A 1 is
+    // large and c is just a harmless initial guess.
+    R c0 = 0;
+    if (deflate) {
+        double sb = 0, sq = 0, sd = 0;
+        for (int i = t; i < n; i += T) {
+            R o = 0;
+            if (cn16) for (int k = rs[i]; k < rs[i + 1]; k++) o += ev[k];
+            else for (int k = rs[i]; k < rs[i + 1]; k++) o += ev[k];
+            sb += (double)b[i]; sq += (double)(dg[i] - o); sd += (double)dg[i];
+            Ap[i] = dg[i] - o;  // row sums, used once below
+        }
+        sb = tail_block_sum(sb, sh); sq = tail_block_sum(sq, sh); sd = tail_block_sum(sd, sh);
+        c0 = sq > 1e-12 * sd ? (R)(sb / sq) : R(0);
+    }
     double loc = 0;
-    for (int i = t; i < n; i += T) { x[i] = 0; R bi = b[i]; r[i] = bi; R z = bi / dg[i]; p[i] = z; loc += (double)bi * (double)z; }
+    for (int i = t; i < n; i += T) { x[i] = c0; R bi = deflate ? b[i] - c0 * Ap[i] : b[i]; r[i] = bi; R z = bi / dg[i]; p[i] = z; loc += (double)bi * (double)z; }
     double rz = tail_block_sum(loc, sh);
     const double rz0 = rz;
     if (rz > 0)
@@ -393,7 +413,7 @@ __global__ void __launch_bounds__(TAIL_THREADS, 1) vk_tail(const TailArgs<R> A) 
         }
         gsync(gb);
     }
-    if (blockIdx.x == 0) tail_coarse_cg(A.lv[A.T - 1], A.cgR, A.cgP, A.cgAp, A.cgIter, A.cgTol, sh, smem, A.cgSmem);
+    if (blockIdx.x == 0) tail_coarse_cg(A.lv[A.T - 1], A.cgR, A.cgP, A.cgAp, A.cgIter, A.cgTol, sh, smem, A.cgSmem, A.cgDeflate);
     gsync(gb);
     for (int t = A.T - 2; t >= 0; t--) {
         const TLv<R>& L = A.lv[t];
@@ -745,8 +765,18 @@ inline void tail_host_once(const TailArgs<R>& A) {
         const int n = L.n;
         R *x = L.x, *r = A.cgR, *p = A.cgP, *Ap = A.cgAp;
         std::vector<R> pv(n);
+        // constant-mode deflation (see tail_coarse_cg)
+        double sb = 0, sq = 0, sd = 0;
+        std::vector<R> rsum(n);
+        for (int i = 0; i < n; i++) {
+            R o = 0;
+            for (int k = L.rs[i]; k < L.rs[i + 1]; k++) o += L.ev[k];
+            rsum[i] = L.diag[i] - o;
+            sb += (double)L.b[i]; sq += (double)rsum[i]; sd += (double)L.diag[i];
+        }
+        const R c0 = (A.cgDeflate && sq > 1e-12 * sd) ? (R)(sb / sq) : R(0);
         double rz = 0;
-        for (int i = 0; i < n; i++) { x[i] = 0; r[i] = L.b[i]; p[i] = L.b[i] / L.diag[i]; rz += (double)L.b[i] * (double)p[i]; }
+        for (int i = 0; i < n; i++) { x[i] = c0; R ri = L.b[i] - c0 * rsum[i]; r[i] = ri; p[i] = ri / L.diag[i]; rz += (double)ri * (double)p[i]; }
         const double rz0 = rz;
         if (rz > 0)
             for (int it = 0; it < A.cgIter; it++) {

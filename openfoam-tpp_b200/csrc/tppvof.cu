@@ -1644,6 +1644,7 @@ struct tpp_solver {
         for (int k = 0; k < TAIL_MAXSW; k++) { A.omPre[k] = (R)smootherOmega(k, std::max(A.nPre, 1)); A.omPost[k] = (R)smootherOmega(k, std::max(A.nPost, 1)); }
         A.cgIter = knob("TPP_CITER", 8); A.cgTol = knobd("TPP_CTOL", 0.05);
         A.cgR = v.cgR; A.cgP = v.cgP; A.cgAp = v.cgAp; A.cgSmem = tailSmem > 0;
+        A.cgDeflate = knob("TPP_DEFLATE", 1);
         prof_begin(ctx, "v_tail");
 #ifdef TPP_EMU
         tail_host(A);
@@ -2025,7 +2026,7 @@ int tpp_create(const tpp_mesh_t* mesh, const tpp_config_t* cfg, int device, tpp_
     tpp_solver* s = new tpp_solver();
     s->device = device;
 #ifndef TPP_EMU
-    CUDA_CHECK(cudaStreamCreate(&s->ctx.stream));
+    CUDA_CHECK(cudaStreamCreateWithFlags(&s->ctx.stream, cudaStreamNonBlocking));  // no implicit ordering against the legacy stream or other handles
     s->ctx.ownStream = true;
 #endif
     if (!s->build(mesh, cfg)) { s->destroy(); delete s; return -1; }
