@@ -176,7 +176,7 @@ struct TailArgs {
     double cgTol;
     int cgDeflate;        // remove the constant mode before the CG (closed domains: see tail_coarse_cg)
     R *cgR, *cgP, *cgAp;  // coarsest-level CG scratch (global memory; unused when the level is staged in shared memory)
-    int cgSmem;           // the coarsest level fits the CTA's shared memory
+    int cgSmem;           // > 0: the coarsest level is staged in shared memory in ELL form of this width
 };
 #ifndef TPP_EMU
 struct GridBar {
@@ -294,43 +294,73 @@ DEV double tail_block_sum(double v, double* sh) {
 // shared memory when it fits (`useSmem`, decided on the host), so an iteration costs a few
 // hundred cycles instead of a chain of L2 round trips.
 template <class R>
-DEV void tail_coarse_cg(const TLv<R>& L, R* gr, R* gp, R* gAp, int maxIter, double relTol, double* sh, unsigned char* smem, int useSmem, int deflate) {
+DEV void tail_coarse_cg(const TLv<R>& L, R* gr, R* gp, R* gAp, int maxIter, double relTol, double* sh, unsigned char* smem, int ellW, int deflate) {
+    // ellW > 0: the level is staged in shared memory in ELL form - the first ellW entries of every row
+    // slot-major (entry s of row i at [s n + i]: the lanes of a warp, which hold consecutive rows, hit
+    // consecutive banks; a CSR copy costs 3-4-way bank conflicts on every load because neighbouring rows
+    // start ~15 words apart), 16-bit columns, padding = (0, the row itself); the few longer rows finish
+    // from the CSR arrays in L2.  The CG vectors live in shared memory as well.  ellW == 0: CSR from L2.
     const int n = L.n, t = threadIdx.x, T = blockDim.x;
-    const int nnz = L.rs[n];
     const int* rs = L.rs;
-    const R *ev = L.ev, *dg = L.diag;
-    const int* cn32 = L.cn;
-    const unsigned short* cn16 = nullptr;
+    const R* dg = L.diag;
     R *x = L.x, *r = gr, *p = gp, *Ap = gAp;
-    if (useSmem) {
-        // layout: ev[nnz] diag[n] x[n] r[n] p[n] Ap[n] (R) | rs[n+1] (int) | cn[nnz] (u16)
-        R* sev = (R*)smem;
-        R* sdg = sev + nnz;
+    const R* sev = nullptr;
+    const unsigned short* scn = nullptr;
+    if (ellW > 0) {
+        // layout: ev[ellW n] diag[n] x[n] r[n] p[n] Ap[n] (R) | cn[ellW n] (u16)
+        R* wev = (R*)smem;
+        R* sdg = wev + (size_t)ellW * n;
         R* sx = sdg + n; R* sr = sx + n; R* sp = sr + n; R* sAp = sp + n;
-        int* srs = (int*)(sAp + n);
-        unsigned short* scn = (unsigned short*)(srs + n + 1);
-        for (int k = t; k < nnz; k += T) { sev[k] = L.ev[k]; scn[k] = (unsigned short)L.cn[k]; }
-        for (int i = t; i < n; i += T) { sdg[i] = L.diag[i]; srs[i] = L.rs[i]; }
-        if (t == 0) srs[n] = nnz;
-        ev = sev; dg = sdg; rs = srs; cn16 = scn; x = sx; r = sr; p = sp; Ap = sAp;
+        unsigned short* wcn = (unsigned short*)(sAp + n);
+        for (int i = t; i < n; i += T) {
+            const int b0 = rs[i], e0 = rs[i + 1];
+            for (int q = 0; q < ellW; q++) {
+                const int k = b0 + q;
+                const bool in = k < e0;
+                wev[(size_t)q * n + i] = in ? L.ev[k] : R(0);
+                wcn[(size_t)q * n + i] = (unsigned short)(in ? L.cn[k] : i);
+            }
+            sdg[i] = L.diag[i];
+        }
+        sev = wev; scn = wcn; dg = sdg; x = sx; r = sr; p = sp; Ap = sAp;
         __syncthreads();
     }
+    // off-diagonal sum of row i applied to the vector v (shared or global)
+    auto offsum = [&](int i, const R* v) {
+        R s0 = 0, s1 = 0, s2 = 0, s3 = 0;
+        int k = rs[i];
+        const int e = rs[i + 1];
+        if (sev) {
+#pragma unroll 2
+            for (int q = 0; q < ellW; q += 4) {  // ellW is a multiple of 4
+                s0 += sev[(size_t)q * n + i] * v[scn[(size_t)q * n + i]];
+                s1 += sev[(size_t)(q + 1) * n + i] * v[scn[(size_t)(q + 1) * n + i]];
+                s2 += sev[(size_t)(q + 2) * n + i] * v[scn[(size_t)(q + 2) * n + i]];
+                s3 += sev[(size_t)(q + 3) * n + i] * v[scn[(size_t)(q + 3) * n + i]];
+            }
+            for (k += ellW; k < e; k++) s0 += L.ev[k] * v[L.cn[k]];
+        } else {
+            for (; k + 3 < e; k += 4) { s0 += L.ev[k] * v[L.cn[k]]; s1 += L.ev[k + 1] * v[L.cn[k + 1]]; s2 += L.ev[k + 2] * v[L.cn[k + 2]]; s3 += L.ev[k + 3] * v[L.cn[k + 3]]; }
+            for (; k < e; k++) s0 += L.ev[k] * v[L.cn[k]];
+        }
+        return (s0 + s1) + (s2 + s3);
+    };
     const R* b = L.b;
     // Constant-mode deflation.  A closed tank (pressure level fixed by a reference cell only,
     // fvSolution:85-86) leaves the operator nearly singular: the constant vector has the energy of the
     // one doubled diagonal entry, and a handful of Jacobi-CG iterations does not see it - the outer PCG
     // then stalls (24 k-cell tutorial tank: 20 capped iterations at 1e-7 instead of 9-13).  The best
     // constant c = (1.b)/(1.A 1) is taken out first; with a Dirichlet boundary (the open tanks) 1.A 1 is
-    // large and c is just a harmless initial guess.
+    // large and the step is skipped.
     R c0 = 0;
     if (deflate) {
         double sb = 0, sq = 0, sd = 0;
+        for (int i = t; i < n; i += T) p[i] = R(1);
+        __syncthreads();
         for (int i = t; i < n; i += T) {
-            R o = 0;
-            if (cn16) for (int k = rs[i]; k < rs[i + 1]; k++) o += ev[k];
-            else for (int k = rs[i]; k < rs[i + 1]; k++) o += ev[k];
-            sb += (double)b[i]; sq += (double)(dg[i] - o); sd += (double)dg[i];
-            Ap[i] = dg[i] - o;  // row sums, used once below
+            const R rsum = dg[i] - offsum(i, p);
+            sb += (double)b[i]; sq += (double)rsum; sd += (double)dg[i];
+            Ap[i] = rsum;  // row sums, used once below
         }
         sb = tail_block_sum(sb, sh); sq = tail_block_sum(sq, sh); sd = tail_block_sum(sd, sh);
         c0 = sq > 1e-12 * sd ? (R)(sb / sq) : R(0);
@@ -344,24 +374,21 @@ DEV void tail_coarse_cg(const TLv<R>& L, R* gr, R* gp, R* gAp, int maxIter, doub
             loc = 0;
             __syncthreads();
             for (int i = t; i < n; i += T) {
-                R s = 0;
-                if (cn16) for (int k = rs[i]; k < rs[i + 1]; k++) s += ev[k] * p[cn16[k]];
-                else for (int k = rs[i]; k < rs[i + 1]; k++) s += ev[k] * p[cn32[k]];
-                R y = dg[i] * p[i] - s;
+                R y = dg[i] * p[i] - offsum(i, p);
                 Ap[i] = y;
                 loc += (double)y * (double)p[i];
             }
             double pAp = tail_block_sum(loc, sh);
             R alpha = (R)(rz / pAp);
             loc = 0;
-            for (int i = t; i < n; i += T) { x[i] += alpha * p[i]; R rr = r[i] - alpha * Ap[i]; r[i] = rr; loc += (double)rr * (double)rr / (double)dg[i]; }
+            for (int i = t; i < n; i += T) { x[i] += alpha * p[i]; R rr = r[i] - alpha * Ap[i]; r[i] = rr; loc += (double)(rr * rr / dg[i]); }
             double rzn = tail_block_sum(loc, sh);
             if (rzn <= relTol * relTol * rz0) break;
             R beta = (R)(rzn / rz);
             rz = rzn;
             for (int i = t; i < n; i += T) p[i] = r[i] / dg[i] + beta * p[i];
         }
-    if (useSmem) {
+    if (ellW > 0) {
         __syncthreads();
         for (int i = t; i < n; i += T) L.x[i] = x[i];
     }

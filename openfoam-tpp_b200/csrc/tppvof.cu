@@ -137,7 +137,7 @@ struct tpp_solver {
     // multigrid
     std::vector<Level> levels;  // distributed coarse levels (levels[0] = first coarse); the last one is gathered
     std::vector<Level> tail;    // tail[0] = levels[gatherLevel] over all ranks, then the replicated coarser levels
-    int gatherLevel = -1, tailRowOff = 0, tailFaceOff = 0, tailGrid = 1;
+    int gatherLevel = -1, tailRowOff = 0, tailFaceOff = 0, tailGrid = 1, tailCgW = 0;
     size_t tailSmem = 0;  // dynamic shared memory of vk_tail (coarsest level staged on chip), 0: not staged
     std::vector<std::array<int, 3>> tailCopy;  // processor-face coefficient ranges (src face, count, dst face) of the gather
     unsigned* tailBar = nullptr;
@@ -1202,7 +1202,7 @@ struct tpp_solver {
         csrOf(cur, rs, cf, cn);
         v.nnz = rs[cur.n];
         v.rs = upNew(ctx, rs); v.cf = upNew(ctx, cf); v.cn = upNew(ctx, cn); v.own = upNew(ctx, cur.own); v.nei = upNew(ctx, cur.nei);
-        if (knob("TPP_ELLC", 1)) buildEllc(v, rs, cn, dist ? 25 : 12);
+        if (knob("TPP_ELLC", 1)) buildEllc(v, rs, cn, knob("TPP_ELLC_OV", dist ? 25 : 12));
         v.agg = upNew(ctx, aggTot); v.segStart = upNew(ctx, segS); v.segFaces = upNew(ctx, segF);
         std::vector<int> howner(cur.own.begin() + cur.nfLoc, cur.own.end());
         v.dOwner = upNew(ctx, howner);
@@ -1305,11 +1305,23 @@ struct tpp_solver {
             int dev = 0, sms = 0, perSm = 0;
             cudaGetDevice(&dev);
             cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
-            // the coarsest level staged in the CTA's shared memory: CSR values + 5 vectors in R,
-            // row starts, 16-bit columns
-            const size_t rb = knob("TPP_FP32", 1) ? 4 : 8, cn_ = (size_t)tail.back().n, cz = (size_t)tail.back().nnz;
-            const size_t need_ = (cz + 5 * cn_) * rb + (cn_ + 1) * 4 + cz * 2 + 16;
-            tailSmem = (cn_ < 65536 && need_ <= 200 * 1024 && knob("TPP_CG_SMEM", 1)) ? need_ : 0;
+            // the coarsest level staged in the CTA's shared memory in ELL form (tail_coarse_cg): the
+            // smallest width (multiple of 4) that leaves at most 2 % of the entries to the CSR overflow
+            // and fits 200 KB together with the diagonal and the four CG vectors
+            const size_t rb = knob("TPP_FP32", 1) ? 4 : 8, cn_ = (size_t)tail.back().n;
+            tailSmem = 0; tailCgW = 0;
+            if (cn_ < 65536 && knob("TPP_CG_SMEM", 1)) {
+                std::vector<int> rsH(cn_ + 1);
+                d2h(ctx, rsH.data(), tail.back().rs, (cn_ + 1) * sizeof(int));
+                for (int w = 4; w <= 64; w += 4) {
+                    long ov = 0;
+                    for (size_t i = 0; i < cn_; i++) ov += std::max(0, rsH[i + 1] - rsH[i] - w);
+                    const size_t need_ = cn_ * w * (rb + 2) + 5 * cn_ * rb + 64;
+                    if (need_ > 200 * 1024) break;
+                    tailCgW = w; tailSmem = need_;
+                    if (ov * 50 <= (long)rsH[cn_]) break;
+                }
+            }
             if (knob("TPP_FP32", 1)) {
                 if (tailSmem) CUDA_CHECK(cudaFuncSetAttribute(vk_tail<float>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)tailSmem));
                 cudaOccupancyMaxActiveBlocksPerMultiprocessor(&perSm, vk_tail<float>, TAIL_THREADS, tailSmem);
@@ -1643,8 +1655,8 @@ struct tpp_solver {
         A.nPre = std::min(knob("TPP_TAIL_NPRE", nPre), TAIL_MAXSW); A.nPost = std::min(knob("TPP_TAIL_NPOST", nPost), TAIL_MAXSW);
         for (int k = 0; k < TAIL_MAXSW; k++) { A.omPre[k] = (R)smootherOmega(k, std::max(A.nPre, 1)); A.omPost[k] = (R)smootherOmega(k, std::max(A.nPost, 1)); }
         A.cgIter = knob("TPP_CITER", 8); A.cgTol = knobd("TPP_CTOL", 0.05);
-        A.cgR = v.cgR; A.cgP = v.cgP; A.cgAp = v.cgAp; A.cgSmem = tailSmem > 0;
-        A.cgDeflate = knob("TPP_DEFLATE", 1);
+        A.cgR = v.cgR; A.cgP = v.cgP; A.cgAp = v.cgAp; A.cgSmem = tailSmem > 0 ? tailCgW : 0;
+        A.cgDeflate = knob("TPP_DEFLATE", d.needRef ? 1 : 0);  // closed domains only: an open boundary pins the level
         prof_begin(ctx, "v_tail");
 #ifdef TPP_EMU
         tail_host(A);
