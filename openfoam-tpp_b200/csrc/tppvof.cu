@@ -165,10 +165,40 @@ struct tpp_solver {
     Comm comm;
     double* permBuf = nullptr;
     int* dPerm = nullptr;
+    // Internal renumbering (single-rank meshes): cells in Morton order of their centres, internal faces
+    // by (lower cell, higher cell).  Files, tpp_get / tpp_set / tpp_solve stay in OpenFOAM order - the
+    // reference never renumbers its gmsh meshes (circularSloshingTank/Makefile:71-86) - and so does every
+    // floating-point sum: face orientation is kept and a cell's ELL slots follow the FILE face index.
+    bool renumbered = false;
+    std::vector<int> cellFileOf, cellNewOf, faceFileOf, faceNewOf;  // new -> file and file -> new (faces: all nF, identity beyond nI)
+    int *dCellFileOf = nullptr, *dFaceFileOf = nullptr;
+    // (kind, components) of a registered array from its length: 'C' cells, 'F' all faces, 'I' internal faces
+    std::pair<char, int> kindOf(long n) const {
+        std::pair<char, int> k{0, 0};
+        int hits = 0;
+        auto tryK = [&](char c, long base) { for (int nc : {1, 3, 9}) if (base > 0 && n == nc * base && !(c != 'C' && nc == 9)) { k = {c, nc}; hits++; } };
+        tryK('C', nC); tryK('F', nF); tryK('I', nI);
+        if (hits != 1) k = {0, hits > 1 ? -1 : 0};  // ambiguous lengths: (0, -1)
+        return k;
+    }
     void ensurePermBuf() {
         if (permBuf) return;
-        permBuf = A<double>(3 * (size_t)nF);
+        permBuf = A<double>(std::max(3 * (size_t)nF, 9 * (size_t)nC));
         dPerm = upload(permDev2File);
+    }
+    // device (internal) order <-> OpenFOAM file order of a registered array, on the device.
+    // toFile: dst[file] = src[internal] ; else dst[internal] = src[file].  Returns false when the array
+    // needs no permutation (boundary arrays, unknown lengths, no renumbering).
+    bool permute(const double* src, double* dst, long n, bool toFile) {
+        if (!renumbered) return false;
+        auto k = kindOf(n);
+        if (k.first == 0) return false;
+        const int* perm = k.first == 'C' ? dCellFileOf : dFaceFileOf;
+        const int rows = k.first == 'C' ? nC : k.first == 'F' ? nF : nI;
+        d.xsrc = src; d.xbuf = dst; d.xnc = k.second; d.procOwner = perm;
+        if (toFile) LAUNCH(ctx, face_to_file, d, rows); else LAUNCH(ctx, file_to_face, d, rows);
+        d.procOwner = dProcOwner;
+        return true;
     }
     std::vector<double> hW, hDc, hCorr, hDPN;  // kept for the processor-face geometry pass
     // time
@@ -308,6 +338,75 @@ struct tpp_solver {
         return p;
     }
 
+    // Morton (Z-order) key of a point in the bounding box, 21 bits per axis
+    static unsigned long long mortonKey(const double* x, const double* lo, const double* inv) {
+        unsigned long long key = 0;
+        unsigned q[3];
+        for (int k = 0; k < 3; k++) { double t = (x[k] - lo[k]) * inv[k]; q[k] = (unsigned)std::min(2097151.0, std::max(0.0, t * 2097151.0)); }
+        for (int b = 20; b >= 0; b--) for (int k = 0; k < 3; k++) key = (key << 1) | ((q[k] >> b) & 1u);
+        return key;
+    }
+    // TPP_RENUMBER: 0 never, 1 always, default -1 = when it pays: the mean label distance |owner -
+    // neighbour| over the internal faces (what decides whether a gather hits the same cache lines as
+    // its neighbours) drops at least threefold.  A mesh written layer by layer keeps its order; a gmsh
+    // mesh (no spatial coherence in its labels) is renumbered: 2.2 x faster steps at 6.2 M cells.
+    void decideRenumbering(std::vector<double>& w, std::vector<double>& dc, std::vector<double>& corr, std::vector<double>& dPN) {
+        const int mode = knob("TPP_RENUMBER", -1);
+        if (mode == 0 || nG > 0 || nC < 2 || nI < 1) return;
+        for (long n : {(long)nC, (long)nF, (long)nI})  // lengths must tell the array kinds apart (tpp_get / tpp_set)
+            for (long m2 : {(long)nC, (long)nF, (long)nI, (long)nB})
+                for (int a : {1, 3, 9}) for (int b : {1, 3, 9}) if (!(n == m2 && a == b) && (long)a * n == (long)b * m2 && n != m2) return;
+        if (nC == nI || nC == nF || nB == nC || nB == nI) return;
+        double lo[3] = {1e300, 1e300, 1e300}, hi[3] = {-1e300, -1e300, -1e300}, inv[3];
+        for (int c = 0; c < nC; c++) for (int k = 0; k < 3; k++) { lo[k] = std::min(lo[k], C0[3 * c + k]); hi[k] = std::max(hi[k], C0[3 * c + k]); }
+        double ext = std::max(hi[0] - lo[0], std::max(hi[1] - lo[1], hi[2] - lo[2]));
+        for (int k = 0; k < 3; k++) inv[k] = ext > 0 ? 1.0 / ext : 0.0;  // one scale for all axes: cubic Morton cells
+        std::vector<std::pair<unsigned long long, int>> keyed(nC);
+        for (int c = 0; c < nC; c++) keyed[c] = {mortonKey(&C0[3 * c], lo, inv), c};
+        std::sort(keyed.begin(), keyed.end());
+        std::vector<int> newOf(nC), fileOf(nC);
+        for (int i = 0; i < nC; i++) { fileOf[i] = keyed[i].second; newOf[keyed[i].second] = i; }
+        double before = 0, after = 0;
+        for (int f = 0; f < nI; f++) { before += std::abs(own[f] - nei[f]); after += std::abs(newOf[own[f]] - newOf[nei[f]]); }
+        if (mode < 0 && !(after * 3.0 <= before)) return;
+        renumbered = true;
+        cellFileOf = fileOf; cellNewOf = newOf;
+        // internal faces by (lower new cell, higher new cell); orientation (owner / neighbour roles) kept
+        std::vector<std::pair<unsigned long long, int>> fk(nI);
+        for (int f = 0; f < nI; f++) {
+            unsigned a = (unsigned)newOf[own[f]], b = (unsigned)newOf[nei[f]];
+            fk[f] = {((unsigned long long)std::min(a, b) << 32) | std::max(a, b), f};
+        }
+        std::sort(fk.begin(), fk.end());
+        faceFileOf.resize(nF);
+        for (int f = 0; f < nI; f++) { faceFileOf[f] = fk[f].second; faceNewOf[fk[f].second] = f; }
+        for (int f = nI; f < nF; f++) faceFileOf[f] = f;
+        auto permF = [&](std::vector<double>& a, int nc, int n) {  // face arrays: entry f <- file entry faceFileOf[f]
+            std::vector<double> o(a.size());
+            for (int f = 0; f < n; f++) for (int k = 0; k < nc; k++) o[(size_t)f * nc + k] = a[(size_t)faceFileOf[f] * nc + k];
+            for (size_t i = (size_t)n * nc; i < a.size(); i++) o[i] = a[i];
+            a.swap(o);
+        };
+        auto permC = [&](std::vector<double>& a, int nc) {
+            std::vector<double> o(a.size());
+            for (int c = 0; c < nC; c++) for (int k = 0; k < nc; k++) o[(size_t)c * nc + k] = a[(size_t)fileOf[c] * nc + k];
+            a.swap(o);
+        };
+        permF(Cf0, 3, nI); permF(Sf0, 3, nI); permF(magSf, 1, nI); permF(w, 1, nI); permF(dc, 1, nI); permF(corr, 3, nI); permF(dPN, 3, nI);
+        permC(C0, 3); permC(V, 1);
+        std::vector<int> own2(nF), nei2(nI), off2(nF + 1, 0), lab2;
+        lab2.reserve(fLab.size());
+        for (int f = 0; f < nF; f++) {
+            const int ff = faceFileOf[f];
+            own2[f] = newOf[own[ff]];
+            if (f < nI) nei2[f] = newOf[nei[ff]];
+            for (int k = fOff[ff]; k < fOff[ff + 1]; k++) lab2.push_back(fLab[k]);
+            off2[f + 1] = (int)lab2.size();
+        }
+        own.swap(own2); nei.swap(nei2); fOff.swap(off2); fLab.swap(lab2);
+        if (knob("TPP_VERBOSE", 0)) fprintf(stderr, "tppvof: cells renumbered in Morton order (mean |owner - neighbour| %.0f -> %.0f)\n", before / nI, after / nI);
+    }
+
     bool build(const tpp_mesh_t* m, const tpp_config_t* c) {
         nP = m->n_points; nF = m->n_faces; nI = m->n_internal; nC = m->n_cells; nB = nF - nI; nPatch = m->n_patches;
         points0.assign(m->points, m->points + 3 * (size_t)nP);
@@ -374,7 +473,16 @@ struct tpp_solver {
             }
         }
         for (int b = 0; b < nB; b++) if (fU[b] < 0) { g_err = "boundary face without a patch"; return false; }
-        // ELL cell->face table, slots ascending in face index
+        // geometry in FILE order first: OpenFOAM's face loops accumulate the cell centres and volumes in
+        // that order, and the oracle does the same (bit-exact V, C)
+        std::vector<double> w, dc, corr, dPN;
+        hostGeometry(w, dc, corr, dPN);
+        faceNewOf.resize(nF);
+        for (int f = 0; f < nF; f++) faceNewOf[f] = f;
+        decideRenumbering(w, dc, corr, dPN);
+        // ELL cell->face table.  Slots follow the FILE face index (a cell's neighbour-side and owner-side
+        // faces interleave in face order), which is the order OpenFOAM's face loops scatter in; the entries
+        // are internal face labels.
         std::vector<int> cnt(nC, 0);
         for (int f = 0; f < nF; f++) cnt[own[f]]++;
         for (int f = 0; f < nI; f++) if (nei[f] < nC) cnt[nei[f]]++;
@@ -382,8 +490,8 @@ struct tpp_solver {
         for (int c = 0; c < nC; c++) W = std::max(W, cnt[c]);
         nCp = (nC + 31) / 32 * 32;
         std::vector<int> cf((size_t)W * nCp, -1), cn((size_t)W * nCp, -1), fill(nC, 0);
-        // a cell's neighbour-side faces and owner-side faces interleave in face order: visit faces ascending
-        for (int f = 0; f < nF; f++) {
+        for (int ff = 0; ff < nF; ff++) {
+            const int f = faceNewOf[ff];
             int o = own[f];
             cf[(size_t)fill[o] * nCp + o] = f << 1;
             cn[(size_t)fill[o] * nCp + o] = f < nI ? nei[f] : -1;
@@ -395,11 +503,10 @@ struct tpp_solver {
                 fill[n]++;
             }
         }
-        std::vector<double> w, dc, corr, dPN;
-        hostGeometry(w, dc, corr, dPN);
         memset(&d, 0, sizeof(d));
         d.nC = nC; d.nF = nF; d.nI = nI; d.nB = nB; d.nCp = nCp; d.W = W;
         d.own = upload(own); d.nei = upload(nei); d.cf = upload(cf); d.cn = upload(cn);
+        if (renumbered) { dCellFileOf = upload(cellFileOf); dFaceFileOf = upload(faceFileOf); }
         d.bcU = upload(fU); d.bcA = upload(fA); d.bcP = upload(fP);
         d.bInletAlpha = upload(fInlet); d.bP0 = upload(fP0);
         d.Sf = uploadD("Sf", Sf0); d.magSf = uploadD("magSf", magSf); d.w = uploadD("w", w); d.dc = uploadD("dc", dc);
@@ -2101,6 +2208,13 @@ long tpp_get(tpp_handle s, const char* name, double* out, long cap) try {
         d2h(s->ctx, out, s->permBuf, n * sizeof(double));
         return it->second.second;
     }
+    if (s->renumbered) {
+        s->ensurePermBuf();
+        if (s->permute(it->second.first, s->permBuf, it->second.second, true)) {
+            d2h(s->ctx, out, s->permBuf, n * sizeof(double));
+            return it->second.second;
+        }
+    }
     d2h(s->ctx, out, it->second.first, n * sizeof(double));
     return it->second.second;
 } API_CATCH(-100)
@@ -2118,6 +2232,13 @@ long tpp_set(tpp_handle s, const char* name, const double* in, long n) try {
         dev_sync(s->ctx);
         return n;
     }
+    if (s->renumbered && s->kindOf(n).first != 0) {
+        s->ensurePermBuf();
+        h2d(s->ctx, s->permBuf, in, n * sizeof(double));
+        s->permute(s->permBuf, it->second.first, n, false);
+        dev_sync(s->ctx);
+        return n;
+    }
     h2d(s->ctx, it->second.first, in, n * sizeof(double));
     return n;
 } API_CATCH(-100)
@@ -2129,6 +2250,12 @@ long tpp_get_int(tpp_handle s, const char* name, int* out, long cap) try {
     else if (!strcmp(name, "cn")) { src = s->d.cn; n = (long)s->W * s->nCp; }
     else if (!strcmp(name, "owner")) { src = s->d.own; n = s->nF; }
     else if (!strcmp(name, "neighbour")) { src = s->d.nei; n = s->nI; }
+    else if (!strcmp(name, "cellFileOf") || !strcmp(name, "faceFileOf")) {  // internal label -> file label (identity: not renumbered)
+        const bool cells = name[0] == 'c';
+        const long m = cells ? s->nC : s->nF;
+        for (long i = 0; out && i < std::min(cap, m); i++) out[i] = s->renumbered ? (cells ? s->cellFileOf[i] : s->faceFileOf[i]) : (int)i;
+        return m;
+    }
     else if (!strcmp(name, "layout")) {
         int v[6] = {s->nC, s->nCp, s->W, s->nI, s->nB, s->nG};
         memcpy(out, v, std::min<long>(cap, 6) * sizeof(int));
@@ -2214,7 +2341,7 @@ int tpp_info(tpp_handle s, double* o) try {
     o[0] = s->t; o[1] = s->dt; o[2] = (double)s->step; o[3] = s->Co; o[4] = s->alphaCo;
     o[5] = s->lastSolve[0].iters; o[6] = s->lastSolve[0].r0; o[7] = s->lastSolve[0].r;
     o[8] = s->lastSolve[1].iters; o[9] = s->lastSolve[1].r0; o[10] = s->lastSolve[1].r;
-    o[11] = s->d.needRef ? s->d.refCell : -1; o[12] = s->d.deltaN; o[13] = s->writeTimeIndex;
+    o[11] = s->d.needRef ? (s->renumbered && s->d.refCell >= 0 ? s->cellFileOf[s->d.refCell] : s->d.refCell) : -1; o[12] = s->d.deltaN; o[13] = s->writeTimeIndex;
     o[14] = (double)s->levels.size(); o[15] = (double)s->ctx.launches;
     return 0;
 } API_CATCH(-100)
@@ -2230,17 +2357,23 @@ int tpp_stats(tpp_handle s, int reset, double* o) try {
 } API_CATCH(-100)
 int tpp_solve(tpp_handle s, const tpp_solver_t* ctl, const double* diag, const double* upper, const double* b, double* x, double* r0, double* r) try {
     API_DEVICE(s);
-    h2d(s->ctx, s->d.pDiag, diag, s->nC * sizeof(double));
-    h2d(s->ctx, s->d.pUpper, upper, s->nI * sizeof(double));
-    h2d(s->ctx, s->d.pSource, b, s->nC * sizeof(double));
     double* xd = s->d.cellTmp;
-    h2d(s->ctx, xd, x, s->nC * sizeof(double));
+    auto put = [&](double* dst, const double* src, long n) {  // file order in
+        if (s->renumbered) { s->ensurePermBuf(); h2d(s->ctx, s->permBuf, src, n * sizeof(double)); s->permute(s->permBuf, dst, n, false); dev_sync(s->ctx); }
+        else h2d(s->ctx, dst, src, n * sizeof(double));
+    };
+    put(s->d.pDiag, diag, s->nC); put(s->d.pUpper, upper, s->nI); put(s->d.pSource, b, s->nC); put(xd, x, s->nC);
     SolveStats st = s->solve(*ctl, s->d.pDiag, s->d.pUpper, s->d.pSource, xd);
-    d2h(s->ctx, x, xd, s->nC * sizeof(double));
+    if (s->renumbered) { s->permute(xd, s->permBuf, s->nC, true); d2h(s->ctx, x, s->permBuf, s->nC * sizeof(double)); }
+    else d2h(s->ctx, x, xd, s->nC * sizeof(double));
     *r0 = st.r0; *r = st.r;
     return st.iters;
 } API_CATCH(-100)
-int tpp_set_probes(tpp_handle s, int n, const int* cells) { s->probeCells.assign(cells, cells + n); return 0; }
+int tpp_set_probes(tpp_handle s, int n, const int* cells) {  // cell labels of the mesh FILE (as tpp_find_cell returns them)
+    s->probeCells.assign(cells, cells + n);
+    if (s->renumbered) for (int& c : s->probeCells) if (c >= 0 && c < s->nC) c = s->cellNewOf[c];
+    return 0;
+}
 long tpp_probe_log(tpp_handle s, double* out, long cap_rows) try {
     API_DEVICE(s);
     long w = 1 + (long)s->probeCells.size();
@@ -2250,7 +2383,10 @@ long tpp_probe_log(tpp_handle s, double* out, long cap_rows) try {
     s->probeLog.erase(s->probeLog.begin(), s->probeLog.begin() + n * w);
     return n;
 } API_CATCH(-100)
-int tpp_find_cell(tpp_handle s, const double* xyz) { return s->findCell(xyz); }
+int tpp_find_cell(tpp_handle s, const double* xyz) {
+    int c = s->findCell(xyz);
+    return (c >= 0 && s->renumbered) ? s->cellFileOf[c] : c;
+}
 int tpp_use_stream(tpp_handle s, void* stream) try {
     API_DEVICE(s);
 #ifndef TPP_EMU

@@ -36,20 +36,43 @@ def _ell_reference(mesh):
     return cell, slot, code, other, int(slot.max()) + 1
 
 
-def _check(lib):
+def _check(lib, renumber=None):
+    import os
+
+    if renumber is None:
+        for r in ("0", "1", "-1"):
+            os.environ["TPP_RENUMBER"] = r
+            try:
+                _check(lib, r)
+            finally:
+                os.environ.pop("TPP_RENUMBER", None)
+        return
     for name, mesh in _meshes():
         cfg = bench.make_config(mesh)
         g = sv.Solver(mesh, cfg, device=0, lib_path=lib)
         o = oracle.Oracle(mesh, cfg)
         nC, nCp, W, nI, nB, nG = g.get_int("layout")
         assert (nC, nI, nB, nG) == (mesh.n_cells, mesh.n_internal, mesh.n_faces - mesh.n_internal, 0), name
-        assert np.array_equal(g.get_int("owner"), mesh.owner) and np.array_equal(g.get_int("neighbour"), mesh.neighbour), name
+        # the library may renumber cells and internal faces internally (Morton order; a shuffled or
+        # Delaunay mesh is, a layer-by-layer one is not): integer tables are compared through its maps,
+        # which must be permutations, keep the boundary faces in place and leave every cell's slots in
+        # FILE face order (that is what keeps the floating-point sums bit-exact)
+        cfo, ffo = g.get_int("cellFileOf").astype(np.int64), g.get_int("faceFileOf").astype(np.int64)
+        assert np.array_equal(np.sort(cfo), np.arange(nC)) and np.array_equal(np.sort(ffo[:nI]), np.arange(nI)) and np.array_equal(ffo[nI:], np.arange(nI, nI + nB)), name
+        if renumber == "0":
+            assert np.array_equal(cfo, np.arange(nC)) and np.array_equal(ffo, np.arange(nI + nB)), name
+        if renumber == "1":
+            assert not np.array_equal(cfo, np.arange(nC)), name
+        assert np.array_equal(cfo[g.get_int("owner")], mesh.owner[ffo]) and np.array_equal(cfo[g.get_int("neighbour")], mesh.neighbour[ffo[:nI]]), name
         cell, slot, code, other, Wref = _ell_reference(mesh)
         assert W == Wref and nCp >= nC and nCp % 32 == 0, (name, W, Wref)
-        cf, cn = g.get_int("cf").reshape(W, nCp), g.get_int("cn").reshape(W, nCp)
-        ref_cf, ref_cn = -np.ones((W, nCp), dtype=np.int64), -np.ones((W, nCp), dtype=np.int64)
+        cf, cn = g.get_int("cf").reshape(W, nCp).astype(np.int64), g.get_int("cn").reshape(W, nCp).astype(np.int64)
+        ref_cf, ref_cn = -np.ones((W, nC), dtype=np.int64), -np.ones((W, nC), dtype=np.int64)
         ref_cf[slot, cell], ref_cn[slot, cell] = code, other
-        assert np.array_equal(cf, ref_cf) and np.array_equal(cn, ref_cn), name
+        got_cf = np.where(cf[:, :nC] >= 0, (ffo[np.maximum(cf[:, :nC], 0) >> 1] << 1) | (cf[:, :nC] & 1), -1)
+        got_cn = np.where(cn[:, :nC] >= 0, cfo[np.maximum(cn[:, :nC], 0)], -1)
+        assert np.array_equal(got_cf, ref_cf[:, cfo]) and np.array_equal(got_cn, ref_cn[:, cfo]), name
+        assert np.all(cf[:, nC:] == -1) and np.all(cn[:, nC:] == -1)
         # geometry: bit for bit against the oracle's face-loop arithmetic
         Cc, Cf = o.get("C").reshape(-1, 3), o.get("Cf").reshape(-1, 3)
         own, nei = mesh.owner.astype(np.int64), mesh.neighbour.astype(np.int64)
