@@ -754,7 +754,19 @@ struct tpp_solver {
             h2d(ctx, scal + S_TMP0, &fixes, sizeof(double));
             allreduce(S_TMP0, 1, 1);
             d2h(ctx, &fixes, scal + S_TMP0, sizeof(double));
-            if (fixes == 0 && comm.size > 1) { g_err = "a closed domain (p_rgh reference cell) cannot be decomposed yet"; return false; }
+            if (fixes == 0 && comm.size > 1) {
+                // a closed domain (sloshingTank3D6DoF: one wall patch, hierarchical (4 2 2),
+                // system/decomposeParDict:17-29): p_rgh needs the reference of fvSolution:85-86 on ONE
+                // rank - the lowest one whose share of the mesh contains pRefPoint
+                d.needRef = 1;
+                const int c = findCell(cfg.p_ref_point);
+                double who = c >= 0 ? (double)(comm.size - comm.rank) : 0.0;  // max picks the lowest rank with a hit
+                h2d(ctx, scal + S_TMP0, &who, sizeof(double));
+                allreduce(S_TMP0, 1, 1);
+                d2h(ctx, &who, scal + S_TMP0, sizeof(double));
+                if (who == 0.0) { g_err = "pRefPoint is outside the mesh and p_rgh needs a reference"; return false; }
+                d.refCell = (comm.size - (int)(who + 0.5)) == comm.rank ? c : -1;
+            }
         }
         double ng = (double)nC;
         h2d(ctx, scal + S_TMP0, &ng, sizeof(double));
@@ -931,7 +943,13 @@ struct tpp_solver {
         LAUNCH(ctx, p, d, nC);
         if (d.needRef) {
             double pc;
-            d2h(ctx, &pc, d.p + d.refCell, sizeof(double));
+            if (comm.active) {  // the rank that owns the reference cell tells the others
+                if (d.refCell >= 0) d2d(ctx, scal + S_TMP0, d.p + d.refCell, sizeof(double));
+                else dev_zero(ctx, scal + S_TMP0, sizeof(double));
+                allreduce(S_TMP0, 1, 0);
+                d2h(ctx, &pc, scal + S_TMP0, sizeof(double));
+            } else
+                d2h(ctx, &pc, d.p + d.refCell, sizeof(double));
             d.pRefShift = cfg.p_ref_value - pc;
             LAUNCH(ctx, p_shift, d, nC);
             LAUNCH(ctx, p_evaluate, d, nB);

@@ -205,3 +205,41 @@ def test_foamrun_parallel_matches_serial(tmp_path, emu_lib):
         va, vb = [float(x) for x in a.split()], [float(x) for x in b.split()]
         assert va[0] == vb[0]
         assert all(abs(x - y) <= 1e-5 * max(abs(y), 1.0) for x, y in zip(va[1:], vb[1:])), (a, b)
+
+
+def test_closed_tank_parallel_matches_serial(tmp_path, emu_lib):
+    """The tutorial's own parallel set-up in small: sloshingTank3D6DoF (closed, one wall patch, p_rgh
+    pinned by pRefPoint / pRefValue, rotating 6-DoF motion) decomposed `hierarchical` as in
+    sloshingTank3D6DoF/system/decomposeParDict:17-29 - the reference cell lives on one rank only and
+    the others learn its pressure - gives the serial run's fields."""
+    from openfoam_tpp_b200 import foamrun
+
+    steps = 4
+    serial, par = str(tmp_path / "serial"), str(tmp_path / "par")
+    for d in (serial, par):
+        cs.setup_tutorial_case(d, nx=6, ny=10, nz=8, end_time=1.0, p_final_max_iter=400)
+        p = os.path.join(d, "system", "fvSolution")
+        s = open(p).read().replace("tolerance       1e-08;", "tolerance       1e-13;").replace("tolerance       2e-09;", "tolerance       1e-13;").replace("relTol          0.01;", "relTol          0;")
+        open(p, "w").write(s)
+        p = os.path.join(d, "system", "controlDict")
+        s = open(p).read().replace("writeInterval   0.05;", "writeInterval   0.02;")
+        open(p, "w").write(s)
+    with open(os.path.join(par, "system", "decomposeParDict"), "w") as f:
+        f.write(ff._hdr("dictionary", "decomposeParDict", "system") + "numberOfSubdomains 3;\nmethod hierarchical;\nhierarchicalCoeffs { n (1 3 1); order xyz; delta 0.001; }\n" + ff.END)
+    foamrun.run_case(serial, lib_path=emu_lib, max_steps=steps, log=None)
+    dc.decompose_par(par)
+    script = tmp_path / "worker.py"
+    script.write_text(textwrap.dedent(WORKER.format(root=ROOT, case=par, lib=emu_lib, steps=steps)))
+    r = subprocess.run([sys.executable, "-m", "torch.distributed.run", "--nnodes=1", "--nproc-per-node=3", "--master-addr", "127.0.0.1", "--master-port", "29647", str(script)],
+                       capture_output=True, text=True, timeout=900)
+    o = r.stdout + r.stderr
+    assert r.returncode == 0 and all(f"RANK{k}OK" in o for k in range(3)), o[-3000:]
+    times = [nm for _, nm in ff.time_dirs(os.path.join(par, "processor0")) if nm != "0"]
+    assert times and times == [nm for _, nm in ff.time_dirs(serial) if nm != "0"][: len(times)]
+    dc.reconstruct_par(par, times)
+    mesh = ff.read_polymesh(serial)
+    for tn in times:
+        a, b = _fields(par, tn), _fields(serial, tn)
+        for nm, tol in (("alpha.water", 1e-9), ("U", 1e-7), ("p_rgh", 1e-7), ("p", 1e-7)):
+            x, y = a[nm].internal_array(mesh.n_cells), b[nm].internal_array(mesh.n_cells)
+            assert np.abs(x - y).max() <= tol * max(np.abs(y).max(), 1e-300), (tn, nm, np.abs(x - y).max())

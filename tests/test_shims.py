@@ -107,7 +107,8 @@ def test_make_run_on_the_gpu_matches_the_oracle(tmp_path, gpu_lib):
     d, mesh = _case(tmp_path)
     _tighten(d)
     cd = os.path.join(d, "system", "controlDict")  # endTime 0.01: two write times
-    open(cd, "w").write(open(cd).read().replace("writeInterval   0.05;", "writeInterval   0.005;"))
+    txt = open(cd).read().replace("writeInterval   0.05;", "writeInterval   0.005;")
+    open(cd, "w").write(txt)
     # probes inside the tank (the reference's own locations lie outside every mesh, system/functions:25-26)
     fp = os.path.join(d, "system", "functions")
     s = open(fp).read().replace("(0 9.95 19.77)", "(0.002 0.001 0.001)").replace("(0 -9.95 19.77)", "(-0.003 0.002 0.003)")
