@@ -544,6 +544,69 @@ __global__ void __launch_bounds__(64) k_allreduce_ll(const ARArgs a) {
 }
 #endif
 
+#ifndef TPP_EMU
+// ---- all-gather of the tail right-hand side over the peer windows ---------------------------------
+// Once per V-cycle every rank contributes its slice of the gathered level's restricted residual
+// (a few thousand values) and needs everybody else's: with NCCL an all-reduce of zero-padded vectors
+// (~40 us at 8 ranks), here LL words stored straight into every rank's window and polled from the
+// own one (slices are disjoint, so nothing is summed and every rank ends with identical bits).
+// Slots: [parity][global row][word].
+struct GatherArgs2 {
+    int rank, size;
+    int rowOff[AR_MAXR + 1];    // slice of every rank in the gathered vector
+    uint2* win[AR_MAXR];        // the gather window of every rank (win[rank] = mine)
+    void* vec;                  // in: my slice filled; out: all slices
+    unsigned long long* seq;
+    unsigned* done;
+    int* err;
+};
+template <class T>
+__global__ void __launch_bounds__(256) k_gather_ll(const GatherArgs2 a) {
+    constexpr int WPV = sizeof(T) / 4;
+    __shared__ int s_last;
+    const unsigned long long seq = *(volatile unsigned long long*)a.seq + 1;
+    const unsigned flag = (unsigned)seq;
+    const size_t n = (size_t)a.rowOff[a.size];
+    const size_t par = (size_t)(seq & 1) * n * WPV;
+    T* v = (T*)a.vec;
+    const int lo = a.rowOff[a.rank], hi = a.rowOff[a.rank + 1];
+    // put: my rows into every other rank's window (one peer after the other: consecutive threads write
+    // consecutive words of one destination)
+    for (int r = 0; r < a.size; r++) {
+        if (r == a.rank) continue;
+        uint2* dst = a.win[r] + par;
+        for (int e = lo + blockIdx.x * 256 + threadIdx.x; e < hi; e += gridDim.x * 256) {
+            union { T x; unsigned w[WPV]; } u;
+            u.x = v[e];
+#pragma unroll
+            for (int q = 0; q < WPV; q++) st_ll(dst + (size_t)e * WPV + q, u.w[q], flag);
+        }
+    }
+    // get: everybody else's rows from my window
+    const uint2* src = a.win[a.rank] + par;
+    const unsigned long long t0 = global_ns();
+    for (int e = blockIdx.x * 256 + threadIdx.x; e < (int)n; e += gridDim.x * 256) {
+        if (e >= lo && e < hi) continue;
+        union { T x; unsigned w[WPV]; } u;
+#pragma unroll
+        for (int q = 0; q < WPV; q++) {
+            uint2 w = ld_ll(src + (size_t)e * WPV + q);
+            long spins = 0;
+            while (w.y != flag) {
+                if ((++spins & 1023) == 0 && (*(volatile int*)a.err != 0 || global_ns() - t0 > 30000000000ull)) { *(volatile int*)a.err = 4; break; }
+                w = ld_ll(src + (size_t)e * WPV + q);
+            }
+            u.w[q] = w.x;
+        }
+        v[e] = u.x;
+    }
+    __syncthreads();
+    if (threadIdx.x == 0) s_last = atomicAdd(a.done, 1u) == gridDim.x - 1;
+    __syncthreads();
+    if (s_last && threadIdx.x == 0) { *a.done = 0; *(volatile unsigned long long*)a.seq = seq; }
+}
+#endif
+
 struct Reducer {
     double *partial = nullptr, *partial2 = nullptr;
     int cap = RED_BLOCKS;  // partials: at least one per 256 rows of the mesh (full-grid kernels)

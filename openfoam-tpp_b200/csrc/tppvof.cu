@@ -110,6 +110,12 @@ struct Comm {
     std::vector<char*> allBase;              // every rank's window (all-reduce over peer memory), empty: NCCL
     unsigned* putDone = nullptr;
     int* p2pErr = nullptr;
+    // all-gather of the tail right-hand side (k_gather_ll): a second window, sized when the tail is known
+    char* gwin = nullptr;
+    std::vector<char*> gBase;                // every rank's gather window, empty: NCCL all-reduce
+    std::vector<int> gRowOff;                // slice of every rank in the gathered level
+    unsigned long long* gSeq = nullptr;
+    unsigned* gDone = nullptr;
 #endif
 };
 
@@ -1127,6 +1133,58 @@ struct tpp_solver {
         h2d(ctx, p, h.data(), n * sizeof(R));
     }
 
+    // every rank's slice of the tail right-hand side -> every rank (the slices are disjoint)
+    template <class R> void gatherTail(R* vec) {
+        if (!comm.active) return;
+#ifndef TPP_EMU
+        if (!comm.gBase.empty()) {
+            GatherArgs2 a;
+            memset(&a, 0, sizeof(a));
+            a.rank = comm.rank; a.size = comm.size;
+            for (int r = 0; r <= comm.size; r++) a.rowOff[r] = comm.gRowOff[r];
+            for (int r = 0; r < comm.size; r++) a.win[r] = reinterpret_cast<uint2*>(comm.gBase[r]);
+            a.vec = vec; a.seq = comm.gSeq; a.done = comm.gDone; a.err = comm.p2pErr;
+            const int nb = std::max(1, std::min(32, (tail[0].n + 255) / 256));
+            prof_begin(ctx, "tail_gather_ll");
+            k_gather_ll<R><<<nb, 256, 0, ctx.stream>>>(a);
+            LAUNCH_CHECK("k_gather_ll");
+            prof_end(ctx);
+            ctx.launches++;
+            return;
+        }
+#endif
+        allreduceDev(vec, (size_t)tail[0].n);
+    }
+    // the gather windows: allocated once the tail is known, handles exchanged like the halo windows'
+    void setupGatherWindow() {
+#ifndef TPP_EMU
+        if (!comm.active || comm.allBase.empty() || tail.empty() || comm.size > AR_MAXR || !knob("TPP_LLGATHER", 1)) return;
+        const size_t bytes = 2 * (size_t)tail[0].n * 2 * sizeof(uint2) + 256;  // two parities, up to two words per value
+        comm.gwin = (char*)dev_alloc(bytes);
+        comm.gSeq = (unsigned long long*)dev_alloc(64); comm.gDone = (unsigned*)dev_alloc(64);
+        cudaIpcMemHandle_t mine;
+        double fail = cudaIpcGetMemHandle(&mine, comm.gwin) != cudaSuccess ? 1.0 : 0.0;
+        if (fail != 0.0) cudaGetLastError();
+        std::vector<double> hv(64 * (size_t)comm.size, 0.0);
+        for (int k = 0; k < 64; k++) hv[64 * (size_t)comm.rank + k] = (double)((unsigned char*)&mine)[k];
+        hostAllreduce(hv, 0);
+        std::vector<char*> base(comm.size, nullptr);
+        for (int q = 0; q < comm.size && fail == 0.0; q++) {
+            if (q == comm.rank) { base[q] = comm.gwin; continue; }
+            cudaIpcMemHandle_t h;
+            for (int k = 0; k < 64; k++) ((unsigned char*)&h)[k] = (unsigned char)(hv[64 * (size_t)q + k] + 0.5);
+            void* ptr = nullptr;
+            if (cudaIpcOpenMemHandle(&ptr, h, cudaIpcMemLazyEnablePeerAccess) != cudaSuccess) { cudaGetLastError(); fail = 1.0; break; }
+            comm.opened.push_back(ptr);
+            base[q] = (char*)ptr;
+        }
+        std::vector<double> fv(1, fail);
+        dev_sync(ctx);
+        hostAllreduce(fv, 1);  // also the barrier: nobody stores before everybody has opened and zeroed
+        if (fv[0] == 0.0) comm.gBase = base;
+#endif
+    }
+
     // one pairwise matching pass on the device; returns host `root`
     int matchCap = 0;
     void matchPass(LV G, int n, const double* fwDev, std::vector<int>& rootH) {
@@ -1361,6 +1419,9 @@ struct tpp_solver {
         G.n = rowOff[world]; G.nf = G.nfLoc = faceOff[world]; G.nGlob = G.n;
         std::vector<double> own(G.nf, 0.0), nei(G.nf, 0.0), fw(G.nf, 0.0);
         tailRowOff = rowOff[me]; tailFaceOff = faceOff[me];
+#ifndef TPP_EMU
+        comm.gRowOff = rowOff;
+#endif
         tailCopy.clear();
         int at = faceOff[me];
         for (int f = 0; f < g.nfLoc; f++, at++) { own[at] = g.own[f] + rowOff[me]; nei[at] = g.nei[f] + rowOff[me]; fw[at] = g.fw[f]; }
@@ -1422,6 +1483,7 @@ struct tpp_solver {
             if (!makeLevel(G, false, false, coarsestTarget, v)) break;
             tail.push_back(v);
         }
+        setupGatherWindow();
         tailBar = (unsigned*)dev_alloc(64);
         tailErr = (int*)dev_alloc(64);
         tailPartial = dalloc<double>(2 * 1024);
@@ -1830,7 +1892,7 @@ struct tpp_solver {
         } else Cn.out = v.b[lv + 1];
         VLAUNCH(ctx, restrict, Cn, Cn.n);
         if (toTail) {
-            allreduceDev(v.tb[0], (size_t)tail[0].n);
+            gatherTail<R>(v.tb[0]);
             runTail<R>(nPre, nPost);
         } else vcycleT<R>(lv + 1, v.b[lv + 1], v.x[lv + 1], true, nPre, nPost);
         // prolonged correction c = P x_c in `oth`, A c, scaling, x += ...
@@ -2124,6 +2186,7 @@ struct tpp_solver {
 #else
         for (auto& g : graphs) cudaGraphExecDestroy(g.second.exec);
         for (void* p : comm.opened) cudaIpcCloseMemHandle(p);
+        dev_free(comm.gwin); dev_free(comm.gSeq); dev_free(comm.gDone);
         dev_free(comm.window); dev_free(comm.seq); dev_free(comm.arSeq); dev_free(comm.putDone); dev_free(comm.p2pErr);
         if (hscal) cudaFreeHost(hscal);
         if (ctx.stream && ctx.ownStream) cudaStreamDestroy(ctx.stream);
