@@ -347,24 +347,62 @@ HD double mu_of(const DV& d, double a, double r) {
 // ---- S4 momentum matrix ---------------------------------------------------------------------
 template <int WT> HD void b_grad_U(const DV& d, int c) {
     double g[9] = {0, 0, 0, 0, 0, 0, 0, 0, 0};
-    FOR_CELL_FACES(d, c)
-        if (f < d.nI) {
-            int P = isN ? o : c, N = isN ? c : o;
-            double wl = d.w[f];
-            double uf[3];
-            for (int j = 0; j < 3; j++) uf[j] = wl * d.U[3 * P + j] + (1.0 - wl) * d.U[3 * N + j];
-            for (int i = 0; i < 3; i++)
-                for (int j = 0; j < 3; j++) {
-                    double v = d.Sf[3 * f + i] * uf[j];
-                    if (isN) g[3 * i + j] -= v; else g[3 * i + j] += v;
-                }
-        } else {
-            const double* ub = &d.U_b[3 * (f - d.nI)];
-            for (int i = 0; i < 3; i++)
-                for (int j = 0; j < 3; j++) g[3 * i + j] += d.Sf[3 * f + i] * ub[j];
+    if constexpr (WT > 0) {
+        // load first (indices, then every gathered operand of all slots), accumulate in slot order
+        int e[WT], o[WT];
+        load_slots<WT>(d, c, e, o);
+        const double uc[3] = {d.U[3 * c], d.U[3 * c + 1], d.U[3 * c + 2]};
+        double wv[WT], S[WT][3], uo[WT][3];
+#pragma unroll
+        for (int k = 0; k < WT; k++) {
+            const bool live = e[k] >= 0;
+            const int f = live ? e[k] >> 1 : 0;
+            wv[k] = d.w[f];
+            S[k][0] = d.Sf[3 * f]; S[k][1] = d.Sf[3 * f + 1]; S[k][2] = d.Sf[3 * f + 2];
+            const double* q = f >= d.nI ? &d.U_b[3 * (f - d.nI)] : &d.U[3 * (live ? o[k] : c)];
+            uo[k][0] = q[0]; uo[k][1] = q[1]; uo[k][2] = q[2];
         }
-    END_CELL_FACES
-    for (int k = 0; k < 9; k++) d.gradU[9 * c + k] = g[k] / d.V[c];
+#pragma unroll
+        for (int k = 0; k < WT; k++) {
+            if (e[k] < 0) continue;
+            const int f = e[k] >> 1;
+            const bool isN = e[k] & 1;
+            if (f < d.nI) {
+                const double wl = wv[k];
+                double uf[3];
+                // uf = w U_P + (1 - w) U_N with P the face's owner
+                for (int j = 0; j < 3; j++) uf[j] = isN ? wl * uo[k][j] + (1.0 - wl) * uc[j] : wl * uc[j] + (1.0 - wl) * uo[k][j];
+                for (int i = 0; i < 3; i++)
+                    for (int j = 0; j < 3; j++) {
+                        double v = S[k][i] * uf[j];
+                        if (isN) g[3 * i + j] -= v; else g[3 * i + j] += v;
+                    }
+            } else {
+                for (int i = 0; i < 3; i++)
+                    for (int j = 0; j < 3; j++) g[3 * i + j] += S[k][i] * uo[k][j];
+            }
+        }
+    } else {
+        FOR_CELL_FACES(d, c)
+            if (f < d.nI) {
+                int P = isN ? o : c, N = isN ? c : o;
+                double wl = d.w[f];
+                double uf[3];
+                for (int j = 0; j < 3; j++) uf[j] = wl * d.U[3 * P + j] + (1.0 - wl) * d.U[3 * N + j];
+                for (int i = 0; i < 3; i++)
+                    for (int j = 0; j < 3; j++) {
+                        double v = d.Sf[3 * f + i] * uf[j];
+                        if (isN) g[3 * i + j] -= v; else g[3 * i + j] += v;
+                    }
+            } else {
+                const double* ub = &d.U_b[3 * (f - d.nI)];
+                for (int i = 0; i < 3; i++)
+                    for (int j = 0; j < 3; j++) g[3 * i + j] += d.Sf[3 * f + i] * ub[j];
+            }
+        END_CELL_FACES
+    }
+    const double V = d.V[c];
+    for (int k = 0; k < 9; k++) d.gradU[9 * c + k] = g[k] / V;
 }
 
 HD double vanLeerV_limiter(double flux, const double* uP, const double* uN, const double* gP, const double* gN, const double* dd) {
@@ -496,20 +534,51 @@ template <int WT> HD void b_HbyA(const DV& d, int c) {
     double D = d.mDiag[c];
     double hb[3] = {0, 0, 0}, ldu[3] = {0, 0, 0}, bbc[3] = {0, 0, 0};
     const double* Uc = &d.U[3 * c];
-    FOR_CELL_FACES(d, c)
-        if (f < d.nI) {
-            double a = isN ? d.mLower[f] : d.mUpper[f];
-            for (int k = 0; k < 3; k++) ldu[k] -= a * d.U[3 * o + k];
-        } else {
-            int b = f - d.nI;
-            double av = (d.mBIC[3 * b] + d.mBIC[3 * b + 1] + d.mBIC[3 * b + 2]) / 3.0;
-            D += av;
-            for (int k = 0; k < 3; k++) {
-                hb[k] += (av - d.mBIC[3 * b + k]) * Uc[k];
-                bbc[k] += d.mBBC[3 * b + k];
+    if constexpr (WT > 0) {
+        // load first: the off-diagonal coefficient and the neighbour's velocity of every internal slot
+        int e[WT], o[WT];
+        load_slots<WT>(d, c, e, o);
+        double a[WT], un[WT][3];
+#pragma unroll
+        for (int k = 0; k < WT; k++) {
+            const int f = e[k] >= 0 ? e[k] >> 1 : 0;
+            const bool internal = e[k] >= 0 && f < d.nI;
+            const int fi = internal ? f : 0, oc = internal ? o[k] : c;
+            a[k] = (e[k] & 1) ? d.mLower[fi] : d.mUpper[fi];
+            un[k][0] = d.U[3 * oc]; un[k][1] = d.U[3 * oc + 1]; un[k][2] = d.U[3 * oc + 2];
+        }
+#pragma unroll
+        for (int k = 0; k < WT; k++) {
+            if (e[k] < 0) continue;
+            const int f = e[k] >> 1;
+            if (f < d.nI) {
+                for (int q = 0; q < 3; q++) ldu[q] -= a[k] * un[k][q];
+            } else {
+                int b = f - d.nI;
+                double av = (d.mBIC[3 * b] + d.mBIC[3 * b + 1] + d.mBIC[3 * b + 2]) / 3.0;
+                D += av;
+                for (int q = 0; q < 3; q++) {
+                    hb[q] += (av - d.mBIC[3 * b + q]) * Uc[q];
+                    bbc[q] += d.mBBC[3 * b + q];
+                }
             }
         }
-    END_CELL_FACES
+    } else {
+        FOR_CELL_FACES(d, c)
+            if (f < d.nI) {
+                double a = isN ? d.mLower[f] : d.mUpper[f];
+                for (int k = 0; k < 3; k++) ldu[k] -= a * d.U[3 * o + k];
+            } else {
+                int b = f - d.nI;
+                double av = (d.mBIC[3 * b] + d.mBIC[3 * b + 1] + d.mBIC[3 * b + 2]) / 3.0;
+                D += av;
+                for (int k = 0; k < 3; k++) {
+                    hb[k] += (av - d.mBIC[3 * b + k]) * Uc[k];
+                    bbc[k] += d.mBBC[3 * b + k];
+                }
+            }
+        END_CELL_FACES
+    }
     double V = d.V[c];
     double A = D / V;
     double r = 1.0 / A;
@@ -630,23 +699,29 @@ template <int WT> HD void b_U_recon(const DV& d, int c) {
     if constexpr (WT > 0) {
         int e[WT], o[WT];
         load_slots<WT>(d, c, e, o);
-        double mv[WT], S[WT][3], rc[WT];
+        // two faces in flight at a time (their five operands each), accumulated in slot order: the
+        // all-four-at-once form needs 87 registers (2 CTAs per SM, 23 % of the warps resident)
 #pragma unroll
-        for (int k = 0; k < WT; k++) {
-            const int f = e[k] >= 0 ? e[k] >> 1 : 0;
-            mv[k] = d.magSf[f];
-            S[k][0] = d.Sf[3 * f]; S[k][1] = d.Sf[3 * f + 1]; S[k][2] = d.Sf[3 * f + 2];
-            rc[k] = d.rec[f];
-        }
+        for (int k0 = 0; k0 < WT; k0 += 2) {
+            double mv[2], S[2][3], rc[2];
 #pragma unroll
-        for (int k = 0; k < WT; k++) {
-            if (e[k] < 0) continue;
-            double m = mv[k];
-            double sh[3] = {S[k][0] / m, S[k][1] / m, S[k][2] / m};
-            double ssf = rc[k];
-            for (int i = 0; i < 3; i++) {
-                for (int j = 0; j < 3; j++) T[3 * i + j] += sh[i] * S[k][j];
-                rv[i] += sh[i] * ssf;
+            for (int q = 0; q < 2; q++) {
+                const int k = k0 + q < WT ? k0 + q : WT - 1;
+                const int f = e[k] >= 0 ? e[k] >> 1 : 0;
+                mv[q] = d.magSf[f];
+                S[q][0] = d.Sf[3 * f]; S[q][1] = d.Sf[3 * f + 1]; S[q][2] = d.Sf[3 * f + 2];
+                rc[q] = d.rec[f];
+            }
+#pragma unroll
+            for (int q = 0; q < 2; q++) {
+                if (k0 + q >= WT || e[k0 + q] < 0) continue;
+                double m = mv[q];
+                double sh[3] = {S[q][0] / m, S[q][1] / m, S[q][2] / m};
+                double ssf = rc[q];
+                for (int i = 0; i < 3; i++) {
+                    for (int j = 0; j < 3; j++) T[3 * i + j] += sh[i] * S[q][j];
+                    rv[i] += sh[i] * ssf;
+                }
             }
         }
     } else {
@@ -815,17 +890,17 @@ DEF_KERNEL_W(mules_update)
 DEF_KERNEL(mixture_cell, DV)
 DEF_KERNEL(mixture_bnd, DV)
 DEF_KERNEL(rhophi, DV)
-DEF_KERNEL_W(grad_U)
+DEF_KERNEL_WB(grad_U, 3)
 DEF_KERNEL(mom_face, DV)
 DEF_KERNEL(mom_bnd, DV)
 DEF_KERNEL_W(mom_cell)
-DEF_KERNEL_W(HbyA)
+DEF_KERNEL_WB(HbyA, 3)
 DEF_KERNEL(HbyA_bnd, DV)
 DEF_KERNEL(phiHbyA, DV)
 DEF_KERNEL(p_face, DV)
 DEF_KERNEL_W(p_cell)
 DEF_KERNEL(flux, DV)
-DEF_KERNEL_WB(U_recon, 2)  // 9 + 3 accumulators and 4 x 5 operands in flight: needs > 64 registers
+DEF_KERNEL_WB(U_recon, 3)  // 9 + 3 accumulators and 2 x 5 operands in flight
 DEF_KERNEL(Uf, DV)
 DEF_KERNEL(p, DV)
 DEF_KERNEL(p_shift, DV)
