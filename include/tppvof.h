@@ -130,6 +130,13 @@ long tpp_get_int(tpp_handle, const char* name, int* out, long cap);
 
 int tpp_info(tpp_handle, double* out16);
 
+/* The reference's interface metric, computed on the device from the current alpha.water
+ * (extract_interface, main.py:727-806, without PyVista): cell values averaged to the mesh points,
+ * the `iso` contour (0.5) = one point per mesh edge whose end values straddle it, on the mesh at its
+ * current rigid position.  out5 = max z, min z, mean z, number of contour points (the four columns of
+ * postProcessing/interface/interface_summary.csv) and the time.  Single-rank meshes only. */
+int tpp_interface(tpp_handle, double iso, double* out5);
+
 /* Run statistics over the steps since the last reset (what an OpenFOAM log is grepped for:
  * "No Iterations", and the alpha.water volume balance).  out9 (may be NULL): steps, sum and
  * maximum of the p_rgh / p_rghFinal iteration counts [1..4], steps whose p_rghFinal solve stopped at

@@ -544,6 +544,69 @@ __global__ void __launch_bounds__(64) k_allreduce_ll(const ARArgs a) {
 }
 #endif
 
+// ---- alpha = iso surface statistics on the device (the reference's interface_summary.csv) -------
+// main.py:761-780: cell data averaged to the points, contour at 0.5, max / min / mean z and the
+// number of the contour's points - one point per mesh edge whose end values straddle the level.
+struct IsoArgs {
+    int nP, nE;
+    const int *pcStart, *pcCells;  // point -> cells (CSR)
+    const int *edgeA, *edgeB;      // mesh edges (point pairs)
+    const double *alpha, *points0;
+    double* ptAlpha;
+    double iso;
+    double R[9], T[3], cofg[3];    // rigid transform to the lab frame
+    double* partial;               // [4][RED_BLOCKS]: sum z, count, max z, max(-z)
+    double* out;                   // [4]: max z, min z, mean z, count
+};
+HD void b_iso_point(const IsoArgs& a, int p) {
+    double s = 0;
+    const int b = a.pcStart[p], e = a.pcStart[p + 1];
+    for (int k = b; k < e; k++) s += a.alpha[a.pcCells[k]];
+    a.ptAlpha[p] = e > b ? s / (double)(e - b) : 0.0;
+}
+HD bool iso_edge_z(const IsoArgs& a, int e, double& z) {
+    const int pa = a.edgeA[e], pb = a.edgeB[e];
+    const double va = a.ptAlpha[pa], vb = a.ptAlpha[pb];
+    if ((va >= a.iso) == (vb >= a.iso)) return false;
+    const double t = (a.iso - va) / (vb - va);
+    double q[3];
+    for (int k = 0; k < 3; k++) q[k] = (a.points0[3 * pa + k] + t * (a.points0[3 * pb + k] - a.points0[3 * pa + k])) - a.cofg[k];
+    z = (a.R[6] * q[0] + a.R[7] * q[1] + a.R[8] * q[2]) + a.cofg[2] + a.T[2];
+    return true;
+}
+#ifndef TPP_EMU
+__global__ void __launch_bounds__(256) k_iso_point(const IsoArgs a) {
+    int p = blockIdx.x * blockDim.x + threadIdx.x;
+    if (p < a.nP) b_iso_point(a, p);
+}
+__global__ void __launch_bounds__(256) k_iso_edges(const IsoArgs a) {
+    double s = 0, n = 0, mx = -1e300, mn = -1e300;
+    for (int e = blockIdx.x * blockDim.x + threadIdx.x; e < a.nE; e += gridDim.x * blockDim.x) {
+        double z;
+        if (iso_edge_z(a, e, z)) { s += z; n += 1.0; mx = fmax(mx, z); mn = fmax(mn, -z); }
+    }
+    // block_max starts from the values given (no clamp at 0): shift by using sums of indicator-free maxima
+    __shared__ double sh[4][BLOCK / 32];
+    for (int o = 16; o > 0; o >>= 1) {
+        s += __shfl_down_sync(0xffffffffu, s, o); n += __shfl_down_sync(0xffffffffu, n, o);
+        mx = fmax(mx, __shfl_down_sync(0xffffffffu, mx, o)); mn = fmax(mn, __shfl_down_sync(0xffffffffu, mn, o));
+    }
+    const int lane = threadIdx.x & 31, wp = threadIdx.x >> 5;
+    if (lane == 0) { sh[0][wp] = s; sh[1][wp] = n; sh[2][wp] = mx; sh[3][wp] = mn; }
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        for (int k = 1; k < BLOCK / 32; k++) { s += sh[0][k]; n += sh[1][k]; mx = fmax(mx, sh[2][k]); mn = fmax(mn, sh[3][k]); }
+        a.partial[blockIdx.x] = s; a.partial[gridDim.x + blockIdx.x] = n; a.partial[2 * gridDim.x + blockIdx.x] = mx; a.partial[3 * gridDim.x + blockIdx.x] = mn;
+    }
+}
+__global__ void k_iso_final(const IsoArgs a, int nb) {
+    if (threadIdx.x != 0) return;
+    double s = 0, n = 0, mx = -1e300, mn = -1e300;
+    for (int k = 0; k < nb; k++) { s += a.partial[k]; n += a.partial[nb + k]; mx = fmax(mx, a.partial[2 * nb + k]); mn = fmax(mn, a.partial[3 * nb + k]); }
+    a.out[0] = n > 0 ? mx : 0.0; a.out[1] = n > 0 ? -mn : 0.0; a.out[2] = n > 0 ? s / n : 0.0; a.out[3] = n;
+}
+#endif
+
 #ifndef TPP_EMU
 // ---- all-gather of the tail right-hand side over the peer windows ---------------------------------
 // Once per V-cycle every rank contributes its slice of the gathered level's restricted residual

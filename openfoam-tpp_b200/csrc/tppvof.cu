@@ -999,6 +999,58 @@ struct tpp_solver {
             stBndInt += dt * v;
         }
     }
+    // ---- interface statistics on the device (tpp_interface) ---------------------------
+    bool isoBuilt = false;
+    IsoArgs iso;
+    void buildIso() {
+        isoBuilt = true;
+        memset(&iso, 0, sizeof(iso));
+        // distinct (point, cell) incidences and distinct edges from the face loops
+        std::vector<unsigned long long> pc, ed;
+        pc.reserve(fLab.size() * 2); ed.reserve(fLab.size());
+        for (int f = 0; f < nF; f++) {
+            const int b = fOff[f], n = fOff[f + 1] - b;
+            for (int i = 0; i < n; i++) {
+                const unsigned p0 = (unsigned)fLab[b + i], p1 = (unsigned)fLab[b + (i + 1) % n];
+                pc.push_back(((unsigned long long)p0 << 32) | (unsigned)own[f]);
+                if (f < nI && nei[f] < nC) pc.push_back(((unsigned long long)p0 << 32) | (unsigned)nei[f]);
+                ed.push_back(((unsigned long long)std::min(p0, p1) << 32) | std::max(p0, p1));
+            }
+        }
+        std::sort(pc.begin(), pc.end()); pc.erase(std::unique(pc.begin(), pc.end()), pc.end());
+        std::sort(ed.begin(), ed.end()); ed.erase(std::unique(ed.begin(), ed.end()), ed.end());
+        std::vector<int> st(nP + 1, 0), cells(pc.size()), ea(ed.size()), eb(ed.size());
+        for (size_t k = 0; k < pc.size(); k++) { st[(pc[k] >> 32) + 1]++; cells[k] = (int)(pc[k] & 0xffffffffu); }
+        for (int p = 0; p < nP; p++) st[p + 1] += st[p];
+        for (size_t k = 0; k < ed.size(); k++) { ea[k] = (int)(ed[k] >> 32); eb[k] = (int)(ed[k] & 0xffffffffu); }
+        iso.nP = nP; iso.nE = (int)ed.size();
+        iso.pcStart = upload(st); iso.pcCells = upload(cells); iso.edgeA = upload(ea); iso.edgeB = upload(eb);
+        iso.points0 = d.points0 ? d.points0 : upload(points0);
+        iso.ptAlpha = A<double>(nP); iso.partial = A<double>(4 * (size_t)RED_BLOCKS); iso.out = A<double>(4);
+    }
+    void interfaceSummary(double level, double* out4) {
+        if (!isoBuilt) buildIso();
+        iso.alpha = d.alpha; iso.iso = level;
+        for (int k = 0; k < 9; k++) iso.R[k] = Rn[k];
+        for (int k = 0; k < 3; k++) { iso.T[k] = Tn[k]; iso.cofg[k] = cfg.cofg[k]; }
+#ifdef TPP_EMU
+        for (int p = 0; p < nP; p++) b_iso_point(iso, p);
+        double s = 0, n = 0, mx = -1e300, mn = 1e300;
+        for (int e = 0; e < iso.nE; e++) { double z; if (iso_edge_z(iso, e, z)) { s += z; n += 1; mx = std::max(mx, z); mn = std::min(mn, z); } }
+        out4[0] = n > 0 ? mx : 0; out4[1] = n > 0 ? mn : 0; out4[2] = n > 0 ? s / n : 0; out4[3] = n;
+        ctx.launches += 3;
+#else
+        prof_begin(ctx, "iso_surface");
+        k_iso_point<<<(nP + 255) / 256, 256, 0, ctx.stream>>>(iso);
+        const int nb = std::max(1, std::min(RED_BLOCKS, (iso.nE + 255) / 256));
+        k_iso_edges<<<nb, 256, 0, ctx.stream>>>(iso);
+        k_iso_final<<<1, 32, 0, ctx.stream>>>(iso, nb);
+        LAUNCH_CHECK("k_iso");
+        prof_end(ctx);
+        ctx.launches += 3;
+        d2h(ctx, out4, iso.out, 4 * sizeof(double));
+#endif
+    }
     void fail(const std::string& msg) {
         if (ctx.err.empty()) { ctx.err = msg; fprintf(stderr, "tppvof: %s\n", msg.c_str()); }
     }
@@ -2424,6 +2476,13 @@ int tpp_info(tpp_handle s, double* o) try {
     o[8] = s->lastSolve[1].iters; o[9] = s->lastSolve[1].r0; o[10] = s->lastSolve[1].r;
     o[11] = s->d.needRef ? (s->renumbered && s->d.refCell >= 0 ? s->cellFileOf[s->d.refCell] : s->d.refCell) : -1; o[12] = s->d.deltaN; o[13] = s->writeTimeIndex;
     o[14] = (double)s->levels.size(); o[15] = (double)s->ctx.launches;
+    return 0;
+} API_CATCH(-100)
+int tpp_interface(tpp_handle s, double iso, double* out5) try {
+    API_DEVICE(s);
+    if (s->comm.active) { g_err = "tpp_interface: a decomposed mesh is not supported (points on processor patches see only this rank's cells); reconstruct first"; return -1; }
+    s->interfaceSummary(iso, out5);
+    out5[4] = s->t;
     return 0;
 } API_CATCH(-100)
 int tpp_stats(tpp_handle s, int reset, double* o) try {

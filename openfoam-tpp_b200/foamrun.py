@@ -121,7 +121,7 @@ class ProbesWriter:
         self.f.close()
 
 
-def run_case(case_dir, device=0, lib_path=None, max_steps=None, log=sys.stdout, write=True, parallel=False):
+def run_case(case_dir, device=0, lib_path=None, max_steps=None, log=sys.stdout, write=True, parallel=False, interface=None):
     """Advance a case from its latest time to endTime.  Returns a summary dict.
 
     parallel: `foamRun -parallel` - this process is one rank of a torch.distributed job
@@ -206,6 +206,18 @@ def run_case(case_dir, device=0, lib_path=None, max_steps=None, log=sys.stdout, 
         row0 = merge_rows([[case.start_value] + [pnow[c] if c >= 0 else vg for c in cells]])
         if probes is not None:
             probes.rows(row0)
+    # in-situ interface statistics (opt-in: `interface=True`, `foamRun -interface` or TPP_INTERFACE=1):
+    # the rows the reference's extract_interface derives from the time directories afterwards
+    # (main.py:751-780), computed on the device at every write time
+    if interface is None:
+        interface = os.environ.get("TPP_INTERFACE", "0") == "1"
+    iface = None
+    if interface and not multi:
+        os.makedirs(os.path.join(case.dir, "postProcessing", "interface"), exist_ok=True)
+        iface = open(os.path.join(case.dir, "postProcessing", "interface", "interface_summary.csv"), "a" if case.start_value > 0 else "w")
+        if case.start_value == 0:
+            iface.write("time,max_z,min_z,mean_z,num_points")
+            iface.write("\n{},{},{},{},{}".format(*s.interface_summary()))
     t0 = _time.perf_counter()
     steps0 = s.info()["step"]
     n_writes = 0
@@ -224,6 +236,9 @@ def run_case(case_dir, device=0, lib_path=None, max_steps=None, log=sys.stdout, 
             if write:
                 write_time(case, s, name, cfg.write_binary, cfg.write_precision)
             n_writes += 1
+            if iface is not None:
+                iface.write("\n{},{},{},{},{}".format(*s.interface_summary()))
+                iface.flush()
             if log:
                 el = _time.perf_counter() - t0
                 print(f"Time = {name}  step {int(info['step'])}  deltaT = {info['dt']:.6g}  Co = {info['Co']:.3g}  p_rghFinal iters {int(info['it1'])} res {info['r1']:.2e}  ExecutionTime = {el:.2f} s", file=log, flush=True)
@@ -234,6 +249,8 @@ def run_case(case_dir, device=0, lib_path=None, max_steps=None, log=sys.stdout, 
     nsteps = int(info["step"] - steps0)
     if probes is not None:
         probes.close()
+    if iface is not None:
+        iface.close()
     ncells = case.mesh.n_cells
     if parallel and world > 1:
         from . import ensemble
@@ -266,6 +283,8 @@ def main(argv=None):
             parallel = int(os.environ.get("WORLD_SIZE", "1")) > 1
         elif a == "-noFunctionObjects":
             pass
+        elif a == "-interface":
+            os.environ["TPP_INTERFACE"] = "1"
         elif a == "-solver":
             if argv.pop(0) != "incompressibleVoF":
                 raise SystemExit("only the incompressibleVoF solver module is provided")

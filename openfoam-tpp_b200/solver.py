@@ -68,6 +68,7 @@ def load(lib_path=None):
     L.tpp_step.argtypes = [H, C.c_int]
     L.tpp_run_to_write.argtypes = [H, C.c_long]
     L.tpp_stats.argtypes = [H, C.c_int, abi.c_double_p]
+    L.tpp_interface.argtypes = [H, C.c_double, abi.c_double_p]
     L.tpp_get_int.restype = C.c_long
     L.tpp_get_int.argtypes = [H, C.c_char_p, abi.c_int_p, C.c_long]
     L.tpp_stage.argtypes = [H, C.c_char_p]
@@ -181,6 +182,14 @@ class Solver:
         if self.L.tpp_get_int(self.h, name.encode(), a.ctypes.data_as(abi.c_int_p), n) < 0:
             self._err("tpp_get_int")
         return a
+
+    def interface_summary(self, iso=0.5):
+        """(time, max_z, min_z, mean_z, num_points) of the alpha = iso contour, computed on the device:
+        the columns of the reference's interface_summary.csv (main.py:751,780)."""
+        o = np.zeros(5)
+        if self.L.tpp_interface(self.h, float(iso), o.ctypes.data_as(abi.c_double_p)) != 0:
+            self._err("tpp_interface")
+        return float(o[4]), float(o[0]), float(o[1]), float(o[2]), int(o[3])
 
     def stats(self, reset=-1):
         """tpp_stats: iteration statistics and alpha-volume balance since the last reset."""

@@ -197,3 +197,45 @@ def test_gmsh_msh2_ingest_roundtrip(tmp_path):
     with pytest.raises(ff.FoamError):
         (tmp_path / "bad.msh").write_text("$MeshFormat\n4.1 0 8\n$EndMeshFormat\n")
         gmsh.msh_to_polymesh(str(tmp_path / "bad.msh"))
+
+
+def test_device_interface_summary_matches_the_host_metric(emu_lib, tmp_path):
+    _interface_check(emu_lib, tmp_path)
+
+
+@pytest.mark.gpu
+def test_device_interface_summary_gpu(gpu_lib, tmp_path):
+    _interface_check(None, tmp_path)
+
+
+def _interface_check(emu_lib, tmp_path):
+    """tpp_interface: the alpha = 0.5 contour statistics computed by the library's own
+    kernels equal the host restatement of the reference's metric (cell -> point average, one point
+    per straddling edge) on a sloshed state, also on an internally renumbered mesh, and foamRun
+    -interface writes them in the reference's interface_summary.csv layout."""
+    import bench
+    from openfoam_tpp_b200 import foamrun, interface, meshgen
+
+    for mesh, renum in ((meshgen.cylinder_mesh(bench.CASE["H"], bench.CASE["D"], 5, 8, "flat", "tet"), "0"), (meshgen.shuffled(meshgen.cylinder_mesh(bench.CASE["H"], bench.CASE["D"], 5, 8, "flat", "prism"), 3), "1")):
+        os.environ["TPP_RENUMBER"] = renum
+        try:
+            g = sv.Solver(mesh, bench.make_config(mesh), lib_path=emu_lib)
+        finally:
+            os.environ.pop("TPP_RENUMBER", None)
+        C, _ = meshgen.cell_geometry(mesh)
+        a = np.clip(0.5 + (0.104 + 0.2 * C[:, 0] - 0.1 * C[:, 1] - C[:, 2]) / 0.02, 0.0, 1.0)  # a tilted, smeared surface
+        g.set("alpha", a)
+        t, mx, mn, me, n = g.interface_summary()
+        pts = interface.iso_points(mesh, mesh.points, interface.cell_to_point(mesh, a), 0.5)
+        assert n == len(pts) > 20
+        assert abs(mx - pts[:, 2].max()) < 1e-12 and abs(mn - pts[:, 2].min()) < 1e-12 and abs(me - pts[:, 2].mean()) < 1e-12
+        g.close()
+    d = str(tmp_path / "case_H0.004_D0.0221_flat_R0.005_f2.0")
+    cs.setup_case(d, H=0.004, D=0.0221, R=0.005, freq=2.0, duration=0.004, n_rings=4, n_layers=4, write_interval=0.002)
+    foamrun.run_case(d, lib_path=emu_lib, log=None, interface=True)
+    rows = open(os.path.join(d, "postProcessing", "interface", "interface_summary.csv")).read().splitlines()
+    assert rows[0] == "time,max_z,min_z,mean_z,num_points" and len(rows) == 4  # t = 0 and two write times
+    ref = interface.extract_interface(d, write=False)
+    for r, (t, mx, mn, me, n) in zip(rows[1:], ref):
+        v = [float(x) for x in r.split(",")]
+        assert abs(v[0] - t) < 1e-12 and int(v[4]) == n and abs(v[1] - mx) < 1e-9 and abs(v[2] - mn) < 1e-9 and abs(v[3] - me) < 1e-9
