@@ -77,6 +77,8 @@ ALG_BYTES = {
     # label 4 B; C cells, F internal faces).  V-cycle kernels (v_*) move VB-byte values.
     "v_jacobi": lambda C, F: 4 * VB * C + (VB + 8) * F,      # x, b, diag in; x out; upper + addressing
     "v_residual": lambda C, F: 4 * VB * C + (VB + 8) * F,
+    "v_jacobi_first": lambda C, F: 3 * VB * C + (VB + 8) * F,        # b, diag in (own row and, re-read, the neighbours'); x out
+    "v_jacobi_corr": lambda C, F: (4 * VB + 4) * C + (VB + 8) * F,   # x, b, diag, aggregate map in (+ the coarse vector, L2-resident); x out
     "v_spmv_dot2": lambda C, F: 4 * VB * C + (VB + 8) * F,   # c, r, diag in; A c out
     "spmv_dot": lambda C, F: 24 * C + 16 * F,
     "update_xr": lambda C, F: 48 * C,                       # x, r in/out; pA, wA in
@@ -484,7 +486,7 @@ def main():
         """algorithmic bytes of ALL launches of a kernel in the profiled window"""
         if name in ALG_BYTES:
             return ALG_BYTES[name](nC, mesh.n_internal) * launches
-        per_row = {"v_jacobi_csr": 4 * VB, "v_residual_csr": 4 * VB, "v_spmv_dot2_csr": 4 * VB}.get(name)
+        per_row = {"v_jacobi_csr": 4 * VB, "v_residual_csr": 4 * VB, "v_spmv_dot2_csr": 4 * VB, "v_jacobi_first_csr": 3 * VB, "v_jacobi_corr_csr": 4 * VB + 4}.get(name)
         if per_row and coarse:  # one launch per coarse level and sweep: bytes summed over the levels
             sweep = sum(per_row * n + (VB + 8) * f for n, f in coarse)
             return sweep * launches / len(coarse)
@@ -507,10 +509,10 @@ def main():
         json.dump({"profiled_steps": 2, "cells": nC, "internal_faces": nI, "total_ms": tot_ms, "kernels_launches_ms_GBps": full}, open(args.kernel_table, "w"), indent=1)
     # measured DRAM traffic of the dominant kernel (committed ncu --set full capture), scaled per cell
     traffic = None
-    tp = os.path.join(ROOT, "profiles", "ncu_traffic_r1.json")
+    tp = os.path.join(ROOT, "profiles", "ncu_traffic_r2.json")
     if os.path.exists(tp):
         tr = json.load(open(tp))
-        if dom in tr["kernels"]:
+        if dom in tr["kernels"] and "dram_bytes" in tr["kernels"][dom]:
             traffic = tr["kernels"][dom]["dram_bytes"] * nC / tr["cells"]
     # the whole step against the roofline: algorithmic bytes of every kernel with a byte model
     # (measured launch counts, i.e. measured iteration counts) over the graph-mode step time
