@@ -1085,13 +1085,42 @@ struct tpp_solver {
         checkDeviceFlags();
         return wr;
     }
+    // probes (system/functions:17-33): one small gather kernel per step appends a row to a device
+    // ring; the rows come to the host in one copy when the ring is full, at a write time
+    // (tpp_run_to_write returns) or when tpp_probe_log asks - not one blocking copy per probe and step
+    static constexpr int PROBE_RING = 1024;
+    int* dProbeCells = nullptr;
+    double* dProbeRing = nullptr;
+    int probePending = 0, probeUploaded = -1;
+    std::vector<double> probeTimes;
     void sampleProbes() {
-        probeLog.push_back(t);
-        for (int c : probeCells) {
-            double v = -1.79769e+307;
-            if (c >= 0) d2h(ctx, &v, d.p + c, sizeof(double));
-            probeLog.push_back(v);
+        const int np = (int)probeCells.size();
+        if (probeUploaded != np || dProbeCells == nullptr) {
+            flushProbes();
+            dProbeCells = upload(probeCells);
+            dProbeRing = A<double>((size_t)PROBE_RING * np);
+            probeUploaded = np;
         }
+#ifdef TPP_EMU
+        for (int k = 0; k < np; k++) dProbeRing[(size_t)probePending * np + k] = probeCells[k] >= 0 ? d.p[probeCells[k]] : -1.79769e+307;
+#else
+        k_probe_row<<<1, 64, 0, ctx.stream>>>(d.p, dProbeCells, np, dProbeRing + (size_t)probePending * np);
+#endif
+        ctx.launches++;
+        probeTimes.push_back(t);
+        if (++probePending == PROBE_RING) flushProbes();
+    }
+    void flushProbes() {
+        const int np = probeUploaded;
+        if (probePending == 0 || np <= 0) return;
+        std::vector<double> rows((size_t)probePending * np);
+        d2h(ctx, rows.data(), dProbeRing, rows.size() * sizeof(double));
+        for (int r = 0; r < probePending; r++) {
+            probeLog.push_back(probeTimes[r]);
+            for (int k = 0; k < np; k++) probeLog.push_back(rows[(size_t)r * np + k]);
+        }
+        probeTimes.clear();
+        probePending = 0;
     }
 
     // ---- multigrid hierarchy (cached: the mesh only moves rigidly) ------------------------------
@@ -2510,12 +2539,15 @@ int tpp_solve(tpp_handle s, const tpp_solver_t* ctl, const double* diag, const d
     return st.iters;
 } API_CATCH(-100)
 int tpp_set_probes(tpp_handle s, int n, const int* cells) {  // cell labels of the mesh FILE (as tpp_find_cell returns them)
+    s->flushProbes();
     s->probeCells.assign(cells, cells + n);
+    s->probeUploaded = -1;
     if (s->renumbered) for (int& c : s->probeCells) if (c >= 0 && c < s->nC) c = s->cellNewOf[c];
     return 0;
 }
 long tpp_probe_log(tpp_handle s, double* out, long cap_rows) try {
     API_DEVICE(s);
+    s->flushProbes();
     long w = 1 + (long)s->probeCells.size();
     long rows = (long)s->probeLog.size() / w;
     long n = std::min(rows, cap_rows);

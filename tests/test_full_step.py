@@ -59,6 +59,36 @@ def test_full_steps_gpu(tmp_path, gpu_lib):
 
 
 @pytest.mark.gpu
+def test_full_steps_bench_layout_gpu(gpu_lib):
+    """The hierarchy layout the bench runs in - mesh level (two-rows-per-thread ELL kernels), an
+    ELL + overflow level of > 60 k rows smoothed kernel by kernel, the persistent tail kernel below -
+    on a 0.41 M-cell mesh of the bench's own tank, against the oracle (OpenFOAM-style sequential
+    GAMG), both solving tightly: time-step sequence and fields as in the small-mesh test."""
+    import bench
+    import oracle
+
+    mesh, nr, nl = bench.mesh_for(4.1e5)
+    cfg = bench.make_config(mesh)
+    _tight(cfg)
+    g = sv.Solver(mesh, cfg)
+    o = oracle.Oracle(mesh, cfg)
+    a0 = bench.initial_alpha(mesh)
+    g.set("alpha", a0); g.init_fields()
+    o.set("alpha", a0); o.stage("alphaBCs"); o.stage("mixture")
+    for i in range(2):
+        g.step(1); o.step(1)
+        gi, oi = g.info(), o.info()
+        assert abs(gi["t"] - oi["t"]) <= 1e-12 * oi["t"] and abs(gi["dt"] - oi["dt"]) <= 1e-9 * oi["dt"]
+        for nm, tol in (("alpha", 1e-9), ("U", 1e-7), ("p_rgh", 1e-7), ("phi", 1e-7)):
+            a, b = g.get(nm), o.get(nm)
+            err = np.abs(a - b).max() / max(np.abs(b).max(), 1e-300)
+            assert err <= tol, f"step {i}: {nm} differs by {err:.2e} of its scale (> {tol})"
+    lay = g.amg_layout()
+    assert lay["kernel_levels"] >= 2 and lay["tail_levels"] >= 2, lay
+    g.close(); o.close()
+
+
+@pytest.mark.gpu
 def test_full_steps_cap_prism_gpu(tmp_path, gpu_lib):
     _full_steps(str(tmp_path / "c"), gpu_lib, 4, geo="cap", cell="prism", n_rings=10)
 

@@ -239,3 +239,35 @@ def _interface_check(emu_lib, tmp_path):
     for r, (t, mx, mn, me, n) in zip(rows[1:], ref):
         v = [float(x) for x in r.split(",")]
         assert abs(v[0] - t) < 1e-12 and int(v[4]) == n and abs(v[1] - mx) < 1e-9 and abs(v[2] - mn) < 1e-9 and abs(v[3] - me) < 1e-9
+
+
+def test_a_diverged_run_stops_with_an_error(emu_lib, tmp_path):
+    """a run whose Courant number is not finite must not carry on, write time
+    directories and exit 0 - tpp_step / tpp_run_to_write return an error, the Python host raises and
+    foamRun exits non-zero (what `check=True`, main.py:345, relies on)."""
+    import bench
+    from openfoam_tpp_b200 import foamrun
+
+    mesh = mg.cylinder_mesh(bench.CASE["H"], bench.CASE["D"], 4, 6, "flat", "tet")
+    g = sv.Solver(mesh, bench.make_config(mesh), lib_path=emu_lib)
+    g.set("alpha", bench.initial_alpha(mesh))
+    g.init_fields()
+    g.step(2)
+    phi = g.get("phi")
+    phi[3] = np.nan
+    g.set("phi", phi)
+    with pytest.raises(sv.SolverError, match="not finite"):
+        g.run_to_write(5)
+    with pytest.raises(sv.SolverError):
+        g.step(1)
+    g.close()
+    d = str(tmp_path / "case_H0.004_D0.0221_flat_R0.005_f2.0")
+    cs.setup_case(d, H=0.004, D=0.0221, R=0.005, freq=2.0, duration=0.004, n_rings=4, n_layers=4, write_interval=0.002)
+    U = ff.read_field(os.path.join(d, "0", "U"))
+    bad = np.zeros((ff.read_polymesh(d).n_cells, 3))
+    bad[5, 0] = np.inf
+    ff.write_field(os.path.join(d, "0", "U"), ff.Field(U.cls, U.name, U.dimensions, bad, U.boundary), True, location="0")
+    os.environ["TPP_LIB_PATH_FOR_TEST"] = emu_lib
+    with pytest.raises(Exception):
+        foamrun.run_case(d, lib_path=emu_lib, log=None)
+    assert not any(v > 0 for v, _ in ff.time_dirs(d))  # nothing was written after the failure

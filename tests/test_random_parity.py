@@ -23,10 +23,11 @@ _CASES = {}
 
 def _pair(tmp, cell, geo, lib):
     key = (cell, geo)
+    geo, tag = geo.split(":")
     if key not in _CASES:
         import oracle
 
-        d = str(tmp / f"case_{cell}_{geo}")
+        d = str(tmp / f"case_{cell}_{geo}_{tag}")
         if cell == "hex":
             cs.setup_tutorial_case(d, nx=4, ny=6, nz=5, end_time=1.0)  # the tutorial tank's hex block mesh
         else:
@@ -57,7 +58,20 @@ def _exact(g, o, names, what):
 @settings(max_examples=20, deadline=None, suppress_health_check=[HealthCheck.function_scoped_fixture])
 @given(seed=st.integers(0, 2**31 - 1), sharp=st.booleans(), umag=st.sampled_from([1e-3, 0.05, 1.0]))
 def test_random_state_step_is_bit_exact_emu(tmp_path_factory, emu_lib, cell, geo, seed, sharp, umag):
-    c, g, o = _pair(tmp_path_factory.getbasetemp(), cell, geo, emu_lib)
+    _random_state_step(tmp_path_factory.getbasetemp(), emu_lib, "emu", cell, geo, seed, sharp, umag)
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("cell,geo", [("tet", "flat"), ("prism", "cap"), ("hex", "tank")])
+def test_random_state_step_is_bit_exact_gpu(tmp_path_factory, gpu_lib, cell, geo):
+    """the same property on the sm_100a kernels themselves (fixed seeds: sharp and smeared alpha,
+    slow and fast flow), hex cells included"""
+    for seed, sharp, umag in ((11, True, 0.05), (12, False, 1.0), (13, False, 1e-3), (14, True, 1.0)):
+        _random_state_step(tmp_path_factory.getbasetemp(), None, "gpu", cell, geo, seed, sharp, umag)
+
+
+def _random_state_step(base, lib, tag, cell, geo, seed, sharp, umag):
+    c, g, o = _pair(base, cell, geo + ":" + tag, lib)
     rng = np.random.default_rng(seed)
     nC, nF, nI = c.mesh.n_cells, c.mesh.n_faces, c.mesh.n_internal
     a = rng.random(nC)
