@@ -176,13 +176,104 @@ def beat_fit(t, amp, phase, f_forcing, t0=2.0, t1=None):
     return {"f0": float(f0), "gamma": float(g), "A_forced": float(abs(c[0])), "A_free": float(abs(c[1])), "rms": r}
 
 
-def extract_interface(case_dir, r_target=None, write=True):
+def tet_points(mesh):
+    """(nC, 4) point labels of every cell of a tetrahedral mesh, or None when some cell is not a tet."""
+    off, lab = mesh.face_offsets.astype(np.int64), mesh.face_labels.astype(np.int64)
+    cnt = np.diff(off)
+    if np.any(cnt != 3):
+        return None
+    nI = mesh.n_internal
+    cells = np.concatenate([np.repeat(mesh.owner.astype(np.int64), 3), np.repeat(mesh.neighbour.astype(np.int64), 3)])
+    pts = np.concatenate([lab, lab[: 3 * nI]])
+    key = np.unique(cells * mesh.n_points + pts)
+    if key.size != 4 * mesh.n_cells or np.any(np.bincount(key // mesh.n_points, minlength=mesh.n_cells) != 4):
+        return None
+    return (key % mesh.n_points).reshape(mesh.n_cells, 4)
+
+
+def iso_surface(mesh, points, point_values, iso=0.5, edges=None, tets=None):
+    """Contour points AND triangles (marching tetrahedra) of a tetrahedral mesh: what the contour
+    filter of the reference produces on its gmsh tets (main.py:770).  -> (pts (N,3), tris (M,3) into
+    pts, (edge end a, edge end b, weight t) of every point for interpolating other fields).  On a
+    non-tetrahedral mesh tris is empty."""
+    a, b = edges if edges is not None else mesh_edges(mesh)
+    va, vb = point_values[a], point_values[b]
+    cut = (va >= iso) != (vb >= iso)
+    ca, cb = a[cut], b[cut]
+    t = (iso - va[cut]) / (vb[cut] - va[cut])
+    pts = points[ca] + t[:, None] * (points[cb] - points[ca])
+    tets = tet_points(mesh) if tets is None else tets
+    if tets is None or pts.shape[0] == 0:
+        return pts, np.zeros((0, 3), dtype=np.int64), (ca, cb, t)
+    nP = mesh.n_points
+    ekey = ca * nP + cb  # ascending (edges come sorted from mesh_edges, a < b)
+
+    def eid(p, q):
+        lo, hi = np.minimum(p, q), np.maximum(p, q)
+        return np.searchsorted(ekey, lo * nP + hi)
+
+    above = point_values[tets] >= iso
+    k = above.sum(axis=1)
+    tris = []
+    for lone_above in (True, False):  # one vertex on its own side: a triangle
+        sel = np.nonzero(k == (1 if lone_above else 3))[0]
+        if sel.size:
+            tv = tets[sel]
+            m = above[sel] == lone_above
+            lone = tv[m]
+            rest = tv[~m].reshape(-1, 3)
+            tris.append(np.stack([eid(lone, rest[:, 0]), eid(lone, rest[:, 1]), eid(lone, rest[:, 2])], axis=1))
+    sel = np.nonzero(k == 2)[0]  # two and two: a quadrilateral, split into two triangles
+    if sel.size:
+        tv = tets[sel]
+        m = above[sel]
+        up = tv[m].reshape(-1, 2)
+        dn = tv[~m].reshape(-1, 2)
+        q0, q1, q2, q3 = eid(up[:, 0], dn[:, 0]), eid(up[:, 0], dn[:, 1]), eid(up[:, 1], dn[:, 1]), eid(up[:, 1], dn[:, 0])
+        tris.append(np.stack([q0, q1, q2], axis=1))
+        tris.append(np.stack([q0, q2, q3], axis=1))
+    tris = np.concatenate(tris) if tris else np.zeros((0, 3), dtype=np.int64)
+    return pts, tris, (ca, cb, t)
+
+
+def write_vtp(path, pts, tris, point_data=None):
+    """A VTK XML PolyData file (ASCII arrays) of the contour: the `interface_t<time>.vtp` files
+    extract_interface leaves next to its CSVs (main.py:772-774), readable by ParaView / PyVista."""
+    point_data = point_data or {}
+
+    def arr(a, typ, name=None, nc=None):
+        a = np.asarray(a)
+        head = f'<DataArray type="{typ}"' + (f' Name="{name}"' if name else "") + (f' NumberOfComponents="{nc}"' if nc else "") + ' format="ascii">'
+        fmt = "%d" if typ.startswith("Int") else "%.9g"
+        return head + "\n" + " ".join(fmt % v for v in a.reshape(-1)) + "\n</DataArray>\n"
+
+    n, m = int(pts.shape[0]), int(tris.shape[0])
+    with open(path, "w") as f:
+        f.write('<?xml version="1.0"?>\n<VTKFile type="PolyData" version="0.1" byte_order="LittleEndian">\n<PolyData>\n')
+        f.write(f'<Piece NumberOfPoints="{n}" NumberOfVerts="{0 if m else n}" NumberOfLines="0" NumberOfStrips="0" NumberOfPolys="{m}">\n')
+        scal = [k for k, v in point_data.items() if np.asarray(v).ndim == 1]
+        vec = [k for k, v in point_data.items() if np.asarray(v).ndim == 2]
+        f.write("<PointData" + (f' Scalars="{scal[0]}"' if scal else "") + (f' Vectors="{vec[0]}"' if vec else "") + ">\n")
+        for k, v in point_data.items():
+            v = np.asarray(v, dtype=np.float32)
+            f.write(arr(v, "Float32", k, v.shape[1] if v.ndim == 2 else None))
+        f.write("</PointData>\n<Points>\n" + arr(np.asarray(pts, dtype=np.float32), "Float32", "Points", 3) + "</Points>\n")
+        if m:
+            f.write("<Polys>\n" + arr(tris, "Int64", "connectivity") + arr(3 * np.arange(1, m + 1), "Int64", "offsets") + "</Polys>\n")
+        else:
+            f.write("<Verts>\n" + arr(np.arange(n), "Int64", "connectivity") + arr(np.arange(1, n + 1), "Int64", "offsets") + "</Verts>\n")
+        f.write("</Piece>\n</PolyData>\n</VTKFile>\n")
+
+
+def extract_interface(case_dir, r_target=None, write=True, vtp=False):
     """VTK-free restatement of the reference's `extract_interface` (main.py:727-818): for every
     time directory the alpha.water = 0.5 iso-surface of the point-averaged field on the mesh at
     that time (`<time>/polyMesh/points`: lab frame), reduced to
     postProcessing/interface/interface_summary.csv (time,max_z,min_z,mean_z,num_points) and
     wall_elevation.csv (time,theta,zeta_wall; points with r > 0.98 R in 64 theta bins).
-    (The per-frame .vtp files are not written.)  Returns the summary rows."""
+    vtp=True also writes the per-frame `interface_t<time>.vtp` files (main.py:772-774): contour points,
+    triangles (tetrahedral meshes) and the point data alpha.water / p_rgh / U / p / rho interpolated along
+    the cut edges.  Returns the summary rows."""
     import os
     import re
 
@@ -190,6 +281,7 @@ def extract_interface(case_dir, r_target=None, write=True):
 
     mesh = ff.read_polymesh(case_dir)
     edges = mesh_edges(mesh)
+    tets = tet_points(mesh) if vtp else None
     if r_target is None:
         m = re.search(r"_D([\d.]+)_", os.path.basename(os.path.normpath(case_dir)))
         r_target = float(m.group(1)) / 2.0 if m else 0.1
@@ -203,7 +295,20 @@ def extract_interface(case_dir, r_target=None, write=True):
         alpha = ff.read_field(fp).internal_array(mesh.n_cells)
         pp = os.path.join(case_dir, name, "polyMesh", "points")
         pts_mesh = ff.read_points(pp) if os.path.exists(pp) else mesh.points
-        pts = iso_points(mesh, pts_mesh, cell_to_point(mesh, alpha), 0.5, edges)
+        pa = cell_to_point(mesh, alpha)
+        pts = iso_points(mesh, pts_mesh, pa, 0.5, edges)
+        if vtp and write:
+            p2, tris, (ca, cb, tt) = iso_surface(mesh, pts_mesh, pa, 0.5, edges, tets)
+            data = {"alpha.water": np.full(len(p2), 0.5)}
+            for fld in ("p_rgh", "p", "rho", "U"):
+                fq = os.path.join(case_dir, name, fld)
+                if os.path.exists(fq):
+                    pv = ff.read_field(fq).internal_array(mesh.n_cells)
+                    pv = np.stack([cell_to_point(mesh, pv[:, k]) for k in range(3)], axis=1) if pv.ndim == 2 else cell_to_point(mesh, pv)
+                    data[fld] = pv[ca] + (tt[:, None] if pv.ndim == 2 else tt) * (pv[cb] - pv[ca])
+            out = os.path.join(case_dir, "postProcessing", "interface")
+            os.makedirs(out, exist_ok=True)
+            write_vtp(os.path.join(out, f"interface_t{t:.6f}.vtp"), p2, tris, data)
         if len(pts) == 0:
             summary.append(f"{t},0,0,0,0")
             rows.append((t, 0.0, 0.0, 0.0, 0))

@@ -50,3 +50,38 @@ def test_extract_interface_files(tmp_path):
     assert head[0] == "time,max_z,min_z,mean_z,num_points" and len(head) == 2
     wall = open(os.path.join(out, "wall_elevation.csv")).read().splitlines()
     assert wall[0] == "time,theta,zeta_wall" and 1 < len(wall) <= 65
+
+
+def test_marching_tets_surface_and_vtp(tmp_path):
+    """The contour as a triangulated surface (what PyVista's contour filter gives the reference on its
+    tets, main.py:770-774): for a planar field the triangles tile the plane's cut through the
+    cylinder (area of the ellipse to the accuracy of the polygonal rim), every triangle lies in the
+    plane, and the .vtp file carries the points, the triangles and the point data."""
+    import xml.etree.ElementTree as ET
+
+    from openfoam_tpp_b200 import interface as it
+    from openfoam_tpp_b200 import meshgen as mg
+
+    R, H = 0.1, 0.208
+    mesh = mg.cylinder_mesh(H, 2 * R, 8, 12, "flat", "tet")
+    n = np.array([0.2, -0.1, 1.0])
+    pv = 0.5 + (0.104 - mesh.points @ n)  # a plane through z = 0.104 at the axis, tilted
+    pts, tris, (ca, cb, t) = it.iso_surface(mesh, mesh.points, pv, 0.5)
+    assert len(pts) == len(it.iso_points(mesh, mesh.points, pv, 0.5)) and len(tris) > len(pts)
+    assert np.abs(pts @ n - 0.104).max() < 1e-12
+    a, b, c = pts[tris[:, 0]], pts[tris[:, 1]], pts[tris[:, 2]]
+    area = 0.5 * np.linalg.norm(np.cross(b - a, c - a), axis=1).sum()
+    exact = np.pi * R * R * np.linalg.norm(n) / n[2]
+    assert abs(area / exact - 1) < 0.03, (area, exact)
+    f = tmp_path / "interface_t0.000000.vtp"
+    it.write_vtp(str(f), pts, tris, {"alpha.water": np.full(len(pts), 0.5), "U": np.zeros((len(pts), 3))})
+    piece = ET.parse(str(f)).getroot().find("PolyData/Piece")
+    assert int(piece.get("NumberOfPoints")) == len(pts) and int(piece.get("NumberOfPolys")) == len(tris)
+    names = [d.get("Name") for d in piece.find("PointData")]
+    assert names == ["alpha.water", "U"]
+    conn = np.array(piece.find("Polys/DataArray[@Name='connectivity']").text.split(), dtype=np.int64)
+    assert conn.size == 3 * len(tris) and conn.max() < len(pts)
+    # prisms: points only (vertices)
+    pm = mg.cylinder_mesh(H, 2 * R, 4, 4, "flat", "prism")
+    p2, t2, _ = it.iso_surface(pm, pm.points, 0.5 + (0.104 - pm.points @ n), 0.5)
+    assert len(p2) > 0 and len(t2) == 0
