@@ -338,6 +338,9 @@ __global__ void __launch_bounds__(256) k_init_residual(LV L, const double* x, co
     if (threadIdx.x == 0) { partialRes[blockIdx.x] = v; partialNorm[blockIdx.x] = w; }
 }
 __global__ void k_scal_copy(double* scal, int dst, int src) { scal[dst] = scal[src]; }
+__global__ void __launch_bounds__(256) k_add(int n, double* x, const double* z) {
+    for (int c = blockIdx.x * blockDim.x + threadIdx.x; c < n; c += gridDim.x * blockDim.x) x[c] += z[c];
+}
 // one row of the probes log: p at the probe cells (OpenFOAM's "not found" value outside the mesh)
 __global__ void k_probe_row(const double* p, const int* cells, int n, double* row) {
     for (int k = threadIdx.x; k < n; k += blockDim.x) row[k] = cells[k] >= 0 ? p[cells[k]] : -1.79769e+307;

@@ -2071,6 +2071,29 @@ struct tpp_solver {
         st.r0 = st.r = hscal[S_RES] / nf;
         auto conv = [&](double r) { return r < ctl.tolerance || (ctl.rel_tol > 0 && r < ctl.rel_tol * st.r0); };
         if (conv(st.r)) return st;
+        if (ctl.type == 1 && useAMG && knob("TPP_GAMG_STATIONARY", 0)) {
+            // `solver GAMG` taken literally (fvSolution:42-48): stationary V-cycle iterations
+            // x += V(b - A x) until the residual criterion is met.  Off by default: the same V-cycle as the
+            // preconditioner of PCG (the default for both solver entries) reaches relTol 0.01 in about
+            // half the cycles, and OpenFOAM's own criterion (tolerance, relTol) is what the caller asked for.
+            const int maxIt = ctl.max_iter > 0 ? ctl.max_iter : 1000;
+            do {
+                precondition(F0, ctl, kr, kz);
+#ifdef TPP_EMU
+                for (int c = 0; c < nC; c++) x[c] += kz[c];
+#else
+                k_add<<<RED_BLOCKS, BLOCK, 0, ctx.stream>>>(nC, x, kz);
+#endif
+                ctx.launches++;
+                X(x, 1);
+                initResidual(FG, x, b);
+                allreduce(S_RES, 2, 0);
+                readScal();
+                st.r = hscal[S_RES] / nf;
+            } while (++st.iters < maxIt && !conv(st.r) && std::isfinite(st.r));
+            if (!std::isfinite(st.r)) fail("the p_rgh solver residual is not finite (diverged)");
+            return st;
+        }
         // The stopping rule runs on the device (k_pcg_check after every iteration).  Large meshes read the
         // scalars back after every iteration (an iteration is ~1 ms, the round trip nothing); small ones
         // (the reference's own 8 k - 42 k-cell cases) launch as many iterations as the previous solve of

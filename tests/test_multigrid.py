@@ -82,3 +82,30 @@ def test_tail_kernel_equals_kernel_per_operation_emu(emu_lib):
 @pytest.mark.gpu
 def test_tail_kernel_equals_kernel_per_operation_gpu(gpu_lib):
     _check(None)
+
+
+def test_gamg_as_a_stationary_iteration_emu(emu_lib):
+    """`solver GAMG` (fvSolution:42-48) taken literally - V-cycles as a stationary iteration, no Krylov
+    acceleration (TPP_GAMG_STATIONARY=1) - converges to the same solution under the same residual
+    criterion; by default the entry runs as PCG preconditioned by the same V-cycle (fewer cycles)."""
+    import copy as _copy
+
+    its = {}
+    for flag in ("0", "1"):
+        os.environ["TPP_GAMG_STATIONARY"] = flag
+        try:
+            mesh = mg.cylinder_mesh(bench.CASE["H"], bench.CASE["D"], 10, 20, "flat", "tet")
+            cfg = bench.make_config(mesh)
+            g = sv.Solver(mesh, cfg, device=0, lib_path=emu_lib)
+            diag, upper, b, A = _system(mesh)
+            ctl = _copy.copy(cfg.p_rgh)  # type GAMG
+            assert ctl.type == 1
+            ctl.tolerance, ctl.rel_tol, ctl.max_iter = 1e-10, 0.0, 400
+            x, it, r0, r = g.solve(ctl, diag, upper, b)
+            g.close()
+        finally:
+            os.environ.pop("TPP_GAMG_STATIONARY", None)
+        xs = spla.spsolve(A, b)
+        assert r < 1e-10 and np.abs(x - xs).max() <= 1e-6 * np.abs(xs).max(), (flag, it, r)
+        its[flag] = it
+    assert its["0"] <= its["1"] < 400, its
