@@ -198,7 +198,7 @@ struct tpp_solver {
     bool permute(const double* src, double* dst, long n, bool toFile) {
         if (!renumbered) return false;
         auto k = kindOf(n);
-        if (k.first == 0) return false;
+        if (k.first == 0 || (k.first == 'F' && nG > 0)) return false;  // (all-face arrays of a processor mesh: permDev2File, tpp_get / tpp_set)
         const int* perm = k.first == 'C' ? dCellFileOf : dFaceFileOf;
         const int rows = k.first == 'C' ? nC : k.first == 'F' ? nF : nI;
         d.xsrc = src; d.xbuf = dst; d.xnc = k.second; d.procOwner = perm;
@@ -358,7 +358,8 @@ struct tpp_solver {
     // mesh (no spatial coherence in its labels) is renumbered: 2.2 x faster steps at 6.2 M cells.
     void decideRenumbering(std::vector<double>& w, std::vector<double>& dc, std::vector<double>& corr, std::vector<double>& dPN) {
         const int mode = knob("TPP_RENUMBER", -1);
-        if (mode == 0 || nG > 0 || nC < 2 || nI < 1) return;
+        const int nIl = nG > 0 ? nIloc : nI;  // faces between two cells of this rank (processor faces keep their place)
+        if (mode == 0 || nC < 2 || nIl < 1) return;
         for (long n : {(long)nC, (long)nF, (long)nI})  // lengths must tell the array kinds apart (tpp_get / tpp_set)
             for (long m2 : {(long)nC, (long)nF, (long)nI, (long)nB})
                 for (int a : {1, 3, 9}) for (int b : {1, 3, 9}) if (!(n == m2 && a == b) && (long)a * n == (long)b * m2 && n != m2) return;
@@ -373,21 +374,22 @@ struct tpp_solver {
         std::vector<int> newOf(nC), fileOf(nC);
         for (int i = 0; i < nC; i++) { fileOf[i] = keyed[i].second; newOf[keyed[i].second] = i; }
         double before = 0, after = 0;
-        for (int f = 0; f < nI; f++) { before += std::abs(own[f] - nei[f]); after += std::abs(newOf[own[f]] - newOf[nei[f]]); }
+        for (int f = 0; f < nIl; f++) { before += std::abs(own[f] - nei[f]); after += std::abs(newOf[own[f]] - newOf[nei[f]]); }
+        // every rank decides for itself: the labels are private to the rank (ghost rows and processor faces stay)
         if (mode < 0 && !(after * 3.0 <= before)) return;
         renumbered = true;
         cellFileOf = fileOf; cellNewOf = newOf;
-        // internal faces by (lower new cell, higher new cell); orientation (owner / neighbour roles) kept
-        std::vector<std::pair<unsigned long long, int>> fk(nI);
-        for (int f = 0; f < nI; f++) {
+        // local internal faces by (lower new cell, higher new cell); orientation (owner / neighbour roles) kept
+        std::vector<std::pair<unsigned long long, int>> fk(nIl);
+        for (int f = 0; f < nIl; f++) {
             unsigned a = (unsigned)newOf[own[f]], b = (unsigned)newOf[nei[f]];
             fk[f] = {((unsigned long long)std::min(a, b) << 32) | std::max(a, b), f};
         }
         std::sort(fk.begin(), fk.end());
         faceFileOf.resize(nF);
-        for (int f = 0; f < nI; f++) { faceFileOf[f] = fk[f].second; faceNewOf[fk[f].second] = f; }
-        for (int f = nI; f < nF; f++) faceFileOf[f] = f;
-        auto permF = [&](std::vector<double>& a, int nc, int n) {  // face arrays: entry f <- file entry faceFileOf[f]
+        for (int f = 0; f < nIl; f++) { faceFileOf[f] = fk[f].second; faceNewOf[fk[f].second] = f; }
+        for (int f = nIl; f < nF; f++) faceFileOf[f] = f;
+        auto permF = [&](std::vector<double>& a, int nc, int n) {  // face arrays: entry f <- old entry faceFileOf[f]
             std::vector<double> o(a.size());
             for (int f = 0; f < n; f++) for (int k = 0; k < nc; k++) o[(size_t)f * nc + k] = a[(size_t)faceFileOf[f] * nc + k];
             for (size_t i = (size_t)n * nc; i < a.size(); i++) o[i] = a[i];
@@ -398,19 +400,27 @@ struct tpp_solver {
             for (int c = 0; c < nC; c++) for (int k = 0; k < nc; k++) o[(size_t)c * nc + k] = a[(size_t)fileOf[c] * nc + k];
             a.swap(o);
         };
-        permF(Cf0, 3, nI); permF(Sf0, 3, nI); permF(magSf, 1, nI); permF(w, 1, nI); permF(dc, 1, nI); permF(corr, 3, nI); permF(dPN, 3, nI);
+        permF(Cf0, 3, nIl); permF(Sf0, 3, nIl); permF(magSf, 1, nIl); permF(w, 1, nIl); permF(dc, 1, nIl); permF(corr, 3, nIl); permF(dPN, 3, nIl);
         permC(C0, 3); permC(V, 1);
         std::vector<int> own2(nF), nei2(nI), off2(nF + 1, 0), lab2;
         lab2.reserve(fLab.size());
         for (int f = 0; f < nF; f++) {
             const int ff = faceFileOf[f];
             own2[f] = newOf[own[ff]];
-            if (f < nI) nei2[f] = newOf[nei[ff]];
+            if (f < nI) nei2[f] = nei[ff] < nC ? newOf[nei[ff]] : nei[ff];  // ghost rows keep their labels
             for (int k = fOff[ff]; k < fOff[ff + 1]; k++) lab2.push_back(fLab[k]);
             off2[f + 1] = (int)lab2.size();
         }
         own.swap(own2); nei.swap(nei2); fOff.swap(off2); fLab.swap(lab2);
-        if (knob("TPP_VERBOSE", 0)) fprintf(stderr, "tppvof: cells renumbered in Morton order (mean |owner - neighbour| %.0f -> %.0f)\n", before / nI, after / nI);
+        for (int& c : procOwner) c = newOf[c];
+        if (nG > 0) {
+            // face arrays cross the ABI through permDev2File (device face -> file face of the rank's
+            // processorN mesh): compose it with the renumbering, and point faceFileOf at the file too
+            std::vector<int> comp(nF);
+            for (int f = 0; f < nF; f++) comp[f] = permDev2File[faceFileOf[f]];
+            permDev2File.swap(comp);
+        }
+        if (knob("TPP_VERBOSE", 0)) fprintf(stderr, "tppvof: cells renumbered in Morton order (mean |owner - neighbour| %.0f -> %.0f)\n", before / nIl, after / nIl);
     }
 
     bool build(const tpp_mesh_t* m, const tpp_config_t* c) {
@@ -2417,7 +2427,7 @@ long tpp_set(tpp_handle s, const char* name, const double* in, long n) try {
         dev_sync(s->ctx);
         return n;
     }
-    if (s->renumbered && s->kindOf(n).first != 0) {
+    if (s->renumbered && s->kindOf(n).first != 0 && !(s->kindOf(n).first == 'F' && s->nG > 0)) {
         s->ensurePermBuf();
         h2d(s->ctx, s->permBuf, in, n * sizeof(double));
         s->permute(s->permBuf, it->second.first, n, false);
