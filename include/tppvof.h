@@ -122,6 +122,14 @@ int tpp_stage(tpp_handle, const char* name);
 
 /* out[16]: t, deltaT, step, Co, alphaCo, iters/initial/final residual of the last p_rgh and
  * p_rghFinal solves, reference cell, deltaN, write index, AMG levels, kernel launches */
+/* Asynchronous read-back for hosts that stream results out while the solver carries on: a snapshot
+ * of the array (OpenFOAM file order) is taken on the solver's stream into a staging buffer owned by the
+ * handle, the copy into `out` (pinned host memory, or it will not overlap) runs on a second stream.
+ * `out` may be read after tpp_sync().  Requesting the same array again is allowed (its next snapshot
+ * waits, on the device, until the previous one has left the staging buffer). */
+long tpp_get_async(tpp_handle, const char* name, double* out, long cap);
+int tpp_sync(tpp_handle);
+
 /* Integer addressing as the kernels use it (for the bit-exactness tests of SURVEY.md 8a row a1):
  * "owner" [n_faces], "neighbour" [n_internal] (lduAddressing, device face order), the cell -> face
  * ELL table "cf" / "cn" [W x nCp, slot-major: (face << 1) | isNeighbourSide, other cell or -1], and

@@ -1009,6 +1009,15 @@ struct tpp_solver {
             stBndInt += dt * v;
         }
     }
+    // ---- asynchronous read-back (tpp_get_async / tpp_sync): a snapshot of the array (file order) is
+    // taken on the solver's stream into a staging buffer of its own, the copy to the host runs on a
+    // second stream and overlaps whatever the solver does next (the next step, the next tpp_set)
+    std::map<std::string, double*> stage;
+#ifndef TPP_EMU
+    cudaStream_t d2hStream = nullptr;
+    cudaEvent_t snapEvent = nullptr;
+    std::map<std::string, cudaEvent_t> copied;  // per array: its last copy to the host has left the staging buffer
+#endif
     // ---- interface statistics on the device (tpp_interface) ---------------------------
     bool isoBuilt = false;
     IsoArgs iso;
@@ -2289,6 +2298,7 @@ struct tpp_solver {
     }
 
     void destroy() {
+        for (auto& kv : stage) dev_free(kv.second);
         for (void* p : allocs) dev_free(p);
         for (auto& l : levels) l.free();
         for (auto& l : tail) l.free();
@@ -2299,6 +2309,7 @@ struct tpp_solver {
         free(hscal);
 #else
         for (auto& g : graphs) cudaGraphExecDestroy(g.second.exec);
+        if (d2hStream) { cudaStreamSynchronize(d2hStream); cudaStreamDestroy(d2hStream); cudaEventDestroy(snapEvent); for (auto& kv : copied) cudaEventDestroy(kv.second); }
         for (void* p : comm.opened) cudaIpcCloseMemHandle(p);
         dev_free(comm.gwin); dev_free(comm.gSeq); dev_free(comm.gDone);
         dev_free(comm.window); dev_free(comm.seq); dev_free(comm.arSeq); dev_free(comm.putDone); dev_free(comm.p2pErr);
@@ -2412,6 +2423,53 @@ long tpp_get(tpp_handle s, const char* name, double* out, long cap) try {
     }
     d2h(s->ctx, out, it->second.first, n * sizeof(double));
     return it->second.second;
+} API_CATCH(-100)
+long tpp_get_async(tpp_handle s, const char* name, double* out, long cap) try {
+    API_DEVICE(s);
+    auto it = s->reg.find(name);
+    if (it == s->reg.end()) { g_err = std::string("unknown array ") + name; return -1; }
+    const long len = it->second.second, n = std::min<long>(cap, len);
+    double*& st = s->stage[name];
+    if (!st) st = dalloc<double>((size_t)len);
+#ifndef TPP_EMU
+    if (!s->d2hStream) { CUDA_CHECK(cudaStreamCreateWithFlags(&s->d2hStream, cudaStreamNonBlocking)); CUDA_CHECK(cudaEventCreateWithFlags(&s->snapEvent, cudaEventDisableTiming)); }
+    cudaEvent_t& cp = s->copied[name];
+    if (!cp) CUDA_CHECK(cudaEventCreateWithFlags(&cp, cudaEventDisableTiming));
+    else CUDA_CHECK(cudaStreamWaitEvent(s->ctx.stream, cp, 0));  // the previous snapshot of this array is on its way out: do not overwrite it yet
+#endif
+    // snapshot in file order on the solver's stream
+    bool done = false;
+    if (int nc = faceComp(s, name)) {
+        s->ensurePermBuf();
+        s->d.xsrc = it->second.first; s->d.xbuf = st; s->d.xnc = nc; s->d.procOwner = s->dPerm;
+        LAUNCH(s->ctx, face_to_file, s->d, s->nF);
+        s->d.procOwner = s->dProcOwner;
+        done = true;
+    } else if (s->renumbered) {
+        s->ensurePermBuf();
+        done = s->permute(it->second.first, st, len, true);
+    }
+    if (!done) d2d(s->ctx, st, it->second.first, (size_t)len * sizeof(double));
+#ifdef TPP_EMU
+    memcpy(out, st, (size_t)n * sizeof(double));
+#else
+    CUDA_CHECK(cudaEventRecord(s->snapEvent, s->ctx.stream));
+    CUDA_CHECK(cudaStreamWaitEvent(s->d2hStream, s->snapEvent, 0));
+    CUDA_CHECK(cudaMemcpyAsync(out, st, (size_t)n * sizeof(double), cudaMemcpyDeviceToHost, s->d2hStream));
+    CUDA_CHECK(cudaEventRecord(cp, s->d2hStream));
+#endif
+    return len;
+} API_CATCH(-100)
+int tpp_sync(tpp_handle s) try {
+    API_DEVICE(s);
+#ifndef TPP_EMU
+    if (s->d2hStream) {
+        // the next snapshot of an array must not overtake the copy of its previous one
+        CUDA_CHECK(cudaStreamSynchronize(s->d2hStream));
+    }
+#endif
+    dev_sync(s->ctx);
+    return 0;
 } API_CATCH(-100)
 long tpp_set(tpp_handle s, const char* name, const double* in, long n) try {
     API_DEVICE(s);

@@ -69,6 +69,9 @@ def load(lib_path=None):
     L.tpp_run_to_write.argtypes = [H, C.c_long]
     L.tpp_stats.argtypes = [H, C.c_int, abi.c_double_p]
     L.tpp_interface.argtypes = [H, C.c_double, abi.c_double_p]
+    L.tpp_get_async.restype = C.c_long
+    L.tpp_get_async.argtypes = [H, C.c_char_p, abi.c_double_p, C.c_long]
+    L.tpp_sync.argtypes = [H]
     L.tpp_get_int.restype = C.c_long
     L.tpp_get_int.argtypes = [H, C.c_char_p, abi.c_int_p, C.c_long]
     L.tpp_stage.argtypes = [H, C.c_char_p]
