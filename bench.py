@@ -547,13 +547,11 @@ def main():
 
     h2d_b = sum(host[n].numel() * 8 for n in names_in)
     d2h_b = sum(host[n].numel() * 8 for n in names_out)
-    # results are streamed out: tpp_get_async snapshots every output array on the solver's stream and
-    # copies it to a second set of pinned buffers on a copy stream, overlapping the next step's input
-    # copies (PCIe is full duplex) and kernels; the inputs of a step are copied in before it starts.
-    # Every byte of both directions moves inside the timed region, which ends with tpp_sync().
-    host_out = {n: torch.empty_like(host[n]).pin_memory() for n in names_out}
+    # The next step's input is this step's output (same pinned buffers, no host-side copy), so the
+    # three phases of a step cannot overlap: input copy, step, output copy are timed back to back.
+    # (tpp_get_async streams results out behind the next step - 55 -> 46 ms per step when the inputs do
+    # not depend on them, tools/e2e_probe.py - but feeding a stale state back in is not a simulation.)
     e2e_steps = max(2, args.steps // 2)
-    g.L.tpp_sync(g.h)
     barrier()
     t0 = time.perf_counter()
     for _ in range(e2e_steps):
@@ -561,12 +559,9 @@ def main():
             g.L.tpp_set(g.h, n.encode(), dp(host[n]), host[n].numel())
         g.step(1)
         for n in names_out:
-            g.L.tpp_get_async(g.h, n.encode(), dp(host_out[n]), host_out[n].numel())
-    g.L.tpp_sync(g.h)
+            g.L.tpp_get(g.h, n.encode(), dp(host[n]), host[n].numel())
     barrier()
     sec_e2e = time.perf_counter() - t0
-    for n in names_out:  # the streamed copies are the state the solver holds
-        assert torch.equal(host_out[n], torch.from_numpy(g.get(n))), f"asynchronous read-back of {n} differs"
 
     sec, sec_e2e, it0_mean, it1_mean, it1_max, cap_hits, bal = ensemble.max_over_ranks([sec, sec_e2e, stats["it0_mean"], stats["it1_mean"], stats["it1_max"], stats["cap_hits"], 0.0])
     vols = ensemble.sum_over_ranks([stats["alpha_volume_start"], stats["alpha_volume"], stats["alpha_boundary_outflow"]])
@@ -597,7 +592,7 @@ def main():
                        "precision": "FP64 fields, operators, Krylov iteration and residuals; multigrid preconditioner in " + ("FP64" if VB == 8 else "FP32")},
             "clocks": sampler.summary(), "gpu_launches": launches,
             "e2e": {"value": e2e, "unit": UNIT, "h2d_bytes_per_step": h2d_b, "d2h_bytes_per_step": d2h_b, "steps": e2e_steps,
-                    "how": "per step: tpp_set of the restart state from pinned host memory (blocking), tpp_step, tpp_get_async of the written fields + state into pinned host memory (copy stream, overlapping the next step); tpp_sync before the clock stops"},
+                    "how": "per step: tpp_set of the restart state from pinned host memory, tpp_step, tpp_get of the written fields + that state into the same pinned buffers (the next step's input is this step's output)"},
             "roofline": roofline, "cpu_baseline": cpu, "checks": checks,
         }
         if parity is not None:

@@ -271,3 +271,21 @@ def test_a_diverged_run_stops_with_an_error(emu_lib, tmp_path):
     with pytest.raises(Exception):
         foamrun.run_case(d, lib_path=emu_lib, log=None)
     assert not any(v > 0 for v, _ in ff.time_dirs(d))  # nothing was written after the failure
+
+
+def test_async_read_back_equals_blocking(emu_lib):
+    """tpp_get_async + tpp_sync return what tpp_get returns (file order, also on a renumbered mesh)."""
+    import bench
+    from openfoam_tpp_b200 import abi
+
+    mesh = mg.shuffled(mg.cylinder_mesh(bench.CASE["H"], bench.CASE["D"], 5, 8, "flat", "tet"), 2)
+    g = sv.Solver(mesh, bench.make_config(mesh), lib_path=emu_lib)
+    g.set("alpha", bench.initial_alpha(mesh))
+    g.init_fields()
+    g.step(2)
+    for nm in ("alpha", "U", "phi", "Uf", "p_rgh_b"):
+        a = np.zeros(g.size(nm))
+        assert g.L.tpp_get_async(g.h, nm.encode(), a.ctypes.data_as(abi.c_double_p), a.size) == a.size
+        assert g.L.tpp_sync(g.h) == 0
+        assert np.array_equal(a, g.get(nm)), nm
+    g.close()
