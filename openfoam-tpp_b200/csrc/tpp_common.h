@@ -35,8 +35,19 @@ constexpr double SMALL = 1e-15, VSMALL = 1e-300, ROOTVSMALL = 1e-150;
 constexpr int BLOCK = 256;
 constexpr int RED_BLOCKS = 148 * 8;  // fixed grid of the reducing kernels (2048 threads per SM), one partial per CTA -> deterministic sums
 
+// Scalars that change every time step.  Kernels launched one by one get them by value inside DV; the
+// graph-captured step (small meshes: launch overhead is the cost) reads them from this block, which
+// the first node of the step's graph copies in from pinned host memory, so the same captured
+// kernels serve every step.  Translation-only motion (the reference's orbital shaker).
+struct StepScal {
+    double dt, rdt[2];  // rdt[0] = 1/deltaT, rdt[1] = 1/(deltaT / nAlphaSubCycles)
+    double dT[3], wallU[3], Tn[3];
+};
+
 // Device view: raw pointers + per-launch scalars, passed by value to every kernel.
 struct DV {
+    const StepScal* ss;  // nullptr: the by-value scalars below are current
+    int rdtSel;          // which of ss->rdt this launch means by rDeltaT
     // sizes
     int nC, nF, nI, nB, nCp;  // nCp: padded cell count (ELL stride)
     int W;                    // ELL width (max faces per cell)
@@ -79,6 +90,11 @@ struct DV {
     int rotating;
 };
 
+HD double s_dt(const DV& d) { return d.ss ? d.ss->dt : d.dt; }
+HD double s_rdt(const DV& d) { return d.ss ? d.ss->rdt[d.rdtSel] : d.rDeltaT; }
+HD double s_dT(const DV& d, int k) { return d.ss ? d.ss->dT[k] : d.dT[k]; }
+HD double s_wallU(const DV& d, int k) { return d.ss ? d.ss->wallU[k] : d.wallU[k]; }
+HD double s_Tn(const DV& d, int k) { return d.ss ? d.ss->Tn[k] : d.Tn[k]; }
 HD double sign_(double x) { return x >= 0 ? 1.0 : -1.0; }
 HD double pos0_(double x) { return x >= 0 ? 1.0 : 0.0; }
 HD double dot3(const double* a, const double* b) { return a[0] * b[0] + a[1] * b[1] + a[2] * b[2]; }

@@ -73,7 +73,7 @@ HD void b_U_bc(const DV& d, int b) {
                     Up[k] = (cn_ - co_) / d.dt;
                 }
             } else
-                for (int k = 0; k < 3; k++) Up[k] = d.wallU[k];
+                for (int k = 0; k < 3; k++) Up[k] = s_wallU(d, k);
             double Un = d.meshPhi[f] / (m + VSMALL);
             double nUp = dot3(n, Up);
             for (int k = 0; k < 3; k++) d.U_b[3 * b + k] = Up[k] + n[k] * (Un - nUp);
@@ -245,8 +245,9 @@ template <int WT> HD void b_mules_setup(const DV& d, int c) {
     }
     mx = dmin(mx, 1.0);
     mn = dmax(mn, 0.0);
-    d.psiMaxn[c] = V * (d.rDeltaT * mx) - (V * d.rDeltaT) * a0 + sBD;
-    d.psiMinn[c] = V * (0.0 - d.rDeltaT * mn) + (V * d.rDeltaT) * a0 - sBD;
+    const double rdt = s_rdt(d);
+    d.psiMaxn[c] = V * (rdt * mx) - (V * rdt) * a0 + sBD;
+    d.psiMinn[c] = V * (0.0 - rdt * mn) + (V * rdt) * a0 - sBD;
     d.sumPhip[c] = sP;
     d.mSumPhim[c] = mM;
 }
@@ -330,7 +331,8 @@ template <int WT> HD void b_mules_update(const DV& d, int c) {
         END_CELL_FACES
     }
     double psiIf = div / V;
-    d.alpha[c] = (V * a0 * d.rDeltaT / V - psiIf) / d.rDeltaT;
+    const double rdt = s_rdt(d);
+    d.alpha[c] = (V * a0 * rdt / V - psiIf) / rdt;
 }
 
 HD void b_mixture_cell(const DV& d, int c) { d.rho[c] = d.alpha[c] * d.rho1 + (1.0 - d.alpha[c]) * d.rho2; }
@@ -521,12 +523,13 @@ template <int WT> HD void b_mom_cell(const DV& d, int c) {
         }
     END_CELL_FACES
     double V = d.V[c];
-    double D0 = d.rDeltaT * d.rho[c] * V + ds;
+    const double rdt = s_rdt(d);
+    double D0 = rdt * d.rho[c] * V + ds;
     double D = D0 + bmax;
     D = dmax(fabs(D), so);
     D = D - bmin;
     d.mDiag[c] = D;
-    for (int k = 0; k < 3; k++) d.mSource[3 * c + k] = (d.rDeltaT * d.rho0[c] * d.U0[3 * c + k] * V + src[k]) + (D - D0) * d.U[3 * c + k];
+    for (int k = 0; k < 3; k++) d.mSource[3 * c + k] = (rdt * d.rho0[c] * d.U0[3 * c + k] * V + src[k]) + (D - D0) * d.U[3 * c + k];
 }
 
 // ---- S5 pressure corrector ---------------------------------------------------------------------
@@ -613,7 +616,7 @@ HD void b_phiHbyA(const DV& d, int f) {
         double phiUf0 = dot3(S, &d.Uf0[3 * f]);
         double pc = phiUf0 - dot3(S, u0f);
         double coeff = 1.0 - dmin(fabs(pc) / (fabs(phiUf0) + SMALL), 1.0);
-        ddtCorr = coeff * d.rDeltaT * pc;
+        ddtCorr = coeff * s_rdt(d) * pc;
         rhorAUf = wf * (d.rho[P] * d.rAU[P]) + (1.0 - wf) * (d.rho[N] * d.rAU[N]);
         snGradRho = d.dc[f] * (d.rho[N] - d.rho[P]) + dot3(&d.corrVec[3 * f], gr);
     } else {
@@ -623,7 +626,7 @@ HD void b_phiHbyA(const DV& d, int f) {
         double phiUf0 = dot3(S, &d.Uf0[3 * f]);
         double pc = phiUf0 - dot3(S, &d.U0_b[3 * b]);
         double coeff = d.bcU[b] == 0 ? 0.0 : 1.0 - dmin(fabs(pc) / (fabs(phiUf0) + SMALL), 1.0);
-        ddtCorr = coeff * d.rDeltaT * pc;
+        ddtCorr = coeff * s_rdt(d) * pc;
         rhorAUf = d.rho_b[b] * d.rAU[P];
         snGradRho = d.dc[f] * (d.rho_b[b] - d.rho[P]);
     }
@@ -770,7 +773,10 @@ HD void b_p_shift(const DV& d, int c) {
 
 // ---- S2 rigid mesh motion ------------------------------------------------------------------------
 // translation: swept volume of a rigidly translated face = Sf . dT (exact)
-HD void b_meshphi_trans(const DV& d, int f) { d.meshPhi[f] = dot3(&d.Sf[3 * f], d.dT) / d.dt; }
+HD void b_meshphi_trans(const DV& d, int f) {
+    const double dT[3] = {s_dT(d, 0), s_dT(d, 1), s_dT(d, 2)};
+    d.meshPhi[f] = dot3(&d.Sf[3 * f], dT) / s_dt(d);
+}
 
 HD void rot3(const double* R, const double* v, double* out);
 HD void rigid_point(const double* R, const double* T, const double* cofg, const double* p0, double* out) {
@@ -844,13 +850,13 @@ HD void b_rotate_face(const DV& d, int f) {
 HD void b_gh_face(const DV& d, int f) {
     double q[3] = {d.Cf0[3 * f] - d.cofg[0], d.Cf0[3 * f + 1] - d.cofg[1], d.Cf0[3 * f + 2] - d.cofg[2]}, x[3];
     rot3(d.R, q, x);
-    for (int k = 0; k < 3; k++) x[k] = x[k] + d.cofg[k] + d.Tn[k];
+    for (int k = 0; k < 3; k++) x[k] = x[k] + d.cofg[k] + s_Tn(d, k);
     d.ghf[f] = dot3(d.g, x);
 }
 HD void b_gh_cell(const DV& d, int c) {
     double q[3] = {d.C0[3 * c] - d.cofg[0], d.C0[3 * c + 1] - d.cofg[1], d.C0[3 * c + 2] - d.cofg[2]}, x[3];
     rot3(d.R, q, x);
-    for (int k = 0; k < 3; k++) x[k] = x[k] + d.cofg[k] + d.Tn[k];
+    for (int k = 0; k < 3; k++) x[k] = x[k] + d.cofg[k] + s_Tn(d, k);
     d.gh[c] = dot3(d.g, x);
 }
 

@@ -32,6 +32,11 @@ thread_local std::string g_err;
 // device current for the calling thread
 #define API_DEVICE(s) do { if ((s) != nullptr) cudaSetDevice((s)->device); } while (0)
 #endif
+#ifdef TPP_EMU
+#define CUDA_CHECK_OR_EMU(x) (void)0
+#else
+#define CUDA_CHECK_OR_EMU(x) CUDA_CHECK(x)
+#endif
 #define API_CATCH(code)                                                                         \
     catch (const tpp::CudaFailure& e) { g_err = e.what; fprintf(stderr, "tppvof: %s\n", g_err.c_str()); return (code); } \
     catch (const std::exception& e) { g_err = std::string("internal error: ") + e.what(); return (code); }               \
@@ -848,28 +853,123 @@ struct tpp_solver {
             if (nd >= dt) dt = std::min(nd, 2.0 * dt); else dt = std::max(nd, 0.2 * dt);
         }
     }
-    bool advanceTime() {
+    // ---- the per-step scalar block (StepScal) and the graph-captured explicit part of a step -------
+    // Small meshes (the reference's own 8 k - 42 k-cell cases, and every case of a sweep) spend a step
+    // on launch overhead: ~85 explicit kernels between the two pressure solves.  With translation-only
+    // motion, an open tank and one rank their arguments never change except for a handful of scalars,
+    // so the three explicit segments of a step (up to the first solve, between the solves, after the
+    // last) are captured once into CUDA graphs whose kernels read those scalars from `ssDev`.  A step is
+    // then ~3 graph launches + the solver's iteration graphs: 8 concurrent sweep cases no longer queue
+    // behind the context's launch path.
+    StepScal* ssDev = nullptr;
+    StepScal* ssHost = nullptr;  // pinned (CUDA) / the block itself (host emulation)
+    struct SegGraph { bool have = false;
+#ifndef TPP_EMU
+        cudaGraphExec_t exec = nullptr;
+#endif
+        long nodes = 0; };
+    SegGraph seg[3];
+    bool stepScalMode() const { return !comm.active && !hasRotation && cfg.n_motion >= 0 && knob("TPP_STEP_SS", 1) != 0; }
+    bool stepGraphMode() const {
+#ifdef TPP_EMU
+        return false;
+#else
+        return stepScalMode() && !d.needRef && !ctx.prof && cfg.n_non_orth == 0 && ctx.stream != nullptr && ctx.stream != cudaStreamLegacy && knob("TPP_STEP_GRAPH", nGlobal <= 1000000 ? 1 : 0) != 0;
+#endif
+    }
+    void ensureStepScal() {
+        if (ssHost) return;
+#ifdef TPP_EMU
+        ssHost = (StepScal*)calloc(1, sizeof(StepScal));
+        ssDev = ssHost;
+#else
+        CUDA_CHECK(cudaMallocHost(&ssHost, sizeof(StepScal)));
+        memset(ssHost, 0, sizeof(StepScal));
+        ssDev = (StepScal*)dev_alloc(sizeof(StepScal));
+#endif
+    }
+    // the current values -> the pinned block (and, outside a captured segment, on to the device)
+    void fillStepScal(bool upload) {
+        if (!stepScalMode()) { d.ss = nullptr; return; }
+        ensureStepScal();
+        ssHost->dt = dt;
+        ssHost->rdt[0] = 1.0 / dt;
+        ssHost->rdt[1] = 1.0 / (dt / std::max(cfg.n_alpha_subcycles, 1));
+        for (int k = 0; k < 3; k++) { ssHost->dT[k] = Tn[k] - To[k]; ssHost->wallU[k] = (Tn[k] - To[k]) / dt; ssHost->Tn[k] = Tn[k]; }
+        d.ss = ssDev;
+#ifndef TPP_EMU
+        if (upload) CUDA_CHECK(cudaMemcpyAsync(ssDev, ssHost, sizeof(StepScal), cudaMemcpyHostToDevice, ctx.stream));
+#else
+        (void)upload;
+#endif
+    }
+    // run `body` (kernel launches with fixed arguments) as segment k: captured on first use, replayed after
+    template <class F> void segment(int k, F body) {
+#ifndef TPP_EMU
+        if (stepGraphMode()) {
+            SegGraph& g = seg[k];
+            if (!g.have) {
+                const long l0 = ctx.launches;
+                cudaGraph_t gr;
+                CUDA_CHECK(cudaStreamBeginCapture(ctx.stream, cudaStreamCaptureModeThreadLocal));
+                body();
+                CUDA_CHECK(cudaStreamEndCapture(ctx.stream, &gr));
+                CUDA_CHECK(cudaGraphInstantiate(&g.exec, gr, 0));
+                cudaGraphDestroy(gr);
+                g.nodes = ctx.launches - l0;
+                ctx.launches = l0;
+                g.have = true;
+            }
+            CUDA_CHECK(cudaGraphLaunch(g.exec, ctx.stream));
+            ctx.launches += g.nodes;
+            return;
+        }
+#endif
+        (void)k;
+        body();
+    }
+    void dropStepGraphs() {
+#ifndef TPP_EMU
+        for (auto& g : seg) { if (g.have) cudaGraphExecDestroy(g.exec); g = SegGraph(); }
+#endif
+    }
+    bool advanceTimeHost() {
         dt0 = dt;
         t += dt;
         step++;
+        int wi = (int)(((t - startTime) + 0.5 * dt) / cfg.write_interval);
+        if (wi > writeTimeIndex) { writeTimeIndex = wi; return true; }
+        return false;
+    }
+    void advanceTimeDevice() {
         X(d.U, 3);  // ghosts may be stale after a tpp_set
         d2d(ctx, d.U0, d.U, 3 * (size_t)(nC + nG) * sizeof(double));
         d2d(ctx, d.U0_b, d.U_b, 3 * (size_t)nB * sizeof(double));
         d2d(ctx, d.rho0, d.rho, (size_t)(nC + nG) * sizeof(double));
         d2d(ctx, d.Uf0, d.Uf, 3 * (size_t)nF * sizeof(double));
-        int wi = (int)(((t - startTime) + 0.5 * dt) / cfg.write_interval);
-        if (wi > writeTimeIndex) { writeTimeIndex = wi; return true; }
-        return false;
     }
-    void moveMesh() {
+    bool advanceTime() {
+        bool wr = advanceTimeHost();
+        advanceTimeDevice();
+        return wr;
+    }
+    void moveMeshHost() {
         d.dt = dt;
         if (cfg.n_motion <= 0) return;
         memcpy(Ro, Rn, sizeof(Rn)); memcpy(To, Tn, sizeof(Tn));
         motionAt(t, Rn, Tn);
         setTransform();
+    }
+    void moveMeshDevice() {
+        if (cfg.n_motion <= 0) return;
         orientGeometry();
         if (hasRotation) LAUNCH(ctx, meshphi_rot, d, nF);
         else LAUNCH(ctx, meshphi_trans, d, nF);
+    }
+    void moveMesh() {
+        moveMeshHost();
+        fillStepScal(true);
+        moveMeshDevice();
     }
     void alphaBCs() { LAUNCH(ctx, alpha_bc, d, nB); }
     void UBCs() { d.dt = dt; LAUNCH(ctx, U_bc, d, nB); }
@@ -879,7 +979,7 @@ struct tpp_solver {
         LAUNCH_W(ctx, grad_scalar, d, nC);
     }
     void alphaSubCycle(double dts) {
-        d.rDeltaT = 1.0 / dts;
+        d.rDeltaT = 1.0 / dts; d.rdtSel = cfg.n_alpha_subcycles > 1 ? 1 : 0;
         d2d(ctx, d.alpha0, d.alpha, nC * sizeof(double));
         alphaBCs();
         X(d.alpha, 1);
@@ -919,7 +1019,7 @@ struct tpp_solver {
     void momentum() {
         UBCs();
         X(d.U, 3);
-        d.rDeltaT = 1.0 / dt;
+        d.rDeltaT = 1.0 / dt; d.rdtSel = 0;
         LAUNCH_W(ctx, grad_U, d, nC);
         X(d.gradU, 9);
         LAUNCH(ctx, mom_face, d, nI);
@@ -933,7 +1033,7 @@ struct tpp_solver {
         X(d.HbyA, 3);
     }
     void pcPrepare() {
-        d.dt = dt; d.rDeltaT = 1.0 / dt;
+        d.dt = dt; d.rDeltaT = 1.0 / dt; d.rdtSel = 0;
         computeHbyA();
         gradScalar(d.rho, d.rho_b, d.grad);
         X(d.grad, 3);
@@ -1094,11 +1194,40 @@ struct tpp_solver {
         if (!std::isfinite(Co) || !std::isfinite(alphaCo)) fail("Courant number is not finite (the solution diverged)");
         adjustDeltaT();
         if (!std::isfinite(dt) || !(dt > 0)) fail("deltaT is not finite / positive");
-        bool wr = advanceTime();
-        moveMesh();
-        alphaPredictor();
-        momentum();
-        for (int corr = 0; corr < cfg.n_correctors; corr++) pressureCorrector(corr == cfg.n_correctors - 1);
+        bool wr = advanceTimeHost();
+        moveMeshHost();
+        if (stepGraphMode()) {
+            // segment 0: everything up to the first pressure solve; 1: between two solves; 2: after the last
+            fillStepScal(false);  // pinned block only: the segment's first node copies it to the device
+            segment(0, [&] {
+                CUDA_CHECK_OR_EMU(cudaMemcpyAsync(ssDev, ssHost, sizeof(StepScal), cudaMemcpyHostToDevice, ctx.stream));
+                ctx.launches++;
+                advanceTimeDevice();
+                moveMeshDevice();
+                alphaPredictor();
+                momentum();
+                pcPrepare();
+                pcAssemble();
+            });
+            for (int corr = 0; corr < cfg.n_correctors; corr++) {
+                const bool last = corr == cfg.n_correctors - 1;
+                const int which = last ? 1 : 0;
+                lastSolve[which] = solve(which ? cfg.p_rgh_final : cfg.p_rgh, d.pDiag, d.pUpper, d.pSource, d.p_rgh);
+                segment(last ? 2 : 1, [&] {
+                    LAUNCH(ctx, p_evaluate, d, nB);
+                    pcFinish();
+                    pcEnd();
+                    if (!last) { pcPrepare(); pcAssemble(); }
+                });
+            }
+        } else {
+            fillStepScal(true);
+            advanceTimeDevice();
+            moveMeshDevice();
+            alphaPredictor();
+            momentum();
+            for (int corr = 0; corr < cfg.n_correctors; corr++) pressureCorrector(corr == cfg.n_correctors - 1);
+        }
         if (!probeCells.empty()) sampleProbes();
         if (statsOn) statsStep();
         checkDeviceFlags();
@@ -2309,6 +2438,9 @@ struct tpp_solver {
         free(hscal);
 #else
         for (auto& g : graphs) cudaGraphExecDestroy(g.second.exec);
+        dropStepGraphs();
+        if (ssHost) cudaFreeHost(ssHost);
+        dev_free(ssDev);
         if (d2hStream) { cudaStreamSynchronize(d2hStream); cudaStreamDestroy(d2hStream); cudaEventDestroy(snapEvent); for (auto& kv : copied) cudaEventDestroy(kv.second); }
         for (void* p : comm.opened) cudaIpcCloseMemHandle(p);
         dev_free(comm.gwin); dev_free(comm.gSeq); dev_free(comm.gDone);
@@ -2541,6 +2673,7 @@ int tpp_set_time(tpp_handle s, double t, double dt) try {
     s->motionAt(t, s->Rn, s->Tn);
     memcpy(s->Ro, s->Rn, sizeof(s->Rn)); memcpy(s->To, s->Tn, sizeof(s->Tn));
     s->setTransform();
+    s->fillStepScal(true);
     s->orientGeometry();
     dev_sync(s->ctx);
     return 0;
@@ -2568,6 +2701,7 @@ int tpp_stage(tpp_handle s, const char* name) try {
     API_DEVICE(s);
     std::string n(name);
     s->d.dt = s->dt;
+    s->fillStepScal(true);
     if (n == "courant") s->courant();
     else if (n == "adjustDeltaT") s->adjustDeltaT();
     else if (n == "advanceTime") s->advanceTime();
@@ -2652,6 +2786,7 @@ int tpp_find_cell(tpp_handle s, const double* xyz) {
 }
 int tpp_use_stream(tpp_handle s, void* stream) try {
     API_DEVICE(s);
+    s->dropStepGraphs();
 #ifndef TPP_EMU
     cudaStreamSynchronize(s->ctx.stream);
     if (s->ctx.ownStream) cudaStreamDestroy(s->ctx.stream);
@@ -2664,6 +2799,7 @@ int tpp_use_stream(tpp_handle s, void* stream) try {
 } API_CATCH(-100)
 int tpp_profile(tpp_handle s, int on) try {
     API_DEVICE(s);
+    s->dropStepGraphs();
     s->ctx.prof = on != 0;
     return 0;
 } API_CATCH(-100)
