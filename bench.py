@@ -240,6 +240,7 @@ def run_sweep_config(args):
     import tempfile
     import time as _t
 
+    os.environ.setdefault("CUDA_DEVICE_MAX_CONNECTIONS", "32")  # more hardware queues than the default 8: one per concurrent case and copy stream
     import torch
 
     from openfoam_tpp_b200 import ensemble
@@ -267,11 +268,13 @@ def run_sweep_config(args):
         torch.cuda.synchronize()
         if world > 1:
             dist.barrier()
+        # (the one-case-at-a-time leg is a sample: the first 8 cases of the sweep, one value of R)
+        seq_sweeps = dict(sweeps, R=sweeps["R"][:1])
         for mode, per in (("concurrent", args.cases_per_gpu), ("sequential", 1)):
             if mode == "concurrent":
                 sampler.start()
             t0 = _t.perf_counter()
-            done = ensemble.run_sweep(tmp, base, sweeps, lc_to_mesh=lc_to_mesh, max_steps=args.steps, log=None, cases_per_gpu=per, write=False)
+            done = ensemble.run_sweep(tmp, base, sweeps if mode == "concurrent" else seq_sweeps, lc_to_mesh=lc_to_mesh, max_steps=args.steps, log=None, cases_per_gpu=per, write=False)
             torch.cuda.synchronize()
             sec = _t.perf_counter() - t0
             if mode == "concurrent":
