@@ -289,7 +289,7 @@ def run_sweep_config(args):
                 "config": {"workload": f"cfg5: {c['cases']} sweep cases (H 0.004,0.008 x R 0.002:0.001:0.005 x f 1.6:0.2:3.0, D 0.0221 flat, 7 776 / 15 552 tets), {args.steps} steps each after {args.warmup} warm-up steps, through foamrun.run_case (case directories, no field writes)",
                            "parallelism": f"ensemble: cases dealt round-robin to {world} GPU(s), {args.cases_per_gpu} concurrent cases (host threads / CUDA streams) per GPU, no collective",
                            "vof_steps_per_s": c["steps"] / c["seconds"], "vof_steps_per_s_one_case_at_a_time": out["sequential"]["steps"] / out["sequential"]["seconds"],
-                           "concurrency_gain": out["sequential"]["seconds"] / c["seconds"], "l2": "every case lives in L2 (a few MB): latency-bound, no HBM roofline (BASELINE.md section 4)"},
+                           "concurrency_gain": (c["steps"] / c["seconds"]) / (out["sequential"]["steps"] / out["sequential"]["seconds"]), "sequential_sample_cases": out["sequential"]["cases"], "l2": "every case lives in L2 (a few MB): latency-bound, no HBM roofline (BASELINE.md section 4)"},
                 "clocks": sampler.summary(), "gpu_launches": None, "e2e": {"value": c["cell_steps"] / c["seconds"] / 1e6, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0, "note": "the sweep is timed end to end on the host clock (case directory in, solver stepping through the C-ABI)"},
                 "roofline": None, "cpu_baseline": None}
         print(json.dumps(line))
