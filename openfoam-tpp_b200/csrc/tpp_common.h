@@ -205,7 +205,7 @@ inline void dev_sync(Ctx& c) { CUDA_CHECK(cudaStreamSynchronize(c.stream)); }
 // cell kernels templated on the ELL width WT (see FOR_CELL_FACES)
 #define DEF_KERNEL_W(name) DEF_KERNEL_WB(name, 4)
 #define DEF_KERNEL_WB(name, minb)                                                       \
-    template <int WT> __global__ void __launch_bounds__(256, minb) k_##name(const DV d, int n) { \
+    template <int WT> __global__ void __launch_bounds__(256, (WT > 4 && (minb) > 2) ? 2 : (minb)) k_##name(const DV d, int n) { \
         int i = blockIdx.x * blockDim.x + threadIdx.x;                                  \
         if (i < n) b_##name<WT>(d, i);                                                  \
     }
