@@ -310,6 +310,23 @@ HD void b_mules_phipsi(const DV& d, int f) {
 }
 
 HD void b_alphaphi_acc(const DV& d, int f) { d.alphaPhi[f] += d.subW * d.alphaPhiUn[f]; }
+// the last limiter iteration's face pass, the limited flux and its share of the step's alpha flux
+// in one pass over the faces (mules_face + mules_phipsi + alphaphi_acc: same operations, same order)
+HD void b_mules_face_final(const DV& d, int f) {
+    double v;
+    if (f < d.nI) {
+        int P = d.own[f], N = d.nei[f];
+        double l = d.lambda[f];
+        const double pc = d.phiCorr[f];
+        if (pc > 0) l = dmin(l, dmin(d.lambdap[P], d.lambdam[N]));
+        else l = dmin(l, dmin(d.lambdam[P], d.lambdap[N]));
+        d.lambda[f] = l;
+        v = d.phiBD[f] + l * pc;
+    } else
+        v = d.phiBD[f] + 1.0 * 0.0;
+    d.alphaPhiUn[f] = v;
+    d.alphaPhi[f] += d.subW * v;
+}
 
 template <int WT> HD void b_mules_update(const DV& d, int c) {
     double div = 0;
@@ -891,6 +908,7 @@ DEF_KERNEL_W(mules_setup)
 DEF_KERNEL_W(mules_cell)
 DEF_KERNEL(mules_face, DV)
 DEF_KERNEL(mules_phipsi, DV)
+DEF_KERNEL(mules_face_final, DV)
 DEF_KERNEL(alphaphi_acc, DV)
 DEF_KERNEL_W(mules_update)
 DEF_KERNEL(mixture_cell, DV)

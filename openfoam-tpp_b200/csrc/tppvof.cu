@@ -978,7 +978,9 @@ struct tpp_solver {
         d.gs = s; d.gsb = sb; d.gout = out;
         LAUNCH_W(ctx, grad_scalar, d, nC);
     }
-    void alphaSubCycle(double dts) {
+    // accumulate: fold this sub-cycle's share of the step's alpha flux (alphaphi_acc) and the limited
+    // flux into the last limiter iteration's face pass
+    void alphaSubCycle(double dts, bool accumulate = false) {
         d.rDeltaT = 1.0 / dts; d.rdtSel = cfg.n_alpha_subcycles > 1 ? 1 : 0;
         d2d(ctx, d.alpha0, d.alpha, nC * sizeof(double));
         alphaBCs();
@@ -987,13 +989,18 @@ struct tpp_solver {
         X(d.grad, 3);
         LAUNCH(ctx, alpha_flux, d, nF);
         LAUNCH_W(ctx, mules_setup, d, nC);
+        const bool fuse = accumulate && cfg.n_limiter_iter > 0 && knob("TPP_MULES_FUSE", 1);
         for (int j = 0; j < cfg.n_limiter_iter; j++) {
             LAUNCH_W(ctx, mules_cell, d, nC);
             X(d.lambdap, 1);
             X(d.lambdam, 1);
-            LAUNCH(ctx, mules_face, d, nI);
+            if (fuse && j == cfg.n_limiter_iter - 1) LAUNCH(ctx, mules_face_final, d, nF);
+            else LAUNCH(ctx, mules_face, d, nI);
         }
-        LAUNCH(ctx, mules_phipsi, d, nF);
+        if (!fuse) {
+            LAUNCH(ctx, mules_phipsi, d, nF);
+            if (accumulate) LAUNCH(ctx, alphaphi_acc, d, nF);
+        }
         LAUNCH_W(ctx, mules_update, d, nC);
         alphaBCs();
     }
@@ -1003,10 +1010,8 @@ struct tpp_solver {
             double total = dt, dts = dt / n;
             dev_zero(ctx, d.alphaPhi, nF * sizeof(double));
             d.subW = dts / total;
-            for (int s = 0; s < n; s++) {
-                for (int a = 0; a < cfg.n_alpha_corr; a++) alphaSubCycle(dts);
-                LAUNCH(ctx, alphaphi_acc, d, nF);
-            }
+            for (int s = 0; s < n; s++)
+                for (int a = 0; a < cfg.n_alpha_corr; a++) alphaSubCycle(dts, a == cfg.n_alpha_corr - 1);
         } else {
             for (int a = 0; a < cfg.n_alpha_corr; a++) alphaSubCycle(dt);
             d2d(ctx, d.alphaPhi, d.alphaPhiUn, nF * sizeof(double));
