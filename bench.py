@@ -97,6 +97,7 @@ ALG_BYTES = {
     "mules_setup": lambda C, F: 40 * C + 32 * F,
     "mules_cell": lambda C, F: 16 * C + 32 * F,
     "mules_face": lambda C, F: 16 * C + 24 * F,
+    "mules_face_final": lambda C, F: 16 * C + 56 * F,               # the face pass + phiBD in, alphaPhiUn out, alphaPhi in/out
     "mules_update": lambda C, F: 24 * C + 16 * F,
     "grad_U": lambda C, F: 96 * C + 40 * F,
     "mom_face": lambda C, F: 120 * C + 100 * F,
