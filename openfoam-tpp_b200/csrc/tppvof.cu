@@ -153,7 +153,6 @@ struct tpp_solver {
     std::vector<std::array<int, 3>> tailCopy;  // processor-face coefficient ranges (src face, count, dst face) of the gather
     unsigned* tailBar = nullptr;
     int* tailErr = nullptr;
-    double* tailPartial = nullptr;
     double *kr = nullptr, *kz = nullptr, *kp = nullptr, *kw = nullptr, *fineEv = nullptr, *fineRsum = nullptr;
     int *match = nullptr, *prop = nullptr, *root = nullptr;
     bool amgBuilt = false;
@@ -1720,7 +1719,6 @@ struct tpp_solver {
         setupGatherWindow();
         tailBar = (unsigned*)dev_alloc(64);
         tailErr = (int*)dev_alloc(64);
-        tailPartial = dalloc<double>(2 * 1024);
 #ifndef TPP_EMU
         {
             int dev = 0, sms = 0, perSm = 0;
@@ -2437,7 +2435,7 @@ struct tpp_solver {
         for (auto& l : levels) l.free();
         for (auto& l : tail) l.free();
         dev_free(match); dev_free(prop); dev_free(root);
-        dev_free(tailBar); dev_free(tailErr); dev_free(tailPartial);
+        dev_free(tailBar); dev_free(tailErr);
         red.free();
 #ifdef TPP_EMU
         free(hscal);
