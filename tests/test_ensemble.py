@@ -87,10 +87,6 @@ def test_run_sweep_sets_up_and_runs_every_case(tmp_path, emu_lib):
 def test_run_sweep_concurrent_cases_match_sequential(tmp_path, emu_lib):
     """cases_per_gpu = 3: the same cases advanced by three host threads at once (one handle each) end
     in the same state as when they run one after another."""
-    import numpy as np
-
-    from openfoam_tpp_b200 import foamfile as ff
-
     base = {"H": 0.004, "D": 0.0221, "geo": "flat", "R": 0.005, "freq": 2.0, "duration": 0.002, "mesh": 0.003}
     sw = {"freq": [1.5, 2.0, 2.5, 3.0]}
     a = en.run_sweep(str(tmp_path / "seq"), base, sw, max_steps=4, lib_path=emu_lib)
