@@ -94,3 +94,33 @@ def test_run_sweep_concurrent_cases_match_sequential(tmp_path, emu_lib):
     assert [n for n, _ in a] == [n for n, _ in b] and len(b) == 4
     for (n, oa), (_, ob) in zip(a, b):
         assert oa["steps"] == ob["steps"] == 4 and oa["t"] == ob["t"], (n, oa, ob)
+
+
+def test_parse_range_reproduces_the_reference_loop():
+    """parse_range sums the step cumulatively and applies the 1e-9 end slack and the 6-decimal rounding
+    exactly like the reference's while-loop (main.py:118-142), restated here as the checker."""
+    from hypothesis import given, settings
+    from hypothesis import strategies as st
+
+    def loop(start, step, end):
+        vals, v = [], start
+        while v <= end + 1e-9:
+            vals.append(round(v, 6))
+            v += step
+        return vals
+
+    @settings(max_examples=300, deadline=None)
+    @given(start=st.floats(-5, 5), step=st.floats(1e-3, 2.0), n=st.integers(0, 60), frac=st.floats(0, 0.999))
+    def check(start, step, n, frac):
+        end = start + (n + frac) * step
+        text = f"{start!r}:{step!r}:{end!r}"
+        assert en.parse_range(text) == loop(float(repr(start)), float(repr(step)), float(repr(end)))
+
+    check()
+    assert en.parse_range("3:1") == [] and en.parse_range("2:2") == [2.0]
+    import pytest
+
+    with pytest.raises(ValueError):
+        en.parse_range("1:0:2")
+    with pytest.raises(ValueError):
+        en.parse_range("1:2:3:4")
