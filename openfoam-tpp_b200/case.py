@@ -212,8 +212,10 @@ def read_config(case_dir, mesh=None):
     if phases != ["water", "air"]:
         raise FoamError(f"{p}:phases: expected (water air), got {phases!r}")
     cfg.sigma = to_float(lookup(pp, "sigma", p))
-    if cfg.sigma != 0.0:
-        raise FoamError(f"{p}:sigma: surface tension (sigma = {cfg.sigma}) is not implemented; the reference runs sigma 0")
+    # the reference runs sigma 0 everywhere (constant/phaseProperties:19); sigma > 0 switches on the continuum
+    # surface force with the walls' zeroGradient alpha (0/alpha.water:22-25), i.e. no contact-angle model
+    if not (cfg.sigma >= 0.0 and np.isfinite(cfg.sigma)):
+        raise FoamError(f"{p}:sigma: expected a non-negative surface tension coefficient, got {cfg.sigma}")
     for ph, rk, nk in (("water", "rho1", "nu1"), ("air", "rho2", "nu2")):
         p = os.path.join(case_dir, "constant", f"physicalProperties.{ph}")
         d = ff.read_dict(p)

@@ -88,6 +88,9 @@ struct DV {
     double pRefShift;
     double R[9], Rold[9], Tn[3], To[3], cofg[3];  // rigid transforms (new / old)
     int rotating;
+    // surface tension (allocated only when sigma != 0; stf == nullptr otherwise)
+    double *gradA, *nHatf, *sigmaK, *stf;
+    double sigma;
 };
 
 HD double s_dt(const DV& d) { return d.ss ? d.ss->dt : d.dt; }

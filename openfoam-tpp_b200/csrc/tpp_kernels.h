@@ -151,6 +151,51 @@ template <int WT> HD void b_grad_scalar(const DV& d, int c) {
     for (int k = 0; k < 3; k++) d.gout[3 * c + k] = g[k] / Vc;
 }
 
+// ---- surface tension, sigma != 0 only (an extension: constant/phaseProperties:19 is sigma 0 in the
+// reference).  interfaceProperties::calculateK + surfaceTensionForce [OF13-MEM]:
+//   nHatf = (interpolate(grad alpha) / (|.| + deltaN)) & Sf ; K = -div(nHatf) ;
+//   stf = interpolate(sigma K) * snGrad(alpha)   (corrected snGrad, system/fvSchemes:47)
+// Boundary faces take the cell gradient with its normal part replaced by the patch's snGrad
+// (zeroGradient walls, 0/alpha.water:22-25: no contact-angle correction) and the cell's curvature.
+HD void face_grad_alpha(const DV& d, int f, double* gf) {
+    const int P = d.own[f];
+    if (f < d.nI) {
+        const int N = d.nei[f];
+        const double wl = d.w[f];
+        for (int k = 0; k < 3; k++) gf[k] = wl * d.gradA[3 * P + k] + (1.0 - wl) * d.gradA[3 * N + k];
+    } else {
+        const double m = d.magSf[f];
+        const double n[3] = {d.Sf[3 * f] / m, d.Sf[3 * f + 1] / m, d.Sf[3 * f + 2] / m};
+        const double corr = d.dc[f] * (d.alpha_b[f - d.nI] - d.alpha[P]) - dot3(n, &d.gradA[3 * P]);
+        for (int k = 0; k < 3; k++) gf[k] = d.gradA[3 * P + k] + n[k] * corr;
+    }
+}
+HD void b_nhat_face(const DV& d, int f) {
+    double gf[3];
+    face_grad_alpha(d, f, gf);
+    const double mg = mag3(gf) + d.deltaN;
+    d.nHatf[f] = (gf[0] / mg) * d.Sf[3 * f] + (gf[1] / mg) * d.Sf[3 * f + 1] + (gf[2] / mg) * d.Sf[3 * f + 2];
+}
+template <int WT> HD void b_curvature(const DV& d, int c) {
+    double s = 0;
+    FOR_CELL_FACES(d, c)
+        if (isN) s -= d.nHatf[f]; else s += d.nHatf[f];
+    END_CELL_FACES
+    d.sigmaK[c] = d.sigma * (0.0 - s / d.V[c]);
+}
+HD void b_stf_face(const DV& d, int f) {
+    const int P = d.own[f];
+    if (f < d.nI) {
+        const int N = d.nei[f];
+        const double wl = d.w[f];
+        double gf[3];
+        face_grad_alpha(d, f, gf);
+        const double sn = d.dc[f] * (d.alpha[N] - d.alpha[P]) + dot3(&d.corrVec[3 * f], gf);
+        d.stf[f] = (wl * d.sigmaK[P] + (1.0 - wl) * d.sigmaK[N]) * sn;
+    } else
+        d.stf[f] = d.sigmaK[P] * (d.dc[f] * (d.alpha_b[f - d.nI] - d.alpha[P]));
+}
+
 // ---- S3 alpha: interfaceCompression(vanLeer) flux, upwind flux, MULES -------------------------
 HD double vanLeer_limiter(double flux, double pP, double pN, const double* gP, const double* gN, const double* dd) {
     double gradf = pN - pP;
@@ -648,7 +693,8 @@ HD void b_phiHbyA(const DV& d, int f) {
         snGradRho = d.dc[f] * (d.rho_b[b] - d.rho[P]);
     }
     d.rAUf[f] = raf;
-    double pg = (0.0 - d.ghf[f] * snGradRho) * raf * d.magSf[f];
+    const double st = d.stf ? d.stf[f] : 0.0;
+    double pg = (st - d.ghf[f] * snGradRho) * raf * d.magSf[f];
     d.phig[f] = pg;
     double ph = (flux + rhorAUf * ddtCorr) + pg;
     d.phiHbyA[f] = ph;
@@ -911,6 +957,9 @@ DEF_KERNEL(mules_phipsi, DV)
 DEF_KERNEL(mules_face_final, DV)
 DEF_KERNEL(alphaphi_acc, DV)
 DEF_KERNEL_W(mules_update)
+DEF_KERNEL(nhat_face, DV)
+DEF_KERNEL_W(curvature)
+DEF_KERNEL(stf_face, DV)
 DEF_KERNEL(mixture_cell, DV)
 DEF_KERNEL(mixture_bnd, DV)
 DEF_KERNEL(rhophi, DV)

@@ -551,6 +551,9 @@ struct tpp_solver {
         d.rAU = AD("rAU", nC); d.HbyA = AD("HbyA", 3 * (size_t)nC); d.HbyA_b = AD("HbyA_b", 3 * (size_t)nB); d.rAUf = AD("rAUf", nF);
         d.phiHbyA = AD("phiHbyA", nF); d.phig = AD("phig", nF); d.pUpper = AD("pUpper", nI); d.pCorrFlux = AD("pCorrFlux", nI);
         d.pDiag = AD("pDiag", nC); d.pSource = AD("pSource", nC); d.rec = AD("rec", nF);
+        if (cfg.sigma != 0.0) {  // surface tension work arrays (the reference's sigma 0 cases never pay for them)
+            d.gradA = AD("gradA", 3 * (size_t)nC); d.nHatf = AD("nHatf", nF); d.sigmaK = AD("sigmaK", nC); d.stf = AD("stf", nF);
+        }
         d.cellTmp = A<double>(2 * (size_t)nC);
         kr = A<double>(nC); kz = A<double>(nC); kp = A<double>(nC); kw = A<double>(nC); fineEv = A<double>((size_t)W * nCp);
         sendbuf = A<double>(9 * (size_t)std::max(nG, 1)); dProcOwner = upload(procOwner); d.procOwner = dProcOwner; nGlobal = nC; fineRsum = A<double>(nC);
@@ -561,6 +564,7 @@ struct tpp_solver {
         CUDA_CHECK(cudaMallocHost(&hscal, S_COUNT * sizeof(double)));
 #endif
         red.init(nC);
+        d.sigma = cfg.sigma;
         d.cAlpha = cfg.c_alpha; d.rho1 = cfg.rho1; d.rho2 = cfg.rho2; d.nu1 = cfg.nu1; d.nu2 = cfg.nu2;
         for (int k = 0; k < 3; k++) { d.g[k] = cfg.g[k]; d.cofg[k] = cfg.cofg[k]; }
         d.moving = cfg.n_motion > 0; d.rotating = hasRotation;
@@ -1019,6 +1023,18 @@ struct tpp_solver {
         X(d.alpha, 1);
         X(d.rho, 1);
         LAUNCH(ctx, rhophi, d, nF);
+        interfaceCorrect();
+    }
+    // interfaceProperties::correct + surfaceTensionForce for sigma != 0 (tpp_kernels.h); alpha, alpha_b and
+    // the alpha ghosts are the predictor's final ones
+    void interfaceCorrect() {
+        if (cfg.sigma == 0.0) return;
+        gradScalar(d.alpha, d.alpha_b, d.gradA);
+        X(d.gradA, 3);
+        LAUNCH(ctx, nhat_face, d, nF);
+        LAUNCH_W(ctx, curvature, d, nC);
+        X(d.sigmaK, 1);
+        LAUNCH(ctx, stf_face, d, nF);
     }
     void momentum() {
         UBCs();
@@ -2523,7 +2539,7 @@ long tpp_size(tpp_handle s, const char* name) try {
 // face-sized arrays are kept in device face order (processor faces right after the internal
 // ones); callers see OpenFOAM's file order
 static int faceComp(tpp_solver* s, const char* name) {
-    static const char* f1[] = {"phi", "meshPhi", "alphaPhi", "rhoPhi", "phiBD", "alphaPhiUn", "rAUf", "phiHbyA", "phig", "rec", "ghf", "magSf", "w", "dc"};
+    static const char* f1[] = {"phi", "meshPhi", "alphaPhi", "rhoPhi", "phiBD", "alphaPhiUn", "rAUf", "phiHbyA", "phig", "rec", "ghf", "magSf", "w", "dc", "nHatf", "stf"};
     static const char* f3[] = {"Uf", "Uf0", "mExpl", "Sf", "Cf0"};
     if (s->nG == 0) return 0;
     for (auto n : f1) if (!strcmp(n, name)) return 1;

@@ -482,6 +482,8 @@ struct orc_state {
     dvec pGrad_b;  // fixedFluxPressure gradient
     // alpha predictor intermediates (last sub-cycle)
     dvec gradAlpha, alphaPhiUn, phiBD, phiCorr, lambda;
+    // surface tension (sigma > 0 only; an extension: the reference runs sigma 0, constant/phaseProperties:19)
+    dvec gradA, nHatf, sigmaK, stf;
     // momentum
     dvec gradU, mLower, mUpper, mDiag, mSource, mBIC, mBBC;
     // pressure
@@ -509,6 +511,7 @@ struct orc_state {
         R(alpha); R(alpha_b); R(U); R(U_b); R(p_rgh); R(p_rgh_b); R(p); R(rho); R(rho_b); R(phi); R(Uf);
         R(U0); R(U0_b); R(rho0); R(Uf0); R(alphaPhi); R(rhoPhi); R(pGrad_b);
         R(gradAlpha); R(alphaPhiUn); R(phiBD); R(phiCorr); R(lambda);
+        R(gradA); R(nHatf); R(sigmaK); R(stf);
         R(gradU); R(mLower); R(mUpper); R(mDiag); R(mSource); R(mBIC); R(mBBC);
         R(rAU); R(HbyA); R(HbyA_b); R(rAUf); R(phiHbyA); R(phig); R(pUpper); R(pDiag); R(pSource);
         R(gradRho); R(gradP); R(pCorrFlux);
@@ -971,6 +974,53 @@ struct orc_state {
         return r * nu;
     }
 
+    // ---- interfaceProperties::correct + surfaceTensionForce (continuum surface force) ------
+    // [OF13-MEM: interfaceProperties::calculateK, surfaceTensionForce]; only when sigma != 0
+    // (constant/phaseProperties:19 is 0 in every reference case; 0/alpha.water:22-25 is
+    // zeroGradient on the walls, so there is no contact-angle correction of nHat):
+    //   gradAlpha = fvc::grad(alpha1)  (Gauss linear; boundary value = cell value with the
+    //               normal component replaced by the patch's snGrad, gaussGrad::correctBoundaryConditions)
+    //   nHatf = (interpolate(gradAlpha) / (|interpolate(gradAlpha)| + deltaN)) & Sf
+    //   K = -fvc::div(nHatf)           (boundary value = the cell's, extrapolatedCalculated)
+    //   stf = interpolate(sigma K) * snGrad(alpha1)   (snGradSchemes corrected, system/fvSchemes:47)
+    double alphaSnGradBnd(int b) const { return dc[nI + b] * (alpha_b[b] - alpha[own[nI + b]]); }
+    void interfaceCorrect() {
+        if (cfg.sigma == 0.0) return;
+        gradScalar(alpha, alpha_b, gradA);
+        nHatf.assign(nF, 0.0); stf.assign(nF, 0.0);
+        dvec div(nC, 0.0);
+        for (int f = 0; f < nF; f++) {
+            int P = own[f];
+            double gf[3];
+            if (f < nI) {
+                int N = nei[f];
+                for (int k = 0; k < 3; k++) gf[k] = w[f] * gradA[3 * P + k] + (1.0 - w[f]) * gradA[3 * N + k];
+            } else {
+                double m = magSf[f];
+                double n[3] = {Sf[3 * f] / m, Sf[3 * f + 1] / m, Sf[3 * f + 2] / m};
+                double corr = alphaSnGradBnd(f - nI) - dot3(n, &gradA[3 * P]);
+                for (int k = 0; k < 3; k++) gf[k] = gradA[3 * P + k] + n[k] * corr;
+            }
+            double mg = mag3(gf) + deltaN;
+            nHatf[f] = (gf[0] / mg) * Sf[3 * f] + (gf[1] / mg) * Sf[3 * f + 1] + (gf[2] / mg) * Sf[3 * f + 2];
+            div[P] += nHatf[f];
+            if (f < nI) div[nei[f]] -= nHatf[f];
+        }
+        sigmaK.resize(nC);
+        for (int c = 0; c < nC; c++) sigmaK[c] = cfg.sigma * (0.0 - div[c] / V[c]);
+        for (int f = 0; f < nF; f++) {
+            int P = own[f];
+            if (f < nI) {
+                int N = nei[f];
+                double gf[3];
+                for (int k = 0; k < 3; k++) gf[k] = w[f] * gradA[3 * P + k] + (1.0 - w[f]) * gradA[3 * N + k];
+                double sn = dc[f] * (alpha[N] - alpha[P]) + dot3(&corrVec[3 * f], gf);
+                stf[f] = (w[f] * sigmaK[P] + (1.0 - w[f]) * sigmaK[N]) * sn;
+            } else
+                stf[f] = sigmaK[P] * alphaSnGradBnd(f - nI);
+        }
+    }
+
     void alphaPredictor() {
         int n = cfg.n_alpha_subcycles;
         if (n > 1) {
@@ -988,6 +1038,7 @@ struct orc_state {
         mixtureCorrect();
         rhoPhi.resize(nF);
         for (int f = 0; f < nF; f++) rhoPhi[f] = alphaPhi[f] * (cfg.rho1 - cfg.rho2) + phi[f] * cfg.rho2;
+        interfaceCorrect();
     }
 
     // ---- S4: momentum matrix (assembled, never solved: fvSolution:80 momentumPredictor no)
@@ -1215,7 +1266,8 @@ struct orc_state {
                 snGradRho = dc[f] * (rho_b[b] - rho[P]);
             }
             double ghf = dot3(cfg.g, &Cf[3 * f]);
-            phig[f] = (0.0 - ghf * snGradRho) * rAUf[f] * magSf[f];
+            double st = cfg.sigma != 0.0 && (int)stf.size() == nF ? stf[f] : 0.0;
+            phig[f] = (st - ghf * snGradRho) * rAUf[f] * magSf[f];
             phiHbyA[f] = (flux + rhorAUf * ddtCorr) + phig[f];
         }
         // constrainPressure: fixedFluxPressure gradient

@@ -37,6 +37,7 @@ k0, k1 = rank * NL // world, (rank + 1) * NL // world
 mesh = mg.cylinder_mesh(C['H'], C['D'], NR, NL, 'flat', 'tet', k0=k0, k1=k1, proc=(rank, rank - 1 if rank > 0 else None, rank + 1 if rank < world - 1 else None))
 def tight(cfg):
     for s in (cfg.p_rgh, cfg.p_rgh_final): s.tolerance, s.rel_tol, s.max_iter = 1e-13, 0.0, 800
+    cfg.sigma = {sigma}
     return cfg
 g = sv.Solver(mesh, tight(bench.make_config(mesh)), device=int(os.environ.get('LOCAL_RANK', 0)), lib_path=LIB)
 ng, patches = g.ghost_layout()
@@ -65,9 +66,9 @@ dist.destroy_process_group()
 """
 
 
-def _run(tmp_path, lib, nr, nl, steps, port, nproc=2, env=None):
+def _run(tmp_path, lib, nr, nl, steps, port, nproc=2, env=None, sigma=0.0):
     script = tmp_path / "worker.py"
-    script.write_text(textwrap.dedent(WORKER.format(root=ROOT, lib=lib, nr=nr, nl=nl, steps=steps)))
+    script.write_text(textwrap.dedent(WORKER.format(root=ROOT, lib=lib, nr=nr, nl=nl, steps=steps, sigma=sigma)))
     r = subprocess.run([sys.executable, "-m", "torch.distributed.run", "--nnodes=1", f"--nproc-per-node={nproc}", "--master-addr", "127.0.0.1", "--master-port", str(port), str(script)],
                        capture_output=True, text=True, timeout=900, env=dict(os.environ, **(env or {})))
     out = r.stdout + r.stderr
@@ -83,6 +84,12 @@ def test_two_rank_decomposition_matches_single_rank_gloo(tmp_path, emu_lib):
 def test_three_rank_decomposition_gloo(tmp_path, emu_lib):
     """a middle slab has two processor patches (two neighbours)"""
     _run(tmp_path, emu_lib, nr=4, nl=9, steps=3, port=29632, nproc=3)
+
+
+def test_two_rank_decomposition_with_surface_tension_gloo(tmp_path, emu_lib):
+    """sigma > 0 (an extension; the reference runs sigma 0): grad alpha and the curvature cross the processor
+    patch by halo exchange before the face normal flux and the face force are formed"""
+    _run(tmp_path, emu_lib, nr=5, nl=8, steps=4, port=29635, sigma=0.072)
 
 
 def test_distributed_coarse_levels_gloo(tmp_path, emu_lib):

@@ -110,7 +110,7 @@ def test_set_fields_and_case_reader(tmp_path):
     ("system/fvSchemes", "Gauss vanLeerV", "Gauss upwind", "div(rhoPhi,U)"),
     ("system/fvSolution", "momentumPredictor no", "momentumPredictor yes", "momentumPredictor"),
     ("system/fvSolution", "smoother        DIC;", "smoother        symGaussSeidel;", "smoother"),
-    ("constant/phaseProperties", "sigma           0", "sigma           0.07", "sigma"),
+    ("constant/phaseProperties", "sigma           0", "sigma           -0.07", "sigma"),
     ("system/controlDict", "incompressibleVoF", "incompressibleFluid", "solver"),
     ("0/U", "movingWallVelocity", "slip", "slip"),
 ])

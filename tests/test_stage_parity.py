@@ -24,6 +24,7 @@ MOM = ["U_b", "gradU", "mLower", "mUpper", "mDiag", "mSource", "mBIC", "mBBC"]
 PREP = ["rAU", "HbyA", "HbyA_b", "rAUf", "phiHbyA", "phig", "pGrad_b", "grad:gradRho"]
 ASM = ["p_rgh_b", "pUpper", "pCorrFlux", "pDiag", "pSource", "grad:gradP"]
 FIN = ["p_rgh_b", "phi", "U", "U_b", "Uf", "p", "p_rgh"]
+SIGMA = ["gradA", "nHatf", "sigmaK", "stf"]  # interfaceProperties (sigma > 0 only; the reference runs sigma 0)
 
 
 def _check(g, o, names, exact, what, rtol=1e-9):
@@ -40,13 +41,14 @@ def _check(g, o, names, exact, what, rtol=1e-9):
             assert err <= rtol, f"{what}: {gn} differs by {err:.3e} of its scale (> {rtol})"
 
 
-def _run(case_dir, lib, moving, n_steps, geo="flat", cell="tet"):
+def _run(case_dir, lib, moving, n_steps, geo="flat", cell="tet", sigma=0.0):
     import oracle
 
     cs.setup_case(case_dir, H=0.004, D=0.0221, geo=geo, R=0.005, freq=2.0, duration=1.0, n_rings=6, n_layers=4, cell=cell)
     c = cs.Case(case_dir)
     if not moving:
         c.cfg.motion = None
+    c.cfg.sigma = sigma
     o = oracle.Oracle(c.mesh, c.cfg)
     o.load_case_fields(c)
     g = sv.Solver(c.mesh, c.cfg, lib_path=lib)
@@ -66,7 +68,9 @@ def _run(case_dir, lib, moving, n_steps, geo="flat", cell="tet"):
         P.sync_state(g, o)
         o.stage("alphaPredictor")
         g.stage("alphaPredictor")
-        _check(g, o, ALPHA, exact, f"step {step} alphaPredictor")
+        _check(g, o, ALPHA + (SIGMA if sigma else []), exact, f"step {step} alphaPredictor")
+        if sigma:
+            assert np.abs(o.get("stf")).max() > 0 and np.abs(o.get("sigmaK")).max() > 0
         P.sync_state(g, o)
         o.stage("momentum")
         g.stage("momentum")
@@ -109,10 +113,26 @@ def test_moving_tolerance_emu(tmp_path, emu_lib):
     _run(str(tmp_path / "c"), emu_lib, moving=True, n_steps=3)
 
 
+@pytest.mark.parametrize("cell,geo", [("tet", "flat"), ("prism", "cap")])
+def test_static_bit_exact_surface_tension_emu(tmp_path, emu_lib, cell, geo):
+    """sigma > 0 (an extension; constant/phaseProperties:19 is 0 in the reference): interface normal flux,
+    curvature and face force bit-exact, and through phig everything downstream of them."""
+    _run(str(tmp_path / "c"), emu_lib, moving=False, n_steps=3, geo=geo, cell=cell, sigma=0.072)
+
+
+def test_moving_tolerance_surface_tension_emu(tmp_path, emu_lib):
+    _run(str(tmp_path / "c"), emu_lib, moving=True, n_steps=2, sigma=0.072)
+
+
 @pytest.mark.gpu
 @pytest.mark.parametrize("cell,geo", [("tet", "flat"), ("prism", "cap")])
 def test_static_bit_exact_gpu(tmp_path, gpu_lib, cell, geo):
     _run(str(tmp_path / "c"), gpu_lib, moving=False, n_steps=3, geo=geo, cell=cell)
+
+
+@pytest.mark.gpu
+def test_static_bit_exact_surface_tension_gpu(tmp_path, gpu_lib):
+    _run(str(tmp_path / "c"), gpu_lib, moving=False, n_steps=3, sigma=0.072)
 
 
 @pytest.mark.gpu
