@@ -190,7 +190,7 @@ DEF_KERNEL(match_root, LV)
 // reductions and fused Krylov kernels (fixed grid -> fixed summation order)
 // ---------------------------------------------------------------------------------------
 // scal[] layout on the device
-enum { S_WARA = 0, S_WARA_OLD, S_WAPA, S_RES, S_NORM, S_XSUM, S_TMP0, S_TMP1, S_MAX0, S_MAX1, S_DONE, S_ITERS, S_TOLA, S_TOLR, S_MAXIT, S_COUNT = 16 };
+enum { S_WARA = 0, S_WARA_OLD, S_WAPA, S_RES, S_NORM, S_XSUM, S_TMP0, S_TMP1, S_MAX0, S_MAX1, S_DONE, S_ITERS, S_TOLA, S_TOLR, S_MAXIT, S_RESF, S_COUNT = 16 };
 
 #ifndef TPP_EMU
 DEV double block_sum(double v) {
@@ -301,7 +301,7 @@ __global__ void __launch_bounds__(256) k_spmv_dot_ell2(LV L, double* partial) {
 }
 // x += alpha pA ; r -= alpha wA ; partial sums of |r|   (alpha = scal[WARA]/scal[WAPA])
 __global__ void __launch_bounds__(256) k_update_xr(int n, double* x, double* r, const double* pA, const double* wA, const double* scal, double* partial) {
-    if (scal[S_DONE] != 0.0) return;  // converged earlier in this chunk of iterations: x, r and the partial sums stay
+    if (scal[S_DONE] != 0.0) return;  // converged earlier in this chunk of iterations: x and r stay (the final residual is in S_RESF)
     double alpha = scal[S_WARA] / scal[S_WAPA];
     double v = 0;
     for (int c = blockIdx.x * blockDim.x + threadIdx.x; c < n; c += gridDim.x * blockDim.x) {
@@ -353,7 +353,10 @@ __global__ void k_pcg_check(double* scal) {
     if (scal[S_DONE] != 0.0) return;
     const double it = scal[S_ITERS] + 1.0, res = scal[S_RES];
     scal[S_ITERS] = it;
-    if (res < scal[S_TOLA] || res < scal[S_TOLR] || !(fabs(scal[S_WAPA]) >= scal[S_NORM] * VSMALL) || it >= scal[S_MAXIT] || !(res == res)) scal[S_DONE] = 1.0;
+    if (res < scal[S_TOLA] || res < scal[S_TOLR] || !(fabs(scal[S_WAPA]) >= scal[S_NORM] * VSMALL) || it >= scal[S_MAXIT] || !(res == res)) {
+        scal[S_DONE] = 1.0;
+        scal[S_RESF] = res;  // the residual the solve ended with: S_RES itself is scratch for the rest of the chunk
+    }
 }
 __global__ void k_pcg_begin(double* scal, double tolA, double tolR, double maxIt) {
     scal[S_DONE] = 0.0; scal[S_ITERS] = 0.0; scal[S_TOLA] = tolA; scal[S_TOLR] = tolR; scal[S_MAXIT] = maxIt;

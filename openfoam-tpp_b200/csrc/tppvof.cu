@@ -2280,7 +2280,8 @@ struct tpp_solver {
             chunk = 1;
         }
         st.iters = (int)(hscal[S_ITERS] + 0.5);
-        st.r = hscal[S_RES] / nf;
+        // (S_RESF, not S_RES: iterations launched after the one that converged leave other reductions' sums there)
+        st.r = (hscal[S_DONE] != 0.0 ? hscal[S_RESF] : hscal[S_RES]) / nf;
         lastIters[which] = st.iters;
         if (!std::isfinite(st.r)) fail("the p_rgh solver residual is not finite (diverged)");
         if (useAMG && !scaledFallback && knob("TPP_NOSCALE_FROM", 0) < 99 && st.iters >= ctl.max_iter && ctl.max_iter >= 20 && !conv(st.r) && st.r > 10 * ctl.tolerance) {
@@ -2346,7 +2347,7 @@ struct tpp_solver {
         if (scal[S_DONE] == 0.0) {
             scal[S_ITERS] += 1.0;
             const double res = scal[S_RES];
-            if (res < scal[S_TOLA] || res < scal[S_TOLR] || !(fabs(scal[S_WAPA]) >= scal[S_NORM] * VSMALL) || scal[S_ITERS] >= scal[S_MAXIT] || !(res == res)) scal[S_DONE] = 1.0;
+            if (res < scal[S_TOLA] || res < scal[S_TOLR] || !(fabs(scal[S_WAPA]) >= scal[S_NORM] * VSMALL) || scal[S_ITERS] >= scal[S_MAXIT] || !(res == res)) { scal[S_DONE] = 1.0; scal[S_RESF] = res; }
         }
 #else
         k_pcg_check<<<1, 1, 0, ctx.stream>>>(scal);
