@@ -69,7 +69,8 @@ typedef struct {
     int adjust_time_step;
     /* constant/g:18, physicalProperties.{water,air}:17-21, phaseProperties:19 */
     double g[3];
-    double rho1, rho2, nu1, nu2, sigma;
+    double rho1, rho2, nu1, nu2;
+    double sigma; /* 0 in every reference case; > 0: continuum surface force, zeroGradient walls (no contact angle) */
     /* system/fvSolution:19-23 (+ MULES nLimiterIter), system/fvSchemes:30 (cAlpha) */
     int n_alpha_subcycles, n_alpha_corr, n_limiter_iter;
     double c_alpha;
