@@ -26,11 +26,11 @@ thread_local std::string g_err;
 // every C-ABI entry point is a function-try-block ending in API_CATCH: nothing escapes as an
 // exception or an abort(); the message is kept for tpp_last_error()
 #ifdef TPP_EMU
-#define API_DEVICE(s) (void)0
+#define API_DEVICE(s) do { if ((s) == nullptr) { g_err = "null handle"; return -1; } } while (0)
 #else
 // a handle may be driven from any host thread (one thread per concurrent sweep case): make its
 // device current for the calling thread
-#define API_DEVICE(s) do { if ((s) != nullptr) cudaSetDevice((s)->device); } while (0)
+#define API_DEVICE(s) do { if ((s) == nullptr) { g_err = "null handle"; return -1; } cudaSetDevice((s)->device); } while (0)
 #endif
 #ifdef TPP_EMU
 #define CUDA_CHECK_OR_EMU(x) (void)0
@@ -427,7 +427,49 @@ struct tpp_solver {
         if (knob("TPP_VERBOSE", 0)) fprintf(stderr, "tppvof: cells renumbered in Morton order (mean |owner - neighbour| %.0f -> %.0f)\n", before / nIl, after / nIl);
     }
 
+    // What gmshToFoam / decomposePar guarantee about constant/polyMesh (Makefile:73,77) and the kernels rely
+    // on: checked once, so a damaged mesh or configuration is an error code (include/tppvof.h), not a
+    // stray index on the device.
+    static bool validate(const tpp_mesh_t* m, const tpp_config_t* c) {
+        char buf[256];
+        auto bad = [&](const char* fmt, long a = 0, long b = 0, long c2 = 0) { snprintf(buf, sizeof buf, fmt, a, b, c2); g_err = std::string("invalid mesh / configuration: ") + buf; return false; };
+        if (!m || !c) return bad("null mesh or configuration");
+        if (m->n_points < 4 || m->n_cells < 1 || m->n_faces < 4 || m->n_internal < 0 || m->n_internal > m->n_faces || m->n_patches < 0)
+            return bad("sizes (points %ld, faces %ld, cells %ld)", m->n_points, m->n_faces, m->n_cells);
+        if (!m->points || !m->face_offsets || !m->face_labels || !m->owner || (m->n_internal > 0 && !m->neighbour)) return bad("null mesh array");
+        if (m->n_patches > 0 && (!m->patch_start || !m->patch_size || !m->patch_bc_u || !m->patch_bc_alpha || !m->patch_bc_p || !m->patch_inlet_alpha || !m->patch_p0)) return bad("null patch array");
+        for (long i = 0; i < 3L * m->n_points; i++) if (!std::isfinite(m->points[i])) return bad("point %ld is not finite", i / 3);
+        if (m->face_offsets[0] != 0) return bad("face_offsets[0] != 0");
+        for (int f = 0; f < m->n_faces; f++) {
+            const int a = m->face_offsets[f], b = m->face_offsets[f + 1];
+            if (b - a < 3) return bad("face %ld has %ld points", f, b - a);
+            for (int k = a; k < b; k++) if (m->face_labels[k] < 0 || m->face_labels[k] >= m->n_points) return bad("face %ld: point label %ld out of range", f, m->face_labels[k]);
+            if (m->owner[f] < 0 || m->owner[f] >= m->n_cells) return bad("face %ld: owner %ld out of range", f, m->owner[f]);
+            if (f < m->n_internal && (m->neighbour[f] <= m->owner[f] || m->neighbour[f] >= m->n_cells))
+                return bad("face %ld: neighbour %ld must lie in (owner %ld, n_cells) - upper-triangular order", f, m->neighbour[f], m->owner[f]);
+        }
+        {
+            std::vector<int> nf(m->n_cells, 0);
+            for (int f = 0; f < m->n_faces; f++) { nf[m->owner[f]]++; if (f < m->n_internal) nf[m->neighbour[f]]++; }
+            for (int c2 = 0; c2 < m->n_cells; c2++) if (nf[c2] < 4) return bad("cell %ld has %ld faces (a closed cell needs 4)", c2, nf[c2]);
+        }
+        int next = m->n_internal;  // the patches tile [n_internal, n_faces) in order
+        for (int p = 0; p < m->n_patches; p++) {
+            if (m->patch_size[p] < 0 || m->patch_start[p] != next) return bad("patch %ld: start %ld, expected %ld", p, m->patch_start[p], next);
+            next += m->patch_size[p];
+        }
+        if (next != m->n_faces) return bad("the patches cover faces up to %ld of %ld", next, m->n_faces);
+        if (!(c->delta_t > 0) || !(c->end_time >= c->start_time) || !(c->max_co > 0) || !(c->max_alpha_co > 0) || !(c->max_delta_t > 0) || !(c->write_interval > 0))
+            return bad("time control (deltaT, endTime, maxCo, maxAlphaCo, maxDeltaT and writeInterval must be positive)");
+        if (c->n_alpha_subcycles < 1 || c->n_alpha_corr < 1 || c->n_limiter_iter < 0 || c->n_correctors < 1) return bad("nAlphaSubCycles / nAlphaCorr / nCorrectors must be >= 1");
+        if (!(c->rho1 > 0) || !(c->rho2 > 0) || !(c->nu1 >= 0) || !(c->nu2 >= 0) || !(c->sigma >= 0)) return bad("rho must be positive, nu and sigma non-negative");
+        if (c->n_motion < 0 || (c->n_motion > 0 && !c->motion)) return bad("motion table");
+        for (const tpp_solver_t* sc : {&c->p_rgh, &c->p_rgh_final})
+            if (!(sc->tolerance >= 0) || !(sc->rel_tol >= 0) || sc->max_iter < 1) return bad("p_rgh solver controls (tolerance, relTol >= 0, maxIter >= 1)");
+        return true;
+    }
     bool build(const tpp_mesh_t* m, const tpp_config_t* c) {
+        if (!validate(m, c)) return false;
         nP = m->n_points; nF = m->n_faces; nI = m->n_internal; nC = m->n_cells; nB = nF - nI; nPatch = m->n_patches;
         points0.assign(m->points, m->points + 3 * (size_t)nP);
         fOff.assign(m->face_offsets, m->face_offsets + nF + 1);
@@ -2489,6 +2531,7 @@ const char* tpp_version(void) {
 }
 
 int tpp_create(const tpp_mesh_t* mesh, const tpp_config_t* cfg, int device, tpp_handle* out) try {
+    if (!out) { g_err = "tpp_create: null handle pointer"; return -1; }
     *out = nullptr;
 #ifndef TPP_EMU
     int ndev = 0;
@@ -2686,7 +2729,11 @@ int tpp_init_fields(tpp_handle s) try {
     dev_sync(s->ctx);
     return 0;
 } API_CATCH(-100)
-int tpp_set_delta_t(tpp_handle s, double dt) { s->dt = s->dt0 = dt; return 0; }
+int tpp_set_delta_t(tpp_handle s, double dt) {
+    if (!s || !(dt > 0)) { g_err = "tpp_set_delta_t: null handle or non-positive deltaT"; return -1; }
+    s->dt = s->dt0 = dt;
+    return 0;
+}
 int tpp_set_time(tpp_handle s, double t, double dt) try {
     API_DEVICE(s);
     s->t = t; s->dt = s->dt0 = dt;
@@ -2783,13 +2830,16 @@ int tpp_solve(tpp_handle s, const tpp_solver_t* ctl, const double* diag, const d
     *r0 = st.r0; *r = st.r;
     return st.iters;
 } API_CATCH(-100)
-int tpp_set_probes(tpp_handle s, int n, const int* cells) {  // cell labels of the mesh FILE (as tpp_find_cell returns them)
+int tpp_set_probes(tpp_handle s, int n, const int* cells) try {  // cell labels of the mesh FILE (as tpp_find_cell returns them)
+    API_DEVICE(s);
+    if (n < 0 || (n > 0 && !cells)) { g_err = "tpp_set_probes: bad probe list"; return -1; }
+    for (int i = 0; i < n; i++) if (cells[i] >= s->nC) { g_err = "tpp_set_probes: cell label " + std::to_string(cells[i]) + " out of range"; return -2; }
     s->flushProbes();
     s->probeCells.assign(cells, cells + n);
     s->probeUploaded = -1;
     if (s->renumbered) for (int& c : s->probeCells) if (c >= 0 && c < s->nC) c = s->cellNewOf[c];
     return 0;
-}
+} API_CATCH(-100)
 long tpp_probe_log(tpp_handle s, double* out, long cap_rows) try {
     API_DEVICE(s);
     s->flushProbes();
@@ -2800,10 +2850,11 @@ long tpp_probe_log(tpp_handle s, double* out, long cap_rows) try {
     s->probeLog.erase(s->probeLog.begin(), s->probeLog.begin() + n * w);
     return n;
 } API_CATCH(-100)
-int tpp_find_cell(tpp_handle s, const double* xyz) {
+int tpp_find_cell(tpp_handle s, const double* xyz) try {  // -1: the point is in no cell (also: null handle)
+    if (!s || !xyz) { g_err = "tpp_find_cell: null handle or point"; return -1; }
     int c = s->findCell(xyz);
     return (c >= 0 && s->renumbered) ? s->cellFileOf[c] : c;
-}
+} API_CATCH(-1)
 int tpp_use_stream(tpp_handle s, void* stream) try {
     API_DEVICE(s);
     s->dropStepGraphs();

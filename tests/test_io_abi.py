@@ -289,3 +289,66 @@ def test_async_read_back_equals_blocking(emu_lib):
         assert g.L.tpp_sync(g.h) == 0
         assert np.array_equal(a, g.get(nm)), nm
     g.close()
+
+
+def _mutations():
+    def owner_out_of_range(m, c): m.owner[-1] = m.n_cells + 7
+    def negative_neighbour(m, c): m.neighbour[3] = -2
+    def neighbour_not_above_owner(m, c): m.neighbour[0] = m.owner[0]
+    def point_label_out_of_range(m, c): m.face_labels[0] = m.n_points + 3
+    def point_not_finite(m, c): m.points[0, 0] = np.nan
+    def degenerate_face(m, c): m.face_offsets[1:] -= 1; m.face_offsets[1] = 2
+    def patches_leave_a_gap(m, c): m.patches[-1]["startFace"] += 1
+    def zero_delta_t(m, c): c.delta_t = 0.0
+    def no_alpha_subcycle(m, c): c.n_alpha_subcycles = 0
+    def negative_density(m, c): c.rho2 = -1.0
+    def negative_sigma(m, c): c.sigma = -0.07
+    def no_solver_iterations(m, c): c.p_rgh_final.max_iter = 0
+    return [(f.__name__, f) for f in (owner_out_of_range, negative_neighbour, neighbour_not_above_owner, point_label_out_of_range, point_not_finite,
+                                      degenerate_face, patches_leave_a_gap, zero_delta_t, no_alpha_subcycle, negative_density, negative_sigma, no_solver_iterations)]
+
+
+@pytest.mark.parametrize("name,mutate", _mutations(), ids=[n for n, _ in _mutations()])
+def test_damaged_input_is_an_error_code_not_a_crash(emu_lib, name, mutate):
+    """every entry point returns 0 or a negative code with a message.  A polyMesh or a configuration
+    that breaks what gmshToFoam / the dictionaries guarantee (Makefile:73; upper-triangular order, patches tiling the
+    boundary faces, positive time control ...) is refused by tpp_create before anything is indexed with it."""
+    import copy
+
+    import bench
+
+    mesh = mg.cylinder_mesh(0.004, 0.0221, 3, 2, "flat", "tet")
+    cfg = bench.make_config(mesh)
+    sv.Solver(mesh, cfg, lib_path=emu_lib).close()  # the undamaged pair is accepted
+    m, c = copy.deepcopy(mesh), copy.deepcopy(cfg)
+    mutate(m, c)
+    with pytest.raises(sv.SolverError) as e:
+        sv.Solver(m, c, lib_path=emu_lib)
+    assert "invalid mesh / configuration" in str(e.value)
+
+
+def test_null_handle_and_bad_arguments_return_codes(emu_lib):
+    """A null handle, an unknown array / stage, a wrong length or an out-of-range probe cell is a negative return
+    code with a message (include/tppvof.h), never a crash."""
+    import ctypes as C
+
+    import bench
+
+    L = sv.load(emu_lib)
+    buf = (C.c_double * 16)()
+    for call in (lambda: L.tpp_step(None, 1), lambda: L.tpp_run_to_write(None, 1), lambda: L.tpp_info(None, buf), lambda: L.tpp_init_fields(None),
+                 lambda: L.tpp_get(None, b"alpha", buf, 16), lambda: L.tpp_set(None, b"alpha", buf, 16), lambda: L.tpp_size(None, b"alpha"),
+                 lambda: L.tpp_stage(None, b"courant"), lambda: L.tpp_set_delta_t(None, 1e-3), lambda: L.tpp_set_probes(None, 0, None),
+                 lambda: L.tpp_find_cell(None, buf), lambda: L.tpp_sync(None), lambda: L.tpp_stats(None, 0, buf)):
+        assert call() < 0
+        assert b"null handle" in L.tpp_last_error()
+    assert L.tpp_destroy(None) == 0  # like free(NULL)
+    mesh = mg.cylinder_mesh(0.004, 0.0221, 3, 2, "flat", "tet")
+    g = sv.Solver(mesh, bench.make_config(mesh), lib_path=emu_lib)
+    assert L.tpp_get(g.h, b"no_such_array", buf, 16) == -1 and b"unknown array" in L.tpp_last_error()
+    assert L.tpp_set(g.h, b"alpha", buf, 16) == -2 and b"size mismatch" in L.tpp_last_error()
+    assert L.tpp_stage(g.h, b"no_such_stage") == -1 and b"unknown stage" in L.tpp_last_error()
+    assert L.tpp_set_delta_t(g.h, 0.0) == -1
+    cells = (C.c_int * 2)(0, mesh.n_cells)
+    assert L.tpp_set_probes(g.h, 2, cells) == -2 and b"out of range" in L.tpp_last_error()
+    g.close()
