@@ -278,14 +278,18 @@ def test_live_ramp_up_on_an_unstructured_mesh_against_g4(gpu_lib):
 def test_cuda_and_oracle_series_agree_within_one_percent():
     """BASELINE.json's floating-point gate between the CUDA path and the CPU oracle (the OpenFOAM
     restatement), on committed series of the reference case on the same unstructured 41 535-tet mesh:
-    over 12 forcing periods (6.5 s, ~20 000 adaptive steps, the reference's solver tolerances, two
-    different linear solvers) the m = 1 interface amplitude agrees within 1 % of its maximum, its
-    phase within 1 % of a period, the total water volume to 1e-6."""
+    over 18.8 forcing periods (10 s, ~32 900 adaptive steps, the reference's solver tolerances, two
+    different linear solvers) the m = 1 interface amplitude agrees within 1 % of its maximum (0.4 %
+    measured), its phase within 1 % of a period (0.2 %), the total water volume to 1e-6, the step
+    count within 1 %.  The oracle is deterministic: its 10 s run repeats its earlier 6.5 s run exactly."""
     d = os.path.join(os.path.dirname(HERE), "profiles", "r2_physics")
     g = np.genfromtxt(os.path.join(d, "gpu_unstructured_lc9_seed0_20s.csv"), delimiter=",", names=True)
-    o = np.genfromtxt(os.path.join(d, "oracle_unstructured_lc9_seed0_6p5s.csv"), delimiter=",", names=True)
+    o = np.genfromtxt(os.path.join(d, "oracle_unstructured_lc9_seed0_10s.csv"), delimiter=",", names=True)
+    o65 = np.genfromtxt(os.path.join(d, "oracle_unstructured_lc9_seed0_6p5s.csv"), delimiter=",", names=True)
     n = len(o)
-    assert n == 131 and o["time"][-1] * 1.88 > 12 and np.allclose(g["time"][:n], o["time"], atol=1e-9)
+    assert n == 201 and o["time"][-1] * 1.88 > 18 and np.allclose(g["time"][:n], o["time"], atol=1e-9)
+    for k in ("iso_A_m1", "iso_phase_m1", "alpha_volume", "step"):
+        assert np.array_equal(o[k][:len(o65)], o65[k])
     A = o["iso_A_m1"]
     assert np.abs(g["iso_A_m1"][:n] - A).max() < 0.01 * A.max()
     w = A > 0.1 * A.max()
