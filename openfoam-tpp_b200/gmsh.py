@@ -7,7 +7,9 @@ recipe (circularSloshingTank/Makefile:73) for the meshes generate_mesh.py descri
 Cells keep the order of the $Elements section; faces are produced in OpenFOAM's upper-triangular
 order; boundary faces that carry no physical surface go to `defaultFaces`, as gmshToFoam does.
 gmsh itself is not available in this image: tests write a .msh from the repo's own tet mesher
-(`write_msh`) and read it back.
+(`write_msh`) and read it back, and read a file laid out by hand the way gmsh writes one (node ids
+with gaps, shuffled nodes, CRLF, $Comments, physical points / lines, three tags, several elementary
+surfaces under one physical name, mixed orientation).
 """
 from __future__ import annotations
 

@@ -352,3 +352,62 @@ def test_null_handle_and_bad_arguments_return_codes(emu_lib):
     cells = (C.c_int * 2)(0, mesh.n_cells)
     assert L.tpp_set_probes(g.h, 2, cells) == -2 and b"out of range" in L.tpp_last_error()
     g.close()
+
+
+def test_gmsh_style_msh2_file_with_gaps_mixed_orientation_and_several_entities(tmp_path):
+    """What a file written by gmsh itself looks like and the repo's own writer never produces (gmsh is not in this
+    image, so the file is laid out by hand after generate_mesh.py:15-51's groups): node ids with gaps and in shuffled
+    order (OpenCASCADE boolean operations leave holes), Windows line ends, `$Comments`, physical points / lines that
+    carry nothing, three tags per element, the wall made of two elementary surfaces (side and bottom) under ONE
+    physical name, triangles and tetrahedra in arbitrary orientation, the volume group listed first.  The polyMesh must
+    equal the one built directly from the same tetrahedra: cell order, volumes, patch order (first appearance),
+    upper-triangular faces."""
+    from openfoam_tpp_b200 import gmsh
+
+    H, D = 0.02, 0.02
+    pts, tets = mg.unstructured_cylinder_tets(H, D, 0.004, seed=3, iters=20)
+    direct = mg.unstructured_cylinder_mesh(H, D, 0.004, seed=3, iters=20)
+    rng = np.random.default_rng(5)
+    nP = len(pts)
+    ids = np.sort(rng.choice(np.arange(1, 3 * nP), nP, replace=False))  # gmsh node id of point k
+    node_order = rng.permutation(nP)
+    flip_t = rng.random(len(tets)) < 0.5
+    tt = np.where(flip_t[:, None], tets[:, [1, 0, 2, 3]], tets)
+    # boundary triangles = faces seen once
+    f = np.concatenate([tets[:, [0, 1, 2]], tets[:, [0, 1, 3]], tets[:, [0, 2, 3]], tets[:, [1, 2, 3]]])
+    key = np.sort(f, axis=1)
+    _, first, cnt = np.unique(key, axis=0, return_index=True, return_counts=True)
+    tri = f[first[cnt == 1]]
+    z = pts[tri][:, :, 2]
+    top, bottom = np.abs(z - H).max(1) < 1e-9, np.abs(z).max(1) < 1e-9
+    tri = np.where((rng.random(len(tri)) < 0.5)[:, None], tri[:, [0, 2, 1]], tri)
+    rows = ['$MeshFormat', '2.2 0 8', '$EndMeshFormat', '$Comments', 'written by hand, gmsh layout', '$EndComments',
+            '$PhysicalNames', '5', '0 7 "corner"', '1 8 "rim"', '2 1 "atmosphere"', '2 2 "walls"', '3 3 "internalMesh"', '$EndPhysicalNames',
+            '$Nodes', str(nP)]
+    rows += [f"{ids[k]} {float(pts[k, 0])!r} {float(pts[k, 1])!r} {float(pts[k, 2])!r}" for k in node_order]
+    rows += ['$EndNodes', '$Elements']
+    el = [f"15 2 7 1 {ids[0]}", f"1 2 8 4 {ids[tri[0, 0]]} {ids[tri[0, 1]]}"]
+    # walls first (side = elementary 5, bottom = elementary 6), then the top: patch order must follow first appearance
+    for k in np.nonzero(~top & ~bottom)[0]:
+        el.append(f"2 3 2 5 0 {ids[tri[k, 0]]} {ids[tri[k, 1]]} {ids[tri[k, 2]]}")
+    for k in np.nonzero(bottom)[0]:
+        el.append(f"2 3 2 6 0 {ids[tri[k, 0]]} {ids[tri[k, 1]]} {ids[tri[k, 2]]}")
+    for k in np.nonzero(top)[0]:
+        el.append(f"2 2 1 4 {ids[tri[k, 0]]} {ids[tri[k, 1]]} {ids[tri[k, 2]]}")
+    for t in tt:
+        el.append(f"4 2 3 1 {ids[t[0]]} {ids[t[1]]} {ids[t[2]]} {ids[t[3]]}")
+    rows += [str(len(el))] + [f"{10 + 3 * i} {e}" for i, e in enumerate(el)] + ['$EndElements']  # element numbers with gaps too
+    p = tmp_path / "cylinder.msh"
+    p.write_bytes(("\r\n".join(rows) + "\r\n").encode())
+    r = gmsh.msh_to_polymesh(str(p))
+    assert r.check()
+    assert [(q["name"], q["type"]) for q in r.patches] == [("walls", "patch"), ("atmosphere", "patch")]
+    assert [q["nFaces"] for q in r.patches] == [q["nFaces"] for q in direct.patches]
+    assert (r.n_cells, r.n_faces, r.n_internal) == (direct.n_cells, direct.n_faces, direct.n_internal)
+    assert list(r.cell_zones) == ["internalMesh"] and np.array_equal(r.cell_zones["internalMesh"], np.arange(r.n_cells))
+    # points come back in the file's node order; cells keep the $Elements order: same cells as the direct mesh
+    C0, V0 = mg.cell_geometry(direct)
+    C1, V1 = mg.cell_geometry(r)
+    assert (V1 > 0).all() and np.allclose(V0, V1, rtol=1e-11) and np.allclose(C0, C1, atol=1e-14)
+    assert np.array_equal(r.owner[: r.n_internal], direct.owner[: direct.n_internal]) and np.array_equal(r.neighbour, direct.neighbour)
+    assert (r.neighbour > r.owner[: r.n_internal]).all()
