@@ -411,3 +411,50 @@ def test_gmsh_style_msh2_file_with_gaps_mixed_orientation_and_several_entities(t
     assert (V1 > 0).all() and np.allclose(V0, V1, rtol=1e-11) and np.allclose(C0, C1, atol=1e-14)
     assert np.array_equal(r.owner[: r.n_internal], direct.owner[: direct.n_internal]) and np.array_equal(r.neighbour, direct.neighbour)
     assert (r.neighbour > r.owner[: r.n_internal]).all()
+
+
+def test_field_files_round_trip_property(tmp_path):
+    """volScalar / volVector / surfaceScalar fields, uniform and nonuniform, ascii and binary, through
+    write_field / read_field: binary payloads come back bit for bit whatever bytes they contain (a double whose
+    bytes spell `);` or `}` or `//` must not end the list), ascii ones to writePrecision 6
+    (system/controlDict:35-37); empty patches and zero-size lists survive."""
+    from hypothesis import given, settings
+    from hypothesis import strategies as st
+    from hypothesis.extra import numpy as hnp
+
+    tricky = np.frombuffer((b");\n}\n//;(" + b"/*(;)*/{" + b"\n)\n;\n//\n" + b"FoamFile")[:32], dtype="<f8")  # 4 doubles of syntax-looking bytes
+    finite = st.floats(-1e12, 1e12, allow_nan=False, width=64)
+    counter = [0]
+
+    @settings(max_examples=60, deadline=None)
+    @given(cls=st.sampled_from(["volScalarField", "volVectorField", "surfaceScalarField"]), binary=st.booleans(), n=st.integers(0, 40),
+           uniform=st.booleans(), data=st.data())
+    def check(cls, binary, n, uniform, data):
+        nc = 3 if cls == "volVectorField" else 1
+        shape = (n, 3) if nc == 3 else (n,)
+        if uniform:
+            internal = np.array(data.draw(st.lists(finite, min_size=3, max_size=3))) if nc == 3 else data.draw(finite)
+        else:
+            internal = data.draw(hnp.arrays(np.float64, shape, elements=finite))
+            if binary and n >= 4:
+                internal.reshape(-1)[:4] = tricky
+        nb = data.draw(st.integers(0, 6))
+        bval = data.draw(hnp.arrays(np.float64, (nb, 3) if nc == 3 else (nb,), elements=finite))
+        boundary = {"walls": {"type": "zeroGradient"}, "atmosphere": {"type": "inletOutlet", "inletValue": "uniform 0", "value": bval},
+                    "empty_one": {"type": "calculated", "value": np.zeros((0, 3) if nc == 3 else (0,))}}
+        counter[0] += 1
+        p = str(tmp_path / f"f{counter[0]}" / "0" / "fld")
+        ff.write_field(p, ff.Field(cls, "fld", "[0 1 -1 0 0 0 0]", internal, boundary), binary=binary, location="0")
+        r = ff.read_field(p)
+        assert r.cls == cls and list(r.boundary) == ["walls", "atmosphere", "empty_one"]
+        assert r.boundary["walls"]["type"] == "zeroGradient" and r.boundary["atmosphere"]["type"] == "inletOutlet"
+        same = (lambda a, b: np.asarray(a, dtype="<f8").tobytes() == np.asarray(b, dtype="<f8").tobytes()) if binary else \
+               (lambda a, b: np.allclose(np.asarray(a), np.asarray(b), rtol=6e-6, atol=0))
+        if uniform:
+            assert np.allclose(np.asarray(r.internal), np.asarray(internal), rtol=6e-6, atol=0)  # `uniform` values are text in both formats
+        else:
+            assert np.asarray(r.internal).shape == shape and same(r.internal, internal)
+        assert np.asarray(r.boundary["atmosphere"]["value"]).reshape(-1).size == bval.size and same(np.asarray(r.boundary["atmosphere"]["value"]).reshape(bval.shape), bval)
+        assert np.asarray(r.boundary["empty_one"]["value"]).size == 0
+
+    check()
