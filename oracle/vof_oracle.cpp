@@ -469,7 +469,8 @@ struct orc_state {
     dvec meshPhi;
     double deltaN = 0;
     // experiment switches for the [OF13-MEM] choices that cannot be checked against upstream source
-    // (tools/of13_toggles.py; all default to the restatement documented in DESIGN.md §2)
+    // (environment switches read at create time, used with tools/validate_run.py; results in profiles/r2_physics/README.md;
+    // all default to the restatement documented in DESIGN.md §2)
     int xClip = 0;       // ORC_X_CLIP=1: clip the compressed face value to [0,1]
     int xOwn = 0;        // ORC_X_OWN=1: MULES local extrema include the cell's own value
     int xBndExt = 0;     // ORC_X_BND=1: boundary face values enter the MULES extrema
