@@ -78,3 +78,63 @@ def test_hydrostatic_rest_state_stays_at_rest_emu(emu_lib):
     assert i["t"] > 0.03
     assert np.abs(U).max() < 1e-5, np.abs(U).max()       # m/s; the gravity-wave speed here is ~1 m/s
     assert np.abs(a - alpha).max() < 1e-6
+
+
+def _linear_forced_elevation(R, a, f, d, r, f0=None, n_modes=60):
+    """Linear potential theory for an orbitally shaken cylinder: amplitude of the rotating m = 1 elevation at radius r.
+    The tank-frame body force a w^2 (cos wt, sin wt) is expanded in the sloshing modes J1(e_n r / R) (Dini series of r:
+    r = sum_n 2 R J1(e_n r / R) / ((e_n^2 - 1) J1(e_n)), J1'(e_n) = 0), each responding with w_n^2 / (w_n^2 - w^2):
+        eta(r) = F [ r + 2 R sum_n S_n J1(e_n r / R) / J1(e_n) ],  S_n = 1 / ((e_n^2 - 1)(w_n^2 / w^2 - 1)),  F = a w^2 / g,
+    i.e. eta(R) = 2 R F (1/2 + sum S_n): the quasi-static tilt R F when w -> 0.  The reference's
+    utils/potential_flow.py:71-116 returns 2 R F (1 + sum S_n) as `A_PT` - R F too much (2 R F for w -> 0; golden G5:
+    31.47 mm where this gives 25.78 mm).  f0: replace the first natural frequency by the discrete mesh's."""
+    from scipy.special import j1, jnp_zeros
+
+    e = jnp_zeros(1, n_modes)
+    w, g = 2 * np.pi * f, 9.81
+    wn2 = g * e / R * np.tanh(e / R * d)
+    if f0 is not None:
+        wn2[0] = (2 * np.pi * f0) ** 2
+    S = 1.0 / ((e**2 - 1) * (wn2 / w**2 - 1))
+    F = a * w * w / g
+    return F * (r + 2 * R * (S * j1(e * r / R) / j1(e)).sum()), 2 * R * F * (1 + S.sum())
+
+
+def test_forced_response_follows_linear_theory_emu(emu_lib):
+    """Off resonance (forcing 1.6 Hz, first mode 2.09 Hz) the D = 0.2 m tank of the reference's m0.009 case must settle
+    on linear theory's rotating wave.  The forced part of the m = 1 wall series (two-mode fit, interface.beat_fit,
+    residual 0.1 mm) is within 5 % of the theory evaluated with the mesh's own first natural frequency (2.3 % measured
+    on 3.5 k prisms) - and 35 % below the reference's `compute_wall_amplitude`, whose constant term is R F too large
+    (see _linear_forced_elevation).  With that term fixed the reference's own OpenFOAM run agrees with theory as well:
+    18.4 mm predicted at its discrete f0 = 2.209 Hz, 17.3 mm in golden G4 (profiles/r2_physics/README.md)."""
+    from openfoam_tpp_b200 import motion
+
+    R, d, H, a, f = 0.1, 0.104, 0.208, 0.004, 1.6
+    assert abs(_linear_forced_elevation(R, a, 1.88, d, R, n_modes=30)[1] - GOLDEN["A_PT"]) < 1e-5  # the reference's formula, restated (its root finder misplaces the zeros from the 6th on: 3e-6 m)
+    assert abs(_linear_forced_elevation(R, a, 1e-3, d, R)[0] / (R * a * (2e-3 * np.pi) ** 2 / 9.81) - 1) < 1e-6  # quasi-static tilt
+    mesh = mg.cylinder_mesh(H, 2 * R, 6, 12, "flat", "prism")
+    cfg = bench.make_config(mesh, freq=f)
+    rows = motion.orbital_table(a, f, 7.5, 0.001, 2.0)
+    cfg.motion, cfg.n_motion = rows, len(rows)
+    cfg.max_delta_t = 0.004
+    g = sv.Solver(mesh, cfg, lib_path=emu_lib)
+    g.set("alpha", bench.initial_alpha(mesh))
+    g.init_fields()
+    cols = interface.ColumnSampler(mesh)
+    m = cols.r > 0.85 * cols.r.max()
+    A = np.stack([np.ones(m.sum()), np.cos(cols.theta[m]), np.sin(cols.theta[m])], 1)
+    ts, q = [], []
+    while not ts or ts[-1] < 7.0:
+        g.step(1)
+        c = np.linalg.lstsq(A, cols.heights(g.get("alpha"))[m], rcond=None)[0]
+        ts.append(g.info()["t"])
+        q.append(c[1] + 1j * c[2])
+    g.close()
+    q = np.array(q)
+    fit = interface.beat_fit(np.array(ts), np.abs(q), np.angle(q), f, t0=2.0)
+    assert fit["rms"] < 2e-4 and 2.0 < fit["f0"] < 2.25, fit
+    r_ring = float(cols.r[m].mean())
+    eta_ring, _ = _linear_forced_elevation(R, a, f, d, r_ring, f0=fit["f0"])
+    eta_wall, a_ref = _linear_forced_elevation(R, a, f, d, R, f0=fit["f0"])
+    assert abs(fit["A_forced"] / eta_ring - 1) < 0.05, (fit, eta_ring)
+    assert fit["A_forced"] * eta_wall / eta_ring < 0.72 * a_ref
