@@ -121,8 +121,6 @@ int tpp_run_to_write(tpp_handle, long max_steps);
  * pcAssemble pcFinish pcEnd pressureCorrector:0 pressureCorrector:1 */
 int tpp_stage(tpp_handle, const char* name);
 
-/* out[16]: t, deltaT, step, Co, alphaCo, iters/initial/final residual of the last p_rgh and
- * p_rghFinal solves, reference cell, deltaN, write index, AMG levels, kernel launches */
 /* Asynchronous read-back for hosts that stream results out while the solver carries on: a snapshot
  * of the array (OpenFOAM file order) is taken on the solver's stream into a staging buffer owned by the
  * handle, the copy into `out` (pinned host memory, or it will not overlap) runs on a second stream.
@@ -137,6 +135,8 @@ int tpp_sync(tpp_handle);
  * "layout" = {nC, nCp, W, nI, nB, nGhost}.  Returns the array length. */
 long tpp_get_int(tpp_handle, const char* name, int* out, long cap);
 
+/* out[16]: t, deltaT, step, Co, alphaCo, iters/initial/final residual of the last p_rgh and
+ * p_rghFinal solves, reference cell, deltaN, write index, AMG levels, kernel launches */
 int tpp_info(tpp_handle, double* out16);
 
 /* The reference's interface metric, computed on the device from the current alpha.water
@@ -202,6 +202,40 @@ int tpp_comm_callbacks(tpp_handle, int rank, int n_ranks,
                        int (*allreduce)(void*, double*, int, int), void* user);
 /* ghost layout: per processor patch the offset/count in ghost order and the neighbour rank */
 int tpp_ghost_layout(tpp_handle, int* n_ghost, int* n_patches, int* off, int* cnt, int* peer, int cap);
+
+/* Case directories inside the library: the boundary as SURVEY.md 8(b) sketches it, for hosts that
+ * are not Python and have no FoamFile reader of their own (tools/tpp_foamrun.c is one, in C).  Together
+ * these are what `foamRun` does when `make run` / `make resume` start it in a case directory
+ * (/root/reference/circularSloshingTank/Makefile:85,98 <- main.py:333-348):
+ *   tpp_open       reads constant/polyMesh (ascii or binary), the dictionaries under system/ and constant/
+ *                  (incl. dynamicMeshDict and its 6DoF table) and the start fields - `startFrom latestTime`
+ *                  (controlDict:19): 0/ after setFields, or the newest complete time directory = resume - and
+ *                  builds the solver on `device`.  processor < 0: the whole case, ready to run.  processor = k:
+ *                  mesh and fields of `processor<k>/` (decomposePar, Makefile:77), dictionaries from the case
+ *                  root; join the ranks with tpp_comm_init / tpp_comm_callbacks, then call tpp_case_start.
+ *                  Keywords the solver cannot honour (another scheme, boundary condition, solver ...) are
+ *                  errors naming file and keyword (-4), exactly as in the Python host (case.read_config).
+ *   tpp_write_time writes the current state as a time directory of the opened case: alpha.water U p_rgh p rho
+ *                  phi Uf [polyMesh/points] uniform/time, in controlDict's writeFormat / writePrecision /
+ *                  timePrecision.  uniform/time is written last and marks the directory complete.
+ *   tpp_run_case   the foamRun loop: steps to each write time (tpp_run_to_write), writes it, appends the
+ *                  `probes` rows to postProcessing/probes/<start>/p (single-rank cases; a processor share
+ *                  leaves its rows in tpp_probe_log for the host to merge), until endTime or max_steps
+ *                  (< 0: no limit).  verbose: one "Time = ..." line per write on stdout.  Returns the number
+ *                  of steps taken, or a negative code (a diverged / failed run is an error, not an `End`).
+ *   tpp_case_query integers of the opened case ("n_cells" "n_faces" "n_internal" "n_points" "n_patches"
+ *                  "n_probes" "write_binary") as the return value, names ("start_time" "time" "dir") copied
+ *                  into text[cap] with their length returned. */
+int tpp_open(const char* case_dir, int processor, int device, tpp_handle* out);
+int tpp_case_start(tpp_handle);
+int tpp_write_time(tpp_handle);
+long tpp_run_case(tpp_handle, long max_steps, int verbose);
+long tpp_case_query(tpp_handle, const char* what, char* text, long cap);
+/* internalField of a vol/surface field file (ascii or binary; no handle needed), for hosts that
+ * post-process time directories (the reference reads alpha.water for its interface metric,
+ * main.py:727-806).  Returns the number of doubles the field holds (values x *n_comp; one value when
+ * `uniform`) and copies up to cap of them into out. */
+long tpp_read_field(const char* path, double* out, long cap, int* n_comp, int* uniform);
 
 #ifdef __cplusplus
 }

@@ -8,9 +8,12 @@
 #include "tpp_kernels.h"
 #include "tpp_linsolve.h"
 #include "tpp_vcycle.h"
+#include "tpp_caseio.h"
 
 #include <array>
+#include <chrono>
 #include <map>
+#include <memory>
 #include <tuple>
 #ifndef TPP_EMU
 #include <dlfcn.h>
@@ -129,6 +132,7 @@ struct Comm {
 struct tpp_solver {
     Ctx ctx;
     int device = 0;
+    caseio::Case* cs = nullptr;  // the case directory behind a handle made by tpp_open (owned)
     // host mesh
     int nP = 0, nF = 0, nI = 0, nC = 0, nB = 0, nPatch = 0, W = 0, nCp = 0;
     std::vector<double> points0;
@@ -2562,6 +2566,7 @@ int tpp_destroy(tpp_handle s) try {
     cudaStreamSynchronize(s->ctx.stream);
 #endif
     s->destroy();
+    delete s->cs;
     delete s;
     return 0;
 } API_CATCH(-100)
@@ -2978,4 +2983,310 @@ int tpp_comm_init(tpp_handle s, int rank, int n_ranks, const char* id128, const 
     return -1;
 #endif
 } API_CATCH(-100)
+}
+
+// ------------------------------------------------------------------------------------
+// case directories (tpp_caseio.h): what `foamRun` does around the time loop - read the case
+// (Makefile:85 `foamRun`, started in the case directory), write the time directories and the
+// probes log.  Host code only; everything below goes through the array ABI above, so the state
+// a handle made by tpp_open holds is bit for bit the one the Python host sets up (tests/test_caseio.py).
+// ------------------------------------------------------------------------------------
+namespace {
+#define CASE_CATCH(code) catch (const caseio::Error& e) { g_err = e.what(); return (code); } API_CATCH(-100)
+
+std::vector<double> getArray(tpp_handle s, const char* name) {
+    long n = tpp_size(s, name);
+    if (n < 0) caseio::fail(std::string("internal: the solver has no array '") + name + "'");
+    std::vector<double> a((size_t)n);
+    if (tpp_get(s, name, a.data(), n) != n) caseio::fail(std::string("tpp_get(") + name + "): " + g_err);
+    return a;
+}
+void setArray(tpp_handle s, const char* name, const std::vector<double>& a) {
+    if (tpp_size(s, name) != (long)a.size()) caseio::fail(std::string("internal: size of '") + name + "' does not match the case");
+    if (tpp_set(s, name, a.data(), (long)a.size()) != (long)a.size()) caseio::fail(std::string("tpp_set(") + name + "): " + g_err);
+}
+void check(int rc, const char* what) {
+    if (rc != 0) caseio::fail(std::string(what) + ": " + g_err);
+}
+
+// start fields of the opened case (Solver.load_case_fields + the restart part of foamrun.run_case)
+void caseStart(tpp_handle s) {
+    caseio::Case& cs = *s->cs;
+    const int nC = cs.mesh.nCells, nI = cs.mesh.nInternal(), nF = cs.mesh.nFaces();
+    const std::string td = cs.dir + "/" + cs.startName;
+    setArray(s, "alpha", cs.alpha.internal.expand(nC, 1, td + "/alpha.water:internalField"));
+    setArray(s, "U", cs.U.internal.expand(nC, 3, td + "/U:internalField"));
+    setArray(s, "p_rgh", cs.p_rgh.internal.expand(nC, 1, td + "/p_rgh:internalField"));
+    check(tpp_init_fields(s), "tpp_init_fields");
+    // boundary values the next step reads before it re-evaluates them (old-time wall / atmosphere
+    // velocity in ddtCorr, p_rgh on the fixedFluxPressure walls): a restart takes them from the files
+    const caseio::Field* flds[2] = {&cs.U, &cs.p_rgh};
+    const char* arrs[2] = {"U_b", "p_rgh_b"};
+    for (int k = 0; k < 2; k++) {
+        const int nc = flds[k]->nc;
+        std::vector<double> cur = getArray(s, arrs[k]);
+        bool changed = false;
+        for (auto& q : cs.mesh.patches) {
+            if (q.type == "processor" || q.nFaces == 0) continue;
+            const caseio::BoundaryEntry* e = flds[k]->patch(q.name);
+            if (!e || !e->value.present) continue;
+            std::vector<double> v = e->value.expand(q.nFaces, nc, td + ":" + q.name + ".value");
+            std::copy(v.begin(), v.end(), cur.begin() + (size_t)(q.startFace - nI) * nc);
+            changed = true;
+        }
+        if (changed) setArray(s, arrs[k], cur);
+    }
+    if (cs.hasRestartDt) check(tpp_set_delta_t(s, cs.restartDt), "tpp_set_delta_t");
+    if (cs.hasFlux && cs.startValue > 0) {  // restart: internal + boundary values of the face fields
+        const caseio::Field* ff[2] = {&cs.phi, &cs.Uf};
+        const char* names[2] = {"phi", "Uf"};
+        for (int k = 0; k < 2; k++) {
+            const int nc = ff[k]->nc;
+            std::vector<double> a((size_t)nF * nc, 0.0), in = ff[k]->internal.expand(nI, nc, td + "/" + names[k] + ":internalField");
+            std::copy(in.begin(), in.end(), a.begin());
+            for (auto& q : cs.mesh.patches) {
+                const caseio::BoundaryEntry* e = ff[k]->patch(q.name);
+                if (!e || !e->value.present) continue;
+                std::vector<double> v = e->value.expand(q.nFaces, nc, td + "/" + names[k] + ":" + q.name + ".value");
+                std::copy(v.begin(), v.end(), a.begin() + (size_t)q.startFace * nc);
+            }
+            setArray(s, names[k], a);
+        }
+        check(tpp_set_time(s, cs.startValue, cs.hasRestartDt && cs.restartDt != 0.0 ? cs.restartDt : cs.cfg.c.delta_t), "tpp_set_time");
+    }
+    cs.started = true;
+}
+
+// one time directory from the device state (foamrun.write_time)
+void caseWrite(tpp_handle s) {
+    caseio::Case& cs = *s->cs;
+    const caseio::Mesh& m = cs.mesh;
+    const int nC = m.nCells, nI = m.nInternal();
+    const bool bin = cs.cfg.writeBinary;
+    const int prec = cs.cfg.writePrecision;
+    double info[16];
+    check(tpp_info(s, info), "tpp_info");
+    const std::string name = caseio::timeName(info[0], cs.cfg.timePrecision), tdir = cs.dir + "/" + name;
+    caseio::makeDirs(tdir);
+    long nBphys = 0;
+    for (auto& q : m.patches) if (q.type != "processor") nBphys += q.nFaces;
+
+    std::vector<std::vector<double>> keep;  // per-patch values stay alive until the file is written
+    // vol field: physical patches from the solver's boundary array, processor patches from the adjacent cells
+    auto volPatches = [&](const caseio::Field* src, const std::vector<double>& cells, const std::vector<double>& bnd, int nc) {
+        std::vector<caseio::PatchOut> out;
+        for (auto& q : m.patches) {
+            caseio::PatchOut po;
+            po.name = q.name;
+            const caseio::BoundaryEntry* e = src ? src->patch(q.name) : nullptr;
+            if (src && e) po.entries = e->entries;
+            else po.entries = {{"type", src ? "calculated" : (q.type == "processor" ? "processor" : "calculated")}};
+            po.n = q.nFaces;
+            if (q.type == "processor") {
+                keep.emplace_back((size_t)q.nFaces * nc);
+                for (int f = 0; f < q.nFaces; f++)
+                    for (int c = 0; c < nc; c++) keep.back()[(size_t)f * nc + c] = cells[(size_t)m.owner[q.startFace + f] * nc + c];
+                po.value = keep.back().data();
+            } else po.value = bnd.data() + (size_t)(q.startFace - nI) * nc;
+            out.push_back(po);
+        }
+        return out;
+    };
+    // surface field: the slice of the boundary part of the array (file face order)
+    auto facePatches = [&](const std::vector<double>& arr, int nc) {
+        std::vector<caseio::PatchOut> out;
+        for (auto& q : m.patches) {
+            caseio::PatchOut po;
+            po.name = q.name;
+            po.entries = {{"type", q.type == "processor" ? "processor" : "calculated"}};
+            po.n = q.nFaces;
+            po.value = arr.data() + (size_t)q.startFace * nc;
+            out.push_back(po);
+        }
+        return out;
+    };
+    std::vector<double> alpha = getArray(s, "alpha"), alpha_b = getArray(s, "alpha_b"), U = getArray(s, "U"), U_b = getArray(s, "U_b");
+    std::vector<double> p_rgh = getArray(s, "p_rgh"), p_rgh_b = getArray(s, "p_rgh_b"), rho = getArray(s, "rho"), rho_b = getArray(s, "rho_b");
+    std::vector<double> p = getArray(s, "p"), phi = getArray(s, "phi"), Uf = getArray(s, "Uf"), ghf = getArray(s, "ghf");
+    if ((long)alpha_b.size() < nBphys || (long)ghf.size() < nI + nBphys) caseio::fail("internal: boundary arrays are smaller than the case's physical patches");
+    caseio::writeField(tdir + "/alpha.water", "volScalarField", "alpha.water", name, "[0 0 0 0 0 0 0]", alpha.data(), nC, 1, volPatches(&cs.alpha, alpha, alpha_b, 1), bin, prec);
+    caseio::writeField(tdir + "/U", "volVectorField", "U", name, "[0 1 -1 0 0 0 0]", U.data(), nC, 3, volPatches(&cs.U, U, U_b, 3), bin, prec);
+    caseio::writeField(tdir + "/p_rgh", "volScalarField", "p_rgh", name, "[1 -1 -2 0 0 0 0]", p_rgh.data(), nC, 1, volPatches(&cs.p_rgh, p_rgh, p_rgh_b, 1), bin, prec);
+    std::vector<double> pb((size_t)nBphys);
+    for (long k = 0; k < nBphys; k++) pb[k] = p_rgh_b[k] + rho_b[k] * ghf[nI + k];
+    caseio::writeField(tdir + "/p", "volScalarField", "p", name, "[1 -1 -2 0 0 0 0]", p.data(), nC, 1, volPatches(nullptr, p, pb, 1), bin, prec);
+    caseio::writeField(tdir + "/rho", "volScalarField", "rho", name, "[1 -3 0 0 0 0 0]", rho.data(), nC, 1, volPatches(nullptr, rho, rho_b, 1), bin, prec);
+    caseio::writeField(tdir + "/phi", "surfaceScalarField", "phi", name, "[0 3 -1 0 0 0 0]", phi.data(), nI, 1, facePatches(phi, 1), bin, prec);
+    caseio::writeField(tdir + "/Uf", "surfaceVectorField", "Uf", name, "[0 1 -1 0 0 0 0]", Uf.data(), nI, 3, facePatches(Uf, 3), bin, prec);
+    if (cs.cfg.c.n_motion > 0) {
+        caseio::makeDirs(tdir + "/polyMesh");
+        std::vector<double> pts = getArray(s, "points");
+        caseio::writePoints(tdir + "/polyMesh/points", name + "/polyMesh", pts.data(), (long)pts.size() / 3, bin);
+    }
+    // uniform/time last: its presence marks the directory as complete (caseio::latestTime)
+    caseio::makeDirs(tdir + "/uniform");
+    caseio::Out o(tdir + "/uniform/time");
+    o.str(caseio::fileHeader("dictionary", "time", name + "/uniform", false));
+    char b[512];
+    snprintf(b, sizeof b, "value           %.17g;\n\nname            \"%s\";\n\nindex           %ld;\n\ndeltaT          %.17g;\n\ndeltaT0         %.17g;\n", info[0], name.c_str(), (long)info[2], info[1], info[1]);
+    o.str(b);
+    o.str(caseio::FILE_END);
+    o.close();
+}
+
+std::string g6(double v) { return caseio::fmtNum(v, 6); }
+void probeRows(caseio::Case& cs, const double* rows, long n, long w) {
+    if (!cs.probesFile) return;
+    for (long r = 0; r < n; r++) {
+        char b[64];
+        snprintf(b, sizeof b, "%-13s ", g6(rows[r * w]).c_str());
+        std::string line = b;
+        for (long k = 1; k < w; k++) {
+            snprintf(b, sizeof b, "%-13s", g6(rows[r * w + k]).c_str());
+            line += std::string(k > 1 ? " " : "") + b;
+        }
+        while (!line.empty() && line.back() == ' ') line.pop_back();
+        fprintf(cs.probesFile, "%s\n", line.c_str());
+    }
+    fflush(cs.probesFile);
+}
+}  // namespace
+
+extern "C" {
+
+int tpp_open(const char* case_dir, int processor, int device, tpp_handle* out) try {
+    if (!out) { g_err = "tpp_open: null handle pointer"; return -1; }
+    *out = nullptr;
+    if (!case_dir) { g_err = "tpp_open: null case directory"; return -1; }
+    std::unique_ptr<caseio::Case> cs(new caseio::Case());
+    caseio::load(case_dir, processor, *cs);
+    tpp_mesh_t m = caseio::meshView(*cs);
+    tpp_handle s = nullptr;
+    int rc = tpp_create(&m, &cs->cfg.c, device, &s);
+    if (rc != 0) return rc;
+    s->cs = cs.release();
+    if (processor < 0) {
+        try {
+            caseStart(s);
+        } catch (...) {
+            std::string keep;
+            try { throw; } catch (const std::exception& e) { keep = e.what(); } catch (const tpp::CudaFailure& e) { keep = e.what; } catch (...) { keep = "internal error"; }
+            tpp_destroy(s);
+            g_err = keep;
+            return -1;
+        }
+    }
+    *out = s;
+    return 0;
+} CASE_CATCH(-4)
+
+int tpp_case_start(tpp_handle s) try {
+    API_DEVICE(s);
+    if (!s->cs) { g_err = "tpp_case_start: the handle was not made by tpp_open"; return -1; }
+    caseStart(s);
+    return 0;
+} CASE_CATCH(-4)
+
+int tpp_write_time(tpp_handle s) try {
+    API_DEVICE(s);
+    if (!s->cs) { g_err = "tpp_write_time: the handle was not made by tpp_open"; return -1; }
+    caseWrite(s);
+    return 0;
+} CASE_CATCH(-4)
+
+long tpp_case_query(tpp_handle s, const char* what, char* text, long cap) try {
+    API_DEVICE(s);
+    if (!s->cs || !what) { g_err = "tpp_case_query: the handle was not made by tpp_open"; return -1; }
+    caseio::Case& cs = *s->cs;
+    std::string w(what), t;
+    long v = 0;
+    if (w == "n_cells") v = cs.mesh.nCells;
+    else if (w == "n_faces") v = cs.mesh.nFaces();
+    else if (w == "n_internal") v = cs.mesh.nInternal();
+    else if (w == "n_points") v = (long)cs.mesh.points.size() / 3;
+    else if (w == "n_patches") v = (long)cs.mesh.patches.size();
+    else if (w == "n_probes") v = (long)cs.cfg.probes.size() / 3;
+    else if (w == "write_binary") v = cs.cfg.writeBinary;
+    else if (w == "start_time") { t = cs.startName; v = (long)t.size(); }
+    else if (w == "time") { double info[16]; tpp_info(s, info); t = caseio::timeName(info[0], cs.cfg.timePrecision); v = (long)t.size(); }
+    else if (w == "dir") { t = cs.dir; v = (long)t.size(); }
+    else { g_err = "tpp_case_query: unknown item '" + w + "'"; return -2; }
+    if (text && cap > 0) { strncpy(text, t.c_str(), (size_t)cap - 1); text[cap - 1] = 0; }
+    return v;
+} CASE_CATCH(-4)
+
+long tpp_run_case(tpp_handle s, long max_steps, int verbose) try {
+    API_DEVICE(s);
+    if (!s->cs) { g_err = "tpp_run_case: the handle was not made by tpp_open"; return -1; }
+    caseio::Case& cs = *s->cs;
+    if (!cs.started) { g_err = "tpp_run_case: call tpp_case_start first (a processor share starts after tpp_comm_init)"; return -1; }
+    const int np = (int)(cs.cfg.probes.size() / 3);
+    double info[16];
+    check(tpp_info(s, info), "tpp_info");
+    if (cs.cfg.hasProbes && np > 0 && cs.probeCells.empty()) {
+        // `probes` function object (system/functions:17-33): postProcessing/probes/<start time>/p
+        for (int k = 0; k < np; k++) cs.probeCells.push_back(tpp_find_cell(s, &cs.cfg.probes[3 * k]));
+        check(tpp_set_probes(s, np, cs.probeCells.data()), "tpp_set_probes");
+        if (s->nG == 0) {  // a processor share leaves the file to its host, which merges the ranks' rows (tpp_probe_log)
+            std::string d = cs.dir + "/postProcessing/probes/" + cs.startName;
+            caseio::makeDirs(d);
+            cs.probesFile = fopen((d + "/p").c_str(), "w");
+            if (!cs.probesFile) caseio::fail(d + "/p: cannot open for writing");
+            for (int k = 0; k < np; k++) fprintf(cs.probesFile, "# Probe %d (%s %s %s)\n", k, g6(cs.cfg.probes[3 * k]).c_str(), g6(cs.cfg.probes[3 * k + 1]).c_str(), g6(cs.cfg.probes[3 * k + 2]).c_str());
+            std::string hdr = "# Time        ";
+            for (int k = 0; k < np; k++) {
+                char b[32];
+                snprintf(b, sizeof b, "%-13d", k);
+                hdr += std::string(k ? " " : "") + b;
+            }
+            fprintf(cs.probesFile, "%s\n", hdr.c_str());
+            std::vector<double> pnow = getArray(s, "p"), row(1 + np);
+            row[0] = cs.startValue;
+            for (int k = 0; k < np; k++) row[1 + k] = cs.probeCells[k] >= 0 ? pnow[cs.probeCells[k]] : -1.79769e307;
+            probeRows(cs, row.data(), 1, 1 + np);
+        }
+    }
+    const long step0 = (long)info[2];
+    const auto t0 = std::chrono::steady_clock::now();
+    std::vector<double> rows;
+    for (;;) {
+        check(tpp_info(s, info), "tpp_info");
+        long budget = max_steps < 0 ? 1000000000L : std::max(0L, max_steps - ((long)info[2] - step0));
+        if (budget == 0) break;
+        int rc = tpp_run_to_write(s, budget);
+        if (rc < 0) return rc;
+        check(tpp_info(s, info), "tpp_info");
+        if (np > 0 && !cs.probeCells.empty()) {
+            rows.resize((size_t)(1 + np) * 4096);
+            for (long n; (n = tpp_probe_log(s, rows.data(), 4096)) > 0;) probeRows(cs, rows.data(), n, 1 + np);
+        }
+        if (rc != 1) break;
+        caseWrite(s);
+        if (verbose) {
+            double el = std::chrono::duration<double>(std::chrono::steady_clock::now() - t0).count();
+            printf("Time = %s  step %ld  deltaT = %.6g  Co = %.3g  p_rghFinal iters %d res %.2e  ExecutionTime = %.2f s\n", caseio::timeName(info[0], cs.cfg.timePrecision).c_str(), (long)info[2], info[1],
+                   info[3], (int)info[8], info[10], el);
+            fflush(stdout);
+        }
+    }
+    check(tpp_info(s, info), "tpp_info");
+    return (long)info[2] - step0;
+} CASE_CATCH(-4)
+}
+
+extern "C" {
+// internalField of an OpenFOAM vol/surface field file (ascii or binary), for hosts that post-process
+// time directories without a FoamFile reader (the reference reads alpha.water for its interface
+// metric, main.py:727-806).  Returns the number of doubles the field holds (values x components;
+// a `uniform` internalField holds one value) and copies up to cap of them; needs no handle.
+long tpp_read_field(const char* path, double* out, long cap, int* n_comp, int* uniform) try {
+    if (!path) { g_err = "tpp_read_field: null path"; return -1; }
+    caseio::Field f = caseio::readField(path);
+    if (n_comp) *n_comp = f.nc;
+    if (uniform) *uniform = f.internal.uniform;
+    const double* src = f.internal.uniform ? f.internal.u : f.internal.a.data();
+    long n = f.internal.uniform ? f.nc : (long)f.internal.a.size();
+    if (out && cap > 0) memcpy(out, src, (size_t)std::min(n, cap) * sizeof(double));
+    return n;
+} CASE_CATCH(-4)
 }

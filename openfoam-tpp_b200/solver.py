@@ -91,8 +91,29 @@ def load(lib_path=None):
     L.tpp_amg_levels.argtypes = [H, abi.c_int_p, abi.c_int_p, C.c_int]
     L.tpp_amg_layout.argtypes = [H, abi.c_int_p]
     L.tpp_ghost_layout.argtypes = [H, abi.c_int_p, abi.c_int_p, abi.c_int_p, abi.c_int_p, abi.c_int_p, C.c_int]
+    L.tpp_open.argtypes = [C.c_char_p, C.c_int, C.c_int, C.POINTER(H)]
+    L.tpp_case_start.argtypes = [H]
+    L.tpp_write_time.argtypes = [H]
+    L.tpp_run_case.restype = C.c_long
+    L.tpp_run_case.argtypes = [H, C.c_long, C.c_int]
+    L.tpp_case_query.restype = C.c_long
+    L.tpp_case_query.argtypes = [H, C.c_char_p, C.c_char_p, C.c_long]
+    L.tpp_read_field.restype = C.c_long
+    L.tpp_read_field.argtypes = [C.c_char_p, abi.c_double_p, C.c_long, C.POINTER(C.c_int), C.POINTER(C.c_int)]
     _LIBS[path] = L
     return L
+
+
+def read_field_file(path, lib_path=None):
+    """internalField of a field file through the library's reader (tpp_read_field): (array, uniform)."""
+    L = load(lib_path)
+    nc, uni = C.c_int(), C.c_int()
+    n = L.tpp_read_field(os.fsencode(path), None, 0, C.byref(nc), C.byref(uni))
+    if n < 0:
+        raise SolverError(f"tpp_read_field failed ({n}): {L.tpp_last_error().decode()}")
+    a = np.empty(n)
+    L.tpp_read_field(os.fsencode(path), a.ctypes.data_as(abi.c_double_p), n, C.byref(nc), C.byref(uni))
+    return (a.reshape(-1, nc.value) if nc.value > 1 else a), bool(uni.value)
 
 
 class Solver:
@@ -108,6 +129,43 @@ class Solver:
         self.h = h
         self.mesh, self.cfg = mesh, cfg
         self._nprobe = 0
+
+    @classmethod
+    def open(cls, case_dir, device=0, lib_path=None, processor=-1):
+        """The library's own case reader (tpp_open, include/tppvof.h): what a host without a FoamFile
+        parser binds.  The Python host normally reads the case itself (case.Case) and uses __init__; the
+        two must give the same solver state (tests/test_caseio.py)."""
+        self = cls.__new__(cls)
+        self.L = load(lib_path)
+        self._keep, self._nprobe = [], 0
+        h = C.c_void_p()
+        rc = self.L.tpp_open(os.fsencode(case_dir), processor, device, C.byref(h))
+        if rc != 0:
+            raise SolverError(f"tpp_open failed ({rc}): {self.L.tpp_last_error().decode()}")
+        self.h = h
+        self.mesh = self.cfg = None
+        return self
+
+    def case_query(self, what):
+        buf = C.create_string_buffer(4096)
+        n = self.L.tpp_case_query(self.h, what.encode(), buf, 4096)
+        if n < 0:
+            self._err("tpp_case_query")
+        return buf.value.decode() if what in ("start_time", "time", "dir") else int(n)
+
+    def case_start(self):
+        if self.L.tpp_case_start(self.h) != 0:
+            self._err("tpp_case_start")
+
+    def write_time(self):
+        if self.L.tpp_write_time(self.h) != 0:
+            self._err("tpp_write_time")
+
+    def run_case(self, max_steps=-1, verbose=False):
+        n = self.L.tpp_run_case(self.h, max_steps, int(verbose))
+        if n < 0:
+            self._err("tpp_run_case")
+        return int(n)
 
     def close(self):
         if getattr(self, "h", None):
