@@ -264,3 +264,48 @@ def test_the_references_own_dictionaries_and_start_fields(tmp_path, emu_lib):
     _same_state(a, b)
     a.close()
     b.close()
+
+
+PAR_WORKER = """
+import os, sys
+sys.path.insert(0, {root!r})
+import torch.distributed as dist
+from openfoam_tpp_b200 import foamrun, solver as sv
+rank = int(os.environ['RANK'])
+foamrun.run_case({py_case!r}, lib_path={lib!r}, parallel=True, log=None)      # the Python host, rank by rank
+s = sv.Solver.open({lib_case!r}, lib_path={lib!r}, processor=rank)           # the library's reader on processor<rank>/
+s.comm_init_callbacks()
+s.case_start()
+n = s.run_case()
+sys.stdout.write('RANK%dOK %d %s\\\\n' % (rank, n, s.case_query('dir'))); sys.stdout.flush()
+s.close()
+dist.destroy_process_group()
+"""
+
+
+def test_processor_shares_open_like_the_python_host(tmp_path, emu_lib):
+    """`foamRun -parallel` on processor<k>/ (Makefile:78): tpp_open(processor=k) -> comm -> tpp_case_start
+    -> tpp_run_case writes the processor time directories the Python host writes"""
+    import sys
+    import textwrap
+
+    from openfoam_tpp_b200 import decompose as dc
+
+    a, b = str(tmp_path / "python"), str(tmp_path / "library")
+    for d in (a, b):
+        _setup(d)
+        _set_entry(os.path.join(d, "system", "controlDict"), "endTime", "0.003")
+        with open(os.path.join(d, "system", "decomposeParDict"), "w") as f:
+            f.write(ff._hdr("dictionary", "decomposeParDict", "system") + "numberOfSubdomains 2;\nmethod simple;\nsimpleCoeffs { n (2 1 1); delta 0.001; }\n" + ff.END)
+        dc.decompose_par(d)
+    script = tmp_path / "worker.py"
+    script.write_text(textwrap.dedent(PAR_WORKER.format(root=ROOT, py_case=a, lib_case=b, lib=emu_lib)))
+    r = subprocess.run([sys.executable, "-m", "torch.distributed.run", "--nnodes=1", "--nproc-per-node=2", "--master-addr", "127.0.0.1", "--master-port", "29647", str(script)],
+                       capture_output=True, text=True, timeout=900)
+    o = r.stdout + r.stderr
+    assert r.returncode == 0 and "RANK0OK" in o and "RANK1OK" in o, o[-3000:]
+    for k in (0, 1):
+        pa, pb = os.path.join(a, f"processor{k}"), os.path.join(b, f"processor{k}")
+        assert cs.latest_time(pa)[1] == cs.latest_time(pb)[1] == "0.003"
+        for nm in ("alpha.water", "U", "p_rgh", "p", "rho", "phi", "Uf"):
+            assert open(os.path.join(pa, "0.003", nm), "rb").read() == open(os.path.join(pb, "0.003", nm), "rb").read(), (k, nm)
