@@ -221,15 +221,18 @@ int tpp_ghost_layout(tpp_handle, int* n_ghost, int* n_patches, int* off, int* cn
  *   tpp_run_case   the foamRun loop: steps to each write time (tpp_run_to_write), writes it, appends the
  *                  `probes` rows to postProcessing/probes/<start>/p (single-rank cases; a processor share
  *                  leaves its rows in tpp_probe_log for the host to merge), until endTime or max_steps
- *                  (< 0: no limit).  verbose: one "Time = ..." line per write on stdout.  Returns the number
- *                  of steps taken, or a negative code (a diverged / failed run is an error, not an `End`).
+ *                  (< 0: no limit).  flags: TPP_RUN_LOG = one "Time = ..." line per write on stdout;
+ *                  TPP_RUN_INTERFACE = a row of postProcessing/interface/interface_summary.csv per write time
+ *                  (tpp_interface; the file extract_interface makes afterwards, main.py:751-780).  Returns the
+ *                  number of steps taken, or a negative code (a diverged / failed run is an error, not an `End`).
  *   tpp_case_query integers of the opened case ("n_cells" "n_faces" "n_internal" "n_points" "n_patches"
  *                  "n_probes" "write_binary") as the return value, names ("start_time" "time" "dir") copied
  *                  into text[cap] with their length returned. */
 int tpp_open(const char* case_dir, int processor, int device, tpp_handle* out);
 int tpp_case_start(tpp_handle);
 int tpp_write_time(tpp_handle);
-long tpp_run_case(tpp_handle, long max_steps, int verbose);
+enum { TPP_RUN_LOG = 1, TPP_RUN_INTERFACE = 2 };
+long tpp_run_case(tpp_handle, long max_steps, int flags);
 long tpp_case_query(tpp_handle, const char* what, char* text, long cap);
 /* internalField of a vol/surface field file (ascii or binary; no handle needed), for hosts that
  * post-process time directories (the reference reads alpha.water for its interface metric,

@@ -1030,7 +1030,7 @@ struct Case {
     // run state of tpp_run_case
     FILE* probesFile = nullptr;
     std::vector<int> probeCells;
-    bool started = false;
+    bool started = false, interfaceStarted = false;
     ~Case() {
         if (probesFile) fclose(probesFile);
     }

@@ -3135,6 +3135,13 @@ void caseWrite(tpp_handle s) {
 }
 
 std::string g6(double v) { return caseio::fmtNum(v, 6); }
+std::string shortest(double v) {  // the fewest digits that read back as v
+    for (int p = 1; p < 17; p++) {
+        std::string t = caseio::fmtNum(v, p);
+        if (strtod(t.c_str(), nullptr) == v) return t;
+    }
+    return caseio::fmtNum(v, 17);
+}
 void probeRows(caseio::Case& cs, const double* rows, long n, long w) {
     if (!cs.probesFile) return;
     for (long r = 0; r < n; r++) {
@@ -3215,7 +3222,8 @@ long tpp_case_query(tpp_handle s, const char* what, char* text, long cap) try {
     return v;
 } CASE_CATCH(-4)
 
-long tpp_run_case(tpp_handle s, long max_steps, int verbose) try {
+long tpp_run_case(tpp_handle s, long max_steps, int flags) try {
+    const bool verbose = flags & TPP_RUN_LOG;
     API_DEVICE(s);
     if (!s->cs) { g_err = "tpp_run_case: the handle was not made by tpp_open"; return -1; }
     caseio::Case& cs = *s->cs;
@@ -3246,6 +3254,27 @@ long tpp_run_case(tpp_handle s, long max_steps, int verbose) try {
             probeRows(cs, row.data(), 1, 1 + np);
         }
     }
+    // in-situ interface statistics (`foamRun -interface`): the rows the reference's extract_interface derives
+    // from the time directories afterwards (main.py:751-780), computed on the device at every write time
+    struct Closer { FILE* f = nullptr; ~Closer() { if (f) fclose(f); } } iface;
+    auto ifaceRow = [&]() {
+        double o[5];
+        check(tpp_interface(s, 0.5, o), "tpp_interface");
+        fprintf(iface.f, "\n%s,%s,%s,%s,%ld", shortest(o[4]).c_str(), shortest(o[0]).c_str(), shortest(o[1]).c_str(), shortest(o[2]).c_str(), (long)o[3]);
+        fflush(iface.f);
+    };
+    if ((flags & TPP_RUN_INTERFACE) && s->nG == 0) {
+        std::string d = cs.dir + "/postProcessing/interface";
+        caseio::makeDirs(d);
+        const bool fresh = cs.startValue == 0 && !cs.interfaceStarted;
+        iface.f = fopen((d + "/interface_summary.csv").c_str(), fresh ? "w" : "a");
+        if (!iface.f) caseio::fail(d + "/interface_summary.csv: cannot open for writing");
+        if (fresh) {
+            fprintf(iface.f, "time,max_z,min_z,mean_z,num_points");
+            ifaceRow();
+        }
+        cs.interfaceStarted = true;
+    }
     const long step0 = (long)info[2];
     const auto t0 = std::chrono::steady_clock::now();
     std::vector<double> rows;
@@ -3262,6 +3291,7 @@ long tpp_run_case(tpp_handle s, long max_steps, int verbose) try {
         }
         if (rc != 1) break;
         caseWrite(s);
+        if (iface.f) ifaceRow();
         if (verbose) {
             double el = std::chrono::duration<double>(std::chrono::steady_clock::now() - t0).count();
             printf("Time = %s  step %ld  deltaT = %.6g  Co = %.3g  p_rghFinal iters %d res %.2e  ExecutionTime = %.2f s\n", caseio::timeName(info[0], cs.cfg.timePrecision).c_str(), (long)info[2], info[1],

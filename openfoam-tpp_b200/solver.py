@@ -161,8 +161,8 @@ class Solver:
         if self.L.tpp_write_time(self.h) != 0:
             self._err("tpp_write_time")
 
-    def run_case(self, max_steps=-1, verbose=False):
-        n = self.L.tpp_run_case(self.h, max_steps, int(verbose))
+    def run_case(self, max_steps=-1, verbose=False, interface=False):
+        n = self.L.tpp_run_case(self.h, max_steps, int(bool(verbose)) | (2 if interface else 0))
         if n < 0:
             self._err("tpp_run_case")
         return int(n)

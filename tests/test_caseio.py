@@ -309,3 +309,20 @@ def test_processor_shares_open_like_the_python_host(tmp_path, emu_lib):
         assert cs.latest_time(pa)[1] == cs.latest_time(pb)[1] == "0.003"
         for nm in ("alpha.water", "U", "p_rgh", "p", "rho", "phi", "Uf"):
             assert open(os.path.join(pa, "0.003", nm), "rb").read() == open(os.path.join(pb, "0.003", nm), "rb").read(), (k, nm)
+
+
+def test_run_case_interface_rows_match_foamrun(tmp_path, emu_lib):
+    """`foamRun -interface`: interface_summary.csv (main.py:751-780) written in situ by both hosts"""
+    a, b = str(tmp_path / "python"), str(tmp_path / "library")
+    for d in (a, b):
+        _setup(d)
+        _set_entry(os.path.join(d, "system", "controlDict"), "endTime", "0.006")
+    foamrun.run_case(a, lib_path=emu_lib, log=None, interface=True)
+    s = sv.Solver.open(b, lib_path=emu_lib)
+    s.run_case(interface=True)
+    s.close()
+    fa = open(os.path.join(a, "postProcessing", "interface", "interface_summary.csv")).read().splitlines()
+    fb = open(os.path.join(b, "postProcessing", "interface", "interface_summary.csv")).read().splitlines()
+    assert fa[0] == fb[0] == "time,max_z,min_z,mean_z,num_points" and len(fa) == len(fb) == 4  # t = 0, 0.003, 0.006
+    for x, y in zip(fa[1:], fb[1:]):
+        assert [float(v) for v in x.split(",")] == [float(v) for v in y.split(",")]

@@ -5,7 +5,7 @@
  * only needs an executable that exits 0 or not) can bind the boundary as it stands.
  *
  *   gcc -Iinclude tools/tpp_foamrun.c -o tpp_foamrun -ldl
- *   ./tpp_foamrun openfoam-tpp_b200/libtppvof.so -case <dir> [-device N] [-maxSteps N]
+ *   ./tpp_foamrun openfoam-tpp_b200/libtppvof.so -case <dir> [-device N] [-maxSteps N] [-interface]
  *
  * The library is named on the command line (not linked) so that the tests can hand it the host
  * emulation build; a deployment links libtppvof.so directly.
@@ -22,10 +22,12 @@ int main(int argc, char** argv) {
     const char* dir = ".";
     int device = 0;
     long max_steps = -1;
+    int flags = TPP_RUN_LOG;
     for (int i = 2; i < argc; i++) {
         if (!strcmp(argv[i], "-case") && i + 1 < argc) dir = argv[++i];
         else if (!strcmp(argv[i], "-device") && i + 1 < argc) device = atoi(argv[++i]);
         else if (!strcmp(argv[i], "-maxSteps") && i + 1 < argc) max_steps = atol(argv[++i]);
+        else if (!strcmp(argv[i], "-interface")) flags |= TPP_RUN_INTERFACE;
         else if (!strcmp(argv[i], "-noFunctionObjects")) continue;
         else {
             fprintf(stderr, "tpp_foamrun: unknown option %s\n", argv[i]);
@@ -58,7 +60,7 @@ int main(int argc, char** argv) {
     char start[256];
     query_(s, "start_time", start, sizeof start);
     printf("Starting time loop from %s (%ld cells)\n", start, query_(s, "n_cells", NULL, 0));
-    long steps = run_(s, max_steps, 1);
+    long steps = run_(s, max_steps, flags);
     if (steps < 0) {
         fprintf(stderr, "--> FOAM FATAL ERROR: %s\n", error_());
         destroy_(s);
