@@ -328,6 +328,9 @@ struct Parser {
         v.kind = Node::NUM;
         v.n = n;
         v.nc = nc;
+        // every value takes at least two bytes of the file (ascii) or its width (binary): refuse a count the
+        // file cannot hold before allocating for it
+        if (n < 0 || (double)n * nc * 2.0 > (double)b.size() + 2.0) fail(name + ": list of " + std::to_string(n) + " entries does not fit in the file");
         v.a.resize((size_t)n * nc);
         skip();
         if (i >= b.size() || b[i] != '(') fail(name + ": expected '(' before the data of a list of " + std::to_string(n));

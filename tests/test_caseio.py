@@ -326,3 +326,20 @@ def test_run_case_interface_rows_match_foamrun(tmp_path, emu_lib):
     assert fa[0] == fb[0] == "time,max_z,min_z,mean_z,num_points" and len(fa) == len(fb) == 4  # t = 0, 0.003, 0.006
     for x, y in zip(fa[1:], fb[1:]):
         assert [float(v) for v in x.split(",")] == [float(v) for v in y.split(",")]
+
+
+def test_product_library_has_no_cpu_path_behind_tpp_open(tmp_path):
+    """without a CUDA device tpp_open on the PRODUCT library is an error, never a silent CPU run"""
+    try:
+        import torch
+
+        if torch.cuda.is_available():
+            pytest.skip("a GPU is present")
+    except ImportError:
+        pass
+    if not os.path.exists(sv.LIB_PATH):
+        pytest.skip("libtppvof.so not built")
+    d = str(tmp_path / "case")
+    _setup(d)
+    with pytest.raises(sv.SolverError, match="no usable CUDA device"):
+        sv.Solver.open(d)
