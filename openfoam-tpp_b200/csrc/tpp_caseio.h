@@ -383,8 +383,7 @@ struct Parser {
                 bool label = false;
                 int nc = !before.empty() && before.back().kind == Node::WORD ? listType(before.back().w, label) : 0;
                 if (nc) return numList(atol(t.c_str()), nc, label);
-                if (binary && !before.empty() && before.back().kind == Node::WORD && before.back().w.rfind("List<", 0) == 0)
-                    fail(name + ": binary list of type " + before.back().w + " is not supported");
+                // anything else (`inGroups List<word> 1(wall)` of a polyMesh/boundary file) is text in both formats
                 i++;
                 return parseList();
             }

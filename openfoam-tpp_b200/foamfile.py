@@ -36,6 +36,7 @@ class FoamError(Exception):
 # tokenizer / recursive-descent parser
 # ----------------------------------------------------------------------------------------
 _PUNCT = b"{}();"
+_BINARY_LISTS = ("List<scalar>", "List<vector>", "List<tensor>", "List<symmTensor>", "List<label>")
 _WS = b" \t\r\n"
 
 
@@ -198,7 +199,9 @@ class _Parser:
             if nxt == "(":
                 # counted list; binary if the stream is binary and the element type is numeric
                 n = int(t)
-                if self.binary and before and isinstance(before[-1], str) and before[-1].startswith("List<"):
+                # numeric element types are raw bytes in a binary stream; `inGroups List<word> 1(wall)` of a
+                # polyMesh/boundary file is text in both formats
+                if self.binary and before and isinstance(before[-1], str) and before[-1] in _BINARY_LISTS:
                     return self._binary_list(n, before[-1])
                 self.next()
                 return self.parse_list()

@@ -29,7 +29,7 @@ def _has_gpu():
 @pytest.fixture(scope="session")
 def emu_lib():
     """Host emulation of the kernel bodies (tests only): same source, TPP_EMU build."""
-    src = [os.path.join(CSRC, f) for f in ("tppvof.cu", "tpp_kernels.h", "tpp_linsolve.h", "tpp_vcycle.h", "tpp_common.h")]
+    src = [os.path.join(CSRC, f) for f in ("tppvof.cu", "tpp_kernels.h", "tpp_linsolve.h", "tpp_vcycle.h", "tpp_common.h", "tpp_caseio.h")]
     if not os.path.exists(EMU_LIB) or os.path.getmtime(EMU_LIB) < max(os.path.getmtime(s) for s in src):
         subprocess.run(["make", "-C", CSRC, "emu"], check=True, capture_output=True)
     return EMU_LIB

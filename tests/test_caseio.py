@@ -343,3 +343,63 @@ def test_product_library_has_no_cpu_path_behind_tpp_open(tmp_path):
     _setup(d)
     with pytest.raises(sv.SolverError, match="no usable CUDA device"):
         sv.Solver.open(d)
+
+
+def test_library_reader_agrees_with_the_python_reader_property(tmp_path, emu_lib):
+    """random field files (scalar / vector, vol / surface, uniform / nonuniform, ascii / binary, payload bytes
+    that spell `);`, `}` or `//`, empty patches): tpp_read_field returns the Python reader's values bit for bit"""
+    from hypothesis import given, settings
+    from hypothesis import strategies as st
+    from hypothesis.extra import numpy as hnp
+
+    tricky = np.frombuffer((b");\n}\n//;(" + b"/*(;)*/{" + b"\n)\n;\n//\n" + b"FoamFile")[:32], dtype="<f8")
+    finite = st.floats(-1e12, 1e12, allow_nan=False, width=64)
+    counter = [0]
+
+    @settings(max_examples=60, deadline=None)
+    @given(cls=st.sampled_from(["volScalarField", "volVectorField", "surfaceScalarField", "surfaceVectorField"]), binary=st.booleans(), n=st.integers(0, 40),
+           uniform=st.booleans(), prec=st.sampled_from([6, 12, 17]), data=st.data())
+    def check(cls, binary, n, uniform, prec, data):
+        nc = 3 if "Vector" in cls else 1
+        shape = (n, 3) if nc == 3 else (n,)
+        if uniform:
+            internal = np.array(data.draw(st.lists(finite, min_size=3, max_size=3))) if nc == 3 else data.draw(finite)
+        else:
+            internal = data.draw(hnp.arrays(np.float64, shape, elements=finite))
+            if binary and n >= 4:
+                internal.reshape(-1)[:4] = tricky
+        nb = data.draw(st.integers(0, 6))
+        bval = data.draw(hnp.arrays(np.float64, (nb, 3) if nc == 3 else (nb,), elements=finite))
+        if binary and bval.size >= 4:
+            bval.reshape(-1)[:4] = tricky
+        boundary = {"walls": {"type": "zeroGradient"}, "atmosphere": {"type": "inletOutlet", "inletValue": "uniform 0", "value": bval},
+                    "empty_one": {"type": "calculated", "value": np.zeros((0, 3) if nc == 3 else (0,))}}
+        counter[0] += 1
+        p = str(tmp_path / f"f{counter[0]}" / "0" / "fld")
+        ff.write_field(p, ff.Field(cls, "fld", "[0 1 -1 0 0 0 0]", internal, boundary), binary=binary, precision=prec, location="0")
+        want = ff.read_field(p).internal
+        got, uni = sv.read_field_file(p, lib_path=emu_lib)
+        assert uni == uniform
+        assert np.asarray(want, dtype="<f8").tobytes() == np.asarray(got, dtype="<f8").tobytes()
+        if not uniform:
+            assert got.shape == shape
+
+    check()
+
+
+def test_boundary_file_as_gmshtofoam_writes_it_in_a_binary_case(tmp_path, emu_lib):
+    """polyMesh/boundary of a `writeFormat binary` case: binary header, text body, `inGroups List<word> 1(wall);`"""
+    d = str(tmp_path / "case")
+    _setup(d)
+    p = os.path.join(d, "constant", "polyMesh", "boundary")
+    s = open(p).read()
+    s = s.replace("format      ascii;", 'format      binary;\n    arch        "LSB;label=32;scalar=64";')
+    s, n = re.subn(r"(\n\s*type\s+patch;)", r"\1\n        physicalType    patch;\n        inGroups        List<word> 1(wall);", s)
+    assert n == 2
+    open(p, "w").write(s)
+    c, a = _python_solver(d, emu_lib)
+    b = sv.Solver.open(d, lib_path=emu_lib)
+    assert [q["type"] for q in c.mesh.patches] == ["patch", "patch"] and b.case_query("n_patches") == 2
+    _same_state(a, b)
+    a.close()
+    b.close()
