@@ -403,3 +403,56 @@ def test_boundary_file_as_gmshtofoam_writes_it_in_a_binary_case(tmp_path, emu_li
     _same_state(a, b)
     a.close()
     b.close()
+
+
+def test_case_handles_run_concurrently_from_host_threads(tmp_path, emu_lib):
+    """the sweep's execution model (main.py:504-534: independent cases) at the case-directory level: one host
+    thread and one handle per case, all running at once, each ending where it ends when run alone"""
+    import threading
+
+    dirs = []
+    for k in range(4):
+        d = str(tmp_path / f"case{k}")
+        cs.setup_case(d, H=0.004, D=0.0221, R=0.004 + 0.001 * k, freq=2.0, duration=1.0, n_rings=5, n_layers=5, write_interval=0.003, end_time=0.006)
+        dirs.append(d)
+    alone = str(tmp_path / "alone")
+    shutil.copytree(dirs[2], alone)
+    s = sv.Solver.open(alone, lib_path=emu_lib)
+    n_alone = s.run_case()
+    s.close()
+    out, errs = {}, []
+
+    def work(d):
+        try:
+            h = sv.Solver.open(d, lib_path=emu_lib)
+            out[d] = h.run_case()
+            h.close()
+        except Exception as e:  # noqa: BLE001
+            errs.append((d, e))
+
+    ts = [threading.Thread(target=work, args=(d,)) for d in dirs]
+    for t in ts:
+        t.start()
+    for t in ts:
+        t.join()
+    assert not errs, errs
+    assert out[dirs[2]] == n_alone
+    for nm in ("alpha.water", "U", "p_rgh", "phi"):
+        assert open(os.path.join(alone, "0.006", nm), "rb").read() == open(os.path.join(dirs[2], "0.006", nm), "rb").read(), nm
+    # a failing case reports its own message to its own thread (thread-local tpp_last_error)
+    _set_entry(os.path.join(dirs[0], "system", "fvSchemes"), "div(rhoPhi,U)", "Gauss upwind")
+    shutil.rmtree(os.path.join(dirs[1], "constant", "polyMesh"))
+    msgs = {}
+
+    def fail(d):
+        try:
+            sv.Solver.open(d, lib_path=emu_lib).close()
+        except sv.SolverError as e:
+            msgs[d] = str(e)
+
+    ts = [threading.Thread(target=fail, args=(d,)) for d in dirs[:2]]
+    for t in ts:
+        t.start()
+    for t in ts:
+        t.join()
+    assert "fvSchemes" in msgs[dirs[0]] and "polyMesh" in msgs[dirs[1]]
