@@ -456,3 +456,20 @@ def test_case_handles_run_concurrently_from_host_threads(tmp_path, emu_lib):
     for t in ts:
         t.join()
     assert "fvSchemes" in msgs[dirs[0]] and "polyMesh" in msgs[dirs[1]]
+
+
+def test_start_fields_of_the_wrong_size_are_refused(tmp_path, emu_lib):
+    d = str(tmp_path / "case")
+    _setup(d)
+    c = cs.Case(d)
+    f = c.fields["alpha.water"]
+    f.internal = f.internal_array(c.mesh.n_cells)[:-1]
+    ff.write_field(os.path.join(d, "0", "alpha.water"), f, binary=True, location="0")
+    with pytest.raises(sv.SolverError, match=r"alpha.water:internalField: holds \d+ values, the mesh needs \d+"):
+        sv.Solver.open(d, lib_path=emu_lib)
+    f = c.fields["U"]
+    f.boundary["walls"]["value"] = np.zeros((3, 3))
+    ff.write_field(os.path.join(d, "0", "alpha.water"), c.fields["alpha.water"].__class__(f.cls.replace("Vector", "Scalar"), "alpha.water", "[0 0 0 0 0 0 0]", 0.0, c.fields["alpha.water"].boundary), binary=True, location="0")
+    ff.write_field(os.path.join(d, "0", "U"), f, binary=True, location="0")
+    with pytest.raises(sv.SolverError, match=r"walls.value: holds 3 values"):
+        sv.Solver.open(d, lib_path=emu_lib)
