@@ -3105,19 +3105,44 @@ void caseWrite(tpp_handle s) {
         }
         return out;
     };
-    std::vector<double> alpha = getArray(s, "alpha"), alpha_b = getArray(s, "alpha_b"), U = getArray(s, "U"), U_b = getArray(s, "U_b");
-    std::vector<double> p_rgh = getArray(s, "p_rgh"), p_rgh_b = getArray(s, "p_rgh_b"), rho = getArray(s, "rho"), rho_b = getArray(s, "rho_b");
-    std::vector<double> p = getArray(s, "p"), phi = getArray(s, "phi"), Uf = getArray(s, "Uf"), ghf = getArray(s, "ghf");
-    if ((long)alpha_b.size() < nBphys || (long)ghf.size() < nI + nBphys) caseio::fail("internal: boundary arrays are smaller than the case's physical patches");
-    caseio::writeField(tdir + "/alpha.water", "volScalarField", "alpha.water", name, "[0 0 0 0 0 0 0]", alpha.data(), nC, 1, volPatches(&cs.alpha, alpha, alpha_b, 1), bin, prec);
-    caseio::writeField(tdir + "/U", "volVectorField", "U", name, "[0 1 -1 0 0 0 0]", U.data(), nC, 3, volPatches(&cs.U, U, U_b, 3), bin, prec);
-    caseio::writeField(tdir + "/p_rgh", "volScalarField", "p_rgh", name, "[1 -1 -2 0 0 0 0]", p_rgh.data(), nC, 1, volPatches(&cs.p_rgh, p_rgh, p_rgh_b, 1), bin, prec);
-    std::vector<double> pb((size_t)nBphys);
-    for (long k = 0; k < nBphys; k++) pb[k] = p_rgh_b[k] + rho_b[k] * ghf[nI + k];
-    caseio::writeField(tdir + "/p", "volScalarField", "p", name, "[1 -1 -2 0 0 0 0]", p.data(), nC, 1, volPatches(nullptr, p, pb, 1), bin, prec);
-    caseio::writeField(tdir + "/rho", "volScalarField", "rho", name, "[1 -3 0 0 0 0 0]", rho.data(), nC, 1, volPatches(nullptr, rho, rho_b, 1), bin, prec);
-    caseio::writeField(tdir + "/phi", "surfaceScalarField", "phi", name, "[0 3 -1 0 0 0 0]", phi.data(), nI, 1, facePatches(phi, 1), bin, prec);
-    caseio::writeField(tdir + "/Uf", "surfaceVectorField", "Uf", name, "[0 1 -1 0 0 0 0]", Uf.data(), nI, 3, facePatches(Uf, 3), bin, prec);
+    // one field at a time: the host copy of a field is dropped before the next one is fetched (a 50 M-cell
+    // tank's Uf alone is 2.4 GB)
+    std::vector<double> p_rgh_b = getArray(s, "p_rgh_b"), rho_b = getArray(s, "rho_b");
+    if ((long)rho_b.size() < nBphys || (long)p_rgh_b.size() < nBphys) caseio::fail("internal: boundary arrays are smaller than the case's physical patches");
+    {
+        std::vector<double> alpha = getArray(s, "alpha"), alpha_b = getArray(s, "alpha_b");
+        caseio::writeField(tdir + "/alpha.water", "volScalarField", "alpha.water", name, "[0 0 0 0 0 0 0]", alpha.data(), nC, 1, volPatches(&cs.alpha, alpha, alpha_b, 1), bin, prec);
+    }
+    {
+        std::vector<double> U = getArray(s, "U"), U_b = getArray(s, "U_b");
+        caseio::writeField(tdir + "/U", "volVectorField", "U", name, "[0 1 -1 0 0 0 0]", U.data(), nC, 3, volPatches(&cs.U, U, U_b, 3), bin, prec);
+    }
+    {
+        std::vector<double> p_rgh = getArray(s, "p_rgh");
+        caseio::writeField(tdir + "/p_rgh", "volScalarField", "p_rgh", name, "[1 -1 -2 0 0 0 0]", p_rgh.data(), nC, 1, volPatches(&cs.p_rgh, p_rgh, p_rgh_b, 1), bin, prec);
+    }
+    {
+        std::vector<double> pb((size_t)nBphys);
+        {
+            std::vector<double> ghf = getArray(s, "ghf");
+            if ((long)ghf.size() < nI + nBphys) caseio::fail("internal: ghf is smaller than the case's faces");
+            for (long k = 0; k < nBphys; k++) pb[k] = p_rgh_b[k] + rho_b[k] * ghf[nI + k];
+        }
+        std::vector<double> p = getArray(s, "p");
+        caseio::writeField(tdir + "/p", "volScalarField", "p", name, "[1 -1 -2 0 0 0 0]", p.data(), nC, 1, volPatches(nullptr, p, pb, 1), bin, prec);
+    }
+    {
+        std::vector<double> rho = getArray(s, "rho");
+        caseio::writeField(tdir + "/rho", "volScalarField", "rho", name, "[1 -3 0 0 0 0 0]", rho.data(), nC, 1, volPatches(nullptr, rho, rho_b, 1), bin, prec);
+    }
+    {
+        std::vector<double> phi = getArray(s, "phi");
+        caseio::writeField(tdir + "/phi", "surfaceScalarField", "phi", name, "[0 3 -1 0 0 0 0]", phi.data(), nI, 1, facePatches(phi, 1), bin, prec);
+    }
+    {
+        std::vector<double> Uf = getArray(s, "Uf");
+        caseio::writeField(tdir + "/Uf", "surfaceVectorField", "Uf", name, "[0 1 -1 0 0 0 0]", Uf.data(), nI, 3, facePatches(Uf, 3), bin, prec);
+    }
     if (cs.cfg.c.n_motion > 0) {
         caseio::makeDirs(tdir + "/polyMesh");
         std::vector<double> pts = getArray(s, "points");
