@@ -63,6 +63,10 @@ def build_structs(mesh, cfg):
         keep.append(a)
         return a
 
+    # the C struct carries no length for face_labels: check the offsets against it before the library indexes with them
+    off, nlab = np.asarray(mesh.face_offsets), len(mesh.face_labels)
+    if off.size != mesh.n_faces + 1 or off[0] != 0 or off[-1] != nlab or np.any(np.diff(off) < 0):
+        raise ValueError(f"polyMesh faces: the offsets do not span the {nlab} point labels")
     pts = arr(mesh.points, np.float64)
     m = MeshStruct()
     m.n_points, m.n_faces, m.n_internal, m.n_cells, m.n_patches = mesh.n_points, mesh.n_faces, mesh.n_internal, mesh.n_cells, len(mesh.patches)

@@ -536,6 +536,10 @@ inline Mesh readPolyMesh(const std::string& caseDir) {
     int nF = m.nFaces(), nI = m.nInternal(), nP = (int)(m.points.size() / 3);
     if ((int)m.fOff.size() != nF + 1) fail(d + ": faces and owner disagree on the number of faces");
     if (nI > nF) fail(d + ": more neighbours than faces");
+    // the array ABI carries no length for face_labels: the offsets are checked against it here
+    if (m.fOff[0] != 0 || m.fOff[nF] != (int)m.fLab.size()) fail(d + "/faces: the offsets do not span the " + std::to_string(m.fLab.size()) + " point labels");
+    for (int f = 0; f < nF; f++)
+        if (m.fOff[f + 1] < m.fOff[f]) fail(d + "/faces: offsets of face " + std::to_string(f) + " decrease");
     for (int l : m.fLab)
         if (l < 0 || l >= nP) fail(d + "/faces: point label out of range");
     int mx = -1;

@@ -473,3 +473,19 @@ def test_start_fields_of_the_wrong_size_are_refused(tmp_path, emu_lib):
     ff.write_field(os.path.join(d, "0", "U"), f, binary=True, location="0")
     with pytest.raises(sv.SolverError, match=r"walls.value: holds 3 values"):
         sv.Solver.open(d, lib_path=emu_lib)
+
+
+def test_face_offsets_that_overrun_the_labels_are_refused_by_both_hosts(tmp_path, emu_lib):
+    """found by mutation fuzzing under AddressSanitizer: the array ABI has no length for face_labels, so a
+    damaged faceCompactList must be stopped by whoever read the file"""
+    d = str(tmp_path / "case")
+    _setup(d)
+    mesh = ff.read_polymesh(d)
+    mesh.face_offsets = mesh.face_offsets.copy()
+    mesh.face_offsets[-1] += 7
+    ff.write_polymesh(d, mesh, binary=True)
+    with pytest.raises(sv.SolverError, match="faces: the offsets do not span"):
+        sv.Solver.open(d, lib_path=emu_lib)
+    c = cs.Case(d)
+    with pytest.raises(ValueError, match="offsets do not span"):
+        sv.Solver(c.mesh, c.cfg, lib_path=emu_lib)
