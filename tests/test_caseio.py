@@ -489,3 +489,27 @@ def test_face_offsets_that_overrun_the_labels_are_refused_by_both_hosts(tmp_path
     c = cs.Case(d)
     with pytest.raises(ValueError, match="offsets do not span"):
         sv.Solver(c.mesh, c.cfg, lib_path=emu_lib)
+
+
+def test_the_binding_integration_md_gives_for_main_py(tmp_path, emu_lib):
+    """the ctypes-only `run_case_local` a maintainer pastes into the reference's
+    main.py (333-348) - extracted from the document and run as it stands"""
+    import subprocess as sp
+
+    text = open(os.path.join(ROOT, "INTEGRATION.md")).read()
+    start = text.index("import ctypes, subprocess\n")
+    code = text[start : text.index("```", start)].replace("/path/to/openfoam-tpp_b200/libtppvof.so", emu_lib)
+    ns = {}
+    exec(compile(code, "INTEGRATION.md", "exec"), ns)
+    d = str(tmp_path / "case")
+    _setup(d)
+    _set_entry(os.path.join(d, "system", "controlDict"), "endTime", "0.003")
+    ns["run_case_local"](d)
+    assert cs.latest_time(d)[1] == "0.003"
+    _set_entry(os.path.join(d, "system", "controlDict"), "endTime", "0.006")
+    ns["run_case_local"](d, n_cpus=4)  # resume
+    assert cs.latest_time(d)[1] == "0.006"
+    _set_entry(os.path.join(d, "system", "fvSolution"), "momentumPredictor", "yes")
+    with pytest.raises(sp.CalledProcessError) as e:
+        ns["run_case_local"](d)
+    assert "momentumPredictor" in e.value.stderr
