@@ -65,7 +65,7 @@ def build_structs(mesh, cfg):
 
     # the C struct carries no length for face_labels: check the offsets against it before the library indexes with them
     off, nlab = np.asarray(mesh.face_offsets), len(mesh.face_labels)
-    if off.size != mesh.n_faces + 1 or off[0] != 0 or off[-1] != nlab or np.any(np.diff(off) < 0):
+    if off.size != mesh.n_faces + 1 or off[0] != 0 or off[-1] > nlab or np.any(np.diff(off) < 0):
         raise ValueError(f"polyMesh faces: the offsets do not span the {nlab} point labels")
     pts = arr(mesh.points, np.float64)
     m = MeshStruct()

@@ -121,7 +121,10 @@ class Solver:
 
     def __init__(self, mesh, cfg, device=0, lib_path=None):
         self.L = load(lib_path)
-        m, c, self._keep = abi.build_structs(mesh, cfg)
+        try:
+            m, c, self._keep = abi.build_structs(mesh, cfg)
+        except ValueError as e:  # what the array ABI cannot check for itself (no length for face_labels)
+            raise SolverError(f"invalid mesh / configuration: {e}") from None
         h = C.c_void_p()
         rc = self.L.tpp_create(C.byref(m), C.byref(c), device, C.byref(h))
         if rc != 0:

@@ -487,7 +487,7 @@ def test_face_offsets_that_overrun_the_labels_are_refused_by_both_hosts(tmp_path
     with pytest.raises(sv.SolverError, match="faces: the offsets do not span"):
         sv.Solver.open(d, lib_path=emu_lib)
     c = cs.Case(d)
-    with pytest.raises(ValueError, match="offsets do not span"):
+    with pytest.raises(sv.SolverError, match="invalid mesh / configuration: polyMesh faces: the offsets do not span"):
         sv.Solver(c.mesh, c.cfg, lib_path=emu_lib)
 
 
