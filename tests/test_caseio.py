@@ -219,12 +219,12 @@ def test_c_host_runs_a_case_directory(tmp_path, emu_lib):
     d = str(tmp_path / "case")
     _setup(d)
     _set_entry(os.path.join(d, "system", "controlDict"), "endTime", "0.003")
-    r = subprocess.run([exe, emu_lib, "-case", d], capture_output=True, text=True)
+    r = subprocess.run([exe, emu_lib, "-case", d], capture_output=True, text=True, timeout=600)
     assert r.returncode == 0, r.stdout + r.stderr
     assert "Time = 0.003" in r.stdout and r.stdout.rstrip().splitlines()[-1].startswith("End")
     assert cs.latest_time(d)[1] == "0.003"
     _set_entry(os.path.join(d, "system", "fvSchemes"), "div(rhoPhi,U)", "Gauss upwind")
-    r = subprocess.run([exe, emu_lib, "-case", d], capture_output=True, text=True)
+    r = subprocess.run([exe, emu_lib, "-case", d], capture_output=True, text=True, timeout=600)
     assert r.returncode == 1 and "FOAM FATAL ERROR" in r.stderr and "fvSchemes" in r.stderr
 
 

@@ -52,7 +52,7 @@ def test_c_host_runs_a_case_directory_gpu(tmp_path, gpu_lib):
     _setup(a, 0.006)
     _setup(b, 0.006)
     out = foamrun.run_case(a, device=0, log=None)
-    r = subprocess.run([exe, gpu_lib, "-case", b], capture_output=True, text=True)
+    r = subprocess.run([exe, gpu_lib, "-case", b], capture_output=True, text=True, timeout=600)
     assert r.returncode == 0, r.stdout + r.stderr
     assert r.stdout.rstrip().splitlines()[-1] == f"End  ({out['steps']} steps)"
     assert cs.latest_time(b) == cs.latest_time(a)
