@@ -56,9 +56,13 @@ inline std::string slurp(const std::string& path) {
     FILE* f = fopen(path.c_str(), "rb");
     if (!f) fail(path + ": cannot open");
     std::string s;
+    struct stat st;
+    if (fstat(fileno(f), &st) == 0 && st.st_size > 0) s.resize((size_t)st.st_size);  // one read of the whole file
+    size_t got = s.empty() ? 0 : fread(&s[0], 1, s.size(), f);
+    s.resize(got);
     char buf[1 << 16];
     size_t n;
-    while ((n = fread(buf, 1, sizeof buf, f)) > 0) s.append(buf, n);
+    while ((n = fread(buf, 1, sizeof buf, f)) > 0) s.append(buf, n);  // whatever a growing file still holds
     fclose(f);
     return s;
 }
@@ -599,7 +603,7 @@ struct Field {
         return nullptr;
     }
 };
-inline Value fieldValue(const Stream& s, int nc, const std::string& what) {
+inline Value fieldValue(Stream& s, int nc, const std::string& what) {  // takes the numbers out of the parse tree
     Value v;
     v.present = true;
     if (s.size() >= 2 && s[0].kind == Node::WORD && s[0].w == "uniform") {
@@ -611,7 +615,7 @@ inline Value fieldValue(const Stream& s, int nc, const std::string& what) {
     }
     if (s.size() == 3 && s[0].kind == Node::WORD && s[0].w == "nonuniform" && s[2].kind == Node::NUM && s[2].nc == nc) {
         v.uniform = false;
-        v.a = s[2].a;
+        v.a = std::move(s[2].a);
         return v;
     }
     fail(what + ": unsupported field value '" + join(s).substr(0, 60) + "'");
@@ -625,8 +629,8 @@ inline Field readField(const std::string& path) {
     else fail(path + ": unsupported field class '" + fld.cls + "'");
     Dict d = f.p.parseDictBody(true);
     fld.dimensions = wordOr(d, "dimensions", "");
-    fld.internal = fieldValue(lookup(d, "internalField", path), fld.nc, path + ":internalField");
-    if (const Stream* bf = find(d, "boundaryField")) {
+    fld.internal = fieldValue(const_cast<Stream&>(lookup(d, "internalField", path)), fld.nc, path + ":internalField");
+    if (Stream* bf = const_cast<Stream*>(find(d, "boundaryField"))) {
         if (bf->size() != 1 || (*bf)[0].kind != Node::DICT) fail(path + ": boundaryField is not a dictionary");
         for (auto& kv : (*bf)[0].d) {
             BoundaryEntry e;

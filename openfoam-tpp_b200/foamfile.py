@@ -201,8 +201,23 @@ class _Parser:
                 n = int(t)
                 # numeric element types are raw bytes in a binary stream; `inGroups List<word> 1(wall)` of a
                 # polyMesh/boundary file is text in both formats
-                if self.binary and before and isinstance(before[-1], str) and before[-1] in _BINARY_LISTS:
-                    return self._binary_list(n, before[-1])
+                if before and isinstance(before[-1], str) and before[-1] in _BINARY_LISTS:
+                    if self.binary:
+                        return self._binary_list(n, before[-1])
+                    # ascii numbers in bulk (numpy), not token by token: a 3 M-vector field in 2 s instead of 76 s
+                    typ = before[-1][5:-1]
+                    self._skip()
+                    start = self.i + 1
+                    if n == 0:
+                        end = self.b.index(b")", start) + 1
+                        a = np.zeros((0,) if _NCOMP[typ] == 1 else (0, _NCOMP[typ]), dtype=np.int64 if typ == "label" else np.float64)
+                    else:
+                        try:
+                            a, end = _fast_ascii_list(self.b, start, n, _NCOMP[typ], label=(typ == "label"))
+                        except ValueError as e:
+                            raise FoamError(f"{self.name}: malformed {before[-1]} of {n} entries ({e})")
+                    self.i = end
+                    return a
                 self.next()
                 return self.parse_list()
             if nxt == "{":
@@ -349,7 +364,9 @@ _NCOMP = {"scalar": 1, "vector": 3, "tensor": 9, "symmTensor": 6, "label": 1}
 def _decode_list(val, typ, p):
     """val: BinaryBlock | nested python list -> numpy array (n, ncomp) or (n,)"""
     nc = _NCOMP[typ]
-    if isinstance(val, BinaryBlock):
+    if isinstance(val, np.ndarray):  # an ascii list the parser already decoded in bulk
+        a = val.astype(np.int64 if typ == "label" else np.float64, copy=False)
+    elif isinstance(val, BinaryBlock):
         if typ == "label":
             dt = "<i4" if p.label_bytes == 4 else "<i8"
         else:

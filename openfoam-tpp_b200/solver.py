@@ -108,11 +108,14 @@ def read_field_file(path, lib_path=None):
     """internalField of a field file through the library's reader (tpp_read_field): (array, uniform)."""
     L = load(lib_path)
     nc, uni = C.c_int(), C.c_int()
-    n = L.tpp_read_field(os.fsencode(path), None, 0, C.byref(nc), C.byref(uni))
+    # one pass: no field holds more doubles than half its file's bytes (untouched pages of the buffer cost nothing)
+    cap = (os.path.getsize(path) if os.path.exists(path) else 0) // 2 + 16
+    a = np.empty(cap)
+    n = L.tpp_read_field(os.fsencode(path), a.ctypes.data_as(abi.c_double_p), cap, C.byref(nc), C.byref(uni))
     if n < 0:
         raise SolverError(f"tpp_read_field failed ({n}): {L.tpp_last_error().decode()}")
-    a = np.empty(n)
-    L.tpp_read_field(os.fsencode(path), a.ctypes.data_as(abi.c_double_p), n, C.byref(nc), C.byref(uni))
+    assert n <= cap
+    a = a[:n].copy()
     return (a.reshape(-1, nc.value) if nc.value > 1 else a), bool(uni.value)
 
 
